@@ -1,0 +1,68 @@
+"""Deterministic synthetic Arrow-columnar workloads.
+
+The reference's demo_app reads a user file (apps/demo_app.cc:297-330); there is no dataset in this
+environment, so the benchmark and the tests generate TPC-H-lineitem-like fixed-width Arrow value
+buffers instead:  sorted int64 keys, int32 dictionary indices of 7 skewed categories, and float64
+two-decimal prices, concatenated column-major in equal thirds.
+"""
+import numpy as np
+
+SEED = 20261018
+_DICT_P = np.array([.30, .20, .15, .12, .10, .08, .05])
+
+
+def col_sorted_int64(nbytes, rng):
+    n = nbytes // 8
+    return np.cumsum(rng.integers(0, 4, size=n, dtype=np.int64)).astype("<i8").view(np.uint8)
+
+
+def col_dict_int32(nbytes, rng):
+    n = nbytes // 4
+    return rng.choice(7, size=n, p=_DICT_P).astype("<i4").view(np.uint8)
+
+
+def col_price_f64(nbytes, rng):
+    n = nbytes // 8
+    return (rng.integers(90_000, 10_500_000, size=n, dtype=np.int64) / 100.0).astype("<f8").view(np.uint8)
+
+
+COLUMNS = {"sorted_int64": col_sorted_int64, "dict_int32": col_dict_int32, "price_f64": col_price_f64}
+
+
+def column(name, nbytes, seed=SEED):
+    """nbytes of one column type (nbytes rounded down to the value width)."""
+    return np.ascontiguousarray(COLUMNS[name](nbytes, np.random.default_rng(seed)))
+
+
+def lineitem_like(nbytes, seed=SEED):
+    """nbytes (multiple of 24 recommended) of the three columns in equal thirds, column-major."""
+    rng = np.random.default_rng(seed)
+    third = (nbytes // 3) // 8 * 8
+    parts = [col_sorted_int64(third, rng), col_dict_int32(third, rng)]
+    parts.append(col_price_f64(nbytes - 2 * third, rng))
+    out = np.concatenate(parts)
+    if out.size < nbytes:  # tail when nbytes - 2*third is not a multiple of 8
+        out = np.concatenate([out, np.zeros(nbytes - out.size, np.uint8)])
+    return np.ascontiguousarray(out)
+
+
+def edge_cases(seg, seed=SEED):
+    """BASELINE.json config 5 inputs: name -> uint8 array."""
+    rng = np.random.default_rng(seed)
+    cases = {}
+    for n in (0, 1, 7, 8, seg - 1, seg, seg + 1, 3 * seg + 17):
+        cases[f"random_{n}"] = np.frombuffer(rng.bytes(n), np.uint8).copy()
+        cases[f"zeros_{n}"] = np.zeros(n, np.uint8)
+    cases["ab"] = np.frombuffer(b"ab" * (seg // 2 + 5), np.uint8).copy()
+    p258 = np.frombuffer(rng.bytes(258), np.uint8)
+    cases["period258"] = np.tile(p258, (2 * seg) // 258 + 1).copy()
+    p32k = np.frombuffer(rng.bytes(32768), np.uint8)
+    cases["period32768"] = np.tile(p32k, 3).copy()
+    p32k1 = np.frombuffer(rng.bytes(32769), np.uint8)
+    cases["period32769"] = np.tile(p32k1, 3).copy()   # just beyond the 32 KiB window
+    text = (b"the quick brown fox jumps over the lazy dog. " * 40 +
+            b"pack my box with five dozen liquor jugs! " * 30)
+    cases["text"] = np.frombuffer(text * (seg // len(text) + 2), np.uint8).copy()
+    ramp = (np.arange(4 * seg, dtype=np.uint32) * 2654435761 >> 13).astype(np.uint8)
+    cases["lowentropy"] = (ramp & 0x0F).astype(np.uint8)
+    return cases

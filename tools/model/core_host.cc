@@ -1,0 +1,72 @@
+// core_host.cc -- builds the kernels' host/device-shared code for the CPU (TEST TOOL).
+//   * host_inflate_chunk : bitar_b200/csrc/inflate_core.h instantiated with G = 1
+//   * model_deflate_chunk: sequential model of the deflate kernel (deflate_model.h)
+// Loaded through ctypes by tests/; never part of the product library.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../bitar_b200/csrc/inflate_core.h"
+#include "deflate_model.h"
+
+#define API extern "C" __attribute__((visibility("default")))
+
+API int host_inflate_chunk(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t cap,
+                           uint32_t* result4, int lbits) {
+  using namespace bitar::inf;
+  Group<1> g{0, 1u};
+  ChunkResult r;
+  if (lbits == 9) {
+    static thread_local GroupSmem<9, 7, 1024> sm;
+    r = inflate_chunk<1, 9, 7, 1024>(in, in_len, out, cap, &sm, g);
+  } else {
+    static thread_local GroupSmem<10, 8, 1024> sm;
+    r = inflate_chunk<1, 10, 8, 1024>(in, in_len, out, cap, &sm, g);
+  }
+  result4[0] = r.produced;
+  result4[1] = r.status;
+  result4[2] = r.consumed;
+  result4[3] = r.blocks;
+  return 0;
+}
+
+API long model_deflate_chunk(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t cap, int huffman,
+                             int block) {
+  bitar_model::Params P;
+  P.huffman = huffman;
+  if (block > 0) P.block = block;
+  auto out = bitar_model::deflate_chunk(src, n, P);
+  if (out.size() > cap) return -1;
+  memcpy(dst, out.data(), out.size());
+  return (long)out.size();
+}
+
+// symbol-map self check used by tests: returns 0 when the computed maps agree with RFC 1951 tables
+API int model_selfcheck(void) {
+  using namespace bitar::dfl;
+  static const uint16_t lb[29] = {3,  4,  5,  6,  7,  8,  9,  10, 11,  13,  15,  17,  19,  23, 27,
+                                  31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+  static const uint8_t le[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+  static const uint16_t db[30] = {1,   2,   3,   4,   5,   7,    9,    13,   17,   25,   33,   49,   65,    97,    129,
+                                  193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+  static const uint8_t de[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+  static const uint8_t co[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+  for (int s = 0; s < 29; ++s)
+    if (len_base(s) != lb[s] || len_extra_bits(s) != le[s]) return 1;
+  for (int s = 0; s < 30; ++s)
+    if (dist_base(s) != db[s] || dist_extra_bits(s) != de[s]) return 2;
+  for (int len = 3; len <= 258; ++len) {
+    int s = len_sym(len);
+    if (s < 0 || s > 28 || len < lb[s] || (s < 28 && len >= lb[s + 1] && s != 27) ||
+        lb[s] + len_extra_val(len, s) != len)
+      return 3;
+    if (s == 27 && len > 257) return 3;
+  }
+  for (int d = 1; d <= 32768; ++d) {
+    int s = dist_sym(d);
+    if (s < 0 || s > 29 || db[s] + dist_extra_val(d, s) != d || dist_extra_val(d, s) >= (1 << de[s])) return 4;
+  }
+  for (int i = 0; i < 19; ++i)
+    if (cl_order(i) != co[i]) return 5;
+  return 0;
+}

@@ -1,0 +1,87 @@
+// ratio_eval -- tune the GPU match finder's parameters on the CPU model and compare the compressed
+// size with zlib level 1 (the reference's level, /root/reference/src/config.cc:87) chunk by chunk.
+// Every model stream is verified by inflating it with zlib.   usage: ratio_eval FILE SEG [key=val..]
+#include <zlib.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "deflate_model.h"
+
+static std::vector<uint8_t> zdeflate(const uint8_t* d, size_t n, int level, int strategy) {
+  z_stream zs{};
+  deflateInit2(&zs, level, Z_DEFLATED, -15, 8, strategy);
+  std::vector<uint8_t> out(n + n / 8 + 256);
+  zs.next_in = (Bytef*)d;
+  zs.avail_in = (uInt)n;
+  zs.next_out = out.data();
+  zs.avail_out = (uInt)out.size();
+  deflate(&zs, Z_FINISH);
+  out.resize(out.size() - zs.avail_out);
+  deflateEnd(&zs);
+  return out;
+}
+static bool zcheck(const std::vector<uint8_t>& c, const uint8_t* d, size_t n) {
+  z_stream zs{};
+  inflateInit2(&zs, -15);
+  std::vector<uint8_t> out(n + 16);
+  zs.next_in = (Bytef*)c.data();
+  zs.avail_in = (uInt)c.size();
+  zs.next_out = out.data();
+  zs.avail_out = (uInt)out.size();
+  int rc = inflate(&zs, Z_FINISH);
+  size_t got = out.size() - zs.avail_out;
+  inflateEnd(&zs);
+  return rc == Z_STREAM_END && got == n && memcmp(out.data(), d, n) == 0 && zs.avail_in == 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 3) return fprintf(stderr, "usage: %s FILE SEG [key=val ...]\n", argv[0]), 2;
+  FILE* f = fopen(argv[1], "rb");
+  if (!f) return perror("open"), 1;
+  std::vector<uint8_t> data;
+  uint8_t buf[1 << 16];
+  size_t r;
+  while ((r = fread(buf, 1, sizeof buf, f)) > 0) data.insert(data.end(), buf, buf + r);
+  fclose(f);
+  size_t seg = (size_t)atol(argv[2]);
+  bitar_model::Params P;
+  for (int i = 3; i < argc; ++i) {
+    std::string kv = argv[i];
+    auto eq = kv.find('=');
+    std::string k = kv.substr(0, eq);
+    int v = atoi(kv.substr(eq + 1).c_str());
+    if (k == "step") P.step = v;
+    else if (k == "hash_bits") P.hash_bits = v;
+    else if (k == "min_match") P.min_match = v;
+    else if (k == "cand_mode") P.cand_mode = v;
+    else if (k == "far3") P.far3 = v;
+    else if (k == "huffman") P.huffman = v;
+    else if (k == "block") P.block = v;
+    else return fprintf(stderr, "unknown key %s\n", k.c_str()), 2;
+  }
+  uint64_t zsum = 0, msum = 0, lits = 0, matches = 0, mbytes = 0;
+  int types[3] = {0, 0, 0};
+  for (size_t off = 0; off < data.size(); off += seg) {
+    size_t n = std::min(seg, data.size() - off);
+    auto z = zdeflate(data.data() + off, n, 1, P.huffman == 1 ? Z_FIXED : Z_DEFAULT_STRATEGY);
+    std::vector<bitar_model::BlockStats> st;
+    auto m = bitar_model::deflate_chunk(data.data() + off, n, P, &st);
+    if (!zcheck(m, data.data() + off, n)) return fprintf(stderr, "MODEL STREAM INVALID at chunk %zu\n", off / seg), 1;
+    zsum += z.size();
+    msum += m.size();
+    for (auto& s : st) {
+      lits += s.literals;
+      matches += s.matches;
+      mbytes += s.match_bytes;
+      types[s.type]++;
+    }
+  }
+  printf("bytes=%zu zlib1=%llu (%.3f) model=%llu (%.3f) model/zlib=%.4f  lits=%llu matches=%llu avg_mlen=%.1f B/sym=%.2f blocks s/f/d=%d/%d/%d\n",
+         data.size(), (unsigned long long)zsum, (double)data.size() / zsum, (unsigned long long)msum,
+         (double)data.size() / msum, (double)msum / zsum, (unsigned long long)lits,
+         (unsigned long long)matches, matches ? (double)mbytes / matches : 0.0,
+         (double)data.size() / (double)(lits + matches), types[0], types[1], types[2]);
+  return 0;
+}
