@@ -1,0 +1,557 @@
+// capi.cu -- implementation of include/bitar_cuda.h: CUDA device probe, queue pairs (one stream
+// each), the output-slot pool, memory allocation and the kernel launches.
+//
+// Mapping to the reference (/root/reference):
+//   bitar_dev            <- CompressDevice state + DeviceMemory        (src/device.cc:114-154, src/memory.cc:120-235)
+//   QueuePair            <- QueuePairMemory: op/mbuf pools, pending ops (src/memory.cc:237-348, 507-575)
+//   bitar_qp_deflate/... <- AssembleFrom + EnqueueBurst/DequeueBurst    (src/memory.cc:350-505, src/device.cc:464-535)
+//   slot pool            <- DeviceMemory::Take/Put                      (src/memory.cc:160-209)
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <unordered_set>
+#include <vector>
+
+#include "../../include/bitar_cuda.h"
+#include "deflate_kernel.cuh"
+#include "inflate_kernel.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_inflate_variant{-1};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU_TRY(expr, code)                                                                   \
+  do {                                                                                       \
+    cudaError_t e_ = (expr);                                                                 \
+    if (e_ != cudaSuccess) return fail(code, "%s: %s", #expr, cudaGetErrorString(e_));       \
+  } while (0)
+
+struct QueuePair {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_stop = nullptr;
+  bitar_chunk* h_ops = nullptr;    // pinned descriptor ring
+  bitar_chunk* d_ops = nullptr;    // device descriptor ring
+  bitar_result* h_res = nullptr;   // pinned results
+  bitar_result* d_res = nullptr;
+  uint32_t cap = 0;
+  unsigned int* d_counter = nullptr;
+  uint32_t* d_tokens = nullptr;    // deflate token scratch (grid * 64 Ki u32), allocated on first use
+  bitar_result* user_out = nullptr;
+  uint32_t pending_n = 0;
+  std::atomic<int> busy{0};
+  std::atomic<int> last_status{0};
+  bool timed = false;
+};
+
+}  // namespace
+
+struct bitar_dev {
+  int id = 0;
+  int sm_count = 0;
+  bitar_cfg cfg{};
+  std::vector<QueuePair*> qps;
+  int deflate_grid = 0;
+  // slot pool
+  std::mutex mu;
+  std::vector<void*> slabs;
+  std::vector<void*> free_slots;                 // LIFO
+  std::unordered_set<const void*> occupied;
+  uint32_t slot_stride = 0;
+  uint32_t grow_warned = 0;
+};
+
+namespace {
+
+constexpr uint32_t kRteMaxMemzone = 2560;  // RTE_MAX_MEMZONE, the reference's default pool size
+
+uint32_t ref_compressed_seg_size(uint32_t seg) {  // src/config.cc:59-73 with its 16-bit arithmetic
+  if (seg == 0 || seg > 65535u) return 0;
+  uint32_t lower = seg << 1, num = 65536u;
+  while ((num & lower) == 0) num >>= 1;
+  return num > 32768u ? (uint32_t)((double)seg * 1.1) : num;
+}
+uint32_t stored_bound(uint32_t seg) { return seg + 5u * ((seg + 65534u) / 65535u); }
+
+int alloc_kind(int kind, int device, size_t size, void** out) {
+  *out = nullptr;
+  if (size == 0) size = 1;
+  if (kind == BITAR_MEM_DEVICE) {
+    CU_TRY(cudaSetDevice(device), BITAR_E_INVALID);
+    cudaError_t e = cudaMallocAsync(out, size, cudaStreamPerThread);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamPerThread);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(BITAR_E_OUT_OF_MEMORY, "cudaMallocAsync(%zu) on device %d: %s", size, device, cudaGetErrorString(e));
+    }
+    return BITAR_OK;
+  }
+  if (kind == BITAR_MEM_PINNED) {
+    if (device >= 0) CU_TRY(cudaSetDevice(device), BITAR_E_INVALID);
+    cudaError_t e = cudaHostAlloc(out, size, cudaHostAllocPortable | cudaHostAllocMapped);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(BITAR_E_OUT_OF_MEMORY, "cudaHostAlloc(%zu): %s", size, cudaGetErrorString(e));
+    }
+    return BITAR_OK;
+  }
+  return fail(BITAR_E_INVALID, "unknown memory kind %d", kind);
+}
+
+int free_kind(int kind, int device, void* p) {
+  if (!p) return BITAR_OK;
+  if (kind == BITAR_MEM_DEVICE) {
+    CU_TRY(cudaSetDevice(device), BITAR_E_INVALID);
+    CU_TRY(cudaFreeAsync(p, cudaStreamPerThread), BITAR_E_INVALID);
+    CU_TRY(cudaStreamSynchronize(cudaStreamPerThread), BITAR_E_IO_ERROR);
+    return BITAR_OK;
+  }
+  if (kind == BITAR_MEM_PINNED) {
+    CU_TRY(cudaFreeHost(p), BITAR_E_INVALID);
+    return BITAR_OK;
+  }
+  return fail(BITAR_E_INVALID, "unknown memory kind %d", kind);
+}
+
+// grow the slot pool by `count` slots carved from one slab (caller holds dev->mu)
+int pool_grow(bitar_dev* dev, uint32_t count) {
+  void* slab = nullptr;
+  int rc = alloc_kind(dev->cfg.slot_mem_kind, dev->id, (size_t)count * dev->slot_stride, &slab);
+  if (rc) return rc;
+  dev->slabs.push_back(slab);
+  // push in reverse so that Take() hands out ascending addresses (contiguous runs for take_n)
+  for (uint32_t i = count; i-- > 0;) dev->free_slots.push_back(static_cast<uint8_t*>(slab) + (size_t)i * dev->slot_stride);
+  return BITAR_OK;
+}
+
+int qp_reserve(bitar_dev* dev, QueuePair* q, uint32_t n) {
+  if (n <= q->cap) return BITAR_OK;
+  uint32_t cap = q->cap ? q->cap : 1024;
+  while (cap < n) cap *= 2;
+  CU_TRY(cudaStreamSynchronize(q->stream), BITAR_E_IO_ERROR);
+  if (q->h_ops) cudaFreeHost(q->h_ops);
+  if (q->h_res) cudaFreeHost(q->h_res);
+  if (q->d_ops) cudaFree(q->d_ops);
+  if (q->d_res) cudaFree(q->d_res);
+  q->h_ops = nullptr; q->h_res = nullptr; q->d_ops = nullptr; q->d_res = nullptr;
+  q->cap = 0;
+  CU_TRY(cudaHostAlloc((void**)&q->h_ops, (size_t)cap * sizeof(bitar_chunk), cudaHostAllocPortable), BITAR_E_OUT_OF_MEMORY);
+  CU_TRY(cudaHostAlloc((void**)&q->h_res, (size_t)cap * sizeof(bitar_result), cudaHostAllocPortable), BITAR_E_OUT_OF_MEMORY);
+  CU_TRY(cudaMalloc((void**)&q->d_ops, (size_t)cap * sizeof(bitar_chunk)), BITAR_E_OUT_OF_MEMORY);
+  CU_TRY(cudaMalloc((void**)&q->d_res, (size_t)cap * sizeof(bitar_result)), BITAR_E_OUT_OF_MEMORY);
+  q->cap = cap;
+  (void)dev;
+  return BITAR_OK;
+}
+
+// Runs on a CUDA driver thread after the result download: publish results, mark the QP idle.
+void CUDART_CB qp_finish(void* arg) {
+  QueuePair* q = static_cast<QueuePair*>(arg);
+  int bad = 0;
+  for (uint32_t i = 0; i < q->pending_n; ++i)
+    if (q->h_res[i].status != BITAR_OP_OK) bad = 1;
+  if (q->user_out) memcpy(q->user_out, q->h_res, (size_t)q->pending_n * sizeof(bitar_result));
+  q->last_status.store(bad ? BITAR_E_IO_ERROR : BITAR_OK, std::memory_order_release);
+  q->busy.store(0, std::memory_order_release);
+}
+
+template <typename Launch>
+int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, bitar_result* results, Launch&& launch) {
+  if (!dev) return fail(BITAR_E_INVALID, "null device");
+  if (qp >= dev->qps.size()) return fail(BITAR_E_INVALID, "queue_pair_id must be in the range of [0, %zu)", dev->qps.size());
+  QueuePair* q = dev->qps[qp];
+  if (q->busy.load(std::memory_order_acquire))
+    return fail(BITAR_E_CANCELLED, "Queue pair %u of compress device %d is busy", (unsigned)qp, dev->id);
+  if (n == 0) {
+    q->last_status.store(BITAR_OK);
+    return BITAR_OK;
+  }
+  if (!ops || !results) return fail(BITAR_E_INVALID, "null ops/results");
+  CU_TRY(cudaSetDevice(dev->id), BITAR_E_INVALID);
+  int rc = qp_reserve(dev, q, n);
+  if (rc) return rc;
+  memcpy(q->h_ops, ops, (size_t)n * sizeof(bitar_chunk));
+  q->user_out = results;
+  q->pending_n = n;
+  q->busy.store(1, std::memory_order_release);
+  cudaError_t e = cudaEventRecord(q->ev_start, q->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(q->d_ops, q->h_ops, (size_t)n * sizeof(bitar_chunk), cudaMemcpyHostToDevice, q->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(q->d_counter, 0, sizeof(unsigned int), q->stream);
+  if (e == cudaSuccess) e = cudaEventRecord(q->ev_k0, q->stream);
+  if (e == cudaSuccess) e = launch(q);
+  if (e == cudaSuccess) e = cudaEventRecord(q->ev_k1, q->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(q->h_res, q->d_res, (size_t)n * sizeof(bitar_result), cudaMemcpyDeviceToHost, q->stream);
+  if (e == cudaSuccess) e = cudaEventRecord(q->ev_stop, q->stream);
+  if (e == cudaSuccess) e = cudaLaunchHostFunc(q->stream, qp_finish, q);
+  if (e != cudaSuccess) {
+    q->busy.store(0);
+    return fail(BITAR_E_IO_ERROR, "enqueue on queue pair %u of device %d failed: %s", (unsigned)qp, dev->id, cudaGetErrorString(e));
+  }
+  q->timed = true;
+  g_launches.fetch_add(1);
+  return BITAR_OK;
+}
+
+int inflate_variant() {
+  int v = g_inflate_variant.load();
+  if (v < 0) {
+    const char* s = getenv("BITAR_INFLATE_VARIANT");
+    v = s ? atoi(s) : 0;
+    g_inflate_variant.store(v);
+  }
+  return v;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bitar_cuda_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    fail(BITAR_E_INVALID, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return 0;
+  }
+  return n;
+}
+
+int bitar_cuda_device_info(int device_id, bitar_dev_info* info) {
+  if (!info) return fail(BITAR_E_INVALID, "null info");
+  cudaDeviceProp p;
+  CU_TRY(cudaGetDeviceProperties(&p, device_id), BITAR_E_INVALID);
+  memset(info, 0, sizeof *info);
+  info->device_id = device_id;
+  info->cc_major = p.major;
+  info->cc_minor = p.minor;
+  info->sm_count = p.multiProcessorCount;
+  info->total_mem = p.totalGlobalMem;
+  info->max_queue_pairs = 64;
+  info->window_min = 8;
+  info->window_max = 15;
+  info->supports_fixed = 1;
+  info->supports_dynamic = 1;
+  info->supports_crc32 = 1;
+  info->supports_adler32 = 1;
+  info->supports_sgl = 0;
+  snprintf(info->name, sizeof info->name, "%s", p.name);
+  return BITAR_OK;
+}
+
+uint32_t bitar_reference_compressed_seg_size(uint32_t seg) { return ref_compressed_seg_size(seg); }
+
+uint32_t bitar_compressed_seg_size(uint32_t seg) {
+  uint32_t ref = ref_compressed_seg_size(seg);
+  uint32_t widened = (uint32_t)((double)seg * 1.1);
+  uint32_t v = ref ? ref : widened;
+  uint32_t need = stored_bound(seg);
+  return v < need ? need : v;
+}
+
+int bitar_dev_open(int device_id, uint16_t n_qps, const bitar_cfg* cfg_in, bitar_dev** out) {
+  if (!out) return fail(BITAR_E_INVALID, "null out");
+  *out = nullptr;
+  int count = bitar_cuda_device_count();
+  if (device_id < 0 || device_id >= count) return fail(BITAR_E_INVALID, "device id %d not in [0, %d)", device_id, count);
+  if (n_qps == 0) return fail(BITAR_E_INVALID, "a device needs at least one queue pair");
+  bitar_dev_info info;
+  int rc = bitar_cuda_device_info(device_id, &info);
+  if (rc) return rc;
+  if (info.cc_major < 10)
+    return fail(BITAR_E_NOT_IMPLEMENTED, "Unsupported compress device %d (%s, sm_%d%d): kernels are built for sm_100a only",
+                device_id, info.name, info.cc_major, info.cc_minor);
+  if (n_qps > info.max_queue_pairs)
+    return fail(BITAR_E_INVALID, "The requested number of queue pairs (%u) exceeds the maximum (%u) allowed for device %d",
+                (unsigned)n_qps, info.max_queue_pairs, device_id);
+  bitar_cfg cfg{};
+  if (cfg_in) cfg = *cfg_in;
+  // ValidateConfiguration, src/device.cc:352-415 (+ BlueField specifics 558-577)
+  if (cfg.burst_size == 0) cfg.burst_size = 32;
+  if (cfg.max_sgl_segs < 1) cfg.max_sgl_segs = 1;
+  if (cfg.max_sgl_segs > 1) return fail(BITAR_E_INVALID, "Compress device does not support chained mbufs.");
+  if (cfg.decompressed_seg_size == 0) cfg.decompressed_seg_size = 2048;
+  if (cfg.decompressed_seg_size < BITAR_MIN_SEG_SIZE || cfg.decompressed_seg_size > BITAR_MAX_SEG_SIZE)
+    return fail(BITAR_E_INVALID, "decompressed_seg_size is not in the range of [%u, %u]", BITAR_MIN_SEG_SIZE, BITAR_MAX_SEG_SIZE);
+  if (cfg.window_size == 0) cfg.window_size = info.window_max;
+  if (cfg.window_size < info.window_min || cfg.window_size > info.window_max)
+    return fail(BITAR_E_INVALID, "window_size is not in the range of [%u, %u]", info.window_min, info.window_max);
+  if (cfg.huffman_enc == BITAR_HUFFMAN_DEFAULT) cfg.huffman_enc = BITAR_HUFFMAN_DYNAMIC;
+  if (cfg.huffman_enc != BITAR_HUFFMAN_FIXED && cfg.huffman_enc != BITAR_HUFFMAN_DYNAMIC)
+    return fail(BITAR_E_INVALID, "unknown huffman_enc %u", cfg.huffman_enc);
+  if (cfg.checksum_type > BITAR_CHECKSUM_CRC32_ADLER32) return fail(BITAR_E_INVALID, "unknown checksum_type %u", cfg.checksum_type);
+  if (cfg.slot_mem_kind > BITAR_MEM_PINNED) return fail(BITAR_E_INVALID, "unknown slot_mem_kind %u", cfg.slot_mem_kind);
+  if (cfg.max_preallocate_slots == 0) cfg.max_preallocate_slots = kRteMaxMemzone;
+  if (cfg.max_preallocate_slots < BITAR_MIN_PREALLOCATE_SLOTS)
+    return fail(BITAR_E_INVALID, "max_preallocate_memzones (%u) is not in the range of [%u, ...]", cfg.max_preallocate_slots,
+                BITAR_MIN_PREALLOCATE_SLOTS);
+  uint32_t min_slot = stored_bound(cfg.decompressed_seg_size);
+  if (cfg.compressed_seg_size == 0) cfg.compressed_seg_size = bitar_compressed_seg_size(cfg.decompressed_seg_size);
+  if (cfg.compressed_seg_size < min_slot) cfg.compressed_seg_size = min_slot;
+
+  CU_TRY(cudaSetDevice(device_id), BITAR_E_INVALID);
+  bitar_dev* dev = new (std::nothrow) bitar_dev();
+  if (!dev) return fail(BITAR_E_OUT_OF_MEMORY, "out of host memory");
+  dev->id = device_id;
+  dev->sm_count = info.sm_count;
+  dev->cfg = cfg;
+  dev->slot_stride = (cfg.compressed_seg_size + 255u) & ~255u;
+  {
+    // keep freed device memory cached in the pool (allocation is off the timed path, as in
+    // apps/demo_app.cc:517-522,587-590, but re-use must stay cheap)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
+      uint64_t thr = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
+  cudaError_t e = bitar::dk::deflate_grid(device_id, dev->sm_count, &dev->deflate_grid);
+  if (e != cudaSuccess) {
+    delete dev;
+    return fail(BITAR_E_INVALID, "deflate kernel cannot be configured on device %d: %s", device_id, cudaGetErrorString(e));
+  }
+  for (uint16_t i = 0; i < n_qps; ++i) {
+    QueuePair* q = new (std::nothrow) QueuePair();
+    if (!q) {
+      bitar_dev_close(dev);
+      return fail(BITAR_E_OUT_OF_MEMORY, "out of host memory");
+    }
+    dev->qps.push_back(q);
+    cudaError_t e2 = cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking);
+    if (e2 == cudaSuccess) e2 = cudaEventCreate(&q->ev_start);
+    if (e2 == cudaSuccess) e2 = cudaEventCreate(&q->ev_k0);
+    if (e2 == cudaSuccess) e2 = cudaEventCreate(&q->ev_k1);
+    if (e2 == cudaSuccess) e2 = cudaEventCreate(&q->ev_stop);
+    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&q->d_counter, sizeof(unsigned int));
+    if (e2 != cudaSuccess) {
+      bitar_dev_close(dev);
+      return fail(BITAR_E_INVALID, "Failed to setup queue pair %u for device %d: %s", (unsigned)i, device_id, cudaGetErrorString(e2));
+    }
+  }
+  {
+    std::lock_guard<std::mutex> lock(dev->mu);
+    rc = pool_grow(dev, cfg.max_preallocate_slots);
+  }
+  if (rc) {
+    bitar_dev_close(dev);
+    return rc;
+  }
+  *out = dev;
+  return BITAR_OK;
+}
+
+int bitar_dev_close(bitar_dev* dev) {
+  if (!dev) return BITAR_OK;
+  cudaSetDevice(dev->id);
+  for (QueuePair* q : dev->qps) {
+    if (q->stream) cudaStreamSynchronize(q->stream);
+    if (q->h_ops) cudaFreeHost(q->h_ops);
+    if (q->h_res) cudaFreeHost(q->h_res);
+    if (q->d_ops) cudaFree(q->d_ops);
+    if (q->d_res) cudaFree(q->d_res);
+    if (q->d_counter) cudaFree(q->d_counter);
+    if (q->d_tokens) cudaFree(q->d_tokens);
+    if (q->ev_start) cudaEventDestroy(q->ev_start);
+    if (q->ev_k0) cudaEventDestroy(q->ev_k0);
+    if (q->ev_k1) cudaEventDestroy(q->ev_k1);
+    if (q->ev_stop) cudaEventDestroy(q->ev_stop);
+    if (q->stream) cudaStreamDestroy(q->stream);
+    delete q;
+  }
+  for (void* slab : dev->slabs) free_kind(dev->cfg.slot_mem_kind, dev->id, slab);
+  delete dev;
+  return BITAR_OK;
+}
+
+int bitar_dev_config(const bitar_dev* dev, bitar_cfg* cfg_out) {
+  if (!dev || !cfg_out) return fail(BITAR_E_INVALID, "null argument");
+  *cfg_out = dev->cfg;
+  return BITAR_OK;
+}
+
+uint16_t bitar_dev_num_qps(const bitar_dev* dev) { return dev ? (uint16_t)dev->qps.size() : 0; }
+
+int bitar_qp_deflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, bitar_result* results) {
+  return qp_submit(dev, qp, ops, n, results, [&](QueuePair* q) -> cudaError_t {
+    if (!q->d_tokens) {
+      cudaError_t e = cudaMalloc((void**)&q->d_tokens, bitar::dk::deflate_scratch_bytes(dev->deflate_grid));
+      if (e != cudaSuccess) return e;
+    }
+    return bitar::dk::deflate_launch(q->d_ops, n, q->d_res, q->d_counter, q->d_tokens, dev->deflate_grid,
+                                     dev->cfg.huffman_enc, dev->cfg.checksum_type, q->stream);
+  });
+}
+
+int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, bitar_result* results) {
+  return qp_submit(dev, qp, ops, n, results, [&](QueuePair* q) -> cudaError_t {
+    using namespace bitar::ik;
+    const int ck = dev->cfg.checksum_type, id = dev->id, sms = dev->sm_count;
+    switch (inflate_variant()) {
+      default:
+      case 0: return InflateConfig<8, 10, 8, 1024, 2>::launch(q->d_ops, n, q->d_res, q->d_counter, ck, id, sms, q->stream);
+      case 1: return InflateConfig<8, 9, 7, 1024, 2>::launch(q->d_ops, n, q->d_res, q->d_counter, ck, id, sms, q->stream);
+      case 2: return InflateConfig<4, 10, 8, 1024, 1>::launch(q->d_ops, n, q->d_res, q->d_counter, ck, id, sms, q->stream);
+      case 3: return InflateConfig<4, 9, 7, 1024, 1>::launch(q->d_ops, n, q->d_res, q->d_counter, ck, id, sms, q->stream);
+      case 4: return InflateConfig<16, 10, 8, 1024, 4>::launch(q->d_ops, n, q->d_res, q->d_counter, ck, id, sms, q->stream);
+      case 5: return InflateConfig<32, 10, 8, 1024, 4>::launch(q->d_ops, n, q->d_res, q->d_counter, ck, id, sms, q->stream);
+      case 6: return InflateConfig<2, 9, 7, 1024, 1>::launch(q->d_ops, n, q->d_res, q->d_counter, ck, id, sms, q->stream);
+      case 7: return InflateConfig<8, 10, 8, 1024, 1>::launch(q->d_ops, n, q->d_res, q->d_counter, ck, id, sms, q->stream);
+    }
+  });
+}
+
+int bitar_qp_wait(bitar_dev* dev, uint16_t qp) {
+  if (!dev || qp >= dev->qps.size()) return fail(BITAR_E_INVALID, "bad device/queue pair");
+  QueuePair* q = dev->qps[qp];
+  CU_TRY(cudaSetDevice(dev->id), BITAR_E_INVALID);
+  cudaError_t e = cudaStreamSynchronize(q->stream);
+  if (e != cudaSuccess) {
+    q->busy.store(0);
+    return fail(BITAR_E_IO_ERROR, "queue pair %u of device %d failed: %s", (unsigned)qp, dev->id, cudaGetErrorString(e));
+  }
+  int st = q->last_status.load(std::memory_order_acquire);
+  if (st) return fail(st, "at least one operation on queue pair %u of device %d did not succeed", (unsigned)qp, dev->id);
+  return BITAR_OK;
+}
+
+int bitar_qp_busy(bitar_dev* dev, uint16_t qp) {
+  if (!dev || qp >= dev->qps.size()) return 0;
+  return dev->qps[qp]->busy.load(std::memory_order_acquire);
+}
+
+int bitar_qp_on_complete(bitar_dev* dev, uint16_t qp, void (*fn)(void*), void* arg) {
+  if (!dev || qp >= dev->qps.size() || !fn) return fail(BITAR_E_INVALID, "bad argument");
+  CU_TRY(cudaSetDevice(dev->id), BITAR_E_INVALID);
+  CU_TRY(cudaLaunchHostFunc(dev->qps[qp]->stream, (cudaHostFn_t)fn, arg), BITAR_E_IO_ERROR);
+  return BITAR_OK;
+}
+
+int bitar_qp_last_ms(bitar_dev* dev, uint16_t qp, float* kernel_ms, float* total_ms) {
+  if (!dev || qp >= dev->qps.size()) return fail(BITAR_E_INVALID, "bad device/queue pair");
+  QueuePair* q = dev->qps[qp];
+  if (!q->timed) return fail(BITAR_E_INVALID, "no completed call on this queue pair");
+  CU_TRY(cudaSetDevice(dev->id), BITAR_E_INVALID);
+  if (kernel_ms) CU_TRY(cudaEventElapsedTime(kernel_ms, q->ev_k0, q->ev_k1), BITAR_E_INVALID);
+  if (total_ms) CU_TRY(cudaEventElapsedTime(total_ms, q->ev_start, q->ev_stop), BITAR_E_INVALID);
+  return BITAR_OK;
+}
+
+void* bitar_qp_stream(bitar_dev* dev, uint16_t qp) {
+  if (!dev || qp >= dev->qps.size()) return nullptr;
+  return dev->qps[qp]->stream;
+}
+
+uint64_t bitar_kernel_launches(void) { return g_launches.load(); }
+
+void* bitar_slot_take(bitar_dev* dev) {
+  if (!dev) return nullptr;
+  std::lock_guard<std::mutex> lock(dev->mu);
+  if (dev->free_slots.empty()) {
+    // growing on the critical path, as DeviceMemory::Take does with a warning (src/memory.cc:167-175)
+    if (dev->grow_warned++ % 32 == 0)
+      fprintf(stderr, "[bitar] WARNING: allocating output slots in the critical path (performance will be impacted)\n");
+    uint32_t add = dev->cfg.burst_size ? dev->cfg.burst_size : 32;
+    if (pool_grow(dev, add) != BITAR_OK) return nullptr;
+  }
+  void* p = dev->free_slots.back();
+  dev->free_slots.pop_back();
+  dev->occupied.insert(p);
+  return p;
+}
+
+int bitar_slot_take_n(bitar_dev* dev, uint32_t n, void** slots) {
+  if (!dev || (!slots && n)) return fail(BITAR_E_INVALID, "bad argument");
+  std::lock_guard<std::mutex> lock(dev->mu);
+  if (dev->free_slots.size() < n) {
+    uint32_t add = n - (uint32_t)dev->free_slots.size();
+    if (dev->grow_warned++ % 32 == 0)
+      fprintf(stderr, "[bitar] WARNING: allocating %u output slots in the critical path (performance will be impacted)\n", add);
+    // new slots must come out before older free ones to keep runs contiguous: grow, then rotate
+    std::vector<void*> old;
+    old.swap(dev->free_slots);
+    int rc = pool_grow(dev, add);
+    if (rc) {
+      dev->free_slots.swap(old);
+      return fail(BITAR_E_IO_ERROR, "output slot pool exhausted");
+    }
+    std::vector<void*> fresh;
+    fresh.swap(dev->free_slots);
+    dev->free_slots = old;
+    dev->free_slots.insert(dev->free_slots.begin(), fresh.begin(), fresh.end());
+  }
+  for (uint32_t i = 0; i < n; ++i) {
+    void* p = dev->free_slots.back();
+    dev->free_slots.pop_back();
+    dev->occupied.insert(p);
+    slots[i] = p;
+  }
+  return BITAR_OK;
+}
+
+int bitar_slot_put(bitar_dev* dev, const void* addr) {
+  if (!dev || !addr) return 0;
+  std::lock_guard<std::mutex> lock(dev->mu);
+  if (dev->occupied.erase(addr) == 0) return 0;  // not a slot we handed out: ignore (src/memory.cc:201-205)
+  dev->free_slots.push_back(const_cast<void*>(addr));
+  return 1;
+}
+
+uint32_t bitar_slot_size(const bitar_dev* dev) { return dev ? dev->cfg.compressed_seg_size : 0; }
+
+uint32_t bitar_slots_free(bitar_dev* dev) {
+  if (!dev) return 0;
+  std::lock_guard<std::mutex> lock(dev->mu);
+  return (uint32_t)dev->free_slots.size();
+}
+
+int bitar_mem_alloc(int kind, int device_id, size_t size, size_t alignment, void** out) {
+  if (!out) return fail(BITAR_E_INVALID, "null out");
+  if (alignment > 256) return fail(BITAR_E_INVALID, "alignment %zu above the 256-byte allocation granularity", alignment);
+  return alloc_kind(kind, device_id, size, out);
+}
+
+int bitar_mem_free(int kind, int device_id, void* ptr) { return free_kind(kind, device_id, ptr); }
+
+int bitar_host_register(void* ptr, size_t size) {
+  cudaError_t e = cudaHostRegister(ptr, size, cudaHostRegisterPortable | cudaHostRegisterMapped);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(e == cudaErrorMemoryAllocation ? BITAR_E_OUT_OF_MEMORY : BITAR_E_INVALID, "cudaHostRegister(%p, %zu): %s", ptr, size,
+                cudaGetErrorString(e));
+  }
+  return BITAR_OK;
+}
+
+int bitar_host_unregister(void* ptr) {
+  CU_TRY(cudaHostUnregister(ptr), BITAR_E_INVALID);
+  return BITAR_OK;
+}
+
+int bitar_qp_memcpy(bitar_dev* dev, uint16_t qp, void* dst, const void* src, size_t n) {
+  if (!dev || qp >= dev->qps.size()) return fail(BITAR_E_INVALID, "bad device/queue pair");
+  CU_TRY(cudaSetDevice(dev->id), BITAR_E_INVALID);
+  CU_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyDefault, dev->qps[qp]->stream), BITAR_E_IO_ERROR);
+  return BITAR_OK;
+}
+
+const char* bitar_last_error(void) { return g_err; }
+const char* bitar_version(void) { return "bitar-b200 0.1.0 (sm_100a)"; }
+
+// not part of the public header: selects the inflate kernel instantiation for tuning sweeps
+BITAR_API void bitar_tune_inflate_variant(int v) { g_inflate_variant.store(v); }
+
+}  // extern "C"

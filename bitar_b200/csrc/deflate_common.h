@@ -10,7 +10,7 @@
 
 #if defined(__CUDACC__)
 #define BITAR_HD __host__ __device__ __forceinline__
-#define BITAR_HD_NOINLINE __host__ __device__
+#define BITAR_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define BITAR_HD inline
 #define BITAR_HD_NOINLINE inline

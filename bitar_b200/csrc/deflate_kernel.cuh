@@ -1,0 +1,720 @@
+// deflate_kernel.cuh -- K1 + K2 + K3 + K5: one CTA compresses one chunk into one raw DEFLATE stream.
+//
+// Pipeline inside a CTA (17 warps: 1 dictionary warp + 16 worker warps), per <=64 KiB sub-block:
+//   load    : the sub-block is pulled into shared memory with a 1-D TMA bulk copy (cp.async.bulk +
+//             mbarrier), so match extension and literal look-ups never touch HBM again.
+//   match   : the DICTIONARY WARP walks the block in 32-position windows, in order: hash of 4 bytes,
+//             look-up of the most recent earlier position with that hash (u16 table in shared memory,
+//             plus __match_any_sync for positions inside the same window) and in-order insert.
+//             Exact "nearest previous occurrence" semantics, no atomics, deterministic.
+//             The 16 WORKER WARPS run one step (16 windows) behind it: match extension against the
+//             candidate, then the greedy parse.  The parse is order-dependent across windows; it is
+//             solved with a per-window transfer function (5 shuffle-doubling rounds) and a short
+//             carry chain through shared memory instead of a serial walk.
+//   count   : literal/length and distance frequencies with shared-memory atomics.
+//   plan    : CTA-wide bitonic sort of the used symbols, then length-limited Huffman code
+//             construction, code-length RLE and header costing (deflate_common.h, serial, thread 0)
+//             while the worker warps compute CRC-32 / Adler-32 of the block in parallel.
+//   encode  : cheapest of stored / fixed / dynamic; every thread encodes 8 consecutive positions,
+//             a block-wide prefix sum of code lengths (warp shuffles) gives each thread its bit
+//             offset, codes are packed into a shared-memory stage and leave the SM as aligned
+//             16-byte vector stores.
+//
+// The token stream between match and encode is a sparse u32 per input position in a per-CTA global
+// scratch area (L2 resident, written and read once, fully coalesced).
+//
+// Output is bit-identical to tools/model/deflate_model.h (tests pin this) and always a valid
+// RFC 1951 stream that zlib inflates to the input.
+//
+// Replaces: the compress ops assembled at /root/reference/src/memory.cc:350-430 and executed behind
+// src/device.cc:464-535 with the xform of src/config.cc:83-91 (DEFLATE, level 1, fixed | dynamic).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bitar_cuda.h"
+#include "checksum.h"
+#include "deflate_common.h"
+
+namespace bitar {
+namespace dk {
+
+constexpr int kWorkers = 16;                     // worker warps
+constexpr int kThreads = (kWorkers + 1) * 32;    // warp 0 is the dictionary warp
+constexpr int kStep = kWorkers * 32;             // positions per step
+constexpr int kBlockMax = 65536;                 // sub-block size (positions fit 16 bits)
+constexpr int kHashBits = 12;
+constexpr int kPosPerThread = 8;                 // encode: consecutive positions per thread
+constexpr int kTile = kThreads * kPosPerThread;  // encode: positions per tile (4352)
+constexpr int kStageWords = 3584;                // 14 KiB bit stage (a tile emits < 8.6 KiB)
+constexpr uint32_t kNoCand = 0xFFFFu;
+
+struct __align__(16) Smem {
+  uint8_t raw[kBlockMax + 48];       // input block, shifted so that raw + (src & 15) is the first byte
+  uint32_t stage[kStageWords];       // output bit stage, stage[0] is virtual byte `sbase`
+  uint16_t head[1 << kHashBits];     // hash -> most recent position (kNoCand = empty)
+  uint16_t cand[2][kStep];           // dictionary warp -> workers, double buffered by step parity
+  uint16_t exits[kWorkers][32];      // per-window transfer function of the parse
+  uint32_t ll_freq[288];
+  uint32_t d_freq[32];
+  uint32_t ll_enc[288];              // code | (length << 16) under the chosen block type
+  uint32_t d_enc[32];
+  uint32_t sort_keys[512];
+  uint32_t d_sorted[32];
+  uint32_t warp_sums[kThreads / 32];
+  uint32_t carry[2];                 // next token start (absolute position), by step parity
+  uint32_t crc_tab[256];
+  uint32_t x2n[32];
+  uint32_t cks_crc, cks_a, cks_b;    // checksum accumulators
+  uint32_t ll_m, d_m;
+  uint32_t block_type;
+  uint32_t tile_bits;
+  unsigned long long mbar;           // TMA completion barrier
+  dfl::BlockPlan plan;
+  dfl::PlanScratch scratch;
+};
+
+// ---- small helpers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared (16-byte aligned addresses, size multiple of 16)
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                            unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void worker_barrier() {  // named barrier 1: the 16 worker warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(kWorkers * 32) : "memory");
+}
+
+// unaligned little-endian 32-bit read from shared memory (two aligned loads + funnel shift)
+__device__ __forceinline__ uint32_t ld32u(const uint8_t* p) {
+  uintptr_t a = reinterpret_cast<uintptr_t>(p);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+  return __funnelshift_r(w[0], w[1], (uint32_t)(a & 3u) * 8u);
+}
+
+__device__ __forceinline__ int match_len(const uint8_t* d, int p, int c, int maxl) {
+  int l = 0;
+  while (l < maxl) {
+    uint32_t x = ld32u(d + p + l) ^ ld32u(d + c + l);
+    if (x) {
+      l += (__ffs((int)x) - 1) >> 3;
+      break;
+    }
+    l += 4;
+  }
+  return min(l, maxl);
+}
+
+// ---- output stream: bit stage in shared memory, flushed as aligned 16-byte vectors ------------------
+// Byte positions are "virtual" (offset + (dst & 15)) so that multiples of 16 are 16-byte aligned
+// addresses.  All fields are CTA-uniform values held redundantly in registers.
+struct OutStream {
+  uint8_t* vbase;      // dst - mis
+  uint32_t vstart;     // mis
+  uint32_t vcap;       // mis + dst_cap
+  uint32_t sbase;      // virtual byte position of stage[0] (multiple of 16)
+  uint32_t vflushed;   // bytes below are in global memory
+  uint64_t bit;        // next bit to write, in virtual bits (8 * virtual byte + bit)
+
+  __device__ __forceinline__ void init(uint8_t* dst, uint32_t cap) {
+    uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);
+    vbase = dst - mis;
+    vstart = mis;
+    vcap = mis + cap;
+    sbase = 0;
+    vflushed = mis;
+    bit = 8ull * mis;
+  }
+  __device__ __forceinline__ uint32_t produced_bytes() const { return (uint32_t)((bit + 7) >> 3) - vstart; }
+};
+
+// OR `nbits` (<= 32) bits of v into the stage at virtual bit position `at`
+__device__ __forceinline__ void stage_or(Smem& sm, const OutStream& o, uint64_t at, uint32_t v, int nbits) {
+  if (nbits == 0) return;
+  uint32_t rel = (uint32_t)(at - 8ull * o.sbase);
+  uint32_t w = rel >> 5, sh = rel & 31u;
+  atomicOr(&sm.stage[w], v << sh);
+  if (sh + (uint32_t)nbits > 32u) atomicOr(&sm.stage[w + 1], v >> (32u - sh));
+}
+
+// Flush the stage up to virtual byte `upto` (all threads).  When `slide`, whole 16-byte units below
+// `upto` are retired and the partially filled unit moves to the front of the stage.
+__device__ void stream_flush(Smem& sm, OutStream& o, uint32_t upto, bool slide) {
+  __syncthreads();
+  const uint8_t* sbytes = reinterpret_cast<const uint8_t*>(sm.stage);
+  uint32_t lo = o.vflushed, hi = upto;
+  if (hi > lo) {
+    uint32_t a = (lo + 15u) & ~15u, b = hi & ~15u;
+    if (a > b) {
+      for (uint32_t v = lo + threadIdx.x; v < hi; v += kThreads) o.vbase[v] = sbytes[v - o.sbase];
+    } else {
+      for (uint32_t v = lo + threadIdx.x; v < a; v += kThreads) o.vbase[v] = sbytes[v - o.sbase];
+      for (uint32_t v = a + 16u * threadIdx.x; v < b; v += 16u * kThreads)
+        *reinterpret_cast<uint4*>(o.vbase + v) = *reinterpret_cast<const uint4*>(sbytes + (v - o.sbase));
+      for (uint32_t v = b + threadIdx.x; v < hi; v += kThreads) o.vbase[v] = sbytes[v - o.sbase];
+    }
+    o.vflushed = hi;
+  }
+  if (!slide) return;
+  __syncthreads();
+  uint32_t new_base = upto & ~15u;
+  uint32_t shift_words = (new_base - o.sbase) >> 2;
+  if (shift_words == 0) return;
+  // keep the 4 words of the partial unit, clear everything else that was used
+  uint32_t keep = 0;
+  if (threadIdx.x < 4) keep = sm.stage[shift_words + threadIdx.x];
+  __syncthreads();
+  uint32_t used_words = min((uint32_t)kStageWords, shift_words + 8u);
+  for (uint32_t i = threadIdx.x; i < used_words; i += kThreads) sm.stage[i] = 0;
+  __syncthreads();
+  if (threadIdx.x < 4) sm.stage[threadIdx.x] = keep;
+  o.sbase = new_base;
+  __syncthreads();
+}
+
+// serial bit writer used by thread 0 for block headers
+struct HeaderWriter {
+  Smem& sm;
+  const OutStream& o;
+  uint64_t at;
+  __device__ __forceinline__ void put(uint32_t v, int n) {
+    stage_or(sm, o, at, v, n);
+    at += (uint64_t)n;
+  }
+};
+
+// CTA-wide bitonic sort of sm.sort_keys[0..512)
+__device__ void sort512(Smem& sm) {
+  for (uint32_t k = 2; k <= 512; k <<= 1) {
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      __syncthreads();
+      uint32_t i = threadIdx.x;
+      if (i < 512) {
+        uint32_t ixj = i ^ j;
+        if (ixj > i) {
+          uint32_t a = sm.sort_keys[i], b = sm.sort_keys[ixj];
+          bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            sm.sort_keys[i] = b;
+            sm.sort_keys[ixj] = a;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ---- match phase -------------------------------------------------------------------------------------
+// Dictionary warp: windows of step `s` (16 windows of 32 positions) -> sm.cand[s & 1].
+__device__ __forceinline__ void dict_step(Smem& sm, const uint8_t* d, int n, int s, int lane) {
+  uint16_t* out = sm.cand[s & 1];
+  for (int wi = 0; wi < kWorkers; ++wi) {
+    int p = s * kStep + wi * 32 + lane;
+    bool valid = p + 4 <= n;
+    uint32_t h = 0;
+    uint32_t c = kNoCand;
+    if (valid) {
+      h = dfl::hash_word(ld32u(d + p), kHashBits, 4);
+      c = sm.head[h];
+    }
+    unsigned m = __match_any_sync(0xFFFFFFFFu, valid ? h : (0x10000u + (uint32_t)lane));
+    unsigned lower = m & ((1u << lane) - 1u);
+    if (valid && lower) c = (uint32_t)(p - (lane - (31 - __clz((int)lower))));
+    if (valid && (m >> lane) == 1u) sm.head[h] = (uint16_t)p;  // highest lane of each hash group
+    out[wi * 32 + lane] = (uint16_t)c;
+    __syncwarp();
+  }
+}
+
+// Worker warp `wi` (0..15), step s: match extension, parse, token emission, frequency counts.
+__device__ __forceinline__ void worker_step(Smem& sm, const uint8_t* d, int n, int s, int wi, int lane,
+                                            uint32_t* __restrict__ tokens) {
+  const int base = s * kStep;
+  const int p = base + wi * 32 + lane;
+  uint32_t c = sm.cand[s & 1][wi * 32 + lane];
+  int adv = 1, dist = 0;
+  if (c != kNoCand && p - (int)c <= dfl::kMaxDist) {
+    int len = match_len(d, p, (int)c, min(dfl::kMaxMatch, n - p));
+    int dd = p - (int)c;
+    if (len >= dfl::kMinMatch && !(len == 3 && dd > 4096)) {
+      adv = len;
+      dist = dd;
+    }
+  }
+  // transfer function of this window: e[r] = lane + (2^r hops), frozen once it leaves the window
+  int e0 = lane + adv, e1, e2, e3, e4, e5;
+  {
+    int t;
+    t = __shfl_sync(0xFFFFFFFFu, e0, e0 & 31); e1 = e0 < 32 ? t : e0;
+    t = __shfl_sync(0xFFFFFFFFu, e1, e1 & 31); e2 = e1 < 32 ? t : e1;
+    t = __shfl_sync(0xFFFFFFFFu, e2, e2 & 31); e3 = e2 < 32 ? t : e2;
+    t = __shfl_sync(0xFFFFFFFFu, e3, e3 & 31); e4 = e3 < 32 ? t : e3;
+    t = __shfl_sync(0xFFFFFFFFu, e4, e4 & 31); e5 = e4 < 32 ? t : e4;
+  }
+  sm.exits[wi][lane] = (uint16_t)e5;  // >= 32: where a chain entering at `lane` leaves the window
+  worker_barrier();
+  // entry offset of this window: follow the carry through the preceding windows of the step
+  int a = (int)sm.carry[s & 1] - base;  // >= 0
+  for (int k = 0; k < wi; ++k) a = a >= 32 ? a - 32 : (int)sm.exits[k][a] - 32;
+  unsigned reach = 0;
+  if (a < 32) {
+    reach = 1u << a;
+    unsigned contrib;
+    contrib = ((reach >> lane) & 1u) && e0 < 32 ? (1u << e0) : 0u; reach |= __reduce_or_sync(0xFFFFFFFFu, contrib);
+    contrib = ((reach >> lane) & 1u) && e1 < 32 ? (1u << e1) : 0u; reach |= __reduce_or_sync(0xFFFFFFFFu, contrib);
+    contrib = ((reach >> lane) & 1u) && e2 < 32 ? (1u << e2) : 0u; reach |= __reduce_or_sync(0xFFFFFFFFu, contrib);
+    contrib = ((reach >> lane) & 1u) && e3 < 32 ? (1u << e3) : 0u; reach |= __reduce_or_sync(0xFFFFFFFFu, contrib);
+    contrib = ((reach >> lane) & 1u) && e4 < 32 ? (1u << e4) : 0u; reach |= __reduce_or_sync(0xFFFFFFFFu, contrib);
+  }
+  if (wi == kWorkers - 1 && lane == 0) {
+    int out = a >= 32 ? a - 32 : (int)sm.exits[wi][a] - 32;
+    sm.carry[(s + 1) & 1] = (uint32_t)(base + kStep + out);
+  }
+  bool start = ((reach >> lane) & 1u) && p < n;
+  uint32_t tok = 0;
+  if (start) {
+    if (adv > 1) {
+      tok = dfl::tok_match(adv, dist);
+      atomicAdd(&sm.ll_freq[257 + dfl::len_sym(adv)], 1u);
+      atomicAdd(&sm.d_freq[dfl::dist_sym(dist)], 1u);
+    } else {
+      tok = 1u;
+      atomicAdd(&sm.ll_freq[d[p]], 1u);
+    }
+  }
+  if (p < n) tokens[p] = tok;
+}
+
+// ---- checksum of the block held in shared memory (threads tid0..tid0+nthr) ---------------------------
+__device__ __forceinline__ void block_checksum(Smem& sm, const uint8_t* d, uint32_t n, uint32_t tail_after,
+                                               bool first_block, int type, int t, int nthr) {
+  uint32_t per = (n + nthr - 1) / nthr;
+  uint32_t lo = min(n, per * (uint32_t)t), hi = min(n, lo + per);
+  if (lo >= hi) return;
+  uint32_t state = (first_block && lo == 0) ? 0xFFFFFFFFu : 0u, s1 = 0, s2 = 0;
+  const bool want_crc = type & BITAR_CHECKSUM_CRC32;
+  for (uint32_t i = lo; i < hi; ++i) {
+    uint32_t b = d[i];
+    if (want_crc) state = cks::crc_step(state, b, sm.crc_tab);
+    s1 += b;
+    s2 += (hi - i) * b;  // per <= 128 -> < 2^23
+  }
+  uint32_t tail = (n - hi) + tail_after;
+  if (want_crc) atomicXor(&sm.cks_crc, cks::crc_contrib(state, tail, sm.x2n));
+  if (type & BITAR_CHECKSUM_ADLER32) {
+    atomicAdd(&sm.cks_a, s1 % cks::kAdlerMod);
+    atomicAdd(&sm.cks_b, cks::adler_b_contrib(s1 % cks::kAdlerMod, s2 % cks::kAdlerMod, tail % cks::kAdlerMod));
+  }
+}
+
+// bits of one token under sm.ll_enc / sm.d_enc; also returns the two code words
+__device__ __forceinline__ int token_bits(const Smem& sm, const uint8_t* d, int p, uint32_t tok,
+                                          uint32_t& lo_bits, int& lo_n, uint32_t& hi_bits, int& hi_n) {
+  lo_n = hi_n = 0;
+  lo_bits = hi_bits = 0;
+  if (tok == 0) return 0;
+  if (tok == 1u) {
+    uint32_t e = sm.ll_enc[d[p]];
+    lo_bits = e & 0xFFFFu;
+    lo_n = (int)(e >> 16);
+    return lo_n;
+  }
+  if (tok == 2u) {  // end of block
+    uint32_t e = sm.ll_enc[dfl::kEob];
+    lo_bits = e & 0xFFFFu;
+    lo_n = (int)(e >> 16);
+    return lo_n;
+  }
+  int len = dfl::tok_len(tok), dist = dfl::tok_dist(tok);
+  int ls = dfl::len_sym(len), ds = dfl::dist_sym(dist);
+  uint32_t e = sm.ll_enc[257 + ls];
+  int cl = (int)(e >> 16), leb = dfl::len_extra_bits(ls);
+  lo_bits = (e & 0xFFFFu) | ((uint32_t)dfl::len_extra_val(len, ls) << cl);
+  lo_n = cl + leb;  // <= 20
+  uint32_t f = sm.d_enc[ds];
+  int dl = (int)(f >> 16), deb = dfl::dist_extra_bits(ds);
+  hi_bits = (f & 0xFFFFu) | ((uint32_t)dfl::dist_extra_val(dist, ds) << dl);
+  hi_n = dl + deb;  // <= 28
+  return lo_n + hi_n;
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 2)
+    deflate_kernel(const bitar_chunk* __restrict__ ops, uint32_t n_ops, bitar_result* __restrict__ results,
+                   unsigned int* __restrict__ counter, uint32_t* __restrict__ token_scratch, int huffman,
+                   int checksum_type) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t* tokens = token_scratch + (size_t)blockIdx.x * kBlockMax;
+
+  if (tid == 0) {
+    mbar_init(&sm.mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (checksum_type != BITAR_CHECKSUM_NONE) {
+    for (int i = tid; i < 256; i += kThreads) sm.crc_tab[i] = cks::crc_table_entry((uint32_t)i);
+    if (tid == 0) cks::crc_x2n_init(sm.x2n);
+  }
+  for (int i = tid; i < kStageWords; i += kThreads) sm.stage[i] = 0;
+  __syncthreads();
+  uint32_t tma_parity = 0;
+
+  uint32_t idx = blockIdx.x;
+  while (idx < n_ops) {
+    const bitar_chunk op = ops[idx];
+    const uint8_t* src = static_cast<const uint8_t*>(op.src);
+    const uint32_t total = op.src_len;
+    OutStream o;
+    o.init(static_cast<uint8_t*>(op.dst), op.dst_cap);
+    uint32_t status = BITAR_OP_OK;
+    if (tid == 0) {
+      sm.cks_crc = 0;
+      sm.cks_a = 0;
+      sm.cks_b = 0;
+    }
+
+    if (total == 0) {  // empty input: a fixed block holding only end-of-block (03 00), as zlib emits
+      __syncthreads();
+      if (op.dst_cap < 2) status = BITAR_OP_OUT_OF_SPACE;
+      else {
+        if (tid == 0) {
+          HeaderWriter hw{sm, o, o.bit};
+          hw.put(1, 1);
+          hw.put(1, 2);
+          hw.put(0, 7);
+        }
+        o.bit += 10;
+      }
+    }
+
+    for (uint32_t off = 0; off < total && status == BITAR_OP_OK; off += kBlockMax) {
+      const int n = (int)min((uint32_t)kBlockMax, total - off);
+      const bool final_block = off + (uint32_t)n == total;
+      // ---- load: TMA bulk copy of [src+off, +n) widened to 16-byte boundaries ----
+      const uint8_t* g0 = src + off;
+      const uint32_t gmis = (uint32_t)(reinterpret_cast<uintptr_t>(g0) & 15u);
+      const uint32_t bytes = (gmis + (uint32_t)n + 15u) & ~15u;
+      __syncthreads();  // previous block fully consumed
+      if (tid == 0) {
+        mbar_expect_tx(&sm.mbar, bytes);
+        tma_load_1d(sm.raw, g0 - gmis, bytes, &sm.mbar);
+      }
+      for (int i = tid; i < (1 << kHashBits); i += kThreads) sm.head[i] = (uint16_t)kNoCand;
+      for (int i = tid; i < 288; i += kThreads) sm.ll_freq[i] = 0;
+      if (tid < 32) sm.d_freq[tid] = 0;
+      if (tid == 0) {
+        sm.carry[0] = 0;
+        sm.carry[1] = 0;
+      }
+      mbar_wait(&sm.mbar, tma_parity);
+      tma_parity ^= 1u;
+      __syncthreads();
+      const uint8_t* d = sm.raw + gmis;
+
+      // ---- match + parse + count ----
+      const int steps = (n + kStep - 1) / kStep;
+      if (warp == 0) dict_step(sm, d, n, 0, lane);
+      __syncthreads();
+      for (int s = 0; s < steps; ++s) {
+        if (warp == 0) {
+          if (s + 1 < steps) dict_step(sm, d, n, s + 1, lane);
+        } else {
+          worker_step(sm, d, n, s, warp - 1, lane, tokens);
+        }
+        __syncthreads();
+      }
+
+      // ---- plan: sort used symbols, Huffman lengths, header; checksums in parallel ----
+      if (tid == 0) sm.ll_freq[dfl::kEob] = 1;
+      __syncthreads();
+      {
+        uint32_t key = 0xFFFFFFFFu;
+        if (tid < dfl::kNumLitLen && sm.ll_freq[tid]) key = (sm.ll_freq[tid] << 9) | (uint32_t)tid;
+        if (tid < 512) sm.sort_keys[tid] = key;
+        int used = __syncthreads_count(key != 0xFFFFFFFFu);
+        if (tid == 0) sm.ll_m = (uint32_t)used;
+      }
+      sort512(sm);
+      if (tid == 0) {
+        // distance tree: at least two used symbols (dummies of frequency 1, as zlib's build_tree)
+        uint32_t df[32];
+        int used = 0;
+        for (int i = 0; i < dfl::kNumDist; ++i) {
+          df[i] = sm.d_freq[i];
+          used += df[i] != 0;
+        }
+        for (int i = 0; used < 2 && i < dfl::kNumDist; ++i)
+          if (!df[i]) {
+            df[i] = 1;
+            used++;
+          }
+        sm.d_m = (uint32_t)dfl::sort_used_small(df, dfl::kNumDist, sm.d_sorted);
+        dfl::build_dynamic_plan(sm.ll_freq, sm.d_freq, sm.sort_keys, (int)sm.ll_m, sm.d_sorted, (int)sm.d_m,
+                                &sm.plan, &sm.scratch);
+        // choose the block type (same rule as the model)
+        uint64_t dyn_bits = (uint64_t)sm.plan.header_bits + sm.plan.dyn_body_bits;
+        uint64_t fix_bits = 3 + sm.plan.fixed_body_bits;
+        int pieces = (n + 65534) / 65535;
+        uint64_t cur = o.bit - 8ull * o.vstart;
+        uint64_t stored_bits = ((cur + 3 + 7) / 8 * 8 - cur) + 32 + (uint64_t)n * 8 + (uint64_t)(pieces - 1) * 40;
+        uint32_t type;
+        uint64_t best;
+        if (huffman == BITAR_HUFFMAN_FIXED) {
+          type = fix_bits <= stored_bits ? dfl::kFixed : dfl::kStored;
+          best = type == dfl::kFixed ? fix_bits : stored_bits;
+        } else {
+          type = dfl::kDynamic;
+          best = dyn_bits;
+          if (fix_bits <= best) {
+            type = dfl::kFixed;
+            best = fix_bits;
+          }
+          if (stored_bits < best) {
+            type = dfl::kStored;
+            best = stored_bits;
+          }
+        }
+        sm.block_type = type;
+        sm.tile_bits = (uint32_t)best;
+      } else if (warp >= 1 && checksum_type != BITAR_CHECKSUM_NONE) {
+        block_checksum(sm, d, (uint32_t)n, total - (off + (uint32_t)n), off == 0, checksum_type, tid - 32,
+                       kThreads - 32);
+      }
+      __syncthreads();
+      const uint32_t type = sm.block_type;
+      {
+        uint64_t end_bit = o.bit + sm.tile_bits;
+        if (((end_bit + 7) >> 3) > (uint64_t)o.vcap) {
+          status = BITAR_OP_OUT_OF_SPACE;
+          break;
+        }
+      }
+
+      if (type == dfl::kStored) {
+        // ---- stored: header bits, byte align, then raw copy straight from shared memory ----
+        int pieces = (n + 65534) / 65535;
+        int done = 0;
+        for (int k = 0; k < pieces; ++k) {
+          int len = min(65535, n - done);
+          bool last = final_block && k == pieces - 1;
+          if (tid == 0) {
+            HeaderWriter hw{sm, o, o.bit};
+            hw.put(last ? 1u : 0u, 1);
+            hw.put(0, 2);
+          }
+          o.bit = (o.bit + 3 + 7) & ~7ull;
+          if (tid == 0) {
+            HeaderWriter hw{sm, o, o.bit};
+            hw.put((uint32_t)len, 16);
+            hw.put((uint32_t)(~len) & 0xFFFFu, 16);
+          }
+          o.bit += 32;
+          uint32_t vb = (uint32_t)(o.bit >> 3);
+          stream_flush(sm, o, vb, false);
+          // payload (byte stores are coalesced; this path only runs for incompressible blocks)
+          for (int i = tid; i < len; i += kThreads) o.vbase[vb + i] = d[done + i];
+          done += len;
+          vb += (uint32_t)len;
+          o.bit = 8ull * vb;
+          // restart the stage at the new position
+          __syncthreads();
+          for (int i = tid; i < kStageWords; i += kThreads) sm.stage[i] = 0;
+          o.sbase = vb & ~15u;
+          o.vflushed = vb;
+          __syncthreads();
+        }
+        continue;
+      }
+
+      // ---- code tables for the encode loop ----
+      for (int i = tid; i < 288; i += kThreads) {
+        uint32_t e;
+        if (type == dfl::kDynamic) e = (uint32_t)sm.plan.ll_code[i] | ((uint32_t)sm.plan.ll_len[i] << 16);
+        else {
+          int l = dfl::fixed_ll_len(i);
+          uint32_t code = i < 144 ? 0x30u + i : i < 256 ? 0x190u + (i - 144) : i < 280 ? (uint32_t)(i - 256) : 0xC0u + (i - 280);
+          e = dfl::bitrev(code, l) | ((uint32_t)l << 16);
+        }
+        sm.ll_enc[i] = e;
+      }
+      if (tid < 32) {
+        uint32_t e;
+        if (type == dfl::kDynamic) e = (uint32_t)sm.plan.d_code[tid] | ((uint32_t)sm.plan.d_len[tid] << 16);
+        else e = dfl::bitrev((uint32_t)tid, 5) | (5u << 16);
+        sm.d_enc[tid] = e;
+      }
+      // ---- header (thread 0, serial) ----
+      uint32_t hdr_bits = type == dfl::kDynamic ? sm.plan.header_bits : 3u;
+      if (tid == 0) {
+        HeaderWriter hw{sm, o, o.bit};
+        hw.put(final_block ? 1u : 0u, 1);
+        hw.put(type, 2);
+        if (type == dfl::kDynamic) {
+          const dfl::BlockPlan& pl = sm.plan;
+          hw.put((uint32_t)(pl.hlit - 257), 5);
+          hw.put((uint32_t)(pl.hdist - 1), 5);
+          hw.put((uint32_t)(pl.hclen - 4), 4);
+          for (int i = 0; i < pl.hclen; ++i) hw.put(pl.cl_len[dfl::cl_order(i)], 3);
+          for (int i = 0; i < pl.n_cl_tok; ++i) {
+            int sym = pl.cl_tok[i] & 31, ev = pl.cl_tok[i] >> 5;
+            hw.put(pl.cl_code[sym], pl.cl_len[sym]);
+            if (sym >= 16) hw.put((uint32_t)ev, dfl::cl_extra_bits(sym));
+          }
+        }
+      }
+      o.bit += hdr_bits;
+      __syncthreads();
+
+      // ---- encode: tiles of kTile positions, 8 consecutive positions per thread ----
+      for (int tb = 0; tb <= n; tb += kTile) {  // position n carries the end-of-block symbol
+        const int p0 = tb + tid * kPosPerThread;
+        uint32_t tk[kPosPerThread];
+        if (p0 + kPosPerThread <= n) {
+          uint4 v0 = *reinterpret_cast<const uint4*>(tokens + p0);
+          uint4 v1 = *reinterpret_cast<const uint4*>(tokens + p0 + 4);
+          tk[0] = v0.x; tk[1] = v0.y; tk[2] = v0.z; tk[3] = v0.w;
+          tk[4] = v1.x; tk[5] = v1.y; tk[6] = v1.z; tk[7] = v1.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < kPosPerThread; ++j) {
+            int p = p0 + j;
+            tk[j] = p < n ? tokens[p] : (p == n ? 2u : 0u);
+          }
+        }
+        uint32_t mybits = 0;
+#pragma unroll
+        for (int j = 0; j < kPosPerThread; ++j) {
+          uint32_t lb, hb;
+          int ln, hn;
+          mybits += (uint32_t)token_bits(sm, d, p0 + j, tk[j], lb, ln, hb, hn);
+        }
+        // block-wide exclusive prefix sum of mybits
+        uint32_t incl = mybits;
+#pragma unroll
+        for (int off2 = 1; off2 < 32; off2 <<= 1) {
+          uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, off2);
+          if (lane >= off2) incl += t;
+        }
+        if (lane == 31) sm.warp_sums[warp] = incl;
+        __syncthreads();
+        uint32_t warp_off = 0, tile_total = 0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) {
+          uint32_t ws = sm.warp_sums[w];
+          if (w < warp) warp_off += ws;
+          tile_total += ws;
+        }
+        uint64_t at = o.bit + warp_off + (incl - mybits);
+        // emit: accumulate into a 64-bit window, flush whole words
+        {
+          uint32_t rel = (uint32_t)(at - 8ull * o.sbase);
+          uint32_t w = rel >> 5;
+          uint32_t fill = rel & 31u;   // bits already owned by the previous thread in word w
+          uint64_t acc = 0;
+          uint32_t accn = fill;
+          bool first = true;
+#pragma unroll
+          for (int j = 0; j < kPosPerThread; ++j) {
+            uint32_t lb, hb;
+            int ln, hn;
+            token_bits(sm, d, p0 + j, tk[j], lb, ln, hb, hn);
+            acc |= (uint64_t)lb << accn;
+            accn += (uint32_t)ln;
+            if (accn >= 32) {
+              if (first) { atomicOr(&sm.stage[w], (uint32_t)acc); first = false; }
+              else sm.stage[w] = (uint32_t)acc;
+              acc >>= 32; accn -= 32; ++w;
+            }
+            acc |= (uint64_t)hb << accn;
+            accn += (uint32_t)hn;
+            if (accn >= 32) {
+              if (first) { atomicOr(&sm.stage[w], (uint32_t)acc); first = false; }
+              else sm.stage[w] = (uint32_t)acc;
+              acc >>= 32; accn -= 32; ++w;
+            }
+          }
+          if (accn > (first ? fill : 0u) || (uint32_t)acc != 0u) atomicOr(&sm.stage[w], (uint32_t)acc);
+        }
+        o.bit += tile_total;
+        stream_flush(sm, o, (uint32_t)(o.bit >> 3) & ~15u, true);
+      }
+    }
+
+    // ---- finish the chunk ----
+    if (status == BITAR_OP_OK) {
+      uint32_t end_byte = (uint32_t)((o.bit + 7) >> 3);
+      if (end_byte > o.vcap) status = BITAR_OP_OUT_OF_SPACE;
+      else stream_flush(sm, o, end_byte, false);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      bitar_result r;
+      r.status = status;
+      r.produced = status == BITAR_OP_OK ? o.produced_bytes() : 0u;
+      uint32_t crc = 0, adler = 0;
+      if (checksum_type & BITAR_CHECKSUM_CRC32) crc = total ? (sm.cks_crc ^ 0xFFFFFFFFu) : 0u;
+      if (checksum_type & BITAR_CHECKSUM_ADLER32) adler = cks::adler_finish(sm.cks_a, sm.cks_b, total);
+      r.checksum = cks::pack(crc, adler);
+      results[idx] = r;
+    }
+    // reset the stage for the next chunk and fetch its index
+    __syncthreads();
+    for (int i = tid; i < kStageWords; i += kThreads) sm.stage[i] = 0;
+    if (tid == 0) sm.tile_bits = gridDim.x + atomicAdd(counter, 1u);
+    __syncthreads();
+    idx = sm.tile_bits;
+    __syncthreads();
+  }
+}
+
+inline size_t deflate_scratch_bytes(int grid) { return (size_t)grid * kBlockMax * sizeof(uint32_t); }
+
+inline cudaError_t deflate_grid(int device, int sm_count, int* grid_out) {
+  static int per_device[64] = {0};
+  int& ctas = per_device[device & 63];
+  if (ctas == 0) {
+    cudaError_t e = cudaFuncSetAttribute(deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, deflate_kernel, kThreads, sizeof(Smem));
+    if (e != cudaSuccess) return e;
+    if (ctas < 1) return cudaErrorLaunchOutOfResources;
+  }
+  *grid_out = sm_count * ctas;
+  return cudaSuccess;
+}
+
+inline cudaError_t deflate_launch(const bitar_chunk* ops, uint32_t n, bitar_result* res, unsigned int* counter,
+                                  uint32_t* scratch, int grid_max, int huffman, int checksum_type,
+                                  cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  int grid = (int)min((uint32_t)grid_max, n);
+  deflate_kernel<<<grid, kThreads, sizeof(Smem), stream>>>(ops, n, res, counter, scratch, huffman, checksum_type);
+  return cudaGetLastError();
+}
+
+}  // namespace dk
+}  // namespace bitar

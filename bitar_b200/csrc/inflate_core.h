@@ -349,7 +349,7 @@ struct ChunkResult {
 
 // ---- the decoder -------------------------------------------------------------------------------------
 template <int G, int LBITS, int DBITS, int RING>
-BITAR_HD_NOINLINE ChunkResult inflate_chunk(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t cap,
+BITAR_HD ChunkResult inflate_chunk(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t cap,
                                             GroupSmem<LBITS, DBITS, RING>* sm, const Group<G>& g) {
   static_assert(DBITS >= 7, "distance table also hosts the 7-bit code-length code");
   ChunkResult res{0, kStatusOk, 0, 0};

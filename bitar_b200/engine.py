@@ -1,0 +1,333 @@
+"""Host-side mirror of bitar's operator interface over the C-ABI (tests + bench harness).
+
+Names, argument meaning and error behaviour follow the reference's C++ API so the parity tests read
+like the reference's own demo_app flow (/root/reference/apps/demo_app.cc:332-357, 487-548):
+
+    CompressDriver.ListAvailableDeviceIds / GetDevices   src/include/driver.h:47-57
+    CompressDevice.Initialize / Compress / Decompress /
+                   Recycle / device_id / num_qps          src/include/device.h:83-134
+    Configuration (BlueFieldConfiguration fields)        src/include/config.h:62-183
+    CompressAsync / DecompressAsync                      src/include/util.h:216-236
+
+The production host side is the C++ facade in bitar_b200/host; this module exists so that Python
+tests and bench.py can drive the same library.  Buffers are device-accessible address ranges
+(CUDA device memory or pinned host memory), described by ``Buf(ptr, size)``.
+"""
+import ctypes as C
+import threading
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _capi as capi
+from ._capi import (CHECKSUM_ADLER32, CHECKSUM_CRC32, CHECKSUM_CRC32_ADLER32, CHECKSUM_NONE,  # noqa: F401
+                    HUFFMAN_DYNAMIC, HUFFMAN_FIXED, MEM_DEVICE, MEM_PINNED, BitarError)
+
+kAsyncReturnOK = 2  # src/include/util.h:45
+kMinSegSize, kRefMaxSegSize, kMaxSegSize = 8, 59460, 1 << 20
+
+
+@dataclass
+class Buf:
+    """A non-owning view (arrow::Buffer analogue): address + size in bytes."""
+    ptr: int
+    size: int
+
+
+@dataclass
+class Configuration:
+    """Configuration<Class_CUDA> + BlueFieldConfiguration knobs (src/include/config.h:146-152,183)."""
+    burst_size: int = 32
+    max_sgl_segs: int = 1
+    decompressed_seg_size: int = 2048        # kDefaultSegSize
+    window_size: int = 0                     # 0 -> device max (15)
+    huffman_enc: int = HUFFMAN_DYNAMIC
+    max_preallocate_memzones: int = 2560     # RTE_MAX_MEMZONE
+    checksum_type: int = CHECKSUM_NONE
+    slot_mem_kind: int = MEM_DEVICE
+    compressed_seg_size: int = 0             # derived unless set
+
+    def resolved_compressed_seg_size(self):
+        return self.compressed_seg_size or int(capi.lib().bitar_compressed_seg_size(self.decompressed_seg_size))
+
+
+class CompressDevice:
+    """One CUDA device with ``num_qps`` queue pairs (CUDA streams)."""
+
+    def __init__(self, device_id, num_qps):
+        self._device_id = int(device_id)
+        self._num_qps = int(num_qps)
+        self._h = None
+        self.cfg = None
+        self._keep = {}
+
+    # -- lifecycle ------------------------------------------------------------------------------
+    def Initialize(self, configuration: Configuration):
+        c = capi.Cfg(configuration.decompressed_seg_size, configuration.compressed_seg_size,
+                     configuration.max_preallocate_memzones, configuration.burst_size,
+                     configuration.max_sgl_segs, configuration.window_size, configuration.huffman_enc,
+                     configuration.checksum_type, configuration.slot_mem_kind)
+        h = C.c_void_p()
+        capi.check(capi.lib().bitar_dev_open(self._device_id, self._num_qps, C.byref(c), C.byref(h)))
+        self._h = h
+        out = capi.Cfg()
+        capi.check(capi.lib().bitar_dev_config(h, C.byref(out)))
+        self.cfg = out
+        return self
+
+    def close(self):
+        if self._h is not None:
+            capi.lib().bitar_dev_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def device_id(self):
+        return self._device_id
+
+    def num_qps(self):
+        return self._num_qps
+
+    @property
+    def seg(self):
+        return int(self.cfg.decompressed_seg_size)
+
+    @property
+    def slot(self):
+        return int(self.cfg.compressed_seg_size)
+
+    def _guard(self):
+        if self._h is None:
+            raise BitarError(capi.E_INVALID, f"Compress device {self._device_id} has not started")
+
+    # -- raw op interface (arrays of bitar_chunk / bitar_result) -------------------------------------
+    def enqueue(self, kind, qp, ops, results=None):
+        """Enqueue ops (numpy CHUNK_DTYPE array) on queue pair qp; returns the results array, which is
+        filled when wait(qp) returns."""
+        self._guard()
+        ops = np.ascontiguousarray(ops, dtype=capi.CHUNK_DTYPE)
+        if results is None:
+            results = np.zeros(ops.size, capi.RESULT_DTYPE)
+            results["status"] = 0xFFFFFFFF
+        fn = capi.lib().bitar_qp_deflate if kind == "deflate" else capi.lib().bitar_qp_inflate
+        capi.check(fn(self._h, qp, ops.ctypes.data if ops.size else None, ops.size,
+                      results.ctypes.data if results.size else None))
+        self._keep[qp] = (ops, results)
+        return results
+
+    def wait(self, qp):
+        self._guard()
+        capi.check(capi.lib().bitar_qp_wait(self._h, qp))
+
+    def busy(self, qp):
+        return bool(capi.lib().bitar_qp_busy(self._h, qp))
+
+    def last_ms(self, qp):
+        k, t = C.c_float(), C.c_float()
+        capi.check(capi.lib().bitar_qp_last_ms(self._h, qp, C.byref(k), C.byref(t)))
+        return k.value, t.value
+
+    def stream(self, qp):
+        return capi.lib().bitar_qp_stream(self._h, qp)
+
+    def take_slots(self, n):
+        arr = np.zeros(n, np.uint64)
+        capi.check(capi.lib().bitar_slot_take_n(self._h, n, arr.ctypes.data if n else None))
+        return arr
+
+    def put_slot(self, ptr):
+        return int(capi.lib().bitar_slot_put(self._h, C.c_void_p(int(ptr))))
+
+    def slots_free(self):
+        return int(capi.lib().bitar_slots_free(self._h))
+
+    # -- array-level Compress/Decompress (what bench.py times) -------------------------------------------
+    def compress_ops(self, src_ptr, nbytes, slots=None):
+        """Op list of Compress(): segment i = [i*S, min((i+1)*S, size)) -> slot i (src/memory.cc:350-430)."""
+        S = self.seg
+        n = (nbytes + S - 1) // S
+        if slots is None:
+            slots = self.take_slots(n)
+        ops = np.zeros(n, capi.CHUNK_DTYPE)
+        off = np.arange(n, dtype=np.uint64) * np.uint64(S)
+        ops["src"] = np.uint64(src_ptr) + off
+        ops["src_len"] = np.minimum(np.uint64(S), np.uint64(nbytes) - off).astype(np.uint32)
+        ops["dst"] = slots
+        ops["dst_cap"] = self.slot
+        return ops, slots
+
+    def decompress_ops(self, comp_ptrs, comp_lens, out_ptr):
+        """Op list of Decompress(): op i inflates buffers[i] to out + i*S, capacity S (src/memory.cc:432-505)."""
+        n = len(comp_ptrs)
+        ops = np.zeros(n, capi.CHUNK_DTYPE)
+        ops["src"] = comp_ptrs
+        ops["src_len"] = comp_lens
+        ops["dst"] = np.uint64(out_ptr) + np.arange(n, dtype=np.uint64) * np.uint64(self.seg)
+        ops["dst_cap"] = self.seg
+        return ops
+
+    # -- the reference's object-level API -------------------------------------------------------------------
+    def Compress(self, queue_pair_id, decompressed_buffer):
+        """-> list[Buf] of compressed segments in input order; views into pool slots that the caller must
+        Recycle() (src/device.cc:156-238).  None/empty input -> [] (src/device.cc:161-164)."""
+        if decompressed_buffer is None or decompressed_buffer.size == 0:
+            return []
+        self._guard()
+        self._entry_guard(queue_pair_id)
+        ops, slots = self.compress_ops(decompressed_buffer.ptr, decompressed_buffer.size)
+        try:
+            res = self.enqueue("deflate", queue_pair_id, ops)
+            self.wait(queue_pair_id)
+        except BitarError:
+            for s in slots[::-1]:   # ReleaseAll, src/device.cc:537-542
+                self.put_slot(s)
+            raise
+        self.last_results = res
+        return [Buf(int(p), int(n)) for p, n in zip(slots, res["produced"])]
+
+    def Decompress(self, queue_pair_id, compressed_buffers, decompressed_buffer):
+        """Inflate buffers[i] to decompressed_buffer.ptr + i*S; returns the total size (the reference
+        Resize()s the ResizableBuffer, src/device.cc:315).  decompressed_buffer.size is its capacity."""
+        if not compressed_buffers:
+            return 0
+        need = len(compressed_buffers) * self.seg
+        if decompressed_buffer is None or decompressed_buffer.size < need:
+            raise BitarError(capi.E_CAPACITY, f"The decompressed_buffer is required to be >= {need} bytes")
+        self._guard()
+        self._entry_guard(queue_pair_id)
+        ops = self.decompress_ops(np.array([b.ptr for b in compressed_buffers], np.uint64),
+                                  np.array([b.size for b in compressed_buffers], np.uint32),
+                                  decompressed_buffer.ptr)
+        res = self.enqueue("inflate", queue_pair_id, ops)
+        self.wait(queue_pair_id)
+        self.last_results = res
+        return int(res["produced"].sum())
+
+    def Recycle(self, buffers):
+        """Returns the number of buffers recycled, walking in reverse (src/device.cc:320-327)."""
+        return sum(self.put_slot(b.ptr) for b in reversed(buffers))
+
+    def _entry_guard(self, qp):  # src/device.cc:443-462
+        if qp >= self._num_qps:
+            raise BitarError(capi.E_INVALID, f"queue_pair_id must be in the range of [0, {self._num_qps})")
+        if self.busy(qp):
+            raise BitarError(capi.E_CANCELLED, f"Queue pair {qp} of compress device {self._device_id} is busy")
+
+
+class CompressDriver:
+    """CompressDriver<Class_CUDA> (src/include/driver.h:40-66)."""
+    _instance = None
+
+    @classmethod
+    def Instance(cls):
+        if cls._instance is None:
+            cls._instance = cls()
+        return cls._instance
+
+    def ListAvailableDeviceIds(self):
+        n = capi.lib().bitar_cuda_device_count()
+        if n == 0:
+            raise BitarError(capi.E_INVALID, "No compress device is available with driver name: CUDA")
+        return list(range(n))
+
+    def GetDevices(self, device_ids, num_workers=None):
+        """Spread ``num_workers`` queue pairs over the devices as evenly as possible, each device at
+        least one; the first W % D devices get one more (src/driver.cc:100-158, 192-223)."""
+        avail = self.ListAvailableDeviceIds()
+        for d in device_ids:
+            if d not in avail:
+                raise BitarError(capi.E_INVALID, f"Device id {d} is not available")
+        if num_workers is None:
+            num_workers = len(device_ids)
+        if num_workers == 0:
+            raise BitarError(capi.E_INVALID, "Not enough worker lcores for setting up queue pairs for devices.")
+        if len(device_ids) > num_workers:
+            raise BitarError(capi.E_INVALID, f"The number of devices to set up ({len(device_ids)}) is greater than "
+                                            f"the number of available worker lcores ({num_workers}).")
+        base, rem = divmod(num_workers, len(device_ids))
+        return [CompressDevice(d, base + (1 if i < rem else 0)) for i, d in enumerate(device_ids)]
+
+
+def distribute_workers(num_workers, num_devices):
+    """The queue-pair distribution rule alone (host logic, testable without a GPU)."""
+    base, rem = divmod(num_workers, num_devices)
+    return [base + (1 if i < rem else 0) for i in range(num_devices)]
+
+
+# -- async (src/include/util.h:47-101, 216-236) ------------------------------------------------------------
+_CB = C.CFUNCTYPE(None, C.c_void_p)
+
+
+class _AsyncCall:
+    """Completion through the queue pair's stream: the callback runs on a CUDA driver thread, the
+    analogue of the worker lcore (src/include/util.h:133-151); its int result is read with wait()."""
+
+    def __init__(self, device, qp, finish):
+        self.device, self.qp = device, qp
+        self.ret = 0          # 0 == never ran (apps/demo_app.cc:267-274)
+        self.done = threading.Event()
+
+        def _run(_arg):
+            try:
+                self.ret = finish()
+            except Exception:  # pragma: no cover - surfaced through ret
+                self.ret = 1   # EXIT_FAILURE
+            self.done.set()
+        self._cb = _CB(_run)
+
+    def launch(self):
+        capi.check(capi.lib().bitar_qp_on_complete(self.device._h, self.qp, C.cast(self._cb, C.c_void_p), None))
+
+    def wait(self):
+        """rte_eal_wait_lcore analogue: returns the callback's int."""
+        self.done.wait()
+        return self.ret
+
+
+def CompressAsync(device, queue_pair_id, decompressed_buffer, result_callback):
+    """result_callback(device_id, queue_pair_id, buffers_or_exception) -> int.  Returns the launched
+    call (0 from the reference) or raises Cancelled when the queue pair is busy (-EBUSY there)."""
+    device._entry_guard(queue_pair_id)
+    if decompressed_buffer is None or decompressed_buffer.size == 0:
+        call = _AsyncCall(device, queue_pair_id, lambda: result_callback(device.device_id(), queue_pair_id, []))
+        call.launch()
+        return call
+    ops, slots = device.compress_ops(decompressed_buffer.ptr, decompressed_buffer.size)
+    res = device.enqueue("deflate", queue_pair_id, ops)
+
+    def finish():
+        if (res["status"] != 0).any():
+            for s in slots[::-1]:
+                device.put_slot(s)
+            return result_callback(device.device_id(), queue_pair_id,
+                                   BitarError(capi.E_IO_ERROR, "compression operation failed"))
+        return result_callback(device.device_id(), queue_pair_id,
+                               [Buf(int(p), int(n)) for p, n in zip(slots, res["produced"])])
+    call = _AsyncCall(device, queue_pair_id, finish)
+    call.launch()
+    return call
+
+
+def DecompressAsync(device, queue_pair_id, compressed_buffers, decompressed_buffer, result_callback):
+    """result_callback(device_id, queue_pair_id, status) -> int, status = total size or a BitarError."""
+    device._entry_guard(queue_pair_id)
+    need = len(compressed_buffers) * device.seg
+    if compressed_buffers and (decompressed_buffer is None or decompressed_buffer.size < need):
+        raise BitarError(capi.E_CAPACITY, f"The decompressed_buffer is required to be >= {need} bytes")
+    ops = device.decompress_ops(np.array([b.ptr for b in compressed_buffers], np.uint64),
+                                np.array([b.size for b in compressed_buffers], np.uint32),
+                                decompressed_buffer.ptr if decompressed_buffer else 0)
+    res = device.enqueue("inflate", queue_pair_id, ops)
+
+    def finish():
+        if (res["status"] != 0).any():
+            return result_callback(device.device_id(), queue_pair_id,
+                                   BitarError(capi.E_IO_ERROR, "decompression operation failed"))
+        return result_callback(device.device_id(), queue_pair_id, int(res["produced"].sum()))
+    call = _AsyncCall(device, queue_pair_id, finish)
+    call.launch()
+    return call

@@ -1,0 +1,117 @@
+"""GPU parity: the sm_100a inflate kernel vs the oracle (zlib through oracle/, RFC 1951 restatement).
+
+Reference-compressed streams (zlib raw deflate, the compress_zlib PMD's codec) must inflate on the GPU
+to the original bytes -- BASELINE.json config 5 -- for every block type zlib can emit.
+Bit-exact comparison (byte data)."""
+import zlib
+
+import numpy as np
+import pytest
+
+import gpu_util as G
+import oracle_lib as O
+from bitar_b200 import _capi as capi
+from bitar_b200 import synth
+
+pytestmark = pytest.mark.gpu
+SEG = 59460
+
+
+def zraw(data, level, strategy=zlib.Z_DEFAULT_STRATEGY):
+    co = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+    return np.frombuffer(co.compress(data.tobytes()) + co.flush(), np.uint8).copy()
+
+
+def corpus(seg=SEG):
+    cases = synth.edge_cases(seg)
+    cases["lineitem"] = synth.lineitem_like(4 * seg)
+    chunks = []
+    for name, d in cases.items():
+        for off in range(0, max(d.size, 1), seg):
+            chunks.append((name, d[off:off + seg]))
+    return chunks
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7])
+def test_reference_streams_inflate_on_gpu(cuda_device, variant):
+    capi.lib().bitar_tune_inflate_variant(variant)
+    dev = G.open_device(SEG)
+    try:
+        chunks = corpus()
+        comps, origs = [], []
+        for name, ch in chunks:
+            for lvl, strat in [(0, 0), (1, 0), (6, 0), (9, 0), (1, zlib.Z_FIXED)]:
+                comps.append(zraw(ch, lvl, strat))
+                origs.append(ch)
+        for shift in (0, 1):
+            outs, res, err = G.gpu_inflate_chunks(dev, comps, [max(o.size, 1) for o in origs],
+                                                  src_shift=shift, dst_shift=4 * shift + shift)
+            assert err is None, err
+            assert (res["status"] == 0).all()
+            for o, ref in zip(outs, origs):
+                assert o.size == ref.size and np.array_equal(o, ref)
+    finally:
+        dev.close()
+        capi.lib().bitar_tune_inflate_variant(0)
+
+
+def test_bitar_decompress_contract(cuda_device):
+    """Decompress(): op i lands at out + i*S, total = sum(produced) (src/device.cc:240-318); checked
+    against oracle_decompress_buffer on the oracle's own compressed slots."""
+    import torch
+    data = synth.lineitem_like(40 * SEG + 12345)
+    slots, produced = O.compress_buffer(data, SEG)
+    ref, _ = O.decompress_buffer(slots, produced, SEG)
+    assert np.array_equal(ref, data)
+    dev = G.open_device(SEG)
+    try:
+        d_slots = G.to_dev(slots.reshape(-1))
+        out = torch.zeros(slots.shape[0] * SEG, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        ptrs = np.uint64(d_slots.data_ptr()) + np.arange(slots.shape[0], dtype=np.uint64) * np.uint64(slots.shape[1])
+        ops = dev.decompress_ops(ptrs, produced, out.data_ptr())
+        res = dev.enqueue("inflate", 0, ops)
+        dev.wait(0)
+        total = int(res["produced"].sum())
+        assert total == data.size
+        assert np.array_equal(out[:total].cpu().numpy(), data)
+    finally:
+        dev.close()
+
+
+def test_inflate_error_statuses(cuda_device):
+    dev = G.open_device(SEG)
+    try:
+        text = synth.edge_cases(SEG)["text"][:20000]
+        good = zraw(text, 6)
+        bad_btype = good.copy()
+        bad_btype[0] |= 6                      # BTYPE = 3
+        stored = zraw(np.frombuffer(np.random.default_rng(3).bytes(1000), np.uint8), 0)
+        bad_nlen = stored.copy()
+        bad_nlen[3] ^= 0xFF                    # LEN != ~NLEN
+        comps = [good, good[:200], good, bad_btype, bad_nlen, good]
+        caps = [text.size, text.size, 1000, text.size, 1000, text.size]
+        outs, res, err = G.gpu_inflate_chunks(dev, comps, caps)
+        assert err is not None and err.code == capi.E_IO_ERROR      # src/device.cc:512-520
+        assert list(res["status"]) == [capi.OP_OK, capi.OP_TRUNCATED, capi.OP_OUT_OF_SPACE,
+                                       capi.OP_DATA_ERROR, capi.OP_DATA_ERROR, capi.OP_OK]
+        assert np.array_equal(outs[0], text) and np.array_equal(outs[5], text)
+        # the queue pair is usable again after a failed call (the reference leaves it busy: quirk not copied)
+        outs, res, err = G.gpu_inflate_chunks(dev, [good], [text.size])
+        assert err is None and np.array_equal(outs[0], text)
+    finally:
+        dev.close()
+
+
+def test_inflate_checksums(cuda_device):
+    dev = G.open_device(SEG, checksum_type=capi.CHECKSUM_CRC32_ADLER32)
+    try:
+        chunks = [c for _, c in corpus()][:40]
+        comps = [zraw(c, 1) for c in chunks]
+        outs, res, err = G.gpu_inflate_chunks(dev, comps, [max(c.size, 1) for c in chunks])
+        assert err is None
+        for c, r in zip(chunks, res):
+            assert int(r["checksum"]) & 0xFFFFFFFF == O.crc32(c)
+            assert int(r["checksum"]) >> 32 == O.adler32(c)
+    finally:
+        dev.close()
