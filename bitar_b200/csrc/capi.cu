@@ -27,6 +27,7 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_inflate_variant{-1};
+std::atomic<unsigned long long*> g_deflate_prof{nullptr};  // device buffer of 8 phase counters (debug)
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -210,7 +211,7 @@ int inflate_variant() {
   int v = g_inflate_variant.load();
   if (v < 0) {
     const char* s = getenv("BITAR_INFLATE_VARIANT");
-    v = s ? atoi(s) : 0;
+    v = s ? atoi(s) : 5;
     g_inflate_variant.store(v);
   }
   return v;
@@ -392,7 +393,7 @@ int bitar_qp_deflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
       if (e != cudaSuccess) return e;
     }
     return bitar::dk::deflate_launch(q->d_ops, n, q->d_res, q->d_counter, q->d_tokens, dev->deflate_grid,
-                                     dev->cfg.huffman_enc, dev->cfg.checksum_type, q->stream);
+                                     dev->cfg.huffman_enc, dev->cfg.checksum_type, g_deflate_prof.load(), q->stream);
   });
 }
 
@@ -550,6 +551,24 @@ int bitar_qp_memcpy(bitar_dev* dev, uint16_t qp, void* dst, const void* src, siz
 
 const char* bitar_last_error(void) { return g_err; }
 const char* bitar_version(void) { return "bitar-b200 0.1.0 (sm_100a)"; }
+
+// not part of the public header: per-phase cycle counters of the deflate kernel (debug/tuning).
+// enable=1 allocates and zeroes the counters; out (8 x u64, host) receives the current totals.
+BITAR_API int bitar_debug_deflate_profile(int enable, unsigned long long* out) {
+  unsigned long long* p = g_deflate_prof.load();
+  if (enable && !p) {
+    if (cudaMalloc((void**)&p, 16 * sizeof(unsigned long long)) != cudaSuccess) return BITAR_E_OUT_OF_MEMORY;
+    cudaMemset(p, 0, 16 * sizeof(unsigned long long));
+    g_deflate_prof.store(p);
+  }
+  if (p && out) {
+    cudaDeviceSynchronize();
+    cudaMemcpy(out, p, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaMemset(p, 0, 16 * sizeof(unsigned long long));
+  }
+  if (!enable && p) g_deflate_prof.store(nullptr);
+  return BITAR_OK;
+}
 
 // not part of the public header: selects the inflate kernel instantiation for tuning sweeps
 BITAR_API void bitar_tune_inflate_variant(int v) { g_inflate_variant.store(v); }

@@ -3,10 +3,10 @@
 // Pipeline inside a CTA (17 warps: 1 dictionary warp + 16 worker warps), per <=64 KiB sub-block:
 //   load    : the sub-block is pulled into shared memory with a 1-D TMA bulk copy (cp.async.bulk +
 //             mbarrier), so match extension and literal look-ups never touch HBM again.
-//   match   : the DICTIONARY WARP walks the block in 32-position windows, in order: hash of 4 bytes,
-//             look-up of the most recent earlier position with that hash (u16 table in shared memory,
-//             plus __match_any_sync for positions inside the same window) and in-order insert.
-//             Exact "nearest previous occurrence" semantics, no atomics, deterministic.
+//   match   : the DICTIONARY WARP walks the block in quads of 4 positions, in order: hash of 4 bytes,
+//             look-up of the most recent earlier position with that hash (u16 table in shared memory)
+//             and in-order insert -- "nearest previous occurrence" semantics at quad granularity,
+//             no atomics, deterministic, one predicated LDS + STS per quad.
 //             The 16 WORKER WARPS run one step (16 windows) behind it: match extension against the
 //             candidate, then the greedy parse.  The parse is order-dependent across windows; it is
 //             solved with a per-window transfer function (5 shuffle-doubling rounds) and a short
@@ -40,7 +40,7 @@ namespace bitar {
 namespace dk {
 
 constexpr int kWorkers = 16;                     // worker warps
-constexpr int kThreads = (kWorkers + 1) * 32;    // warp 0 is the dictionary warp
+constexpr int kThreads = (kWorkers + 1) * 32;    // the last warp is the dictionary warp
 constexpr int kStep = kWorkers * 32;             // positions per step
 constexpr int kBlockMax = 65536;                 // sub-block size (positions fit 16 bits)
 constexpr int kHashBits = 12;
@@ -52,8 +52,9 @@ constexpr uint32_t kNoCand = 0xFFFFu;
 struct __align__(16) Smem {
   uint8_t raw[kBlockMax + 48];       // input block, shifted so that raw + (src & 15) is the first byte
   uint32_t stage[kStageWords];       // output bit stage, stage[0] is virtual byte `sbase`
-  uint16_t head[1 << kHashBits];     // hash -> most recent position (kNoCand = empty)
+  uint16_t head[(1 << kHashBits) + 32];  // hash -> most recent position (kNoCand = empty) + 32 dummy slots
   uint16_t cand[2][kStep];           // dictionary warp -> workers, double buffered by step parity
+  uint32_t rd[2][kStep];             // workers -> dictionary warp (hash_window), by step parity
   uint16_t exits[kWorkers][32];      // per-window transfer function of the parse
   uint32_t ll_freq[288];
   uint32_t d_freq[32];
@@ -103,21 +104,32 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
       "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
-__device__ __forceinline__ void worker_barrier() {  // named barrier 1: the 16 worker warps only
+__device__ __forceinline__ void worker_barrier() {  // named barrier 1: the 16 worker warps (0..15) only
   asm volatile("bar.sync 1, %0;" ::"n"(kWorkers * 32) : "memory");
 }
 
-// unaligned little-endian 32-bit read from shared memory (two aligned loads + funnel shift)
-__device__ __forceinline__ uint32_t ld32u(const uint8_t* p) {
-  uintptr_t a = reinterpret_cast<uintptr_t>(p);
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-  return __funnelshift_r(w[0], w[1], (uint32_t)(a & 3u) * 8u);
+// Shared-memory reads of the input block go through explicit 32-bit shared addresses (`ds` = shared
+// address of byte 0 of the block): a generic pointer would compile to LD.E with 64-bit address math.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
+}
+// unaligned little-endian 32-bit read (two aligned loads + funnel shift)
+__device__ __forceinline__ uint32_t ld32u(uint32_t saddr) {
+  uint32_t a = saddr & ~3u;
+  return __funnelshift_r(lds_u32(a), lds_u32(a + 4), (saddr & 3u) * 8u);
 }
 
-__device__ __forceinline__ int match_len(const uint8_t* d, int p, int c, int maxl) {
+__device__ __forceinline__ int match_len(uint32_t ds, int p, int c, int maxl) {
   int l = 0;
   while (l < maxl) {
-    uint32_t x = ld32u(d + p + l) ^ ld32u(d + c + l);
+    uint32_t x = ld32u(ds + p + l) ^ ld32u(ds + c + l);
     if (x) {
       l += (__ffs((int)x) - 1) >> 3;
       break;
@@ -228,36 +240,64 @@ __device__ void sort512(Smem& sm) {
 }
 
 // ---- match phase -------------------------------------------------------------------------------------
-// Dictionary warp: windows of step `s` (16 windows of 32 positions) -> sm.cand[s & 1].
-__device__ __forceinline__ void dict_step(Smem& sm, const uint8_t* d, int n, int s, int lane) {
+// Dictionary, split in two so that only ~8 instructions per window stay on the serial path:
+//  * hash_window (any worker warp, order independent): 4-byte hash of each position, the nearest lower
+//    lane of the window with the same hash (__match_any_sync) and whether this lane holds the window's
+//    highest position for its hash; packed into sm.rd for the dictionary warp.
+//  * dict_step (dictionary warp, windows in position order): look up the most recent earlier position
+//    with the same hash in the u16 table, insert the window (one LDS + one STS per window; shared-memory
+//    accesses of one warp execute in program order).
+// Semantics == tools/model Params{step = 32, cand_mode = 1}: exact "nearest previous occurrence of the
+// 4-byte hash", no atomics, deterministic.
+//   rd word: [12:0] look-up index | [25:13] insert index | [31:26] nearest lower lane + 1 (0 = none);
+//   indices >= 4096 are per-lane dummy slots (position cannot start a match / is not the writer).
+__device__ __forceinline__ void hash_window(Smem& sm, uint32_t ds, int n, int s, int wi, int lane) {
+  const int p = s * kStep + wi * 32 + lane;
+  const bool valid = p + 4 <= n;
+  const uint32_t dummy = (1u << kHashBits) + (uint32_t)lane;
+  const uint32_t h = valid ? dfl::hash_word(ld32u(ds + p), kHashBits, 4) : dummy;
+  const unsigned m = __match_any_sync(0xFFFFFFFFu, h);   // dummies are unique per lane
+  const unsigned lower = m & ((1u << lane) - 1u);
+  const uint32_t near1 = lower ? (uint32_t)(32 - __clz((int)lower)) : 0u;   // lane index + 1
+  const uint32_t wr = (valid && (m >> lane) == 1u) ? h : dummy;
+  sm.rd[s & 1][wi * 32 + lane] = h | (wr << 13) | (near1 << 26);
+}
+
+__device__ __forceinline__ void dict_step(Smem& sm, int s, int lane) {
+  volatile uint16_t* head = sm.head;            // head[4096..4127] are the dummy slots
+  const uint32_t* rd = sm.rd[s & 1];
   uint16_t* out = sm.cand[s & 1];
-  for (int wi = 0; wi < kWorkers; ++wi) {
-    int p = s * kStep + wi * 32 + lane;
-    bool valid = p + 4 <= n;
-    uint32_t h = 0;
-    uint32_t c = kNoCand;
-    if (valid) {
-      h = dfl::hash_word(ld32u(d + p), kHashBits, 4);
-      c = sm.head[h];
+  constexpr int kBatch = 8;
+#pragma unroll 1
+  for (int w0 = 0; w0 < kWorkers; w0 += kBatch) {
+    uint32_t v[kBatch], c[kBatch];
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) v[j] = rd[(w0 + j) * 32 + lane];
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {          // the serial part: table look-up + insert, in order
+      c[j] = head[v[j] & 0x1FFFu];
+      head[(v[j] >> 13) & 0x1FFFu] = (uint16_t)(s * kStep + (w0 + j) * 32 + lane);
     }
-    unsigned m = __match_any_sync(0xFFFFFFFFu, valid ? h : (0x10000u + (uint32_t)lane));
-    unsigned lower = m & ((1u << lane) - 1u);
-    if (valid && lower) c = (uint32_t)(p - (lane - (31 - __clz((int)lower))));
-    if (valid && (m >> lane) == 1u) sm.head[h] = (uint16_t)p;  // highest lane of each hash group
-    out[wi * 32 + lane] = (uint16_t)c;
-    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < kBatch; ++j) {
+      const uint32_t near1 = v[j] >> 26;
+      uint32_t cand = (v[j] & 0x1000u) ? kNoCand : c[j];
+      if (near1) cand = (uint32_t)(s * kStep + (w0 + j) * 32) + near1 - 1u;
+      out[(w0 + j) * 32 + lane] = (uint16_t)cand;
+    }
   }
+  __syncwarp();
 }
 
 // Worker warp `wi` (0..15), step s: match extension, parse, token emission, frequency counts.
-__device__ __forceinline__ void worker_step(Smem& sm, const uint8_t* d, int n, int s, int wi, int lane,
+__device__ __forceinline__ void worker_step(Smem& sm, uint32_t ds, int n, int s, int wi, int lane,
                                             uint32_t* __restrict__ tokens) {
   const int base = s * kStep;
   const int p = base + wi * 32 + lane;
   uint32_t c = sm.cand[s & 1][wi * 32 + lane];
   int adv = 1, dist = 0;
   if (c != kNoCand && p - (int)c <= dfl::kMaxDist) {
-    int len = match_len(d, p, (int)c, min(dfl::kMaxMatch, n - p));
+    int len = match_len(ds, p, (int)c, min(dfl::kMaxMatch, n - p));
     int dd = p - (int)c;
     if (len >= dfl::kMinMatch && !(len == 3 && dd > 4096)) {
       adv = len;
@@ -302,7 +342,7 @@ __device__ __forceinline__ void worker_step(Smem& sm, const uint8_t* d, int n, i
       atomicAdd(&sm.d_freq[dfl::dist_sym(dist)], 1u);
     } else {
       tok = 1u;
-      atomicAdd(&sm.ll_freq[d[p]], 1u);
+      atomicAdd(&sm.ll_freq[lds_u8(ds + p)], 1u);
     }
   }
   if (p < n) tokens[p] = tok;
@@ -331,13 +371,13 @@ __device__ __forceinline__ void block_checksum(Smem& sm, const uint8_t* d, uint3
 }
 
 // bits of one token under sm.ll_enc / sm.d_enc; also returns the two code words
-__device__ __forceinline__ int token_bits(const Smem& sm, const uint8_t* d, int p, uint32_t tok,
+__device__ __forceinline__ int token_bits(const Smem& sm, uint32_t ds, int p, uint32_t tok,
                                           uint32_t& lo_bits, int& lo_n, uint32_t& hi_bits, int& hi_n) {
   lo_n = hi_n = 0;
   lo_bits = hi_bits = 0;
   if (tok == 0) return 0;
   if (tok == 1u) {
-    uint32_t e = sm.ll_enc[d[p]];
+    uint32_t e = sm.ll_enc[lds_u8(ds + p)];
     lo_bits = e & 0xFFFFu;
     lo_n = (int)(e >> 16);
     return lo_n;
@@ -349,14 +389,14 @@ __device__ __forceinline__ int token_bits(const Smem& sm, const uint8_t* d, int 
     return lo_n;
   }
   int len = dfl::tok_len(tok), dist = dfl::tok_dist(tok);
-  int ls = dfl::len_sym(len), ds = dfl::dist_sym(dist);
+  int ls = dfl::len_sym(len), dsym = dfl::dist_sym(dist);
   uint32_t e = sm.ll_enc[257 + ls];
   int cl = (int)(e >> 16), leb = dfl::len_extra_bits(ls);
   lo_bits = (e & 0xFFFFu) | ((uint32_t)dfl::len_extra_val(len, ls) << cl);
   lo_n = cl + leb;  // <= 20
-  uint32_t f = sm.d_enc[ds];
-  int dl = (int)(f >> 16), deb = dfl::dist_extra_bits(ds);
-  hi_bits = (f & 0xFFFFu) | ((uint32_t)dfl::dist_extra_val(dist, ds) << dl);
+  uint32_t f = sm.d_enc[dsym];
+  int dl = (int)(f >> 16), deb = dfl::dist_extra_bits(dsym);
+  hi_bits = (f & 0xFFFFu) | ((uint32_t)dfl::dist_extra_val(dist, dsym) << dl);
   hi_n = dl + deb;  // <= 28
   return lo_n + hi_n;
 }
@@ -365,7 +405,7 @@ __device__ __forceinline__ int token_bits(const Smem& sm, const uint8_t* d, int 
 __global__ void __launch_bounds__(kThreads, 2)
     deflate_kernel(const bitar_chunk* __restrict__ ops, uint32_t n_ops, bitar_result* __restrict__ results,
                    unsigned int* __restrict__ counter, uint32_t* __restrict__ token_scratch, int huffman,
-                   int checksum_type) {
+                   int checksum_type, unsigned long long* __restrict__ prof) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -382,6 +422,14 @@ __global__ void __launch_bounds__(kThreads, 2)
   for (int i = tid; i < kStageWords; i += kThreads) sm.stage[i] = 0;
   __syncthreads();
   uint32_t tma_parity = 0;
+  // optional phase timers (cycles, thread 0): 0 load, 1 match, 2 sort, 3 plan, 4 tables+header, 5 encode, 6 finish
+  long long t_prev = prof ? clock64() : 0;
+#define BITAR_PHASE(k)                                          \
+  if (prof && tid == 0) {                                       \
+    long long t_now = clock64();                                \
+    atomicAdd(&prof[k], (unsigned long long)(t_now - t_prev));  \
+    t_prev = t_now;                                             \
+  }
 
   uint32_t idx = blockIdx.x;
   while (idx < n_ops) {
@@ -423,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, 2)
         mbar_expect_tx(&sm.mbar, bytes);
         tma_load_1d(sm.raw, g0 - gmis, bytes, &sm.mbar);
       }
-      for (int i = tid; i < (1 << kHashBits); i += kThreads) sm.head[i] = (uint16_t)kNoCand;
+      for (int i = tid; i < (1 << kHashBits) + 32; i += kThreads) sm.head[i] = (uint16_t)kNoCand;
       for (int i = tid; i < 288; i += kThreads) sm.ll_freq[i] = 0;
       if (tid < 32) sm.d_freq[tid] = 0;
       if (tid == 0) {
@@ -434,20 +482,34 @@ __global__ void __launch_bounds__(kThreads, 2)
       tma_parity ^= 1u;
       __syncthreads();
       const uint8_t* d = sm.raw + gmis;
+      BITAR_PHASE(0)
 
       // ---- match + parse + count ----
+      // software pipeline over steps of 512 positions:  workers hash step s+2 and extend/parse step s
+      // while the dictionary warp resolves the candidates of step s+1.
+      const uint32_t ds = smem_u32(d);
       const int steps = (n + kStep - 1) / kStep;
-      if (warp == 0) dict_step(sm, d, n, 0, lane);
+      if (warp < kWorkers) {
+        hash_window(sm, ds, n, 0, warp, lane);
+        hash_window(sm, ds, n, 1, warp, lane);
+      }
+      __syncthreads();
+      if (warp == kWorkers) dict_step(sm, 0, lane);
       __syncthreads();
       for (int s = 0; s < steps; ++s) {
-        if (warp == 0) {
-          if (s + 1 < steps) dict_step(sm, d, n, s + 1, lane);
+        if (warp == kWorkers) {
+          long long dt0 = prof ? clock64() : 0;
+          if (s + 1 < steps) dict_step(sm, s + 1, lane);
+          if (prof && lane == 0) atomicAdd(&prof[12], (unsigned long long)(clock64() - dt0));
         } else {
-          worker_step(sm, d, n, s, warp - 1, lane, tokens);
+          long long wt0 = prof ? clock64() : 0;
+          worker_step(sm, ds, n, s, warp, lane, tokens);
+          if (s + 2 < steps) hash_window(sm, ds, n, s + 2, warp, lane);
+          if (prof && tid == 0) atomicAdd(&prof[8], (unsigned long long)(clock64() - wt0));
         }
         __syncthreads();
       }
-
+      BITAR_PHASE(1)
       // ---- plan: sort used symbols, Huffman lengths, header; checksums in parallel ----
       if (tid == 0) sm.ll_freq[dfl::kEob] = 1;
       __syncthreads();
@@ -459,6 +521,7 @@ __global__ void __launch_bounds__(kThreads, 2)
         if (tid == 0) sm.ll_m = (uint32_t)used;
       }
       sort512(sm);
+      BITAR_PHASE(2)
       if (tid == 0) {
         // distance tree: at least two used symbols (dummies of frequency 1, as zlib's build_tree)
         uint32_t df[32];
@@ -505,6 +568,7 @@ __global__ void __launch_bounds__(kThreads, 2)
                        kThreads - 32);
       }
       __syncthreads();
+      BITAR_PHASE(3)
       const uint32_t type = sm.block_type;
       {
         uint64_t end_bit = o.bit + sm.tile_bits;
@@ -588,6 +652,7 @@ __global__ void __launch_bounds__(kThreads, 2)
       }
       o.bit += hdr_bits;
       __syncthreads();
+      BITAR_PHASE(4)
 
       // ---- encode: tiles of kTile positions, 8 consecutive positions per thread ----
       for (int tb = 0; tb <= n; tb += kTile) {  // position n carries the end-of-block symbol
@@ -610,7 +675,7 @@ __global__ void __launch_bounds__(kThreads, 2)
         for (int j = 0; j < kPosPerThread; ++j) {
           uint32_t lb, hb;
           int ln, hn;
-          mybits += (uint32_t)token_bits(sm, d, p0 + j, tk[j], lb, ln, hb, hn);
+          mybits += (uint32_t)token_bits(sm, ds, p0 + j, tk[j], lb, ln, hb, hn);
         }
         // block-wide exclusive prefix sum of mybits
         uint32_t incl = mybits;
@@ -641,7 +706,7 @@ __global__ void __launch_bounds__(kThreads, 2)
           for (int j = 0; j < kPosPerThread; ++j) {
             uint32_t lb, hb;
             int ln, hn;
-            token_bits(sm, d, p0 + j, tk[j], lb, ln, hb, hn);
+            token_bits(sm, ds, p0 + j, tk[j], lb, ln, hb, hn);
             acc |= (uint64_t)lb << accn;
             accn += (uint32_t)ln;
             if (accn >= 32) {
@@ -664,6 +729,7 @@ __global__ void __launch_bounds__(kThreads, 2)
       }
     }
 
+    BITAR_PHASE(5)
     // ---- finish the chunk ----
     if (status == BITAR_OP_OK) {
       uint32_t end_byte = (uint32_t)((o.bit + 7) >> 3);
@@ -688,7 +754,9 @@ __global__ void __launch_bounds__(kThreads, 2)
     __syncthreads();
     idx = sm.tile_bits;
     __syncthreads();
+    BITAR_PHASE(6)
   }
+#undef BITAR_PHASE
 }
 
 inline size_t deflate_scratch_bytes(int grid) { return (size_t)grid * kBlockMax * sizeof(uint32_t); }
@@ -709,10 +777,10 @@ inline cudaError_t deflate_grid(int device, int sm_count, int* grid_out) {
 
 inline cudaError_t deflate_launch(const bitar_chunk* ops, uint32_t n, bitar_result* res, unsigned int* counter,
                                   uint32_t* scratch, int grid_max, int huffman, int checksum_type,
-                                  cudaStream_t stream) {
+                                  unsigned long long* prof, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   int grid = (int)min((uint32_t)grid_max, n);
-  deflate_kernel<<<grid, kThreads, sizeof(Smem), stream>>>(ops, n, res, counter, scratch, huffman, checksum_type);
+  deflate_kernel<<<grid, kThreads, sizeof(Smem), stream>>>(ops, n, res, counter, scratch, huffman, checksum_type, prof);
   return cudaGetLastError();
 }
 
