@@ -21,6 +21,7 @@
 #include "../../include/bitar_cuda.h"
 #include "deflate_kernel.cuh"
 #include "inflate_kernel.cuh"
+#include "inflate_lane_kernel.cuh"
 
 namespace {
 
@@ -52,6 +53,8 @@ struct QueuePair {
   uint32_t cap = 0;
   unsigned int* d_counter = nullptr;
   uint32_t* d_tokens = nullptr;    // deflate token scratch (grid * 64 Ki u32), allocated on first use
+  void* d_lane_scratch = nullptr;  // inflate per-lane scratch, allocated on first use
+  size_t lane_scratch_bytes = 0;
   bitar_result* user_out = nullptr;
   uint32_t pending_n = 0;
   std::atomic<int> busy{0};
@@ -366,6 +369,7 @@ int bitar_dev_close(bitar_dev* dev) {
     if (q->d_res) cudaFree(q->d_res);
     if (q->d_counter) cudaFree(q->d_counter);
     if (q->d_tokens) cudaFree(q->d_tokens);
+    if (q->d_lane_scratch) cudaFree(q->d_lane_scratch);
     if (q->ev_start) cudaEventDestroy(q->ev_start);
     if (q->ev_k0) cudaEventDestroy(q->ev_k0);
     if (q->ev_k1) cudaEventDestroy(q->ev_k1);
@@ -401,7 +405,31 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
   return qp_submit(dev, qp, ops, n, results, [&](QueuePair* q) -> cudaError_t {
     using namespace bitar::ik;
     const int ck = dev->cfg.checksum_type, id = dev->id, sms = dev->sm_count;
-    switch (inflate_variant()) {
+    const int variant = inflate_variant();
+    if (variant >= 8) {   // lane-per-chunk kernels
+      auto run = [&](auto cfg) -> cudaError_t {
+        using Cfg = decltype(cfg);
+        const size_t need = Cfg::scratch_bytes(id, sms);
+        if (need == 0) return cudaErrorLaunchOutOfResources;
+        if (q->lane_scratch_bytes < need) {
+          if (q->d_lane_scratch) cudaFree(q->d_lane_scratch);
+          q->d_lane_scratch = nullptr;
+          q->lane_scratch_bytes = 0;
+          cudaError_t e = cudaMalloc(&q->d_lane_scratch, need);
+          if (e != cudaSuccess) return e;
+          q->lane_scratch_bytes = need;
+        }
+        return Cfg::launch(q->d_ops, n, q->d_res, q->d_counter, q->d_lane_scratch, ck, id, sms, q->stream);
+      };
+      switch (variant) {
+        default:
+        case 8: return run(bitar::ilk::LaneConfig<9, 704, 7, 160, 256, 1>{});
+        case 9: return run(bitar::ilk::LaneConfig<9, 576, 7, 128, 256, 1>{});
+        case 10: return run(bitar::ilk::LaneConfig<10, 1024, 8, 256, 512, 1>{});
+        case 11: return run(bitar::ilk::LaneConfig<9, 704, 7, 160, 512, 1>{});
+      }
+    }
+    switch (variant) {
       default:
       case 0: return InflateConfig<8, 10, 8, 1024, 2>::launch(q->d_ops, n, q->d_res, q->d_counter, ck, id, sms, q->stream);
       case 1: return InflateConfig<8, 9, 7, 1024, 2>::launch(q->d_ops, n, q->d_res, q->d_counter, ck, id, sms, q->stream);
@@ -569,6 +597,13 @@ BITAR_API int bitar_debug_deflate_profile(int enable, unsigned long long* out) {
   if (!enable && p) g_deflate_prof.store(nullptr);
   return BITAR_OK;
 }
+
+#if defined(BITAR_LANE_DEBUG)
+BITAR_API int bitar_debug_lane(unsigned int* out16) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(out16, bitar::infl::g_dbg, 16 * sizeof(unsigned int));
+}
+#endif
 
 // not part of the public header: selects the inflate kernel instantiation for tuning sweeps
 BITAR_API void bitar_tune_inflate_variant(int v) { g_inflate_variant.store(v); }

@@ -22,7 +22,10 @@ def main():
     gens = {"lineitem": lambda n: synth.lineitem_like(n)}
     for name in synth.COLUMNS:
         gens[name] = (lambda nm: (lambda n: synth.column(nm, n)))(name)
+    only = os.environ.get("SWEEP_ONLY")
     for wname, gen in gens.items():
+        if only and wname != only:
+            continue
         n_bytes = mib << 20 if wname == "lineitem" else (mib << 20) // 4
         data = gen(n_bytes)
         n = (data.size + seg - 1) // seg
@@ -41,7 +44,7 @@ def main():
         print(f"[{wname}] deflate seg={seg} n={n} U={data.size} C={comp} ratio={data.size / comp:.3f} "
               f"kernel={best:.3f} ms  {data.size / best / 1e6:.1f} GB/s", flush=True)
         iops = dev.decompress_ops(slots, res["produced"], out.data_ptr())
-        for v in range(8):
+        for v in (5, 8, 9, 10, 11):
             capi.lib().bitar_tune_inflate_variant(v)
             best = 1e9
             for _ in range(reps + 1):
