@@ -570,6 +570,18 @@ int bitar_host_unregister(void* ptr) {
   return BITAR_OK;
 }
 
+int bitar_ptr_kind(const void* ptr, int* device_id) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  if (device_id) *device_id = a.device;
+  if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return 1;
+  if (a.type == cudaMemoryTypeHost) return 2;
+  return 0;
+}
+
 int bitar_qp_memcpy(bitar_dev* dev, uint16_t qp, void* dst, const void* src, size_t n) {
   if (!dev || qp >= dev->qps.size()) return fail(BITAR_E_INVALID, "bad device/queue pair");
   CU_TRY(cudaSetDevice(dev->id), BITAR_E_INVALID);

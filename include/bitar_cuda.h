@@ -171,6 +171,10 @@ BITAR_API int bitar_mem_alloc(int kind, int device_id, size_t size, size_t align
 BITAR_API int bitar_mem_free(int kind, int device_id, void* ptr);
 BITAR_API int bitar_host_register(void* ptr, size_t size);
 BITAR_API int bitar_host_unregister(void* ptr);
+/* What kind of memory an address is: 0 = pageable host (not device-accessible until registered),
+ * 1 = device memory (*device_id receives the owning device), 2 = pinned / registered host memory.
+ * The analogue of the rte_mem_virt2iova probe in src/memory.cc:388-391. */
+BITAR_API int bitar_ptr_kind(const void* ptr, int* device_id);
 /* Plain copies on the queue pair's stream (host<->device staging for pageable buffers). */
 BITAR_API int bitar_qp_memcpy(bitar_dev* dev, uint16_t qp, void* dst, const void* src, size_t n);
 
