@@ -22,6 +22,7 @@
 #include "deflate_kernel.cuh"
 #include "inflate_kernel.cuh"
 #include "inflate_lane_kernel.cuh"
+#include "inflate_fast_kernel.cuh"
 
 namespace {
 
@@ -406,6 +407,28 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
     using namespace bitar::ik;
     const int ck = dev->cfg.checksum_type, id = dev->id, sms = dev->sm_count;
     const int variant = inflate_variant();
+    if (variant >= 12) {   // lane-per-stream kernels (inflate_fast.h)
+      auto run = [&](auto cfg) -> cudaError_t {
+        using Cfg = decltype(cfg);
+        const size_t need = Cfg::scratch_bytes(id, sms);
+        if (need == 0) return cudaErrorLaunchOutOfResources;
+        if (q->lane_scratch_bytes < need) {
+          if (q->d_lane_scratch) cudaFree(q->d_lane_scratch);
+          q->d_lane_scratch = nullptr;
+          q->lane_scratch_bytes = 0;
+          cudaError_t e = cudaMalloc(&q->d_lane_scratch, need);
+          if (e != cudaSuccess) return e;
+          q->lane_scratch_bytes = need;
+        }
+        return Cfg::launch(q->d_ops, n, q->d_res, q->d_counter, q->d_lane_scratch, ck, id, sms, q->stream);
+      };
+      switch (variant) {
+        default:
+        case 12: return run(bitar::fk::FastConfig<9, 576, 7, 128, 256, 4>{});
+        case 13: return run(bitar::fk::FastConfig<9, 640, 7, 160, 512, 3>{});
+        case 14: return run(bitar::fk::FastConfig<10, 1152, 8, 288, 512, 2>{});
+      }
+    }
     if (variant >= 8) {   // lane-per-chunk kernels
       auto run = [&](auto cfg) -> cudaError_t {
         using Cfg = decltype(cfg);

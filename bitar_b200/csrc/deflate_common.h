@@ -345,5 +345,29 @@ BITAR_HD uint32_t hash_word(uint32_t w, int hash_bits, int min_match) {
 
 enum BlockType { kStored = 0, kFixed = 1, kDynamic = 2 };
 
+// ---- parallel-inflate index ------------------------------------------------------------------------
+// The compressor never lets a match start, end or reach outside the 2 KiB SUB-RANGE of its position, so
+// every sub-range of a block can be decoded on its own once the decoder knows (a) the block's Huffman
+// code and (b) the bit offset of the sub-range's first symbol.  (b) is appended to the chunk AFTER the
+// final block's end-of-block symbol and byte padding: a stock RFC 1951 decoder stops at the final block
+// and never looks at it (zlib returns Z_STREAM_END with the trailer left in avail_in), the sm_100a inflate
+// kernel finds it from the end of the buffer and decodes 32 sub-ranges per warp.  All values are
+// little-endian u32, bit offsets count from the first bit of the chunk's stream:
+//     for each 64 KiB block b:  hdr_bit[b], then sub_bit[b][s] for each sub-range s (0 for stored blocks)
+//     end_bit      bit offset just past the final end-of-block symbol
+//     total_out    uncompressed bytes of the chunk
+//     kIndexMagic
+// The index is omitted when no Huffman-coded block is longer than one sub-range, or when it does not fit
+// the output slot.
+constexpr int kSubLog2 = 11;
+constexpr uint32_t kSub = 1u << kSubLog2;
+constexpr int kIdxBlockLog2 = 16;                  // == the compressor's sub-block size (kBlockMax)
+constexpr uint32_t kIndexMagic = 0xB17A0B01u;      // "bitar", sub-range log2, version
+BITAR_HD uint32_t idx_blocks(uint32_t total) { return (total + 65535u) >> kIdxBlockLog2; }
+BITAR_HD uint32_t idx_subs(uint32_t block_len) { return (block_len + kSub - 1u) >> kSubLog2; }
+BITAR_HD uint32_t idx_entry(uint32_t block, uint32_t sub) { return block * 33u + 1u + sub; }   // hdr_bit at block * 33
+BITAR_HD uint32_t idx_entries(uint32_t total) { return (total >> kIdxBlockLog2) * 33u + ((total & 65535u) ? 1u + idx_subs(total & 65535u) : 0u); }
+BITAR_HD uint32_t idx_bytes(uint32_t total) { return 4u * (idx_entries(total) + 3u); }
+
 }  // namespace dfl
 }  // namespace bitar

@@ -68,6 +68,8 @@ struct __align__(16) Smem {
   uint32_t x2n[32];
   uint32_t cks_crc, cks_a, cks_b;    // checksum accumulators
   uint32_t ll_m, d_m;
+  uint32_t index[(BITAR_MAX_SEG_SIZE >> dfl::kIdxBlockLog2) * 33 + 4];   // parallel-inflate index of the chunk (deflate_common.h)
+  uint32_t any_coded;                // some Huffman-coded block spans more than one sub-range
   uint32_t block_type;
   uint32_t tile_bits;
   unsigned long long mbar;           // TMA completion barrier
@@ -296,8 +298,10 @@ __device__ __forceinline__ void worker_step(Smem& sm, uint32_t ds, int n, int s,
   const int p = base + wi * 32 + lane;
   uint32_t c = sm.cand[s & 1][wi * 32 + lane];
   int adv = 1, dist = 0;
-  if (c != kNoCand && p - (int)c <= dfl::kMaxDist) {
-    int len = match_len(ds, p, (int)c, min(dfl::kMaxMatch, n - p));
+  // matches stay inside the 2 KiB sub-range of their position: sub-ranges decode independently
+  if (c != kNoCand && ((c ^ (uint32_t)p) >> dfl::kSubLog2) == 0) {
+    const int sub_end = ((p >> dfl::kSubLog2) + 1) << dfl::kSubLog2;
+    int len = match_len(ds, p, (int)c, min(dfl::kMaxMatch, min(n, sub_end) - p));
     int dd = p - (int)c;
     if (len >= dfl::kMinMatch && !(len == 3 && dd > 4096)) {
       adv = len;
@@ -443,6 +447,11 @@ __global__ void __launch_bounds__(kThreads, 2)
       sm.cks_crc = 0;
       sm.cks_a = 0;
       sm.cks_b = 0;
+      sm.any_coded = 0;
+    }
+    {
+      const uint32_t idx_words = min(dfl::idx_entries(total), (uint32_t)(sizeof(sm.index) / 4));
+      for (uint32_t i = tid; i < idx_words; i += kThreads) sm.index[i] = 0;
     }
 
     if (total == 0) {  // empty input: a fixed block holding only end-of-block (03 00), as zlib emits
@@ -577,6 +586,11 @@ __global__ void __launch_bounds__(kThreads, 2)
           break;
         }
       }
+      const uint32_t iblk = (off >> dfl::kIdxBlockLog2) * 33u;   // this block's slots in the index
+      if (tid == 0) {
+        sm.index[iblk] = (uint32_t)(o.bit - 8ull * o.vstart);
+        if (type != dfl::kStored && (uint32_t)n > dfl::kSub) sm.any_coded = 1;
+      }
 
       if (type == dfl::kStored) {
         // ---- stored: header bits, byte align, then raw copy straight from shared memory ----
@@ -694,6 +708,8 @@ __global__ void __launch_bounds__(kThreads, 2)
           tile_total += ws;
         }
         uint64_t at = o.bit + warp_off + (incl - mybits);
+        if ((p0 & (int)(dfl::kSub - 1)) == 0 && p0 < n)   // first symbol of a sub-range
+          sm.index[iblk + 1u + ((uint32_t)p0 >> dfl::kSubLog2)] = (uint32_t)(at - 8ull * o.vstart);
         // emit: accumulate into a 64-bit window, flush whole words
         {
           uint32_t rel = (uint32_t)(at - 8ull * o.sbase);
@@ -734,7 +750,21 @@ __global__ void __launch_bounds__(kThreads, 2)
     if (status == BITAR_OP_OK) {
       uint32_t end_byte = (uint32_t)((o.bit + 7) >> 3);
       if (end_byte > o.vcap) status = BITAR_OP_OUT_OF_SPACE;
-      else stream_flush(sm, o, end_byte, false);
+      else {
+        __syncthreads();
+        // the parallel-inflate index goes after the byte-aligned end of the stream when it is useful and fits
+        const uint32_t entries = dfl::idx_entries(total);
+        if (sm.any_coded && (uint64_t)end_byte + 4ull * (entries + 3u) <= (uint64_t)o.vcap) {
+          const uint32_t end_bit = (uint32_t)(o.bit - 8ull * o.vstart);
+          for (uint32_t t = tid; t < entries + 3u; t += kThreads) {
+            const uint32_t w = t < entries ? sm.index[t] : t == entries ? end_bit : t == entries + 1u ? total : dfl::kIndexMagic;
+            stage_or(sm, o, 8ull * end_byte + 32ull * t, w, 32);
+          }
+          end_byte += 4u * (entries + 3u);
+          o.bit = 8ull * end_byte;
+        }
+        stream_flush(sm, o, end_byte, false);
+      }
     }
     __syncthreads();
     if (tid == 0) {

@@ -39,6 +39,50 @@ def test_inflate_core_vs_zlib(lbits):
                 assert np.array_equal(out, ch), (name, lvl)
 
 
+@pytest.mark.parametrize("lbits", [8, 9, 10])
+def test_inflate_fast_lane_vs_zlib(lbits):
+    """inflate_fast.h (the production lane-per-stream decoder) with one lane on the CPU: every block type
+    zlib emits, both alignments, checksums folded in on the way out."""
+    for name, ch in _chunks():
+        for lvl, strat in [(0, 0), (1, 0), (6, 0), (9, 0), (1, zlib.Z_FIXED)]:
+            co = zlib.compressobj(lvl, zlib.DEFLATED, -15, 8, strat)
+            z = np.frombuffer(co.compress(ch.tobytes()) + co.flush(), np.uint8)
+            for mis in (0, 5):
+                out, info = M.host_inflate_fast(z, max(ch.size, 1), lbits, mis, checksum_type=3)
+                assert info["status"] == 0 and info["guard_ok"] and info["consumed"] == z.size, (name, lvl, info)
+                assert np.array_equal(out, ch), (name, lvl)
+                assert info["crc32"] == O.crc32(ch) and info["adler32"] == O.adler32(ch), (name, lvl)
+
+
+def test_inflate_fast_lane_errors():
+    text = synth.edge_cases(SEG)["text"][:5000]
+    z = np.frombuffer(zlib.compress(text.tobytes(), 6)[2:-4], np.uint8).copy()
+    for lbits in (8, 9, 10):
+        assert M.host_inflate_fast(z[:100], 5000, lbits)[1]["status"] == 3          # truncated
+        out, info = M.host_inflate_fast(z, 4000, lbits)
+        assert info["status"] == 1 and info["guard_ok"] and info["produced"] <= 4000  # out of space
+        assert np.array_equal(out, text[:info["produced"]])
+        bad = z.copy()
+        bad[0] |= 6
+        assert M.host_inflate_fast(bad, 5000, lbits)[1]["status"] == 2              # BTYPE 3
+        over = np.frombuffer(bytes([0b00000101, 0xE0, 0xFF]) + bytes([0x49, 0x92, 0x24] * 3) + bytes(16), np.uint8)
+        assert M.host_inflate_fast(over, 100, lbits)[1]["status"] == 2              # over-subscribed code-length code
+        bits = "1" + "10" + "0000001" + "00000" + "0000000"
+        far = np.frombuffer(int(bits[::-1], 2).to_bytes(4, "little"), np.uint8)
+        assert M.host_inflate_fast(far, 100, lbits)[1]["status"] == 2               # distance before the start
+        stored = np.frombuffer(zlib.compressobj(0, zlib.DEFLATED, -15).compress(bytes(1000)) +
+                               zlib.compressobj(0, zlib.DEFLATED, -15).flush(), np.uint8)
+    rnd = np.frombuffer(np.random.default_rng(3).bytes(1000), np.uint8)
+    co = zlib.compressobj(0, zlib.DEFLATED, -15)
+    st = np.frombuffer(co.compress(rnd.tobytes()) + co.flush(), np.uint8).copy()
+    st[3] ^= 0xFF
+    assert M.host_inflate_fast(st, 1000)[1]["status"] == 2                          # LEN != ~NLEN
+    # tiny capacity, every length: the deferred capacity check never writes past dst_cap
+    for cap in (1, 2, 15, 16, 17, 31, 33, 100):
+        out, info = M.host_inflate_fast(z, cap)
+        assert info["status"] == 1 and info["guard_ok"] and np.array_equal(out, text[:info["produced"]]), cap
+
+
 def test_inflate_core_errors():
     text = synth.edge_cases(SEG)["text"][:5000]
     z = np.frombuffer(zlib.compress(text.tobytes(), 6)[2:-4], np.uint8).copy()
@@ -66,20 +110,61 @@ def test_deflate_model_streams_are_valid(huffman):
         m = M.model_deflate(ch, huffman)
         assert np.array_equal(O.inflate_chunk(m, max(ch.size, 1)), ch), name
         out, info = O.rfc_inflate(m, max(ch.size, 1))
-        assert np.array_equal(out, ch) and info["consumed"] == m.size
+        body, index = M.split_index(m)
+        assert np.array_equal(out, ch) and info["consumed"] == body.size
+        # the parallel-inflate index: present iff the chunk has more than one sub-range and a coded block
+        assert (index is not None) == (ch.size > M.SUB and (body[0] & 6) != 0), name
+        if index is not None:
+            assert index["total_out"] == ch.size
         out2, info2 = M.host_inflate(m, max(ch.size, 1))
         assert info2["status"] == 0 and np.array_equal(out2, ch)
         if name == "lineitem":
             total_model += m.size
             total_zlib += O.deflate_chunk(ch, 1, 15, huffman).size
-    assert total_model <= 1.05 * total_zlib       # north_star ratio tolerance, on the columnar workload
+    # north_star ratio tolerance (5 % of zlib level 1, dynamic Huffman) on the columnar workload; the fixed
+    # code pays more for the matches the 2 KiB sub-range rule gives up (DESIGN.md "Ratio"): 8 % there
+    assert total_model <= (1.05 if huffman == 2 else 1.08) * total_zlib
+
+
+@pytest.mark.parametrize("huffman", [1, 2])
+def test_indexed_inflate_of_model_streams(huffman):
+    """Sub-range parallel decode through the index == the original bytes; a damaged index is detected."""
+    seen = 0
+    for name, ch in _chunks():
+        m = M.model_deflate(ch, huffman)
+        body, index = M.split_index(m)
+        for mis in (0, 7):
+            out, info = M.host_inflate_indexed(m, max(ch.size, 1), mis)
+            assert info["indexed"] == (index is not None), name
+            if index is None:
+                continue
+            assert info["status"] == 0 and info["guard_ok"] and np.array_equal(out, ch), (name, info)
+            seen += 1
+        if index is not None and name == "lineitem":
+            bad = m.copy()
+            k = m.size - 12 - 4 * 5      # a sub_bit entry
+            bad[k] ^= 1
+            assert M.host_inflate_indexed(bad, ch.size)[1]["status"] == 2
+            assert M.host_inflate_indexed(m, ch.size - 1)[1]["status"] == 1      # total_out > capacity
+    assert seen > 10
+    big = synth.lineitem_like(3 * 65536 + 5000)
+    m = M.model_deflate(big, huffman)
+    out, info = M.host_inflate_indexed(m, big.size)
+    assert info["status"] == 0 and info["subs"] == 3 * 32 + 3 and np.array_equal(out, big)
+    mixed = np.concatenate([np.frombuffer(np.random.default_rng(9).bytes(65536), np.uint8), synth.lineitem_like(30000)])
+    m = M.model_deflate(mixed, huffman)       # a stored block followed by a coded one
+    out, info = M.host_inflate_indexed(m, mixed.size)
+    assert info["indexed"] and info["status"] == 0 and np.array_equal(out, mixed)
 
 
 def test_deflate_model_large_chunks_multi_block():
     data = synth.lineitem_like(3 * 65536 + 1000)
     m = M.model_deflate(data, 2)
     out, info = O.rfc_inflate(m, data.size)
-    assert np.array_equal(out, data) and info["blocks"] == 4
+    body, index = M.split_index(m)
+    assert np.array_equal(out, data) and info["blocks"] == 4 and info["consumed"] == body.size
+    assert index is not None and [b["len"] for b in index["blocks"]] == [65536, 65536, 65536, 1000]
+    assert all(len(b["sub_bit"]) == (b["len"] + 2047) // 2048 for b in index["blocks"])
     rnd = np.frombuffer(np.random.default_rng(5).bytes(65536 + 10), np.uint8)
     m = M.model_deflate(rnd, 2)
     assert np.array_equal(O.inflate_chunk(m, rnd.size), rnd)

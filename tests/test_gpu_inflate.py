@@ -32,7 +32,7 @@ def corpus(seg=SEG):
     return chunks
 
 
-@pytest.mark.parametrize("variant", [0, 5, 8, 9, 10, 11])
+@pytest.mark.parametrize("variant", [0, 5, 9, 12, 13, 14])
 def test_reference_streams_inflate_on_gpu(cuda_device, variant):
     capi.lib().bitar_tune_inflate_variant(variant)
     dev = G.open_device(SEG)

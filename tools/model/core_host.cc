@@ -8,6 +8,7 @@
 
 #include "../../bitar_b200/csrc/inflate_core.h"
 #include "../../bitar_b200/csrc/inflate_lane.h"
+#include "../../bitar_b200/csrc/inflate_fast.h"
 #include "deflate_model.h"
 
 #define API extern "C" __attribute__((visibility("default")))
@@ -58,6 +59,113 @@ API int host_inflate_lane(const uint8_t* in, uint32_t in_len, uint8_t* out, uint
   if (lbits == 9) run_lane<9, 576, 7, 128, 256>(in, in_len, out, cap, result4);   // tight sub-table budget: exercises the slow path too
   else if (lbits == 8) run_lane<8, 704, 7, 160, 256>(in, in_len, out, cap, result4);
   else run_lane<10, 1024, 8, 256, 512>(in, in_len, out, cap, result4);
+  return 0;
+}
+
+// the lane-per-stream decoder of the production inflate kernel (inflate_fast.h), one lane on the CPU
+template <int LB, int LT, int DB, int DT, int RG>
+static void run_fast(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t cap, uint32_t* result6, int checksum_type) {
+  using namespace bitar::fl;
+  using L = FastLane<LB, LT, DB, DT, RG>;
+  alignas(16) static thread_local uint8_t smem[LaneLayout<LB, LT, DB, DT, RG>::kStride];
+  static thread_local LaneScratch scratch;
+  static CtaTables cta;
+  static bool init = false;
+  if (!init) {
+    for (int i = 0; i < 32; ++i) cta.dinfo[i] = dist_info(i);
+    for (uint32_t i = 0; i < 256; ++i) cta.crc[0][i] = bitar::cks::crc_table_entry(i);
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = cta.crc[0][i];
+      for (int k = 1; k < 4; ++k) {
+        c = (c >> 8) ^ cta.crc[0][c & 0xFFu];
+        cta.crc[k][i] = c;
+      }
+    }
+    init = true;
+  }
+  L lane;
+  lane.bind(smem, &cta, &scratch, (uint32_t)checksum_type);
+  lane.start(in, in_len, out, cap);
+  uint64_t steps = 0;
+  while (lane.state != L::kDone) {
+    lane.step();
+    if (++steps > (1ull << 32)) break;
+  }
+  result6[0] = lane.produced();
+  result6[1] = lane.status;
+  result6[2] = lane.consumed_bytes();
+  result6[3] = lane.blocks;
+  const uint64_t ck = lane.checksum();
+  result6[4] = (uint32_t)ck;
+  result6[5] = (uint32_t)(ck >> 32);
+}
+
+API int host_inflate_fast(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t cap, uint32_t* result6, int lbits,
+                          int checksum_type) {
+  if (lbits == 9) run_fast<9, 576, 7, 128, 256>(in, in_len, out, cap, result6, checksum_type);
+  else if (lbits == 8) run_fast<8, 264, 7, 128, 256>(in, in_len, out, cap, result6, checksum_type);   // starved second level: slow path
+  else run_fast<10, 1152, 8, 288, 512>(in, in_len, out, cap, result6, checksum_type);
+  return 0;
+}
+
+// The indexed path of the production inflate kernel on the CPU: the index is parsed with the kernel's own
+// parse_index(), block headers are parsed by a whole-stream lane, and every 2 KiB sub-range is decoded by a
+// SUB lane that starts at its indexed bit offset (the kernel runs 32 of these per warp).
+// result: [0] produced, [1] status, [2] 1 when the chunk carried an index, [3] sub-ranges decoded.
+API int host_inflate_indexed(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t cap, uint32_t* result4) {
+  using namespace bitar::fl;
+  using namespace bitar;
+  constexpr int LB = 10, LT = 1344, DB = 8, DT = 512, RG = 128;
+  using Gen = FastLane<LB, LT, DB, DT, RG, false>;
+  using Sub = FastLane<LB, LT, DB, DT, RG, true>;
+  alignas(16) static thread_local uint8_t smem[LaneLayout<LB, LT, DB, DT, 256>::kStride];
+  static thread_local LaneScratch scratch;
+  static CtaTables cta;
+  for (int i = 0; i < 32; ++i) cta.dinfo[i] = dist_info(i);
+  result4[0] = result4[1] = result4[2] = result4[3] = 0;
+  IndexInfo ix;
+  if (!parse_index(in, in_len, &ix)) return 0;
+  result4[2] = 1;
+  if (ix.total_out > cap) {
+    result4[1] = kStatusOutOfSpace;
+    return 0;
+  }
+  const uint32_t nb = dfl::idx_blocks(ix.total_out);
+  uint32_t status = kStatusOk;
+  for (uint32_t b = 0; b < nb && status == kStatusOk; ++b) {
+    const uint32_t blen = ix.total_out - (b << 16) < 65536u ? ix.total_out - (b << 16) : 65536u;
+    const uint32_t ns = dfl::idx_subs(blen), hdr = index_word(ix, b * 33u);
+    const uint32_t block_end = b + 1 < nb ? index_word(ix, (b + 1) * 33u) : ix.end_bit;
+    Gen g;
+    g.bind(smem, &cta, &scratch, 0);
+    g.start(in, ix.stream_bytes, out + (b << 16), blen);
+    g.bits_init(hdr >> 3);
+    g.drop(hdr & 7u);
+    g.header();
+    if (g.status != kStatusOk) { status = g.status; break; }
+    if (g.state == Gen::kStored) {   // stored block(s): the whole-stream lane copies them
+      uint64_t steps = 0;
+      while (g.state != Gen::kDone && g.produced() < blen && ++steps < (1ull << 30)) g.step();
+      while (g.state != Gen::kDone) { g.state = Gen::kFinish; g.step(); }
+      if (g.status != kStatusOk || g.produced() != blen) status = g.status ? g.status : (uint32_t)kStatusDataError;
+      continue;
+    }
+    if ((uint32_t)(8ll * g.start_off + g.consumed_bits()) != index_word(ix, b * 33u + 1u)) { status = kStatusDataError; break; }
+    for (uint32_t s = 0; s < ns; ++s) {
+      Sub l;
+      l.bind_parts(g.lt, g.dt, smem + 2 * LT + 2 * DT, &cta, &scratch, 0);
+      const uint32_t len = blen - s * dfl::kSub < dfl::kSub ? blen - s * dfl::kSub : dfl::kSub;
+      const uint32_t sbit = index_word(ix, b * 33u + 1u + s);
+      const uint32_t ebit = s + 1 < ns ? index_word(ix, b * 33u + 2u + s) : block_end;
+      l.start_sub(in, ix.stream_bytes, sbit, ebit, s + 1 == ns, out + (b << 16) + s * dfl::kSub, len);
+      uint64_t steps = 0;
+      while (l.state != Sub::kDone && ++steps < (1ull << 30)) l.step();
+      result4[3]++;
+      if (l.status != kStatusOk) { status = l.status; break; }
+    }
+  }
+  result4[0] = status == kStatusOk ? ix.total_out : 0;
+  result4[1] = status;
   return 0;
 }
 

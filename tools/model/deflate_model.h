@@ -27,6 +27,8 @@ struct Params {
   int far3 = 4096;      // reject length-3 matches farther than this (0 = keep all)
   int huffman = 2;      // 1 fixed only, 2 dynamic (min of stored/fixed/dynamic)
   int block = 65536;    // sub-block size inside a chunk (window restarts at sub-block start)
+  int sub_log2 = kSubLog2;  // matches stay inside the 2^sub_log2-byte sub-range of their position and the
+                        // parallel-inflate index is appended (deflate_common.h); 0 = off
 };
 
 struct BitWriter {
@@ -55,8 +57,9 @@ inline uint32_t load32(const uint8_t* d, size_t n, size_t p) {  // zero padded p
   return w;
 }
 
-inline int match_len(const uint8_t* d, int n, int p, int c) {
+inline int match_len(const uint8_t* d, int n, int p, int c, int sub_log2 = 0) {
   int maxl = std::min(kMaxMatch, n - p), l = 0;
+  if (sub_log2) maxl = std::min(maxl, (((p >> sub_log2) + 1) << sub_log2) - p);
   while (l < maxl && d[p + l] == d[c + l]) ++l;
   return l;
 }
@@ -96,7 +99,8 @@ inline void find_tokens(const uint8_t* d, int n, const Params& P, std::vector<ui
       int best = 0, bdist = 0;
       auto consider = [&](int c) {
         if (c < 0 || p - c > kMaxDist) return;
-        int l = match_len(d, n, p, c);
+        if (P.sub_log2 && (c >> P.sub_log2) != (p >> P.sub_log2)) return;   // other sub-range
+        int l = match_len(d, n, p, c, P.sub_log2);
         if (l > best) {  // first considered wins ties
           best = l;
           bdist = p - c;
@@ -139,7 +143,7 @@ inline void put_fixed_sym(BitWriter& bw, int sym) {
 
 // Encode one sub-block (tokens already found) as the cheapest of stored / fixed / dynamic.
 inline void encode_block(const uint8_t* d, int n, const std::vector<uint32_t>& tok, bool final_block,
-                         const Params& P, BitWriter& bw, BlockStats* st) {
+                         const Params& P, BitWriter& bw, BlockStats* st, std::vector<uint32_t>* index = nullptr) {
   uint32_t ll_freq[288] = {0}, d_freq[32] = {0};
   for (int p = 0; p < n; ++p) {
     uint32_t t = tok[(size_t)p];
@@ -204,6 +208,11 @@ inline void encode_block(const uint8_t* d, int n, const std::vector<uint32_t>& t
   }
   if (st) st->type = type;
   uint64_t before = bw.bits();
+  if (index) {   // hdr_bit, then one slot per sub-range (stays 0 for stored blocks)
+    index->push_back((uint32_t)before);
+    index->resize(index->size() + idx_subs((uint32_t)n), 0u);
+  }
+  const size_t idx_base = index ? index->size() - idx_subs((uint32_t)n) : 0;
   if (type == kStored) {
     int off = 0;
     for (int k = 0; k < pieces; ++k) {
@@ -233,6 +242,7 @@ inline void encode_block(const uint8_t* d, int n, const std::vector<uint32_t>& t
     }
     for (int p = 0; p < n; ++p) {
       uint32_t t = tok[(size_t)p];
+      if (index && (p & (int)(kSub - 1)) == 0) (*index)[idx_base + ((size_t)p >> kSubLog2)] = (uint32_t)bw.bits();
       if (t == 0) continue;
       if (t == 1) {
         if (type == kDynamic) bw.put(plan.ll_code[d[p]], plan.ll_len[d[p]]);
@@ -264,15 +274,25 @@ inline std::vector<uint8_t> deflate_chunk(const uint8_t* d, size_t n, const Para
     bw.align();
     return bw.out;
   }
-  std::vector<uint32_t> tok;
+  std::vector<uint32_t> tok, index;
+  const bool want_index = P.sub_log2 == kSubLog2 && P.block == (1 << kIdxBlockLog2);
+  bool any_coded = false;
   for (size_t off = 0; off < n; off += (size_t)P.block) {
     int len = (int)std::min((size_t)P.block, n - off);
     find_tokens(d + off, len, P, tok);
     BlockStats st;
-    encode_block(d + off, len, tok, off + (size_t)len == n, P, bw, &st);
+    encode_block(d + off, len, tok, off + (size_t)len == n, P, bw, &st, want_index ? &index : nullptr);
+    any_coded |= st.type != kStored && len > (int)kSub;   // a block the index can split
     if (stats) stats->push_back(st);
   }
+  const uint32_t end_bit = (uint32_t)bw.bits();
   bw.align();
+  if (want_index && any_coded) {   // the parallel-inflate index (deflate_common.h)
+    index.push_back(end_bit);
+    index.push_back((uint32_t)n);
+    index.push_back(kIndexMagic);
+    for (uint32_t w : index) bw.put(w, 32);
+  }
   return bw.out;
 }
 

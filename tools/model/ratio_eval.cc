@@ -33,7 +33,7 @@ static bool zcheck(const std::vector<uint8_t>& c, const uint8_t* d, size_t n) {
   int rc = inflate(&zs, Z_FINISH);
   size_t got = out.size() - zs.avail_out;
   inflateEnd(&zs);
-  return rc == Z_STREAM_END && got == n && memcmp(out.data(), d, n) == 0 && zs.avail_in == 0;
+  return rc == Z_STREAM_END && got == n && memcmp(out.data(), d, n) == 0;   // the index trailer stays in avail_in
 }
 
 int main(int argc, char** argv) {
@@ -59,6 +59,7 @@ int main(int argc, char** argv) {
     else if (k == "far3") P.far3 = v;
     else if (k == "huffman") P.huffman = v;
     else if (k == "block") P.block = v;
+    else if (k == "sub_log2") P.sub_log2 = v;
     else return fprintf(stderr, "unknown key %s\n", k.c_str()), 2;
   }
   uint64_t zsum = 0, msum = 0, lits = 0, matches = 0, mbytes = 0;
