@@ -21,8 +21,8 @@
 #include "../../include/bitar_cuda.h"
 #include "deflate_kernel.cuh"
 #include "inflate_kernel.cuh"
-#include "inflate_lane_kernel.cuh"
 #include "inflate_fast_kernel.cuh"
+#include "inflate_indexed_kernel.cuh"
 
 namespace {
 
@@ -56,6 +56,10 @@ struct QueuePair {
   uint32_t* d_tokens = nullptr;    // deflate token scratch (grid * 64 Ki u32), allocated on first use
   void* d_lane_scratch = nullptr;  // inflate per-lane scratch, allocated on first use
   size_t lane_scratch_bytes = 0;
+  bitar::xk::Task* d_tasks = nullptr;   // indexed inflate: one task per 64 KiB block
+  size_t tasks_cap = 0;
+  uint32_t* d_generic = nullptr;        // ops left to the whole-stream kernel
+  size_t generic_cap = 0;
   bitar_result* user_out = nullptr;
   uint32_t pending_n = 0;
   std::atomic<int> busy{0};
@@ -195,7 +199,7 @@ int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, b
   q->busy.store(1, std::memory_order_release);
   cudaError_t e = cudaEventRecord(q->ev_start, q->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(q->d_ops, q->h_ops, (size_t)n * sizeof(bitar_chunk), cudaMemcpyHostToDevice, q->stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(q->d_counter, 0, sizeof(unsigned int), q->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(q->d_counter, 0, 8 * sizeof(unsigned int), q->stream);
   if (e == cudaSuccess) e = cudaEventRecord(q->ev_k0, q->stream);
   if (e == cudaSuccess) e = launch(q);
   if (e == cudaSuccess) e = cudaEventRecord(q->ev_k1, q->stream);
@@ -215,7 +219,7 @@ int inflate_variant() {
   int v = g_inflate_variant.load();
   if (v < 0) {
     const char* s = getenv("BITAR_INFLATE_VARIANT");
-    v = s ? atoi(s) : 5;
+    v = s ? atoi(s) : 20;
     g_inflate_variant.store(v);
   }
   return v;
@@ -341,7 +345,7 @@ int bitar_dev_open(int device_id, uint16_t n_qps, const bitar_cfg* cfg_in, bitar
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&q->ev_k0);
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&q->ev_k1);
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&q->ev_stop);
-    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&q->d_counter, sizeof(unsigned int));
+    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&q->d_counter, 8 * sizeof(unsigned int));
     if (e2 != cudaSuccess) {
       bitar_dev_close(dev);
       return fail(BITAR_E_INVALID, "Failed to setup queue pair %u for device %d: %s", (unsigned)i, device_id, cudaGetErrorString(e2));
@@ -371,6 +375,8 @@ int bitar_dev_close(bitar_dev* dev) {
     if (q->d_counter) cudaFree(q->d_counter);
     if (q->d_tokens) cudaFree(q->d_tokens);
     if (q->d_lane_scratch) cudaFree(q->d_lane_scratch);
+    if (q->d_tasks) cudaFree(q->d_tasks);
+    if (q->d_generic) cudaFree(q->d_generic);
     if (q->ev_start) cudaEventDestroy(q->ev_start);
     if (q->ev_k0) cudaEventDestroy(q->ev_k0);
     if (q->ev_k1) cudaEventDestroy(q->ev_k1);
@@ -407,6 +413,49 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
     using namespace bitar::ik;
     const int ck = dev->cfg.checksum_type, id = dev->id, sms = dev->sm_count;
     const int variant = inflate_variant();
+    if (variant >= 20) {
+      // default: chunks carrying the parallel-inflate index go to the sub-range kernel, one warp per
+      // 64 KiB block; everything else (zlib streams, stored chunks) to the whole-stream kernel.
+      // Checksums are only folded in by the whole-stream kernel, so they route everything there.
+      using namespace bitar::xk;
+      size_t blocks = 0;
+      for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t cap = q->h_ops[i].dst_cap < BITAR_MAX_SEG_SIZE ? q->h_ops[i].dst_cap : BITAR_MAX_SEG_SIZE;
+        blocks += (cap + 65535u) >> 16;
+      }
+      if (q->tasks_cap < blocks) {
+        if (q->d_tasks) cudaFree(q->d_tasks);
+        q->d_tasks = nullptr;
+        q->tasks_cap = 0;
+        cudaError_t e = cudaMalloc((void**)&q->d_tasks, blocks * sizeof(Task));
+        if (e != cudaSuccess) return e;
+        q->tasks_cap = blocks;
+      }
+      if (q->generic_cap < n) {
+        if (q->d_generic) cudaFree(q->d_generic);
+        q->d_generic = nullptr;
+        q->generic_cap = 0;
+        cudaError_t e = cudaMalloc((void**)&q->d_generic, (size_t)n * sizeof(uint32_t));
+        if (e != cudaSuccess) return e;
+        q->generic_cap = n;
+      }
+      Counters* pc = reinterpret_cast<Counters*>(q->d_counter);
+      inflate_plan_kernel<<<(n + 127) / 128, 128, 0, q->stream>>>(q->d_ops, n, q->d_res, q->d_tasks, q->d_generic, pc,
+                                                                  ck == BITAR_CHECKSUM_NONE ? 1 : 0);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+      g_launches.fetch_add(2);
+      switch (variant) {
+        default:
+        case 20: e = IndexedConfig<10, 1344, 8, 512, 128, 20>::launch(q->d_ops, q->d_res, q->d_tasks, pc, (uint32_t)blocks, id, sms, q->stream); break;
+        case 21: e = IndexedConfig<10, 1344, 8, 512, 128, 16>::launch(q->d_ops, q->d_res, q->d_tasks, pc, (uint32_t)blocks, id, sms, q->stream); break;
+        case 22: e = IndexedConfig<9, 864, 7, 256, 128, 24>::launch(q->d_ops, q->d_res, q->d_tasks, pc, (uint32_t)blocks, id, sms, q->stream); break;
+        case 23: e = IndexedConfig<10, 1344, 8, 512, 256, 14>::launch(q->d_ops, q->d_res, q->d_tasks, pc, (uint32_t)blocks, id, sms, q->stream); break;
+      }
+      if (e != cudaSuccess) return e;
+      return InflateConfig<32, 10, 8, 1024, 4>::launch(q->d_ops, n, q->d_res, &pc->generic_next, ck, id, sms, q->stream,
+                                                       q->d_generic, &pc->n_generic);
+    }
     if (variant >= 12) {   // lane-per-stream kernels (inflate_fast.h)
       auto run = [&](auto cfg) -> cudaError_t {
         using Cfg = decltype(cfg);
@@ -427,29 +476,6 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
         case 12: return run(bitar::fk::FastConfig<9, 576, 7, 128, 256, 4>{});
         case 13: return run(bitar::fk::FastConfig<9, 640, 7, 160, 512, 3>{});
         case 14: return run(bitar::fk::FastConfig<10, 1152, 8, 288, 512, 2>{});
-      }
-    }
-    if (variant >= 8) {   // lane-per-chunk kernels
-      auto run = [&](auto cfg) -> cudaError_t {
-        using Cfg = decltype(cfg);
-        const size_t need = Cfg::scratch_bytes(id, sms);
-        if (need == 0) return cudaErrorLaunchOutOfResources;
-        if (q->lane_scratch_bytes < need) {
-          if (q->d_lane_scratch) cudaFree(q->d_lane_scratch);
-          q->d_lane_scratch = nullptr;
-          q->lane_scratch_bytes = 0;
-          cudaError_t e = cudaMalloc(&q->d_lane_scratch, need);
-          if (e != cudaSuccess) return e;
-          q->lane_scratch_bytes = need;
-        }
-        return Cfg::launch(q->d_ops, n, q->d_res, q->d_counter, q->d_lane_scratch, ck, id, sms, q->stream);
-      };
-      switch (variant) {
-        default:
-        case 8: return run(bitar::ilk::LaneConfig<9, 704, 7, 160, 256, 1>{});
-        case 9: return run(bitar::ilk::LaneConfig<9, 576, 7, 128, 256, 1>{});
-        case 10: return run(bitar::ilk::LaneConfig<10, 1024, 8, 256, 512, 1>{});
-        case 11: return run(bitar::ilk::LaneConfig<9, 704, 7, 160, 512, 1>{});
       }
     }
     switch (variant) {

@@ -65,7 +65,8 @@ __device__ __forceinline__ uint64_t group_checksum(const uint8_t* p, uint32_t n,
 template <int G, int LBITS, int DBITS, int RING, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
     inflate_kernel(const bitar_chunk* __restrict__ ops, uint32_t n_ops, bitar_result* __restrict__ results,
-                   unsigned int* __restrict__ counter, int checksum_type) {
+                   unsigned int* __restrict__ counter, int checksum_type, const uint32_t* __restrict__ list,
+                   const unsigned int* __restrict__ n_list) {
   using GS = inf::GroupSmem<LBITS, DBITS, RING>;
   constexpr int kGroupsPerWarp = 32 / G;
   constexpr int kGroupsPerCta = WARPS * kGroupsPerWarp;
@@ -87,9 +88,12 @@ __global__ void __launch_bounds__(WARPS * 32)
     __syncthreads();
   }
 
+  // with a list (written by the plan kernel of inflate_indexed_kernel.cuh) only the listed ops are decoded
+  if (list) n_ops = *n_list;
   const uint32_t total_groups = gridDim.x * kGroupsPerCta;
-  uint32_t idx = blockIdx.x * kGroupsPerCta + warp * kGroupsPerWarp + group_in_warp;
-  while (idx < n_ops) {
+  uint32_t slot = blockIdx.x * kGroupsPerCta + warp * kGroupsPerWarp + group_in_warp;
+  while (slot < n_ops) {
+    const uint32_t idx = list ? list[slot] : slot;
     const bitar_chunk op = ops[idx];
     inf::ChunkResult r = inf::inflate_chunk<G, LBITS, DBITS, RING>(
         static_cast<const uint8_t*>(op.src), op.src_len, static_cast<uint8_t*>(op.dst), op.dst_cap, sm, g);
@@ -105,7 +109,7 @@ __global__ void __launch_bounds__(WARPS * 32)
     }
     uint32_t next = 0;
     if (g.lane == 0) next = total_groups + atomicAdd(counter, 1u);
-    idx = __shfl_sync(g.mask, next, (int)(group_in_warp * G));
+    slot = __shfl_sync(g.mask, next, (int)(group_in_warp * G));
   }
 }
 
@@ -115,7 +119,8 @@ struct InflateConfig {
   static constexpr size_t kSmem =
       sizeof(inf::GroupSmem<LBITS, DBITS, RING>) * (WARPS * (32 / G)) + sizeof(CksSmem);
   static cudaError_t launch(const bitar_chunk* ops, uint32_t n, bitar_result* res, unsigned int* counter,
-                            int checksum_type, int device, int sm_count, cudaStream_t stream) {
+                            int checksum_type, int device, int sm_count, cudaStream_t stream,
+                            const uint32_t* list = nullptr, const unsigned int* n_list = nullptr) {
     auto kern = inflate_kernel<G, LBITS, DBITS, RING, WARPS>;
     static int per_device[64] = {0};   // resident CTAs per SM, resolved once per device
     int& ctas_per_sm = per_device[device & 63];
@@ -131,7 +136,7 @@ struct InflateConfig {
     uint32_t grid = (uint32_t)(sm_count * ctas_per_sm);
     if (want < grid) grid = want;
     if (grid == 0) return cudaSuccess;
-    kern<<<grid, kThreads, kSmem, stream>>>(ops, n, res, counter, checksum_type);
+    kern<<<grid, kThreads, kSmem, stream>>>(ops, n, res, counter, checksum_type, list, n_list);
     return cudaGetLastError();
   }
 };

@@ -21,7 +21,6 @@ def lib():
         subprocess.check_call(["make", "-C", _DIR, "-s", "libmodel.so"], stderr=subprocess.DEVNULL)
         L = C.CDLL(_LIB)
         L.host_inflate_chunk.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
-        L.host_inflate_lane.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
         L.host_inflate_fast.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_int]
         L.host_inflate_indexed.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
         L.model_deflate_chunk.restype = C.c_long
@@ -31,15 +30,14 @@ def lib():
     return _lib
 
 
-def host_inflate(comp, cap, lbits=10, misalign=0, lane=False):
-    """Run inflate_core.h (G=1) or, with lane=True, the lane-per-chunk state machine of inflate_lane.h.
-    Returns (bytes, dict(status, produced, consumed, blocks))."""
+def host_inflate(comp, cap, lbits=10, misalign=0):
+    """Run inflate_core.h (G=1).  Returns (bytes, dict(status, produced, consumed, blocks))."""
     c = np.ascontiguousarray(comp, dtype=np.uint8)
     buf = np.full(cap + 64, 0xA5, np.uint8)
     base = buf.ctypes.data
     off = (-base) % 16 + misalign
     res = np.zeros(4, np.uint32)
-    fn = lib().host_inflate_lane if lane else lib().host_inflate_chunk
+    fn = lib().host_inflate_chunk
     fn(c.ctypes.data if c.size else None, c.size, base + off, cap, res.ctypes.data, lbits)
     out = buf[off:off + int(res[0])].copy()
     guard_ok = bool((buf[:off] == 0xA5).all() and (buf[off + cap:] == 0xA5).all())

@@ -43,7 +43,8 @@ def test_gpu_streams_inflate_under_zlib_and_match_model(cuda_device, huffman):
                 back = O.inflate_chunk(comp, max(c.size, 1))          # zlib, the reference codec
                 assert np.array_equal(back, c)
                 back2, info = O.rfc_inflate(comp, max(c.size, 1))     # independent decoder
-                assert np.array_equal(back2, c) and info["consumed"] == comp.size
+                body, index = M.split_index(comp)                     # the parallel-inflate index follows the stream
+                assert np.array_equal(back2, c) and info["consumed"] == body.size
                 model = M.model_deflate(c, huffman)
                 assert np.array_equal(comp, model), "GPU stream differs from the kernel model"
                 assert int(r["checksum"]) & 0xFFFFFFFF == O.crc32(c)

@@ -32,7 +32,7 @@ def corpus(seg=SEG):
     return chunks
 
 
-@pytest.mark.parametrize("variant", [0, 5, 9, 12, 13, 14])
+@pytest.mark.parametrize("variant", [0, 5, 12, 13, 14, 20])
 def test_reference_streams_inflate_on_gpu(cuda_device, variant):
     capi.lib().bitar_tune_inflate_variant(variant)
     dev = G.open_device(SEG)
@@ -52,7 +52,44 @@ def test_reference_streams_inflate_on_gpu(cuda_device, variant):
                 assert o.size == ref.size and np.array_equal(o, ref)
     finally:
         dev.close()
-        capi.lib().bitar_tune_inflate_variant(0)
+        capi.lib().bitar_tune_inflate_variant(20)
+
+
+@pytest.mark.parametrize("variant", [20, 21, 22, 23])
+@pytest.mark.parametrize("huffman", [capi.HUFFMAN_DYNAMIC, capi.HUFFMAN_FIXED])
+def test_gpu_streams_inflate_through_the_index(cuda_device, variant, huffman):
+    """Chunks produced by the deflate kernel carry the parallel-inflate index: the sub-range kernel must
+    give back the original bytes (bit-exact), for every edge case, alignment and multi-block chunk; chunks
+    without an index (stored, tiny) take the whole-stream kernel in the same call."""
+    capi.lib().bitar_tune_inflate_variant(variant)
+    seg = 3 * 65536 + 5000
+    dev = G.open_device(seg, huffman_enc=huffman)
+    try:
+        chunks = [c for _, c in corpus()]
+        chunks += [synth.lineitem_like(seg), np.concatenate([np.frombuffer(np.random.default_rng(9).bytes(65536), np.uint8),
+                                                             synth.lineitem_like(30000)])]
+        comps, res, err = G.gpu_deflate_chunks(dev, chunks)
+        assert err is None
+        import model_lib as M
+        n_indexed = sum(M.split_index(c)[1] is not None for c in comps)
+        assert n_indexed >= 20
+        for shift in (0, 3):
+            outs, res, err = G.gpu_inflate_chunks(dev, comps, [max(c.size, 1) for c in chunks], src_shift=shift, dst_shift=5 * shift)
+            assert err is None, err
+            assert (res["status"] == 0).all()
+            for o, ref in zip(outs, chunks):
+                assert o.size == ref.size and np.array_equal(o, ref)
+        # damaged index entries and a short output buffer are reported, never silently wrong
+        big = [i for i, c in enumerate(comps) if M.split_index(c)[1] is not None][:3]
+        bad = [comps[i].copy() for i in big]
+        bad[0][bad[0].size - 12 - 4 * 3] ^= 0x10         # a sub_bit entry
+        bad[1][bad[1].size - 12 - 4 * 7 + 1] ^= 0x01
+        outs, res, err = G.gpu_inflate_chunks(dev, bad, [chunks[big[0]].size, chunks[big[1]].size, chunks[big[2]].size - 1])
+        assert err is not None and err.code == capi.E_IO_ERROR
+        assert list(res["status"]) == [capi.OP_DATA_ERROR, capi.OP_DATA_ERROR, capi.OP_OUT_OF_SPACE]
+    finally:
+        dev.close()
+        capi.lib().bitar_tune_inflate_variant(20)
 
 
 def test_bitar_decompress_contract(cuda_device):

@@ -7,7 +7,6 @@
 #include <vector>
 
 #include "../../bitar_b200/csrc/inflate_core.h"
-#include "../../bitar_b200/csrc/inflate_lane.h"
 #include "../../bitar_b200/csrc/inflate_fast.h"
 #include "deflate_model.h"
 
@@ -29,36 +28,6 @@ API int host_inflate_chunk(const uint8_t* in, uint32_t in_len, uint8_t* out, uin
   result4[1] = r.status;
   result4[2] = r.consumed;
   result4[3] = r.blocks;
-  return 0;
-}
-
-// the lane-per-chunk state machine of the production inflate kernel, one lane on the CPU
-template <int LB, int LT, int DB, int DT, int RG>
-static void run_lane(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t cap, uint32_t* result4) {
-  using namespace bitar::infl;
-  using L = Lane<LB, LT, DB, DT, RG>;
-  alignas(16) static thread_local uint8_t smem[LaneSmem<LB, LT, DB, DT, RG>::kStride];
-  static thread_local LaneScratch scratch;
-  L lane;
-  lane.bind(smem, &scratch);
-  lane.start(in, in_len, out, cap);
-  uint64_t steps = 0;
-  while (lane.state != kDone) {
-    lane.step_pre();
-    lane.step_post(lane.want_copy());
-    if (++steps > (1ull << 32)) break;
-  }
-  result4[0] = lane.produced();
-  result4[1] = lane.status;
-  result4[2] = lane.consumed_bytes();
-  result4[3] = lane.blocks;
-}
-
-API int host_inflate_lane(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t cap, uint32_t* result4,
-                          int lbits) {
-  if (lbits == 9) run_lane<9, 576, 7, 128, 256>(in, in_len, out, cap, result4);   // tight sub-table budget: exercises the slow path too
-  else if (lbits == 8) run_lane<8, 704, 7, 160, 256>(in, in_len, out, cap, result4);
-  else run_lane<10, 1024, 8, 256, 512>(in, in_len, out, cap, result4);
   return 0;
 }
 
