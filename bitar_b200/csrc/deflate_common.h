@@ -138,6 +138,8 @@ BITAR_HD_NOINLINE void huff_lengths_from_sorted(const uint32_t* sorted_key, int 
   int root = next - 1;
   s->depth[root] = 0;
   for (int i = root - 1; i >= 0; --i) s->depth[i] = (uint8_t)(s->depth[s->parent[i]] + 1);
+  // zlib gen_bitlen counts EVERY node below the length limit (leaves and internal nodes, whose clamped
+  // parents push them to max_bits + 1 again); the repair loop below relies on that count
   int overflow = 0;
   for (int i = 0; i < m; ++i) {
     int d = s->depth[i];
@@ -147,6 +149,8 @@ BITAR_HD_NOINLINE void huff_lengths_from_sorted(const uint32_t* sorted_key, int 
     }
     bl_count[d]++;
   }
+  for (int i = m; i < root; ++i)
+    if (s->depth[i] > max_bits) overflow++;
   if (overflow > 0) {
     // zlib gen_bitlen: move one leaf down from the deepest non-full level, pairing an overflow leaf
     do {

@@ -26,6 +26,8 @@ def lib():
         L.model_deflate_chunk.restype = C.c_long
         L.model_deflate_chunk.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.c_int]
         L.model_selfcheck.restype = C.c_int
+        L.model_huffman_fuzz.restype = C.c_int
+        L.model_huffman_fuzz.argtypes = [C.c_int, C.c_uint]
         _lib = L
     return _lib
 

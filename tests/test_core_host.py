@@ -27,6 +27,12 @@ def test_symbol_maps():
     assert M.lib().model_selfcheck() == 0
 
 
+def test_huffman_codes_are_complete():
+    """Length-limited code construction (shared with the deflate kernel): complete (Kraft sum 1) and within
+    15 / 7 bits for skewed frequency sets whose optimal trees are far deeper than the limit."""
+    assert M.lib().model_huffman_fuzz(60000, 7) == 0
+
+
 @pytest.mark.parametrize("lbits", [9, 10])
 def test_inflate_core_vs_zlib(lbits):
     for name, ch in _chunks():

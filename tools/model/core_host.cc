@@ -2,6 +2,7 @@
 //   * host_inflate_chunk : bitar_b200/csrc/inflate_core.h instantiated with G = 1
 //   * model_deflate_chunk: sequential model of the deflate kernel (deflate_model.h)
 // Loaded through ctypes by tests/; never part of the product library.
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -147,6 +148,47 @@ API long model_deflate_chunk(const uint8_t* src, uint32_t n, uint8_t* dst, uint3
   if (out.size() > cap) return -1;
   memcpy(dst, out.data(), out.size());
   return (long)out.size();
+}
+
+// Length-limited Huffman construction (deflate_common.h, shared with the deflate kernel) on random and
+// adversarial frequency sets: returns the number of sets whose code is not complete (Kraft sum != 1) or
+// exceeds the length limit.
+API int model_huffman_fuzz(int trials, unsigned seed) {
+  using namespace bitar::dfl;
+  uint64_t x = seed * 0x9E3779B97F4A7C15ull + 1;
+  auto rnd = [&]() {
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+    return (uint32_t)(x >> 16);
+  };
+  static thread_local HuffScratch hs;
+  int bad = 0;
+  for (int t = 0; t < trials; ++t) {
+    const int n = (t & 1) ? 286 : (t & 2) ? 30 : 19, maxb = n == 19 ? 7 : 15;
+    const int mode = (int)(rnd() % 5);
+    uint32_t key[288];
+    int m = 0;
+    for (int i = 0; i < n; ++i) {
+      const uint32_t r = rnd();
+      uint32_t f = mode == 0 ? (r % 3 == 0 ? 0 : 1u << (r % 20)) : mode == 1 ? r % 1000 : mode == 2 ? (i < 30 ? 1u << (i % 22) : 0)
+                   : mode == 3 ? (r % 5 == 0 ? r % 100000 : r % 3) : (i < 40 ? (uint32_t)(1.0 * (1u << 22) / (1 + i * i * i)) : r % 2);
+      if (f > (1u << 22)) f = 1u << 22;
+      if (f) key[m++] = (f << 9) | (uint32_t)i;
+    }
+    if (m < 2) continue;
+    std::sort(key, key + m);
+    uint8_t len[288] = {0};
+    uint16_t blc[16];
+    huff_lengths_from_sorted(key, m, maxb, len, blc, &hs);
+    uint64_t kraft = 0;
+    bool too_long = false;
+    for (int i = 0; i < n; ++i)
+      if (len[i]) {
+        too_long |= len[i] > maxb;
+        kraft += 1ull << (maxb - len[i]);
+      }
+    bad += too_long || kraft != (1ull << maxb);
+  }
+  return bad;
 }
 
 // symbol-map self check used by tests: returns 0 when the computed maps agree with RFC 1951 tables

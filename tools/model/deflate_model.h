@@ -73,6 +73,7 @@ inline void find_tokens(const uint8_t* d, int n, const Params& P, std::vector<ui
   std::vector<uint8_t> valid(P.step);
   int carry = 0;
   for (int base = 0; base < n; base += P.step) {
+    if (P.sub_log2 && (base & ((1 << P.sub_log2) - 1)) == 0) std::fill(head.begin(), head.end(), 0u);   // per sub-range table
     for (int t = 0; t < P.step; ++t) {
       int p = base + t;
       valid[t] = p + 4 <= n;

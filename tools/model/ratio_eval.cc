@@ -69,7 +69,10 @@ int main(int argc, char** argv) {
     auto z = zdeflate(data.data() + off, n, 1, P.huffman == 1 ? Z_FIXED : Z_DEFAULT_STRATEGY);
     std::vector<bitar_model::BlockStats> st;
     auto m = bitar_model::deflate_chunk(data.data() + off, n, P, &st);
-    if (!zcheck(m, data.data() + off, n)) return fprintf(stderr, "MODEL STREAM INVALID at chunk %zu\n", off / seg), 1;
+    if (!zcheck(m, data.data() + off, n)) {
+      if (getenv("DUMP_BAD")) { FILE* g = fopen(getenv("DUMP_BAD"), "wb"); fwrite(m.data(), 1, m.size(), g); fclose(g); }
+      return fprintf(stderr, "MODEL STREAM INVALID at chunk %zu\n", off / seg), 1;
+    }
     zsum += z.size();
     msum += m.size();
     for (auto& s : st) {
