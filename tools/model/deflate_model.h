@@ -21,7 +21,7 @@ using namespace bitar::dfl;
 
 struct Params {
   int step = 32;        // positions per dictionary step: one warp window (exact nearest-previous semantics)
-  int hash_bits = 12;
+  int hash_bits = 10;   // one 1024-entry table per 2 KiB sub-range (the kernel keeps one per warp)
   int min_match = 4;    // bytes hashed (3 or 4); emitted matches are always >= 3
   int cand_mode = 1;    // 0 table only, 1 warp-near else table, 2 best of both
   int far3 = 4096;      // reject length-3 matches farther than this (0 = keep all)
