@@ -268,31 +268,12 @@ struct PlanScratch {
   uint16_t bl_count[kMaxBits + 1];
 };
 
-// ll_sorted / d_sorted: used symbols sorted ascending by (freq<<9 | sym) -- the caller sorts (the
-// kernel does it with a CTA-wide bitonic sort; the host model with std::sort).  ll_freq[256] must
-// already include the end-of-block count.  As in zlib (build_tree), a tree with fewer than two used
-// symbols gets dummy symbols of frequency 1 so that the emitted code is always complete.
-BITAR_HD_NOINLINE void build_dynamic_plan(const uint32_t* ll_freq, const uint32_t* d_freq,
-                                          const uint32_t* ll_sorted, int ll_m,
-                                          const uint32_t* d_sorted, int d_m, BlockPlan* p,
-                                          PlanScratch* s) {
-  for (int i = 0; i < 288; ++i) p->ll_len[i] = 0;
-  for (int i = 0; i < 32; ++i) p->d_len[i] = 0;
-  huff_lengths_from_sorted(ll_sorted, ll_m, kMaxBits, p->ll_len, s->bl_count, &s->hs);
-  huff_codes(p->ll_len, kNumLitLen, s->bl_count, p->ll_code);
-  huff_lengths_from_sorted(d_sorted, d_m, kMaxBits, p->d_len, s->bl_count, &s->hs);
-  huff_codes(p->d_len, kNumDist, s->bl_count, p->d_code);
-
-  int hlit = kNumLitLen;
-  while (hlit > 257 && p->ll_len[hlit - 1] == 0) hlit--;
-  int hdist = kNumDist;
-  while (hdist > 1 && p->d_len[hdist - 1] == 0) hdist--;
-  p->hlit = hlit;
-  p->hdist = hdist;
-
+// Second half of the plan: code-length RLE, the code-length code and the header size, from the
+// litlen / distance code lengths already in p (ll_len, d_len, hlit, hdist).  Serial.
+BITAR_HD_NOINLINE void plan_header(BlockPlan* p, PlanScratch* s) {
   for (int i = 0; i < kNumCl; ++i) s->cl_freq[i] = 0;
-  int nt = cl_rle(p->ll_len, hlit, p->cl_tok, 0, s->cl_freq);
-  nt = cl_rle(p->d_len, hdist, p->cl_tok, nt, s->cl_freq);
+  int nt = cl_rle(p->ll_len, p->hlit, p->cl_tok, 0, s->cl_freq);
+  nt = cl_rle(p->d_len, p->hdist, p->cl_tok, nt, s->cl_freq);
   p->n_cl_tok = nt;
 
   int cm = sort_used_small(s->cl_freq, kNumCl, s->sorted);
@@ -313,6 +294,33 @@ BITAR_HD_NOINLINE void build_dynamic_plan(const uint32_t* ll_freq, const uint32_
   uint32_t hb = 3 + 5 + 5 + 4 + 3 * (uint32_t)hclen;
   for (int i = 0; i < kNumCl; ++i) hb += s->cl_freq[i] * (uint32_t)(p->cl_len[i] + cl_extra_bits(i));
   p->header_bits = hb;
+}
+
+// ll_sorted / d_sorted: used symbols sorted ascending by (freq<<9 | sym) -- the caller sorts (the
+// kernel does it with a CTA-wide bitonic sort; the host model with std::sort).  ll_freq[256] must
+// already include the end-of-block count.  As in zlib (build_tree), a tree with fewer than two used
+// symbols gets dummy symbols of frequency 1 so that the emitted code is always complete.
+// This is the sequential statement of the plan; the deflate kernel computes the same first half (code
+// lengths, codes, hlit / hdist, body sizes) with all its threads and shares plan_header().
+BITAR_HD_NOINLINE void build_dynamic_plan(const uint32_t* ll_freq, const uint32_t* d_freq,
+                                          const uint32_t* ll_sorted, int ll_m,
+                                          const uint32_t* d_sorted, int d_m, BlockPlan* p,
+                                          PlanScratch* s) {
+  for (int i = 0; i < 288; ++i) p->ll_len[i] = 0;
+  for (int i = 0; i < 32; ++i) p->d_len[i] = 0;
+  huff_lengths_from_sorted(ll_sorted, ll_m, kMaxBits, p->ll_len, s->bl_count, &s->hs);
+  huff_codes(p->ll_len, kNumLitLen, s->bl_count, p->ll_code);
+  huff_lengths_from_sorted(d_sorted, d_m, kMaxBits, p->d_len, s->bl_count, &s->hs);
+  huff_codes(p->d_len, kNumDist, s->bl_count, p->d_code);
+
+  int hlit = kNumLitLen;
+  while (hlit > 257 && p->ll_len[hlit - 1] == 0) hlit--;
+  int hdist = kNumDist;
+  while (hdist > 1 && p->d_len[hdist - 1] == 0) hdist--;
+  p->hlit = hlit;
+  p->hdist = hdist;
+
+  plan_header(p, s);
 
   uint64_t dyn = 0, fix = 0;
   for (int i = 0; i < kNumLitLen; ++i) {

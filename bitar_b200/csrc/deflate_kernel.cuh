@@ -49,10 +49,20 @@ constexpr int kTile = kThreads * kPosPerThread;  // encode: positions per tile (
 constexpr int kStageWords = 3584;                // 14 KiB bit stage (a tile emits < 8.6 KiB)
 constexpr uint32_t kNoCand = 0xFFFFu;
 
+struct PlanPar {                      // scratch of the parallel half of the plan
+  uint32_t ll_bl[16], d_bl[16];      // leaves per code length
+  uint32_t ll_at[16], d_at[16];      // canonical next-code counters
+  uint32_t ll_over, d_over;          // nodes below the length limit
+  uint32_t hlit_max, hdist_max;      // highest used symbol
+  unsigned long long dyn_bits, fix_bits;
+  uint32_t d_node_freq[64];
+  uint16_t d_parent[64];
+};
 struct EncodeArea {
   uint32_t stage[kStageWords];       // output bit stage, stage[0] is virtual byte `sbase`
   uint32_t sort_keys[512];
   dfl::PlanScratch scratch;
+  PlanPar pp;
 };
 struct __align__(16) Smem {
   uint8_t raw[kBlockMax + 48];       // input block, shifted so that raw + (src & 15) is the first byte
@@ -316,6 +326,108 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
   }
 }
 
+// ---- plan, first half, in parallel --------------------------------------------------------------------
+// The same code lengths, codes, hlit / hdist and body sizes as dfl::build_dynamic_plan() (the model pins
+// this bit for bit), computed by the whole CTA: only the two-queue Huffman merge stays serial, and it keeps
+// its queue heads in registers.
+
+// Two-queue merge over leaves sorted ascending by (freq << 9 | symbol); same picks (ties prefer leaves) as
+// dfl::huff_lengths_from_sorted.  Leaves 0..m-1, internal nodes m..2m-2, parent[] for every node but the root.
+__device__ void huff_merge(const uint32_t* __restrict__ key, int m, uint32_t* node_freq, uint16_t* parent) {
+  constexpr uint32_t kInf = 0xFFFFFFFFu;
+  uint32_t lf = key[0] >> 9, lf2 = key[1] >> 9, nf = kInf, nf2 = kInf;   // heads of the leaf / internal queues
+  int leaf = 0, inode = m, next = m;
+  for (int k = 0; k < m - 1; ++k) {
+    uint32_t f = 0;
+#pragma unroll
+    for (int pick = 0; pick < 2; ++pick) {
+      if (lf <= nf) {
+        f += lf;
+        parent[leaf] = (uint16_t)next;
+        ++leaf;
+        lf = lf2;
+        lf2 = leaf + 1 < m ? key[leaf + 1] >> 9 : kInf;
+      } else {
+        f += nf;
+        parent[inode] = (uint16_t)next;
+        ++inode;
+        nf = nf2;
+        nf2 = inode + 1 < next ? node_freq[inode + 1] : kInf;
+      }
+    }
+    node_freq[next] = f;
+    if (inode == next) nf = f;
+    else if (inode + 1 == next) nf2 = f;
+    ++next;
+  }
+}
+
+// depth of every node (walk to the root), leaves counted per clamped length, nodes below the limit counted
+__device__ __forceinline__ void huff_depths(const uint16_t* parent, int m, int max_bits, uint32_t* bl, uint32_t* over,
+                                            int t, int nthr) {
+  const int root = 2 * m - 2;
+  for (int i = t; i < root; i += nthr) {
+    int d = 0, j = i;
+    while (j != root) {
+      j = parent[j];
+      ++d;
+    }
+    if (i < m) atomicAdd(&bl[min(d, max_bits)], 1u);
+    if (d > max_bits) atomicAdd(over, 1u);
+  }
+}
+
+// zlib gen_bitlen repair of an over-long tree (serial; rare)
+__device__ __forceinline__ void huff_repair(uint32_t* bl, int overflow, int max_bits) {
+  while (overflow > 0) {
+    int bits = max_bits - 1;
+    while (bl[bits] == 0) bits--;
+    bl[bits]--;
+    bl[bits + 1] += 2;
+    bl[max_bits]--;
+    overflow -= 2;
+  }
+}
+
+// longest codes to the least frequent symbols
+__device__ __forceinline__ void huff_assign(const uint32_t* key, int m, int max_bits, const uint32_t* bl, uint8_t* len,
+                                            int t, int nthr) {
+  for (int i = t; i < m; i += nthr) {
+    int acc = 0;
+    for (int bits = max_bits; bits >= 1; --bits) {
+      const int c = (int)bl[bits];
+      if (i < acc + c) {
+        len[key[i] & 511u] = (uint8_t)bits;
+        break;
+      }
+      acc += c;
+    }
+  }
+}
+
+// canonical codes (bit-reversed) by one warp: next_code[len]++ in symbol order, 32 symbols per round
+__device__ __forceinline__ void huff_codes_warp(const uint8_t* len, int n, const uint32_t* bl, uint32_t* at, uint16_t* code,
+                                                int lane) {
+  constexpr unsigned kFull = 0xFFFFFFFFu;
+  uint32_t c = 0, mine = 0;
+  for (int b = 1; b <= dfl::kMaxBits; ++b) {
+    c = (c + bl[b - 1]) << 1;
+    if (lane == b) mine = c;
+  }
+  if (lane >= 1 && lane <= dfl::kMaxBits) at[lane] = mine;
+  __syncwarp();
+  const unsigned lt_mask = (1u << lane) - 1u;
+  for (int base = 0; base < n; base += 32) {
+    const int i = base + lane;
+    const uint32_t l = i < n ? len[i] : 0u;
+    const unsigned peers = __match_any_sync(kFull, l);
+    if (i < n) code[i] = l ? (uint16_t)dfl::bitrev(at[l] + (uint32_t)__popc(peers & lt_mask), (int)l) : (uint16_t)0;
+    __syncwarp();
+    if (l && (peers & lt_mask) == 0) at[l] += (uint32_t)__popc(peers);
+    __syncwarp();
+  }
+}
+
 // ---- checksum of the block held in shared memory (threads tid0..tid0+nthr) ---------------------------
 __device__ __forceinline__ void block_checksum(Smem& sm, const uint8_t* d, uint32_t n, uint32_t tail_after,
                                                bool first_block, int type, int t, int nthr) {
@@ -474,7 +586,19 @@ __global__ void __launch_bounds__(kThreads, 2)
       }
       sort512(sm);
       BITAR_PHASE(2)
+      PlanPar& pp = sm.u.enc.pp;
+      dfl::HuffScratch& hs = sm.u.enc.scratch.hs;
+      for (int i = tid; i < 288; i += kThreads) sm.plan.ll_len[i] = 0;
+      if (tid < 32) sm.plan.d_len[tid] = 0;
+      if (tid < 16) {
+        pp.ll_bl[tid] = 0;
+        pp.d_bl[tid] = 0;
+      }
       if (tid == 0) {
+        pp.ll_over = pp.d_over = pp.hlit_max = pp.hdist_max = 0;
+        pp.dyn_bits = pp.fix_bits = 0;
+        huff_merge(sm.u.enc.sort_keys, (int)sm.ll_m, hs.node_freq, hs.parent);   // the serial part
+      } else if (tid == 32) {
         // distance tree: at least two used symbols (dummies of frequency 1, as zlib's build_tree)
         uint32_t df[32];
         int used = 0;
@@ -487,9 +611,63 @@ __global__ void __launch_bounds__(kThreads, 2)
             df[i] = 1;
             used++;
           }
-        sm.d_m = (uint32_t)dfl::sort_used_small(df, dfl::kNumDist, sm.d_sorted);
-        dfl::build_dynamic_plan(sm.ll_freq, sm.d_freq, sm.u.enc.sort_keys, (int)sm.ll_m, sm.d_sorted, (int)sm.d_m,
-                                &sm.plan, &sm.u.enc.scratch);
+        const int dm = dfl::sort_used_small(df, dfl::kNumDist, sm.d_sorted);
+        sm.d_m = (uint32_t)dm;
+        huff_merge(sm.d_sorted, dm, pp.d_node_freq, pp.d_parent);
+      } else if (warp >= 2 && checksum_type != BITAR_CHECKSUM_NONE) {
+        block_checksum(sm, d, (uint32_t)n, total - (off + (uint32_t)n), off == 0, checksum_type, tid - 64,
+                       kThreads - 64);
+      }
+      __syncthreads();
+      {
+        const int ll_m = (int)sm.ll_m, d_m = (int)sm.d_m;
+        if (tid < kThreads - 64) huff_depths(hs.parent, ll_m, dfl::kMaxBits, pp.ll_bl, &pp.ll_over, tid, kThreads - 64);
+        else huff_depths(pp.d_parent, d_m, dfl::kMaxBits, pp.d_bl, &pp.d_over, tid - (kThreads - 64), 64);
+        __syncthreads();
+        if (tid == 0) huff_repair(pp.ll_bl, (int)pp.ll_over, dfl::kMaxBits);
+        if (tid == 32) huff_repair(pp.d_bl, (int)pp.d_over, dfl::kMaxBits);
+        __syncthreads();
+        if (tid < kThreads - 64) huff_assign(sm.u.enc.sort_keys, ll_m, dfl::kMaxBits, pp.ll_bl, sm.plan.ll_len, tid, kThreads - 64);
+        else huff_assign(sm.d_sorted, d_m, dfl::kMaxBits, pp.d_bl, sm.plan.d_len, tid - (kThreads - 64), 64);
+        __syncthreads();
+        if (warp == 0) huff_codes_warp(sm.plan.ll_len, dfl::kNumLitLen, pp.ll_bl, pp.ll_at, sm.plan.ll_code, lane);
+        else if (warp == 1) huff_codes_warp(sm.plan.d_len, dfl::kNumDist, pp.d_bl, pp.d_at, sm.plan.d_code, lane);
+        else {
+          // body sizes under the dynamic and the fixed code, highest used symbols: one symbol per thread
+          const int i = tid - 64;
+          unsigned long long dyn = 0, fix = 0;
+          if (i < dfl::kNumLitLen) {
+            const uint32_t f = sm.ll_freq[i];
+            const int eb = i > 256 ? dfl::len_extra_bits(i - 257) : 0;
+            dyn = (unsigned long long)f * (uint32_t)(sm.plan.ll_len[i] + eb);
+            fix = (unsigned long long)f * (uint32_t)(dfl::fixed_ll_len(i) + eb);
+            if (sm.plan.ll_len[i]) atomicMax(&pp.hlit_max, (uint32_t)i);
+          } else if (i < dfl::kNumLitLen + dfl::kNumDist) {
+            const int j = i - dfl::kNumLitLen;
+            const uint32_t f = sm.d_freq[j];
+            const int eb = dfl::dist_extra_bits(j);
+            dyn = (unsigned long long)f * (uint32_t)(sm.plan.d_len[j] + eb);
+            fix = (unsigned long long)f * (uint32_t)(5 + eb);
+            if (sm.plan.d_len[j]) atomicMax(&pp.hdist_max, (uint32_t)j);
+          }
+#pragma unroll
+          for (int o2 = 16; o2 > 0; o2 >>= 1) {
+            dyn += __shfl_xor_sync(0xFFFFFFFFu, dyn, o2);
+            fix += __shfl_xor_sync(0xFFFFFFFFu, fix, o2);
+          }
+          if (lane == 0 && (dyn | fix)) {
+            atomicAdd(&pp.dyn_bits, dyn);
+            atomicAdd(&pp.fix_bits, fix);
+          }
+        }
+        __syncthreads();
+      }
+      if (tid == 0) {
+        sm.plan.hlit = max(257, (int)pp.hlit_max + 1);
+        sm.plan.hdist = max(1, (int)pp.hdist_max + 1);
+        sm.plan.dyn_body_bits = pp.dyn_bits;
+        sm.plan.fixed_body_bits = pp.fix_bits;
+        dfl::plan_header(&sm.plan, &sm.u.enc.scratch);   // code-length RLE, code-length code, header size (serial)
         // choose the block type (same rule as the model)
         uint64_t dyn_bits = (uint64_t)sm.plan.header_bits + sm.plan.dyn_body_bits;
         uint64_t fix_bits = 3 + sm.plan.fixed_body_bits;
@@ -515,9 +693,6 @@ __global__ void __launch_bounds__(kThreads, 2)
         }
         sm.block_type = type;
         sm.tile_bits = (uint32_t)best;
-      } else if (warp >= 1 && checksum_type != BITAR_CHECKSUM_NONE) {
-        block_checksum(sm, d, (uint32_t)n, total - (off + (uint32_t)n), off == 0, checksum_type, tid - 32,
-                       kThreads - 32);
       }
       __syncthreads();
       BITAR_PHASE(3)
