@@ -252,6 +252,15 @@ class CompressDriver:
         return [CompressDevice(d, base + (1 if i < rem else 0)) for i, d in enumerate(device_ids)]
 
 
+def shard_range(n_chunks, rank, world):
+    """Chunk range [first, last) of rank `rank` out of `world`: contiguous ranges of
+    ceil(n / world) chunks, so that concatenating the ranks' outputs in rank order is the output of one
+    Compress() over the whole buffer (apps/demo_app.cc:577-607 splits the same way over (device, qp))."""
+    per = (n_chunks + world - 1) // world
+    first = min(n_chunks, rank * per)
+    return first, min(n_chunks, first + per)
+
+
 def distribute_workers(num_workers, num_devices):
     """The queue-pair distribution rule alone (host logic, testable without a GPU)."""
     base, rem = divmod(num_workers, num_devices)
