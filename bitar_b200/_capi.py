@@ -50,7 +50,7 @@ EXPORTS = [
     "bitar_dev_num_qps", "bitar_qp_deflate", "bitar_qp_inflate", "bitar_qp_wait", "bitar_qp_busy",
     "bitar_qp_on_complete", "bitar_qp_last_ms", "bitar_qp_stream", "bitar_kernel_launches",
     "bitar_slot_take", "bitar_slot_take_n", "bitar_slot_put", "bitar_slot_size", "bitar_slots_free",
-    "bitar_mem_alloc", "bitar_mem_free", "bitar_host_register", "bitar_host_unregister", "bitar_ptr_kind",
+    "bitar_mem_alloc", "bitar_mem_free", "bitar_host_register", "bitar_host_unregister", "bitar_ptr_kind", "bitar_mem_copy", "bitar_current_device",
     "bitar_qp_memcpy", "bitar_last_error", "bitar_version",
 ]
 
@@ -106,6 +106,8 @@ def lib():
     L.bitar_host_register.argtypes = [vp, C.c_size_t]
     L.bitar_host_unregister.argtypes = [vp]
     L.bitar_ptr_kind.argtypes = [vp, C.POINTER(C.c_int)]
+    L.bitar_mem_copy.argtypes = [vp, vp, C.c_size_t]
+    L.bitar_current_device.argtypes = [C.POINTER(C.c_int)]
     L.bitar_qp_memcpy.argtypes = [vp, u16, vp, vp, C.c_size_t]
     L.bitar_last_error.restype = C.c_char_p
     L.bitar_version.restype = C.c_char_p

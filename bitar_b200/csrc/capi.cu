@@ -631,6 +631,19 @@ int bitar_ptr_kind(const void* ptr, int* device_id) {
   return 0;
 }
 
+int bitar_mem_copy(void* dst, const void* src, size_t n) {
+  if (n == 0) return BITAR_OK;
+  if (!dst || !src) return fail(BITAR_E_INVALID, "null pointer");
+  CU_TRY(cudaMemcpy(dst, src, n, cudaMemcpyDefault), BITAR_E_IO_ERROR);
+  return BITAR_OK;
+}
+
+int bitar_current_device(int* device_id) {
+  if (!device_id) return fail(BITAR_E_INVALID, "null pointer");
+  CU_TRY(cudaGetDevice(device_id), BITAR_E_INVALID);
+  return BITAR_OK;
+}
+
 int bitar_qp_memcpy(bitar_dev* dev, uint16_t qp, void* dst, const void* src, size_t n) {
   if (!dev || qp >= dev->qps.size()) return fail(BITAR_E_INVALID, "bad device/queue pair");
   CU_TRY(cudaSetDevice(dev->id), BITAR_E_INVALID);

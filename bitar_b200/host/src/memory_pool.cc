@@ -1,0 +1,135 @@
+// memory_pool.cc -- arrow::MemoryPool back ends over the C-ABI allocators.
+// Mirrors /root/reference/src/memory_pool.cc:70-350: an allocator per backend (there rte_malloc and
+// rte_memzone, here cudaMallocAsync device memory and pinned host memory), the statistics every Arrow pool
+// keeps, the zero-size sentinel (memory_pool.cc:58-67) and the address tracker (memory_pool.cc:295-319).
+#include "bitar/memory_pool.h"
+
+#include <arrow/memory_pool.h>
+#include <arrow/status.h>
+
+#include <atomic>
+#include <cstring>
+#include <string>
+
+#include "bitar_cuda.h"
+
+namespace bitar {
+
+namespace {
+
+alignas(64) std::uint8_t zero_size_area[64];   // what zero-byte allocations point at
+
+class CudaMemoryPool : public arrow::MemoryPool {
+ public:
+  CudaMemoryPool(int kind, std::string name) : kind_{kind}, name_{std::move(name)} {}
+
+  arrow::Status Allocate(std::int64_t size, std::int64_t alignment, std::uint8_t** out) override {
+    if (size < 0) return arrow::Status::Invalid("negative malloc size");
+    if (size == 0) {
+      *out = zero_size_area;
+      return arrow::Status::OK();
+    }
+    void* p = nullptr;
+    const int device = kind_ == BITAR_MEM_DEVICE ? CurrentDevice() : -1;
+    const int rc = bitar_mem_alloc(kind_, device, static_cast<std::size_t>(size), static_cast<std::size_t>(alignment), &p);
+    if (rc != BITAR_OK) return arrow::Status::OutOfMemory("malloc of size ", size, " failed: ", bitar_last_error());
+    *out = static_cast<std::uint8_t*>(p);
+    CudaAllocatorTracker::Instance()->Emplace(*out, {static_cast<std::size_t>(size), kind_, device});
+    Did(size);
+    return arrow::Status::OK();
+  }
+
+  // realloc = alloc + copy + free, like the Rtememzone allocator (memory_pool.cc:151-174); the copy runs on
+  // the device for device memory
+  arrow::Status Reallocate(std::int64_t old_size, std::int64_t new_size, std::int64_t alignment, std::uint8_t** ptr) override {
+    std::uint8_t* old = *ptr;
+    std::uint8_t* fresh = nullptr;
+    ARROW_RETURN_NOT_OK(Allocate(new_size, alignment, &fresh));
+    const std::int64_t n = old_size < new_size ? old_size : new_size;
+    if (n > 0) {
+      if (kind_ == BITAR_MEM_PINNED) std::memcpy(fresh, old, static_cast<std::size_t>(n));
+      else if (bitar_mem_copy(fresh, old, static_cast<std::size_t>(n)) != BITAR_OK) {
+        Free(fresh, new_size, alignment);
+        return arrow::Status::IOError("device copy failed: ", bitar_last_error());
+      }
+    }
+    Free(old, old_size, alignment);
+    *ptr = fresh;
+    return arrow::Status::OK();
+  }
+
+  void Free(std::uint8_t* buffer, std::int64_t size, std::int64_t /*alignment*/) override {
+    if (buffer == zero_size_area || buffer == nullptr) return;
+    const auto* a = CudaAllocatorTracker::Instance()->Of(buffer);
+    const int device = a != nullptr ? a->device : 0;
+    bitar_mem_free(kind_, device, buffer);
+    CudaAllocatorTracker::Instance()->Release(buffer);
+    bytes_.fetch_sub(size);
+  }
+
+  std::int64_t bytes_allocated() const override { return bytes_.load(); }
+  std::int64_t max_memory() const override { return max_.load(); }
+  std::int64_t total_bytes_allocated() const override { return total_.load(); }
+  std::int64_t num_allocations() const override { return count_.load(); }
+  std::string backend_name() const override { return name_; }
+
+ private:
+  static int CurrentDevice() {
+    int d = 0;
+    bitar_current_device(&d);
+    return d;
+  }
+  void Did(std::int64_t size) {
+    const auto now = bytes_.fetch_add(size) + size;
+    auto prev = max_.load();
+    while (now > prev && !max_.compare_exchange_weak(prev, now)) {
+    }
+    total_.fetch_add(size);
+    count_.fetch_add(1);
+  }
+  const int kind_;
+  const std::string name_;
+  std::atomic<std::int64_t> bytes_{0}, max_{0}, total_{0}, count_{0};
+};
+
+}  // namespace
+
+CudaAllocatorTracker* CudaAllocatorTracker::Instance() {
+  static CudaAllocatorTracker tracker;
+  return &tracker;
+}
+const CudaAllocatorTracker::Allocation* CudaAllocatorTracker::Of(const std::uint8_t* addr) const noexcept {
+  std::lock_guard<std::mutex> lock(mutex_);
+  const auto it = allocations_.find(addr);
+  return it == allocations_.end() ? nullptr : &it->second;
+}
+std::size_t CudaAllocatorTracker::count() const noexcept {
+  std::lock_guard<std::mutex> lock(mutex_);
+  return allocations_.size();
+}
+void CudaAllocatorTracker::Emplace(const std::uint8_t* addr, Allocation a) {
+  std::lock_guard<std::mutex> lock(mutex_);   // the reference's Emplace is unlocked (a race): not copied
+  allocations_[addr] = a;
+}
+void CudaAllocatorTracker::Release(const std::uint8_t* addr) {
+  std::lock_guard<std::mutex> lock(mutex_);
+  allocations_.erase(addr);
+}
+
+arrow::MemoryPool* GetMemoryPool(MemoryPoolBackend backend) {   // memory_pool.cc:321-350: process-lifetime statics
+  switch (backend) {
+    case MemoryPoolBackend::CudaDevice: {
+      static CudaMemoryPool pool(BITAR_MEM_DEVICE, "cuda_device");
+      return &pool;
+    }
+    case MemoryPoolBackend::CudaPinnedHost: {
+      static CudaMemoryPool pool(BITAR_MEM_PINNED, "cuda_pinned_host");
+      return &pool;
+    }
+    case MemoryPoolBackend::System:
+    default:
+      return arrow::system_memory_pool();
+  }
+}
+
+}  // namespace bitar

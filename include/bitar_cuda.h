@@ -175,6 +175,11 @@ BITAR_API int bitar_host_unregister(void* ptr);
  * 1 = device memory (*device_id receives the owning device), 2 = pinned / registered host memory.
  * The analogue of the rte_mem_virt2iova probe in src/memory.cc:388-391. */
 BITAR_API int bitar_ptr_kind(const void* ptr, int* device_id);
+/* Synchronous copy between any two device-accessible or host ranges (cudaMemcpyDefault): what the memory
+ * pool's Reallocate uses in place of rte_memcpy (src/memory_pool.cc:151-174). */
+BITAR_API int bitar_mem_copy(void* dst, const void* src, size_t n);
+/* The calling thread's current CUDA device (device pools allocate there). */
+BITAR_API int bitar_current_device(int* device_id);
 /* Plain copies on the queue pair's stream (host<->device staging for pageable buffers). */
 BITAR_API int bitar_qp_memcpy(bitar_dev* dev, uint16_t qp, void* dst, const void* src, size_t n);
 

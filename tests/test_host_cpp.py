@@ -1,0 +1,41 @@
+"""The C++ host facade (bitar_b200/host): bitar's headers for Class_CUDA over the C-ABI, built against the
+Arrow C++ of this image, and bitar_demo, the reference's demo_app flow (apps/demo_app.cc:487-693:
+sync Compress / Decompress / memcmp / Recycle on device 0, then CompressAsync / DecompressAsync over every
+queue pair with per-part memcmp)."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "bitar_b200", "host")
+DEMO = os.path.join(HOST, "bitar_demo")
+
+
+def _build():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "bitar_b200", "csrc"), "-s"])
+    subprocess.check_call(["make", "-C", HOST, "-s"])
+
+
+def test_host_facade_builds_and_fails_loudly_without_a_device():
+    _build()
+    syms = subprocess.check_output(["nm", "-DC", os.path.join(HOST, "libbitar_host.so")], text=True)
+    for name in ("bitar::CompressDevice<", "::Compress(", "::Decompress(", "::Recycle(", "::Initialize(",
+                 "bitar::CompressDriver<", "::ListAvailableDeviceIds()", "::GetDevices(", "bitar::GetMemoryPool(",
+                 "bitar::CudaConfiguration::to_c()", "bitar::internal::DistributeWorkers("):
+        assert name in syms, name
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: covered by the gpu test")
+    r = subprocess.run([DEMO, "--bytes", "100000"], capture_output=True, text=True)
+    assert r.returncode != 0 and "No compress device is available" in r.stderr      # src/driver.cc:184-187: no CPU fallback
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args", [["--bytes", str(48 << 20)], ["--bytes", str(20 << 20), "--device", "--seg", "65536"],
+                                  ["--bytes", str(3 << 20), "--seg", "4096", "--qps", "3"]])
+def test_demo_app_flow(args):
+    _build()
+    r = subprocess.run([DEMO] + args, capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "PASSED" in r.stdout and "MISMATCH" not in r.stdout
