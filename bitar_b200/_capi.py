@@ -47,7 +47,7 @@ class Cfg(C.Structure):
 EXPORTS = [
     "bitar_cuda_device_count", "bitar_cuda_device_info", "bitar_compressed_seg_size",
     "bitar_reference_compressed_seg_size", "bitar_dev_open", "bitar_dev_close", "bitar_dev_config",
-    "bitar_dev_num_qps", "bitar_qp_deflate", "bitar_qp_inflate", "bitar_qp_wait", "bitar_qp_busy",
+    "bitar_dev_num_qps", "bitar_qp_deflate", "bitar_qp_inflate", "bitar_qp_wait", "bitar_qp_result", "bitar_qp_busy",
     "bitar_qp_on_complete", "bitar_qp_last_ms", "bitar_qp_stream", "bitar_kernel_launches",
     "bitar_slot_take", "bitar_slot_take_n", "bitar_slot_put", "bitar_slot_size", "bitar_slots_free",
     "bitar_mem_alloc", "bitar_mem_free", "bitar_host_register", "bitar_host_unregister", "bitar_ptr_kind", "bitar_mem_copy", "bitar_current_device",

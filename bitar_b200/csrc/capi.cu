@@ -506,6 +506,15 @@ int bitar_qp_wait(bitar_dev* dev, uint16_t qp) {
   return BITAR_OK;
 }
 
+int bitar_qp_result(bitar_dev* dev, uint16_t qp) {
+  if (!dev || qp >= dev->qps.size()) return fail(BITAR_E_INVALID, "bad device/queue pair");
+  QueuePair* q = dev->qps[qp];
+  if (q->busy.load(std::memory_order_acquire)) return fail(BITAR_E_CANCELLED, "queue pair %u of device %d is busy", (unsigned)qp, dev->id);
+  int st = q->last_status.load(std::memory_order_acquire);
+  if (st) return fail(st, "at least one operation on queue pair %u of device %d did not succeed", (unsigned)qp, dev->id);
+  return BITAR_OK;
+}
+
 int bitar_qp_busy(bitar_dev* dev, uint16_t qp) {
   if (!dev || qp >= dev->qps.size()) return 0;
   return dev->qps[qp]->busy.load(std::memory_order_acquire);

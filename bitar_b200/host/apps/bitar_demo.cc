@@ -90,7 +90,11 @@ int main(int argc, char** argv) {
   CHECK_OK(devs_r.status());
   auto devices = std::move(*devs_r);
 
-  auto* pool = bitar::GetMemoryPool(on_device ? bitar::MemoryPoolBackend::CudaDevice : bitar::MemoryPoolBackend::CudaPinnedHost);
+  auto* pool = bitar::GetMemoryPool(bitar::MemoryPoolBackend::CudaPinnedHost);
+  auto allocate = [&](std::int64_t size, int device) -> arrow::Result<std::unique_ptr<arrow::ResizableBuffer>> {
+    if (on_device) return bitar::AllocateDeviceBuffer(size, device);
+    return arrow::AllocateResizableBuffer(size, pool);
+  };
   std::vector<std::uint8_t> host;
   if (!file.empty()) {
     std::ifstream f(file, std::ios::binary);
@@ -100,7 +104,7 @@ int main(int argc, char** argv) {
     host.resize(bytes);
     FillSynthetic(host.data(), bytes);
   }
-  auto in_r = arrow::AllocateResizableBuffer((std::int64_t)bytes, pool);
+  auto in_r = allocate((std::int64_t)bytes, ids[0]);
   CHECK_OK(in_r.status());
   std::shared_ptr<arrow::Buffer> input = std::move(*in_r);
   bitar_mem_copy(const_cast<std::uint8_t*>(input->data()), host.data(), bytes);
@@ -130,7 +134,7 @@ int main(int argc, char** argv) {
       auto compressed = std::move(*comp_r);
       std::int64_t csize = 0;
       for (auto& b : compressed) csize += b->size();
-      auto out_r = arrow::AllocateResizableBuffer((std::int64_t)(compressed.size() * (std::size_t)seg), pool);
+      auto out_r = allocate((std::int64_t)(compressed.size() * (std::size_t)seg), dev->device_id());
       CHECK_OK(out_r.status());
       auto output = std::move(*out_r);
       auto t2 = Clock::now();
@@ -179,7 +183,7 @@ int main(int argc, char** argv) {
 
       std::vector<std::unique_ptr<arrow::ResizableBuffer>> outs;
       for (std::size_t i = 0; i < parts.size(); ++i) {
-        auto r = arrow::AllocateResizableBuffer((std::int64_t)(results[i].size() * (std::size_t)seg), pool);
+        auto r = allocate((std::int64_t)(results[i].size() * (std::size_t)seg), parts[i].dev->device_id());
         CHECK_OK(r.status());
         outs.push_back(std::move(*r));
       }

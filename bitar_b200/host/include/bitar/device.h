@@ -68,10 +68,14 @@ class CompressDevice {
   // --- asynchronous halves used by CompressAsync / DecompressAsync (util.h) ---
   struct PendingCompress;
   arrow::Status EnqueueCompress(std::uint16_t queue_pair_id, const std::shared_ptr<arrow::Buffer>& decompressed_buffer);
-  arrow::Result<BufferVector> FinishCompress(std::uint16_t queue_pair_id);
+  /// \p in_callback: called from an OnComplete() callback (a CUDA driver thread, where no CUDA call is allowed):
+  /// the result is read without waiting and a temporarily registered buffer stays registered until the next
+  /// call on the queue pair.
+  arrow::Result<BufferVector> FinishCompress(std::uint16_t queue_pair_id, bool in_callback = false);
   arrow::Status EnqueueDecompress(std::uint16_t queue_pair_id, const BufferVector& compressed_buffers,
                                   const std::unique_ptr<arrow::ResizableBuffer>& decompressed_buffer);
-  arrow::Status FinishDecompress(std::uint16_t queue_pair_id, const std::unique_ptr<arrow::ResizableBuffer>& decompressed_buffer);
+  arrow::Status FinishDecompress(std::uint16_t queue_pair_id, const std::unique_ptr<arrow::ResizableBuffer>& decompressed_buffer,
+                                 bool in_callback = false);
   arrow::Status OnComplete(std::uint16_t queue_pair_id, void (*fn)(void*), void* arg);
 
  protected:
@@ -85,6 +89,7 @@ class CompressDevice {
  private:
   arrow::Status EntryGuard(std::uint16_t queue_pair_id);
   void ReleaseSlots(std::uint16_t queue_pair_id);
+  void Unregister(std::uint16_t queue_pair_id);
 
   struct QueuePairState {
     std::vector<bitar_chunk> ops;

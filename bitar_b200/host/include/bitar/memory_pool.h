@@ -7,6 +7,11 @@
 #include <mutex>
 #include <unordered_map>
 
+#include <arrow/buffer.h>
+#include <arrow/result.h>
+
+#include <memory>
+
 namespace arrow {
 class MemoryPool;
 }  // namespace arrow
@@ -34,9 +39,16 @@ class CudaAllocatorTracker {
   mutable std::mutex mutex_{};
 };
 
-enum class MemoryPoolBackend : std::uint8_t { System, CudaDevice, CudaPinnedHost };
+enum class MemoryPoolBackend : std::uint8_t { System, CudaPinnedHost };
 
-/// \brief Get the memory pool for the selected backend (CudaDevice uses the current CUDA device).
+/// \brief Get the memory pool for the selected backend.  CudaPinnedHost is the Rtememzone analogue: memory the
+/// device reads and writes in place (zero-copy over PCIe) and the CPU can touch, which Arrow's allocation
+/// helpers do (they zero the padding of every buffer on the CPU) -- the reason there is no device-memory POOL.
 arrow::MemoryPool* GetMemoryPool(MemoryPoolBackend backend);
+
+/// \brief A resizable buffer in the memory of CUDA device \p device_id (cudaMallocAsync), for callers that keep
+/// their data resident in HBM.  Typed as a CPU arrow::Buffer whose data() is a device address (Arrow C++ in this
+/// image ships without arrow::cuda); never dereference it on the host.
+arrow::Result<std::unique_ptr<arrow::ResizableBuffer>> AllocateDeviceBuffer(std::int64_t size, int device_id);
 
 }  // namespace bitar

@@ -74,13 +74,13 @@ namespace internal {
 template <typename Class, typename Callback>
 void CompressDone(void* p) {
   auto* param = static_cast<CompressParam<Class, Callback>*>(p);
-  auto result = param->device_->FinishCompress(param->queue_pair_id_);
+  auto result = param->device_->FinishCompress(param->queue_pair_id_, /*in_callback=*/true);
   param->slot_.Finish(param->result_callback_(param->device_->device_id(), param->queue_pair_id_, std::move(result)));
 }
 template <typename Class, typename Callback>
 void DecompressDone(void* p) {
   auto* param = static_cast<DecompressParam<Class, Callback>*>(p);
-  auto status = param->device_->FinishDecompress(param->queue_pair_id_, param->decompressed_buffer_);
+  auto status = param->device_->FinishDecompress(param->queue_pair_id_, param->decompressed_buffer_, /*in_callback=*/true);
   param->slot_.Finish(param->result_callback_(param->device_->device_id(), param->queue_pair_id_, status));
 }
 }  // namespace internal

@@ -36,7 +36,13 @@ CompressDevice<Class>::CompressDevice(std::uint8_t device_id, std::uint16_t num_
 
 template <typename Class>
 CompressDevice<Class>::~CompressDevice() {   // stop / close, src/device.cc:329-343
-  if (handle_ != nullptr) bitar_dev_close(handle_);
+  if (handle_ != nullptr) {
+    for (std::uint16_t q = 0; q < num_qps_; ++q) {
+      bitar_qp_wait(handle_, q);
+      Unregister(q);
+    }
+    bitar_dev_close(handle_);
+  }
   handle_ = nullptr;
   state_ = internal::DeviceState::kUndefined;
 }
@@ -106,6 +112,13 @@ void CompressDevice<Class>::ReleaseSlots(std::uint16_t queue_pair_id) {   // Rel
   q.slots.clear();
 }
 
+template <typename Class>
+void CompressDevice<Class>::Unregister(std::uint16_t queue_pair_id) {
+  auto& q = qp_state_[queue_pair_id];
+  if (q.registered != nullptr) bitar_host_unregister(q.registered);
+  q.registered = nullptr;
+}
+
 namespace {
 // Caller memory must be reachable from the device: device memory and pinned / registered host memory are
 // used in place (the rte_mem_virt2iova analogue, src/memory.cc:388-391); pageable host memory is
@@ -123,6 +136,7 @@ template <typename Class>
 arrow::Status CompressDevice<Class>::EnqueueCompress(std::uint16_t queue_pair_id,
                                                      const std::shared_ptr<arrow::Buffer>& decompressed_buffer) {
   ARROW_RETURN_NOT_OK(EntryGuard(queue_pair_id));
+  Unregister(queue_pair_id);   // left over from an asynchronous call
   auto& q = qp_state_[queue_pair_id];
   q.ops.clear();
   q.results.clear();
@@ -155,15 +169,13 @@ arrow::Status CompressDevice<Class>::EnqueueCompress(std::uint16_t queue_pair_id
 }
 
 template <typename Class>
-arrow::Result<BufferVector> CompressDevice<Class>::FinishCompress(std::uint16_t queue_pair_id) {
+arrow::Result<BufferVector> CompressDevice<Class>::FinishCompress(std::uint16_t queue_pair_id, bool in_callback) {
   auto& q = qp_state_[queue_pair_id];
   BufferVector out;
   if (q.ops.empty()) return out;
-  const int rc = bitar_qp_wait(handle_, queue_pair_id);   // the dequeue busy-poll, src/device.cc:228-235
-  if (q.registered != nullptr) {
-    bitar_host_unregister(q.registered);
-    q.registered = nullptr;
-  }
+  // the dequeue busy-poll, src/device.cc:228-235 (inside a completion callback the work is already done)
+  const int rc = in_callback ? bitar_qp_result(handle_, queue_pair_id) : bitar_qp_wait(handle_, queue_pair_id);
+  if (!in_callback) Unregister(queue_pair_id);
   if (rc != BITAR_OK) {   // per-op status != SUCCESS -> IOError, src/device.cc:512-520
     ReleaseSlots(queue_pair_id);
     return internal::StatusFromC(rc);
@@ -199,6 +211,7 @@ arrow::Status CompressDevice<Class>::EnqueueDecompress(std::uint16_t queue_pair_
   if (decompressed_buffer == nullptr || static_cast<std::size_t>(decompressed_buffer->capacity()) < n * seg)
     return arrow::Status::CapacityError("The decompressed_buffer is required to be >= ", n * seg, " bytes");   // src/device.cc:248-254
   ARROW_RETURN_NOT_OK(EntryGuard(queue_pair_id));
+  Unregister(queue_pair_id);
   for (const auto& b : compressed_buffers)
     if (b == nullptr || (b->size() > 0 && bitar_ptr_kind(b->data(), nullptr) == 0))
       return arrow::Status::Invalid("compressed buffers must live in device-accessible memory (pool slots, device memory or "
@@ -218,14 +231,12 @@ arrow::Status CompressDevice<Class>::EnqueueDecompress(std::uint16_t queue_pair_
 
 template <typename Class>
 arrow::Status CompressDevice<Class>::FinishDecompress(std::uint16_t queue_pair_id,
-                                                      const std::unique_ptr<arrow::ResizableBuffer>& decompressed_buffer) {
+                                                      const std::unique_ptr<arrow::ResizableBuffer>& decompressed_buffer,
+                                                      bool in_callback) {
   auto& q = qp_state_[queue_pair_id];
   if (q.ops.empty()) return arrow::Status::OK();
-  const int rc = bitar_qp_wait(handle_, queue_pair_id);
-  if (q.registered != nullptr) {
-    bitar_host_unregister(q.registered);
-    q.registered = nullptr;
-  }
+  const int rc = in_callback ? bitar_qp_result(handle_, queue_pair_id) : bitar_qp_wait(handle_, queue_pair_id);
+  if (!in_callback) Unregister(queue_pair_id);
   // unlike the reference (src/device.cc:275-310 leaves the queue pair busy after an error) the queue pair is idle again
   ARROW_RETURN_NOT_OK(internal::StatusFromC(rc));
   std::int64_t total = 0;

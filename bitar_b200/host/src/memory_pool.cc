@@ -4,7 +4,9 @@
 // keeps, the zero-size sentinel (memory_pool.cc:58-67) and the address tracker (memory_pool.cc:295-319).
 #include "bitar/memory_pool.h"
 
+#include <arrow/buffer.h>
 #include <arrow/memory_pool.h>
+#include <arrow/result.h>
 #include <arrow/status.h>
 
 #include <atomic>
@@ -30,7 +32,7 @@ class CudaMemoryPool : public arrow::MemoryPool {
       return arrow::Status::OK();
     }
     void* p = nullptr;
-    const int device = kind_ == BITAR_MEM_DEVICE ? CurrentDevice() : -1;
+    const int device = -1;
     const int rc = bitar_mem_alloc(kind_, device, static_cast<std::size_t>(size), static_cast<std::size_t>(alignment), &p);
     if (rc != BITAR_OK) return arrow::Status::OutOfMemory("malloc of size ", size, " failed: ", bitar_last_error());
     *out = static_cast<std::uint8_t*>(p);
@@ -47,11 +49,7 @@ class CudaMemoryPool : public arrow::MemoryPool {
     ARROW_RETURN_NOT_OK(Allocate(new_size, alignment, &fresh));
     const std::int64_t n = old_size < new_size ? old_size : new_size;
     if (n > 0) {
-      if (kind_ == BITAR_MEM_PINNED) std::memcpy(fresh, old, static_cast<std::size_t>(n));
-      else if (bitar_mem_copy(fresh, old, static_cast<std::size_t>(n)) != BITAR_OK) {
-        Free(fresh, new_size, alignment);
-        return arrow::Status::IOError("device copy failed: ", bitar_last_error());
-      }
+      std::memcpy(fresh, old, static_cast<std::size_t>(n));
     }
     Free(old, old_size, alignment);
     *ptr = fresh;
@@ -74,11 +72,6 @@ class CudaMemoryPool : public arrow::MemoryPool {
   std::string backend_name() const override { return name_; }
 
  private:
-  static int CurrentDevice() {
-    int d = 0;
-    bitar_current_device(&d);
-    return d;
-  }
   void Did(std::int64_t size) {
     const auto now = bytes_.fetch_add(size) + size;
     auto prev = max_.load();
@@ -92,7 +85,57 @@ class CudaMemoryPool : public arrow::MemoryPool {
   std::atomic<std::int64_t> bytes_{0}, max_{0}, total_{0}, count_{0};
 };
 
+// device-resident ResizableBuffer: Resize() never touches the bytes from the CPU
+class DeviceBuffer : public arrow::ResizableBuffer {
+ public:
+  DeviceBuffer(std::uint8_t* data, std::int64_t size, int device) : arrow::ResizableBuffer(data, size), device_{device} {
+    capacity_ = size;
+  }
+  ~DeviceBuffer() override {
+    if (data_ != nullptr) {
+      bitar_mem_free(BITAR_MEM_DEVICE, device_, const_cast<std::uint8_t*>(data_));
+      CudaAllocatorTracker::Instance()->Release(data_);
+    }
+  }
+  arrow::Status Resize(const std::int64_t new_size, bool /*shrink_to_fit*/) override {
+    if (new_size < 0) return arrow::Status::Invalid("Negative buffer resize: ", new_size);
+    if (new_size > capacity_) ARROW_RETURN_NOT_OK(Reserve(new_size));
+    size_ = new_size;
+    return arrow::Status::OK();
+  }
+  arrow::Status Reserve(const std::int64_t new_capacity) override {
+    if (new_capacity <= capacity_) return arrow::Status::OK();
+    void* p = nullptr;
+    if (bitar_mem_alloc(BITAR_MEM_DEVICE, device_, static_cast<std::size_t>(new_capacity), 256, &p) != BITAR_OK)
+      return arrow::Status::OutOfMemory("device allocation of ", new_capacity, " bytes failed: ", bitar_last_error());
+    if (size_ > 0 && bitar_mem_copy(p, data_, static_cast<std::size_t>(size_)) != BITAR_OK) {
+      bitar_mem_free(BITAR_MEM_DEVICE, device_, p);
+      return arrow::Status::IOError("device copy failed: ", bitar_last_error());
+    }
+    if (data_ != nullptr) {
+      bitar_mem_free(BITAR_MEM_DEVICE, device_, const_cast<std::uint8_t*>(data_));
+      CudaAllocatorTracker::Instance()->Release(data_);
+    }
+    data_ = static_cast<std::uint8_t*>(p);
+    capacity_ = new_capacity;
+    CudaAllocatorTracker::Instance()->Emplace(data_, {static_cast<std::size_t>(new_capacity), BITAR_MEM_DEVICE, device_});
+    return arrow::Status::OK();
+  }
+
+ private:
+  const int device_;
+};
+
 }  // namespace
+
+arrow::Result<std::unique_ptr<arrow::ResizableBuffer>> AllocateDeviceBuffer(std::int64_t size, int device_id) {
+  if (size < 0) return arrow::Status::Invalid("negative size");
+  void* p = nullptr;
+  if (bitar_mem_alloc(BITAR_MEM_DEVICE, device_id, static_cast<std::size_t>(size), 256, &p) != BITAR_OK)
+    return arrow::Status::OutOfMemory("device allocation of ", size, " bytes failed: ", bitar_last_error());
+  CudaAllocatorTracker::Instance()->Emplace(static_cast<std::uint8_t*>(p), {static_cast<std::size_t>(size), BITAR_MEM_DEVICE, device_id});
+  return std::unique_ptr<arrow::ResizableBuffer>(new DeviceBuffer(static_cast<std::uint8_t*>(p), size, device_id));
+}
 
 CudaAllocatorTracker* CudaAllocatorTracker::Instance() {
   static CudaAllocatorTracker tracker;
@@ -118,10 +161,6 @@ void CudaAllocatorTracker::Release(const std::uint8_t* addr) {
 
 arrow::MemoryPool* GetMemoryPool(MemoryPoolBackend backend) {   // memory_pool.cc:321-350: process-lifetime statics
   switch (backend) {
-    case MemoryPoolBackend::CudaDevice: {
-      static CudaMemoryPool pool(BITAR_MEM_DEVICE, "cuda_device");
-      return &pool;
-    }
     case MemoryPoolBackend::CudaPinnedHost: {
       static CudaMemoryPool pool(BITAR_MEM_PINNED, "cuda_pinned_host");
       return &pool;

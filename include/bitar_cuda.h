@@ -143,6 +143,9 @@ BITAR_API int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* o
 /* Block until the queue pair drained (the busy-poll of src/device.cc:228-235); returns 0, or
  * BITAR_E_IO_ERROR when any op finished with status != BITAR_OP_OK (src/device.cc:512-520). */
 BITAR_API int bitar_qp_wait(bitar_dev* dev, uint16_t qp);
+/* Non-blocking bitar_qp_wait(): BITAR_E_CANCELLED while ops are pending, else what bitar_qp_wait() would return.
+ * Makes no CUDA call, so it may be used inside a bitar_qp_on_complete() callback. */
+BITAR_API int bitar_qp_result(bitar_dev* dev, uint16_t qp);
 /* 1 while ops are pending (QueuePairMemory::has_pending_operations), else 0. */
 BITAR_API int bitar_qp_busy(bitar_dev* dev, uint16_t qp);
 /* Run fn(arg) on a driver thread once everything enqueued so far on the queue pair completed:
