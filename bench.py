@@ -26,6 +26,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "deflate+inflate round-trip throughput, uncompressed bytes (bitar Compress->Decompress)"
 SEG_DEFAULT = 59460          # apps/app_common.h:39 kDecompressedSegSize
+# DRAM bytes moved per uncompressed byte, from ncu (dram__bytes_read.sum + dram__bytes_write.sum, 256 MiB launch)
+DEFLATE_DRAM_BYTES_PER_BYTE = (379.004672e6 + 782.062592e6) / 268435456
+INFLATE_DRAM_BYTES_PER_BYTE = (142.796032e6 + 240.311040e6) / 268435456
 
 
 def peaks():
@@ -250,11 +253,16 @@ def main():
             "deflate_gbps": world * U / (td_ms * 1e-3) / 1e9, "inflate_gbps": world * U / (ti_ms * 1e-3) / 1e9,
             "deflate_kernel_ms": kd_ms, "inflate_kernel_ms": ki_ms, "wall_ms_per_step": wall_ms,
             "ratio": U / Cbytes, "zlib_level1_ratio": zratio,
+            # dominant kernel = deflate_kernel (79 % of the step's GPU time, profiles/r01_launches_bench_1GiB_c.csv).
+            # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture at 256 MiB
+            # (profiles/r01_ncu_full_deflate_and_indexed_inflate_256MiB.txt), scaled linearly to this launch's bytes.
             "roofline": {"bound": "hbm", "kernel": "deflate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": which,
+                         "frac": achieved / peak, "traffic": DEFLATE_DRAM_BYTES_PER_BYTE * U, "peak_source": which,
                          "algorithmic_bytes": "U + C per launch (read input once, write the stream once)",
-                         "inflate": {"achieved": (U + Cbytes) / (ki_ms * 1e-3) / 1e9,
-                                     "frac": (U + Cbytes) / (ki_ms * 1e-3) / 1e9 / peak}},
+                         "note": "issue- and latency-bound integer kernel: 55 % issue-slot utilisation, 2.9 % DRAM throughput (ncu)",
+                         "inflate": {"kernel": "inflate_indexed_kernel", "achieved": (U + Cbytes) / (ki_ms * 1e-3) / 1e9,
+                                     "frac": (U + Cbytes) / (ki_ms * 1e-3) / 1e9 / peak,
+                                     "traffic": INFLATE_DRAM_BYTES_PER_BYTE * U}},
             "clocks": clocks, "gpu_launches": launches,
         }
         if e2e:
@@ -271,8 +279,8 @@ def run_e2e(args, L, capi, C, torch, dist, world, local_rank, data, seg, n, U):
     application holds them (the Rtememzone pool of apps/demo_app.cc:119-122,517-522):
       compress  : the kernel pulls each chunk from host memory with its TMA bulk copy (H2D = U bytes) and
                   writes the streams straight into pinned output slots (D2H = C bytes) -- zero-copy;
-      decompress: the compressed slots are staged to the device (H2D), inflated, and the result is
-                  copied back to the pinned destination (D2H = U bytes).
+      decompress: called with the pinned slots and the pinned destination; the library gathers the slots into
+                  device memory (H2D = C bytes), inflates, and scatters the result back (D2H = U bytes).
     The input is split evenly over --qps queue pairs that run concurrently (apps/demo_app.cc:577-596)."""
     from bitar_b200.engine import CompressDevice, Configuration
     qps = max(1, args.qps)
@@ -282,40 +290,26 @@ def run_e2e(args, L, capi, C, torch, dist, world, local_rank, data, seg, n, U):
     capi.check(L.bitar_mem_alloc(capi.MEM_PINNED, local_rank, U, 64, C.byref(h_in)))
     capi.check(L.bitar_mem_alloc(capi.MEM_PINNED, local_rank, n * seg, 64, C.byref(h_out)))
     C.memmove(h_in.value, data.ctypes.data, U)
-    stride = (dev.slot + 255) // 256 * 256
-    d_stage = torch.empty(n * stride, dtype=torch.uint8, device="cuda")      # device staging of the slots
-    d_out = torch.empty(n * seg + 64, dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
     ops, slots = dev.compress_ops(h_in.value, U)
-    contiguous = bool((np.diff(slots.astype(np.int64)) == stride).all())
     per = (n + qps - 1) // qps
     parts = [(q * per, min(n, (q + 1) * per)) for q in range(qps) if q * per < n]
 
     def step():
+        # Compress(): every queue pair deflates its part, reading the pinned input and writing the pinned slots
         results = [dev.enqueue("deflate", q, ops[a:b]) for q, (a, b) in enumerate(parts)]
         for q in range(len(parts)):
             dev.wait(q)
         produced = np.concatenate([r["produced"] for r in results])
-        h2d = 0
+        # Decompress(): pinned slots -> pinned destination; the library stages both through device memory
         pending = []
         for q, (a, b) in enumerate(parts):
-            if contiguous:   # one copy per queue pair: the slots of a part are one address range
-                nb = (b - a) * stride
-                capi.check(L.bitar_qp_memcpy(dev._h, q, d_stage.data_ptr() + a * stride, int(slots[a]), nb))
-                h2d += nb
-            else:
-                for i in range(a, b):
-                    capi.check(L.bitar_qp_memcpy(dev._h, q, d_stage.data_ptr() + i * stride, int(slots[i]), int(produced[i])))
-                    h2d += int(produced[i])
-            iops = dev.decompress_ops(np.uint64(d_stage.data_ptr()) + np.arange(a, b, dtype=np.uint64) * np.uint64(stride),
-                                      produced[a:b], d_out.data_ptr() + a * seg)
+            iops = dev.decompress_ops(slots[a:b], produced[a:b], h_out.value + a * seg)
             pending.append(dev.enqueue("inflate", q, iops))
-            nbytes = min(U, b * seg) - a * seg
-            capi.check(L.bitar_qp_memcpy(dev._h, q, h_out.value + a * seg, d_out.data_ptr() + a * seg, nbytes))
         for q in range(len(parts)):
             dev.wait(q)
         total = sum(int(r["produced"].sum()) for r in pending)
-        return int(produced.sum()), h2d, total
+        return int(produced.sum()), int(produced.sum()), total
 
     for _ in range(max(1, args.warmup)):
         cbytes, h2d, total = step()
@@ -339,7 +333,8 @@ def run_e2e(args, L, capi, C, torch, dist, world, local_rank, data, seg, n, U):
     dev.close()
     return {"value": world * U / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(U + h2d),
             "d2h_bytes_per_step": int(cbytes + U), "ms_per_step": dt * 1e3, "queue_pairs": len(parts),
-            "path": "pinned host in/out through the C-ABI; compress zero-copy over PCIe, decompress staged"}
+            "path": "pinned host in/out through the C-ABI: compress reads and writes host memory in place (zero-copy over "
+                    "PCIe), decompress is staged through device memory by the library (gather kernel, inflate, scatter kernel)"}
 
 
 if __name__ == "__main__":

@@ -60,6 +60,15 @@ struct QueuePair {
   size_t tasks_cap = 0;
   uint32_t* d_generic = nullptr;        // ops left to the whole-stream kernel
   size_t generic_cap = 0;
+  // inflate with host (pinned / registered) buffers: stage through device memory
+  bitar_chunk* h_orig = nullptr;        // the caller's pointers (pinned), n entries
+  bitar_chunk* d_orig = nullptr;
+  uint32_t orig_cap = 0;
+  uint8_t* d_stage_in = nullptr;
+  size_t stage_in_cap = 0;
+  uint8_t* d_stage_out = nullptr;
+  size_t stage_out_cap = 0;
+  bool stage_src = false, stage_dst = false;
   bitar_result* user_out = nullptr;
   uint32_t pending_n = 0;
   std::atomic<int> busy{0};
@@ -178,8 +187,98 @@ void CUDART_CB qp_finish(void* arg) {
   q->busy.store(0, std::memory_order_release);
 }
 
+// ---- staging of host-resident inflate buffers ---------------------------------------------------------
+// A DEFLATE decoder reads its input in dependent 4-byte steps and writes 16 bytes at a time: over PCIe that
+// is latency-bound (measured 2 GB/s).  When the compressed buffers and / or the destination of an inflate
+// call live in pinned / registered HOST memory, the call therefore gathers the inputs into device memory
+// with wide coalesced reads, inflates there, and scatters the result back with wide coalesced writes
+// (staged addresses keep the misalignment of the originals so that both sides move 16-byte vectors).
+__global__ void __launch_bounds__(256) stage_copy_kernel(const bitar_chunk* __restrict__ from, const bitar_chunk* __restrict__ to,
+                                                         const bitar_result* __restrict__ results, int out_direction) {
+  const uint32_t i = blockIdx.x;
+  const uint8_t* src;
+  uint8_t* dst;
+  uint32_t n;
+  if (!out_direction) {   // gather: caller's compressed bytes -> stage
+    src = static_cast<const uint8_t*>(from[i].src);
+    dst = const_cast<uint8_t*>(static_cast<const uint8_t*>(to[i].src));
+    n = from[i].src_len;
+  } else {                // scatter: inflated bytes in the stage -> caller's destination
+    src = static_cast<const uint8_t*>(from[i].dst);
+    dst = static_cast<uint8_t*>(to[i].dst);
+    n = min(results[i].produced, to[i].dst_cap);
+  }
+  const uint32_t head = min(n, (16u - (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u)) & 15u);
+  if (threadIdx.x < head) dst[threadIdx.x] = src[threadIdx.x];
+  const uint32_t vecs = (n - head) >> 4;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+  uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+  for (uint32_t v = threadIdx.x; v < vecs; v += blockDim.x) d4[v] = s4[v];
+  const uint32_t done = head + (vecs << 4);
+  if (threadIdx.x < n - done) dst[done + threadIdx.x] = src[done + threadIdx.x];
+}
+
+bool is_host_memory(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// Rewrites q->h_ops to staged device addresses when the call's buffers are host memory (caller's ops are
+// kept in q->h_orig).  Called with the queue pair idle, before the descriptors are uploaded.
+int inflate_prepare_staging(QueuePair* q, uint32_t n) {
+  q->stage_src = q->h_ops[0].src != nullptr && q->h_ops[0].src_len > 0 && is_host_memory(q->h_ops[0].src);
+  q->stage_dst = q->h_ops[0].dst != nullptr && is_host_memory(q->h_ops[0].dst);
+  if (!q->stage_src && !q->stage_dst) return BITAR_OK;
+  if (q->orig_cap < n) {
+    if (q->h_orig) cudaFreeHost(q->h_orig);
+    if (q->d_orig) cudaFree(q->d_orig);
+    q->h_orig = nullptr; q->d_orig = nullptr; q->orig_cap = 0;
+    CU_TRY(cudaHostAlloc((void**)&q->h_orig, (size_t)q->cap * sizeof(bitar_chunk), cudaHostAllocPortable), BITAR_E_OUT_OF_MEMORY);
+    CU_TRY(cudaMalloc((void**)&q->d_orig, (size_t)q->cap * sizeof(bitar_chunk)), BITAR_E_OUT_OF_MEMORY);
+    q->orig_cap = q->cap;
+  }
+  memcpy(q->h_orig, q->h_ops, (size_t)n * sizeof(bitar_chunk));
+  size_t need_in = 0, need_out = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    need_in += (((size_t)q->h_ops[i].src_len + 15u) & ~(size_t)15u) + 32u;
+    need_out += (((size_t)q->h_ops[i].dst_cap + 15u) & ~(size_t)15u) + 32u;
+  }
+  if (q->stage_src && q->stage_in_cap < need_in) {
+    if (q->d_stage_in) cudaFree(q->d_stage_in);
+    q->d_stage_in = nullptr; q->stage_in_cap = 0;
+    CU_TRY(cudaMalloc((void**)&q->d_stage_in, need_in), BITAR_E_OUT_OF_MEMORY);
+    q->stage_in_cap = need_in;
+  }
+  if (q->stage_dst && q->stage_out_cap < need_out) {
+    if (q->d_stage_out) cudaFree(q->d_stage_out);
+    q->d_stage_out = nullptr; q->stage_out_cap = 0;
+    CU_TRY(cudaMalloc((void**)&q->d_stage_out, need_out), BITAR_E_OUT_OF_MEMORY);
+    q->stage_out_cap = need_out;
+  }
+  size_t at_in = 0, at_out = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    bitar_chunk& c = q->h_ops[i];
+    if (q->stage_src) {
+      const size_t mis = reinterpret_cast<uintptr_t>(c.src) & 15u;
+      c.src = q->d_stage_in + at_in + mis;
+      at_in += (((size_t)c.src_len + 15u) & ~(size_t)15u) + 32u;
+    }
+    if (q->stage_dst) {
+      const size_t mis = reinterpret_cast<uintptr_t>(c.dst) & 15u;
+      c.dst = q->d_stage_out + at_out + mis;
+      at_out += (((size_t)c.dst_cap + 15u) & ~(size_t)15u) + 32u;
+    }
+  }
+  return BITAR_OK;
+}
+
 template <typename Launch>
-int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, bitar_result* results, Launch&& launch) {
+int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, bitar_result* results, Launch&& launch,
+              bool inflate = false) {
   if (!dev) return fail(BITAR_E_INVALID, "null device");
   if (qp >= dev->qps.size()) return fail(BITAR_E_INVALID, "queue_pair_id must be in the range of [0, %zu)", dev->qps.size());
   QueuePair* q = dev->qps[qp];
@@ -194,15 +293,32 @@ int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, b
   int rc = qp_reserve(dev, q, n);
   if (rc) return rc;
   memcpy(q->h_ops, ops, (size_t)n * sizeof(bitar_chunk));
+  q->stage_src = q->stage_dst = false;
+  if (inflate) {
+    rc = inflate_prepare_staging(q, n);
+    if (rc) return rc;
+  }
   q->user_out = results;
   q->pending_n = n;
   q->busy.store(1, std::memory_order_release);
   cudaError_t e = cudaEventRecord(q->ev_start, q->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(q->d_ops, q->h_ops, (size_t)n * sizeof(bitar_chunk), cudaMemcpyHostToDevice, q->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(q->d_counter, 0, 8 * sizeof(unsigned int), q->stream);
+  if (e == cudaSuccess && (q->stage_src || q->stage_dst))
+    e = cudaMemcpyAsync(q->d_orig, q->h_orig, (size_t)n * sizeof(bitar_chunk), cudaMemcpyHostToDevice, q->stream);
+  if (e == cudaSuccess && q->stage_src) {
+    stage_copy_kernel<<<n, 256, 0, q->stream>>>(q->d_orig, q->d_ops, nullptr, 0);
+    e = cudaGetLastError();
+    g_launches.fetch_add(1);
+  }
   if (e == cudaSuccess) e = cudaEventRecord(q->ev_k0, q->stream);
   if (e == cudaSuccess) e = launch(q);
   if (e == cudaSuccess) e = cudaEventRecord(q->ev_k1, q->stream);
+  if (e == cudaSuccess && q->stage_dst) {
+    stage_copy_kernel<<<n, 256, 0, q->stream>>>(q->d_ops, q->d_orig, q->d_res, 1);
+    e = cudaGetLastError();
+    g_launches.fetch_add(1);
+  }
   if (e == cudaSuccess) e = cudaMemcpyAsync(q->h_res, q->d_res, (size_t)n * sizeof(bitar_result), cudaMemcpyDeviceToHost, q->stream);
   if (e == cudaSuccess) e = cudaEventRecord(q->ev_stop, q->stream);
   if (e == cudaSuccess) e = cudaLaunchHostFunc(q->stream, qp_finish, q);
@@ -377,6 +493,10 @@ int bitar_dev_close(bitar_dev* dev) {
     if (q->d_lane_scratch) cudaFree(q->d_lane_scratch);
     if (q->d_tasks) cudaFree(q->d_tasks);
     if (q->d_generic) cudaFree(q->d_generic);
+    if (q->h_orig) cudaFreeHost(q->h_orig);
+    if (q->d_orig) cudaFree(q->d_orig);
+    if (q->d_stage_in) cudaFree(q->d_stage_in);
+    if (q->d_stage_out) cudaFree(q->d_stage_out);
     if (q->ev_start) cudaEventDestroy(q->ev_start);
     if (q->ev_k0) cudaEventDestroy(q->ev_k0);
     if (q->ev_k1) cudaEventDestroy(q->ev_k1);
@@ -489,7 +609,7 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
       case 6: return InflateConfig<2, 9, 7, 1024, 1>::launch(q->d_ops, n, q->d_res, q->d_counter, ck, id, sms, q->stream);
       case 7: return InflateConfig<8, 10, 8, 1024, 1>::launch(q->d_ops, n, q->d_res, q->d_counter, ck, id, sms, q->stream);
     }
-  });
+  }, /*inflate=*/true);
 }
 
 int bitar_qp_wait(bitar_dev* dev, uint16_t qp) {

@@ -92,6 +92,51 @@ def test_gpu_streams_inflate_through_the_index(cuda_device, variant, huffman):
         capi.lib().bitar_tune_inflate_variant(20)
 
 
+def test_host_resident_buffers_are_staged(cuda_device):
+    """Compressed slots and the destination in PINNED HOST memory: the inflate call gathers / scatters through
+    device memory (capi.cu stage_copy_kernel); results and guard bytes as for device buffers."""
+    import ctypes as C
+    L = capi.lib()
+    data = synth.lineitem_like(37 * SEG + 4321)
+    n = (data.size + SEG - 1) // SEG
+    dev = G.open_device(SEG, slot_mem_kind=capi.MEM_PINNED, max_preallocate_memzones=n + 8)
+    h_in, h_out = C.c_void_p(), C.c_void_p()
+    try:
+        capi.check(L.bitar_mem_alloc(capi.MEM_PINNED, 0, data.size, 64, C.byref(h_in)))
+        capi.check(L.bitar_mem_alloc(capi.MEM_PINNED, 0, n * SEG + 64, 64, C.byref(h_out)))
+        C.memmove(h_in.value, data.ctypes.data, data.size)
+        C.memset(h_out.value, 0xA5, n * SEG + 64)
+        ops, slots = dev.compress_ops(h_in.value, data.size)
+        res = dev.enqueue("deflate", 0, ops)
+        dev.wait(0)
+        for dst_off in (0, 3):                                  # aligned and misaligned destination
+            iops = dev.decompress_ops(slots, res["produced"], h_out.value + dst_off)
+            ires = dev.enqueue("inflate", 0, iops)
+            dev.wait(0)
+            back = np.ctypeslib.as_array(C.cast(h_out.value, C.POINTER(C.c_uint8)), shape=(n * SEG + 64,))
+            assert int(ires["produced"].sum()) == data.size and (ires["status"] == 0).all()
+            assert np.array_equal(back[dst_off:dst_off + data.size], data)
+            assert (back[dst_off + data.size:] == 0xA5).all(), "inflate wrote past the produced bytes"
+            C.memset(h_out.value, 0xA5, n * SEG + 64)
+        # zlib-produced streams in pinned memory take the whole-stream kernel through the same staging
+        zs, zp = O.compress_buffer(data, SEG)
+        h_z = C.c_void_p()
+        capi.check(L.bitar_mem_alloc(capi.MEM_PINNED, 0, zs.size, 64, C.byref(h_z)))
+        C.memmove(h_z.value, zs.ctypes.data, zs.size)
+        ptrs = np.uint64(h_z.value) + np.arange(n, dtype=np.uint64) * np.uint64(zs.shape[1])
+        ires = dev.enqueue("inflate", 0, dev.decompress_ops(ptrs, zp, h_out.value))
+        dev.wait(0)
+        back = np.ctypeslib.as_array(C.cast(h_out.value, C.POINTER(C.c_uint8)), shape=(n * SEG + 64,))
+        assert int(ires["produced"].sum()) == data.size and np.array_equal(back[:data.size], data)
+        capi.check(L.bitar_mem_free(capi.MEM_PINNED, 0, h_z))
+        assert sum(dev.put_slot(s) for s in slots[::-1]) == n
+    finally:
+        for b in (h_in, h_out):
+            if b.value:
+                L.bitar_mem_free(capi.MEM_PINNED, 0, b)
+        dev.close()
+
+
 def test_bitar_decompress_contract(cuda_device):
     """Decompress(): op i lands at out + i*S, total = sum(produced) (src/device.cc:240-318); checked
     against oracle_decompress_buffer on the oracle's own compressed slots."""
