@@ -15,14 +15,15 @@
 //   plan    : CTA-wide bitonic sort of the used symbols, then length-limited Huffman code
 //             construction, code-length RLE and header costing (deflate_common.h, serial, thread 0)
 //             while the other warps compute CRC-32 / Adler-32 of the block in parallel.
-//   encode  : cheapest of stored / fixed / dynamic; every thread encodes 8 consecutive positions,
+//   encode  : cheapest of stored / fixed / dynamic; every thread encodes 4 consecutive tokens,
 //             a block-wide prefix sum of code lengths (warp shuffles) gives each thread its bit
 //             offset, codes are packed into a shared-memory stage and leave the SM as aligned
 //             16-byte vector stores.  The bit offsets of the sub-range starts are collected on the way
 //             and appended as the parallel-inflate index.
 //
-// The token stream between match and encode is a sparse u32 per input position in a per-CTA global
-// scratch area (L2 resident, written and read once, fully coalesced).
+// The token stream between match and encode is compact: one u32 per token (literal byte, or length and
+// distance), each sub-range's tokens in order at its own offset of a per-CTA global scratch area (L2
+// resident, written and read once).
 //
 // Output is bit-identical to tools/model/deflate_model.h (tests pin this) and always a valid
 // RFC 1951 stream that zlib inflates to the input.
@@ -44,9 +45,12 @@ constexpr int kWarps = 16;
 constexpr int kThreads = kWarps * 32;
 constexpr int kBlockMax = 65536;                 // sub-block size (positions fit 16 bits)
 constexpr int kHashBits = 10;                    // per-warp table: 1024 entries for a 2048-position sub-range
-constexpr int kPosPerThread = 8;                 // encode: consecutive positions per thread
-constexpr int kTile = kThreads * kPosPerThread;  // encode: positions per tile (4096)
-constexpr int kStageWords = 3584;                // 14 KiB bit stage (a tile emits < 8.6 KiB)
+constexpr int kTokPerThread = 4;                 // encode: consecutive tokens per thread
+constexpr int kTile = kThreads * kTokPerThread;  // encode: tokens per tile (2048, at most 48 bits each)
+constexpr int kStageWords = 3584;                // 14 KiB bit stage (a tile emits <= 12 KiB + the partial unit)
+constexpr uint32_t kTokNone = 0x100u;            // compact token stream: padding (emits nothing)
+constexpr uint32_t kTokEob = 0x101u;             //                       end of block
+// other compact tokens: < 0x100 literal byte; >= 0x200 match, (dist << 9) | len (dfl::tok_match)
 constexpr uint32_t kNoCand = 0xFFFFu;
 
 struct PlanPar {                      // scratch of the parallel half of the plan
@@ -81,6 +85,8 @@ struct __align__(16) Smem {
   uint32_t x2n[32];
   uint32_t cks_crc, cks_a, cks_b;    // checksum accumulators
   uint32_t ll_m, d_m;
+  uint32_t sub_cnt[32];              // tokens of each sub-range of the block (compact, at tokens + sub * 2048)
+  uint32_t sub_voff[34];             // encode: first slot of each sub-range (counts rounded up to kTokPerThread)
   uint32_t index[(BITAR_MAX_SEG_SIZE >> dfl::kIdxBlockLog2) * 33 + 4];   // parallel-inflate index of the chunk (deflate_common.h)
   uint32_t any_coded;                // some Huffman-coded block spans more than one sub-range
   uint32_t block_type;
@@ -268,6 +274,8 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
   const uint32_t dummy = (1u << kHashBits) + (uint32_t)lane;
   const int sub_end = min(n, s0 + (int)dfl::kSub);
   int carry = s0;                                     // next token start
+  uint32_t* out = tokens + s0;                        // this sub-range's tokens, compact and in order
+  uint32_t cnt = 0;
   for (int base = s0; base < s1; base += 32) {
     const int p = base + lane;
     const bool valid = p + 4 <= n;
@@ -280,10 +288,7 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
     __syncwarp();
     if (lower) cand = (uint32_t)(base + 31 - __clz((int)lower));
     const int a = carry - base;                       // where the parse enters this window (>= 0)
-    if (a >= 32) {                                    // the whole window lies inside the previous match
-      if (p < n) tokens[p] = 0;
-      continue;
-    }
+    if (a >= 32) continue;                            // the whole window lies inside the previous match
     int adv = 1, dist = 0;
     if (cand != kNoCand && p >= carry) {
       const int len = match_len(ds, p, (int)cand, min(dfl::kMaxMatch, sub_end - p));
@@ -311,19 +316,22 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
     contrib = ((reach >> lane) & 1u) && e4 < 32 ? (1u << e4) : 0u; reach |= __reduce_or_sync(kFull, contrib);
     carry = base + __shfl_sync(kFull, e5, a);         // where the chain entering at lane a leaves the window
     const bool start = ((reach >> lane) & 1u) && p < n;
-    uint32_t tok = 0;
+    const unsigned starts = __ballot_sync(kFull, start);
     if (start) {
+      uint32_t tok;
       if (adv > 1) {
         tok = dfl::tok_match(adv, dist);
         atomicAdd(&sm.ll_freq[257 + dfl::len_sym(adv)], 1u);
         atomicAdd(&sm.d_freq[dfl::dist_sym(dist)], 1u);
       } else {
-        tok = 1u;
-        atomicAdd(&sm.ll_freq[lds_u8(ds + p)], 1u);
+        tok = lds_u8(ds + p);
+        atomicAdd(&sm.ll_freq[tok], 1u);
       }
+      out[cnt + (uint32_t)__popc(starts & lt_mask)] = tok;
     }
-    if (p < n) tokens[p] = tok;
+    cnt += (uint32_t)__popc(starts);
   }
+  if (lane == 0) sm.sub_cnt[s0 >> dfl::kSubLog2] = cnt;
 }
 
 // ---- plan, first half, in parallel --------------------------------------------------------------------
@@ -450,20 +458,14 @@ __device__ __forceinline__ void block_checksum(Smem& sm, const uint8_t* d, uint3
   }
 }
 
-// bits of one token under sm.ll_enc / sm.d_enc; also returns the two code words
-__device__ __forceinline__ int token_bits(const Smem& sm, uint32_t ds, int p, uint32_t tok,
-                                          uint32_t& lo_bits, int& lo_n, uint32_t& hi_bits, int& hi_n) {
+// bits of one compact token under sm.ll_enc / sm.d_enc; also returns the two code words
+__device__ __forceinline__ int token_bits(const Smem& sm, uint32_t tok, uint32_t& lo_bits, int& lo_n, uint32_t& hi_bits,
+                                          int& hi_n) {
   lo_n = hi_n = 0;
   lo_bits = hi_bits = 0;
-  if (tok == 0) return 0;
-  if (tok == 1u) {
-    uint32_t e = sm.ll_enc[lds_u8(ds + p)];
-    lo_bits = e & 0xFFFFu;
-    lo_n = (int)(e >> 16);
-    return lo_n;
-  }
-  if (tok == 2u) {  // end of block
-    uint32_t e = sm.ll_enc[dfl::kEob];
+  if (tok == kTokNone) return 0;
+  if (tok < 0x200u) {   // literal byte, or end of block (0x101 -> symbol 256)
+    const uint32_t e = sm.ll_enc[tok < 0x100u ? tok : (uint32_t)dfl::kEob];
     lo_bits = e & 0xFFFFu;
     lo_n = (int)(e >> 16);
     return lo_n;
@@ -786,28 +788,52 @@ __global__ void __launch_bounds__(kThreads, 2)
       __syncthreads();
       BITAR_PHASE(4)
 
-      // ---- encode: tiles of kTile positions, 8 consecutive positions per thread ----
-      for (int tb = 0; tb <= n; tb += kTile) {  // position n carries the end-of-block symbol
-        const int p0 = tb + tid * kPosPerThread;
-        uint32_t tk[kPosPerThread];
-        if (p0 + kPosPerThread <= n) {
-          uint4 v0 = *reinterpret_cast<const uint4*>(tokens + p0);
-          uint4 v1 = *reinterpret_cast<const uint4*>(tokens + p0 + 4);
-          tk[0] = v0.x; tk[1] = v0.y; tk[2] = v0.z; tk[3] = v0.w;
-          tk[4] = v1.x; tk[5] = v1.y; tk[6] = v1.z; tk[7] = v1.w;
-        } else {
+      // ---- encode: the compact tokens of all sub-ranges as one virtual sequence of slots; every sub-range
+      //      is padded to a multiple of kTokPerThread so that a thread's slots never straddle two sub-ranges,
+      //      and the end-of-block symbol gets a group of its own at the end ----
+      const int n_sub = (int)dfl::idx_subs((uint32_t)n);
+      if (warp == 0) {
+        const uint32_t c = lane < n_sub ? (sm.sub_cnt[lane] + kTokPerThread - 1u) & ~(uint32_t)(kTokPerThread - 1) : 0u;
+        uint32_t incl = c;
 #pragma unroll
-          for (int j = 0; j < kPosPerThread; ++j) {
-            int p = p0 + j;
-            tk[j] = p < n ? tokens[p] : (p == n ? 2u : 0u);
-          }
+        for (int off2 = 1; off2 < 32; off2 <<= 1) {
+          uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, off2);
+          if (lane >= off2) incl += t;
+        }
+        sm.sub_voff[lane] = incl - c;
+        if (lane == 31) sm.sub_voff[32] = sm.sub_voff[33] = incl;
+      }
+      __syncthreads();
+      const int n_slots = (int)sm.sub_voff[32] + kTokPerThread;
+      for (int tb = 0; tb < n_slots; tb += kTile) {
+        const int g = tb + tid * kTokPerThread;
+        uint32_t tk[kTokPerThread];
+        int sr = 0;                          // largest sub-range with voff[sr] <= g (n_sub = the end-of-block group)
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1)
+          if (sr + step <= n_sub && (int)sm.sub_voff[sr + step] <= g) sr += step;
+        if (sr + 1 <= n_sub && (int)sm.sub_voff[sr + 1] <= g) sr += 1;
+        const int l = g - (int)sm.sub_voff[sr];
+        if (g >= n_slots) {
+#pragma unroll
+          for (int j = 0; j < kTokPerThread; ++j) tk[j] = kTokNone;
+        } else if (sr >= n_sub) {
+#pragma unroll
+          for (int j = 0; j < kTokPerThread; ++j) tk[j] = j == 0 ? kTokEob : kTokNone;
+        } else {
+          const uint4 v = *reinterpret_cast<const uint4*>(tokens + sr * (int)dfl::kSub + l);
+          const int have = (int)sm.sub_cnt[sr] - l;
+          tk[0] = v.x;
+          tk[1] = have > 1 ? v.y : kTokNone;
+          tk[2] = have > 2 ? v.z : kTokNone;
+          tk[3] = have > 3 ? v.w : kTokNone;
         }
         uint32_t mybits = 0;
 #pragma unroll
-        for (int j = 0; j < kPosPerThread; ++j) {
+        for (int j = 0; j < kTokPerThread; ++j) {
           uint32_t lb, hb;
           int ln, hn;
-          mybits += (uint32_t)token_bits(sm, ds, p0 + j, tk[j], lb, ln, hb, hn);
+          mybits += (uint32_t)token_bits(sm, tk[j], lb, ln, hb, hn);
         }
         // block-wide exclusive prefix sum of mybits
         uint32_t incl = mybits;
@@ -826,8 +852,8 @@ __global__ void __launch_bounds__(kThreads, 2)
           tile_total += ws;
         }
         uint64_t at = o.bit + warp_off + (incl - mybits);
-        if ((p0 & (int)(dfl::kSub - 1)) == 0 && p0 < n)   // first symbol of a sub-range
-          sm.index[iblk + 1u + ((uint32_t)p0 >> dfl::kSubLog2)] = (uint32_t)(at - 8ull * o.vstart);
+        if (l == 0 && sr < n_sub && g < n_slots)   // first symbol of a sub-range
+          sm.index[iblk + 1u + (uint32_t)sr] = (uint32_t)(at - 8ull * o.vstart);
         // emit: accumulate into a 64-bit window, flush whole words
         {
           uint32_t rel = (uint32_t)(at - 8ull * o.sbase);
@@ -837,10 +863,10 @@ __global__ void __launch_bounds__(kThreads, 2)
           uint32_t accn = fill;
           bool first = true;
 #pragma unroll
-          for (int j = 0; j < kPosPerThread; ++j) {
+          for (int j = 0; j < kTokPerThread; ++j) {
             uint32_t lb, hb;
             int ln, hn;
-            token_bits(sm, ds, p0 + j, tk[j], lb, ln, hb, hn);
+            token_bits(sm, tk[j], lb, ln, hb, hn);
             acc |= (uint64_t)lb << accn;
             accn += (uint32_t)ln;
             if (accn >= 32) {
