@@ -268,14 +268,9 @@ struct PlanScratch {
   uint16_t bl_count[kMaxBits + 1];
 };
 
-// Second half of the plan: code-length RLE, the code-length code and the header size, from the
-// litlen / distance code lengths already in p (ll_len, d_len, hlit, hdist).  Serial.
-BITAR_HD_NOINLINE void plan_header(BlockPlan* p, PlanScratch* s) {
-  for (int i = 0; i < kNumCl; ++i) s->cl_freq[i] = 0;
-  int nt = cl_rle(p->ll_len, p->hlit, p->cl_tok, 0, s->cl_freq);
-  nt = cl_rle(p->d_len, p->hdist, p->cl_tok, nt, s->cl_freq);
-  p->n_cl_tok = nt;
-
+// Last part of the plan: the code-length code and the header size, from the RLE tokens (p->cl_tok,
+// p->n_cl_tok) and their frequencies (s->cl_freq).  Serial (19 symbols).
+BITAR_HD_NOINLINE void plan_cl_tree(BlockPlan* p, PlanScratch* s) {
   int cm = sort_used_small(s->cl_freq, kNumCl, s->sorted);
   for (int i = 0; i < kNumCl; ++i) p->cl_len[i] = 0;
   if (cm == 1) {  // complete the code: give a second symbol a 1-bit code too
@@ -294,6 +289,17 @@ BITAR_HD_NOINLINE void plan_header(BlockPlan* p, PlanScratch* s) {
   uint32_t hb = 3 + 5 + 5 + 4 + 3 * (uint32_t)hclen;
   for (int i = 0; i < kNumCl; ++i) hb += s->cl_freq[i] * (uint32_t)(p->cl_len[i] + cl_extra_bits(i));
   p->header_bits = hb;
+}
+
+// Second half of the plan: code-length RLE, the code-length code and the header size, from the
+// litlen / distance code lengths already in p (ll_len, d_len, hlit, hdist).  Serial; the deflate kernel runs
+// the RLE with one run per thread and shares plan_cl_tree().
+BITAR_HD_NOINLINE void plan_header(BlockPlan* p, PlanScratch* s) {
+  for (int i = 0; i < kNumCl; ++i) s->cl_freq[i] = 0;
+  int nt = cl_rle(p->ll_len, p->hlit, p->cl_tok, 0, s->cl_freq);
+  nt = cl_rle(p->d_len, p->hdist, p->cl_tok, nt, s->cl_freq);
+  p->n_cl_tok = nt;
+  plan_cl_tree(p, s);
 }
 
 // ll_sorted / d_sorted: used symbols sorted ascending by (freq<<9 | sym) -- the caller sorts (the

@@ -436,6 +436,88 @@ __device__ __forceinline__ void huff_codes_warp(const uint8_t* len, int n, const
   }
 }
 
+// CTA-wide exclusive prefix sum (one value per thread); *total receives the sum.  Two barriers.
+__device__ __forceinline__ uint32_t block_excl_scan(Smem& sm, uint32_t v, uint32_t* total, int lane, int warp) {
+  uint32_t incl = v;
+#pragma unroll
+  for (int o2 = 1; o2 < 32; o2 <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o2);
+    if (lane >= o2) incl += t;
+  }
+  __syncthreads();   // warp_sums free again
+  if (lane == 31) sm.warp_sums[warp] = incl;
+  __syncthreads();
+  uint32_t off = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    const uint32_t ws = sm.warp_sums[w];
+    if (w < warp) off += ws;
+    tot += ws;
+  }
+  *total = tot;
+  return off + incl - v;
+}
+
+// Code-length RLE (dfl::cl_rle over the litlen lengths, then over the distance lengths) with one run per
+// thread: thread i owns position i of the concatenated length sequence and emits the tokens of the run that
+// starts there.  Same tokens, in the same order, as the serial function.
+__device__ __forceinline__ void cl_rle_parallel(Smem& sm, int tid, int lane, int warp) {
+  dfl::BlockPlan& pl = sm.plan;
+  const int hlit = pl.hlit, total_syms = pl.hlit + pl.hdist;
+  if (tid < dfl::kNumCl) sm.u.enc.scratch.cl_freq[tid] = 0;
+  int v = 0, run = 0;
+  uint32_t ntok = 0;
+  if (tid < total_syms) {
+    const auto at = [&](int i) -> int { return i < hlit ? pl.ll_len[i] : pl.d_len[i - hlit]; };
+    v = at(tid);
+    const bool start = tid == 0 || tid == hlit || at(tid - 1) != v;
+    if (start) {
+      const int end = tid < hlit ? hlit : total_syms;
+      run = 1;
+      while (tid + run < end && at(tid + run) == v) ++run;
+      if (v == 0) {
+        const int rem = run % 138;
+        ntok = (uint32_t)(run / 138 + (rem >= 3 ? 1 : rem));
+      } else {
+        const int rem = (run - 1) % 6;
+        ntok = (uint32_t)(1 + (run - 1) / 6 + (rem >= 3 ? 1 : rem));
+      }
+    }
+  }
+  uint32_t total = 0;
+  uint32_t o = block_excl_scan(sm, ntok, &total, lane, warp);
+  if (run > 0) {
+    uint32_t* cl_freq = sm.u.enc.scratch.cl_freq;
+    const auto emit = [&](int sym, int extra) {
+      pl.cl_tok[o++] = (uint16_t)(sym | (extra << 5));
+      atomicAdd(&cl_freq[sym], 1u);
+    };
+    if (v == 0) {
+      while (run >= 11) {
+        const int r = run > 138 ? 138 : run;
+        emit(18, r - 11);
+        run -= r;
+      }
+      if (run >= 3) {
+        emit(17, run - 3);
+        run = 0;
+      }
+      while (run-- > 0) emit(0, 0);
+    } else {
+      emit(v, 0);
+      run--;
+      while (run >= 3) {
+        const int r = run > 6 ? 6 : run;
+        emit(16, r - 3);
+        run -= r;
+      }
+      while (run-- > 0) emit(v, 0);
+    }
+  }
+  if (tid == 0) pl.n_cl_tok = (int)total;
+  __syncthreads();
+}
+
 // ---- checksum of the block held in shared memory (threads tid0..tid0+nthr) ---------------------------
 __device__ __forceinline__ void block_checksum(Smem& sm, const uint8_t* d, uint32_t n, uint32_t tail_after,
                                                bool first_block, int type, int t, int nthr) {
@@ -669,7 +751,11 @@ __global__ void __launch_bounds__(kThreads, 2)
         sm.plan.hdist = max(1, (int)pp.hdist_max + 1);
         sm.plan.dyn_body_bits = pp.dyn_bits;
         sm.plan.fixed_body_bits = pp.fix_bits;
-        dfl::plan_header(&sm.plan, &sm.u.enc.scratch);   // code-length RLE, code-length code, header size (serial)
+      }
+      __syncthreads();
+      cl_rle_parallel(sm, tid, lane, warp);            // code-length RLE, one run per thread
+      if (tid == 0) {
+        dfl::plan_cl_tree(&sm.plan, &sm.u.enc.scratch);   // code-length code, header size (serial, 19 symbols)
         // choose the block type (same rule as the model)
         uint64_t dyn_bits = (uint64_t)sm.plan.header_bits + sm.plan.dyn_body_bits;
         uint64_t fix_bits = 3 + sm.plan.fixed_body_bits;
@@ -765,24 +851,33 @@ __global__ void __launch_bounds__(kThreads, 2)
         else e = dfl::bitrev((uint32_t)tid, 5) | (5u << 16);
         sm.d_enc[tid] = e;
       }
-      // ---- header (thread 0, serial) ----
+      // ---- header: fixed fields by thread 0, then one code-length-code length / RLE token per thread at the bit
+      //      offset given by a CTA-wide prefix sum ----
       uint32_t hdr_bits = type == dfl::kDynamic ? sm.plan.header_bits : 3u;
       if (tid == 0) {
         HeaderWriter hw{sm, o, o.bit};
         hw.put(final_block ? 1u : 0u, 1);
         hw.put(type, 2);
         if (type == dfl::kDynamic) {
-          const dfl::BlockPlan& pl = sm.plan;
-          hw.put((uint32_t)(pl.hlit - 257), 5);
-          hw.put((uint32_t)(pl.hdist - 1), 5);
-          hw.put((uint32_t)(pl.hclen - 4), 4);
-          for (int i = 0; i < pl.hclen; ++i) hw.put(pl.cl_len[dfl::cl_order(i)], 3);
-          for (int i = 0; i < pl.n_cl_tok; ++i) {
-            int sym = pl.cl_tok[i] & 31, ev = pl.cl_tok[i] >> 5;
-            hw.put(pl.cl_code[sym], pl.cl_len[sym]);
-            if (sym >= 16) hw.put((uint32_t)ev, dfl::cl_extra_bits(sym));
-          }
+          hw.put((uint32_t)(sm.plan.hlit - 257), 5);
+          hw.put((uint32_t)(sm.plan.hdist - 1), 5);
+          hw.put((uint32_t)(sm.plan.hclen - 4), 4);
         }
+      }
+      if (type == dfl::kDynamic) {
+        const dfl::BlockPlan& pl = sm.plan;
+        uint32_t bits = 0, nb = 0;
+        if (tid < pl.hclen) {
+          bits = pl.cl_len[dfl::cl_order(tid)];
+          nb = 3;
+        } else if (tid < pl.hclen + pl.n_cl_tok) {
+          const int t = pl.cl_tok[tid - pl.hclen], sym = t & 31, ev = t >> 5;
+          bits = (uint32_t)pl.cl_code[sym] | ((uint32_t)ev << pl.cl_len[sym]);
+          nb = (uint32_t)pl.cl_len[sym] + (uint32_t)dfl::cl_extra_bits(sym);
+        }
+        uint32_t total = 0;
+        const uint32_t off2 = block_excl_scan(sm, nb, &total, lane, warp);
+        stage_or(sm, o, o.bit + 17u + off2, bits, (int)nb);
       }
       o.bit += hdr_bits;
       __syncthreads();
