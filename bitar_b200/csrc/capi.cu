@@ -60,6 +60,7 @@ struct QueuePair {
   size_t tasks_cap = 0;
   uint32_t* d_generic = nullptr;        // ops left to the whole-stream kernel
   size_t generic_cap = 0;
+  bitar::xk::CkAcc* d_ck = nullptr;     // per-op checksum accumulators of the indexed path
   // inflate with host (pinned / registered) buffers: stage through device memory
   bitar_chunk* h_orig = nullptr;        // the caller's pointers (pinned), n entries
   bitar_chunk* d_orig = nullptr;
@@ -493,6 +494,7 @@ int bitar_dev_close(bitar_dev* dev) {
     if (q->d_lane_scratch) cudaFree(q->d_lane_scratch);
     if (q->d_tasks) cudaFree(q->d_tasks);
     if (q->d_generic) cudaFree(q->d_generic);
+    if (q->d_ck) cudaFree(q->d_ck);
     if (q->h_orig) cudaFreeHost(q->h_orig);
     if (q->d_orig) cudaFree(q->d_orig);
     if (q->d_stage_in) cudaFree(q->d_stage_in);
@@ -536,7 +538,6 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
     if (variant >= 20) {
       // default: chunks carrying the parallel-inflate index go to the sub-range kernel, one warp per
       // 64 KiB block; everything else (zlib streams, stored chunks) to the whole-stream kernel.
-      // Checksums are only folded in by the whole-stream kernel, so they route everything there.
       using namespace bitar::xk;
       size_t blocks = 0;
       for (uint32_t i = 0; i < n; ++i) {
@@ -555,22 +556,25 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
         if (q->d_generic) cudaFree(q->d_generic);
         q->d_generic = nullptr;
         q->generic_cap = 0;
+        if (q->d_ck) cudaFree(q->d_ck);
+        q->d_ck = nullptr;
         cudaError_t e = cudaMalloc((void**)&q->d_generic, (size_t)n * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&q->d_ck, (size_t)n * sizeof(CkAcc));
         if (e != cudaSuccess) return e;
         q->generic_cap = n;
       }
       Counters* pc = reinterpret_cast<Counters*>(q->d_counter);
-      inflate_plan_kernel<<<(n + 127) / 128, 128, 0, q->stream>>>(q->d_ops, n, q->d_res, q->d_tasks, q->d_generic, pc,
-                                                                  ck == BITAR_CHECKSUM_NONE ? 1 : 0);
+      CkAcc* acc = ck != BITAR_CHECKSUM_NONE ? q->d_ck : nullptr;
+      inflate_plan_kernel<<<(n + 127) / 128, 128, 0, q->stream>>>(q->d_ops, n, q->d_res, q->d_tasks, q->d_generic, pc, acc, 1);
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) return e;
       g_launches.fetch_add(2);
       switch (variant) {
         default:
-        case 20: e = IndexedConfig<10, 1344, 8, 512, 128, 20>::launch(q->d_ops, q->d_res, q->d_tasks, pc, (uint32_t)blocks, id, sms, q->stream); break;
-        case 21: e = IndexedConfig<10, 1344, 8, 512, 128, 16>::launch(q->d_ops, q->d_res, q->d_tasks, pc, (uint32_t)blocks, id, sms, q->stream); break;
-        case 22: e = IndexedConfig<9, 864, 7, 256, 128, 24>::launch(q->d_ops, q->d_res, q->d_tasks, pc, (uint32_t)blocks, id, sms, q->stream); break;
-        case 23: e = IndexedConfig<10, 1344, 8, 512, 256, 14>::launch(q->d_ops, q->d_res, q->d_tasks, pc, (uint32_t)blocks, id, sms, q->stream); break;
+        case 20: e = IndexedConfig<10, 1344, 8, 512, 128, 20>::launch(q->d_ops, q->d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
+        case 21: e = IndexedConfig<10, 1344, 8, 512, 128, 16>::launch(q->d_ops, q->d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
+        case 22: e = IndexedConfig<9, 864, 7, 256, 128, 24>::launch(q->d_ops, q->d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
+        case 23: e = IndexedConfig<10, 1344, 8, 512, 256, 14>::launch(q->d_ops, q->d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
       }
       if (e != cudaSuccess) return e;
       return InflateConfig<32, 10, 8, 1024, 4>::launch(q->d_ops, n, q->d_res, &pc->generic_next, ck, id, sms, q->stream,

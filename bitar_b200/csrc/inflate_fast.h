@@ -222,6 +222,7 @@ BITAR_HD uint32_t index_word(const IndexInfo& ix, uint32_t k) { return load_u32l
 struct CtaTables {
   uint32_t dinfo[32];
   uint32_t crc[4][256];
+  uint32_t x2n[32];       // x^(2^k) mod P, for combining the partial CRCs of sub-ranges (checksum.h)
 };
 
 // LT / DT: total u16 entries of the litlen / distance tables (root + second level)
@@ -300,8 +301,10 @@ struct FastLane {
 
   // SUB: decode `len` bytes to dst from the symbol at stream bit `start_bit`; the sub-range must end at
   // `end_bit`, after an end-of-block symbol when `eob` (it is the last sub-range of its block).
+  // `first`: the sub-range starts the chunk (its CRC register starts at ~0; all partial sums are combined by the
+  // kernel with cks::crc_contrib / adler_b_contrib).
   BITAR_HD void start_sub(const uint8_t* src, uint32_t stream_len, uint32_t start_bit, uint32_t end_bit, bool eob,
-                          uint8_t* dst, uint32_t len) {
+                          uint8_t* dst, uint32_t len, bool first = false) {
     in = src;
     in_len = stream_len;
     bits_init(start_bit >> 3);
@@ -315,7 +318,7 @@ struct FastLane {
     last = blocks = stored_rem = 0;
     sub_end_bit = end_bit;
     sub_eob = eob ? 1u : 0u;
-    crc = 0u;          // partial sums: combined by the kernel (checksum.h)
+    crc = first ? 0xFFFFFFFFu : 0u;   // partial sums: combined by the kernel (checksum.h)
     ad_a = 0;
     ad_b = 0;
   }

@@ -35,10 +35,16 @@ struct Counters {
   unsigned int n_tasks, n_generic, task_next, generic_next;
 };
 
+// per-op checksum accumulators (only touched when a checksum is configured): partial sums of the blocks /
+// sub-ranges are folded in with atomics, the task that finishes last publishes the checksum
+struct CkAcc {
+  uint32_t crc, a, b, remaining;
+};
+
 __global__ void __launch_bounds__(128)
     inflate_plan_kernel(const bitar_chunk* __restrict__ ops, uint32_t n_ops, bitar_result* __restrict__ results,
                         Task* __restrict__ tasks, uint32_t* __restrict__ generic, Counters* __restrict__ pc,
-                        int use_index) {
+                        CkAcc* __restrict__ acc, int use_index) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_ops) return;
   const bitar_chunk op = ops[i];
@@ -56,6 +62,7 @@ __global__ void __launch_bounds__(128)
     r.status = BITAR_OP_OK;
     results[i] = r;
     const uint32_t nb = dfl::idx_blocks(ix.total_out);
+    if (acc) acc[i] = CkAcc{0u, 0u, 0u, nb};
     const uint32_t base = atomicAdd(&pc->n_tasks, nb);
     for (uint32_t b = 0; b < nb; ++b) tasks[base + b] = Task{i, b};
     return;
@@ -172,18 +179,31 @@ __device__ __forceinline__ uint32_t warp_build_table(const uint8_t* lens, int n,
 template <int LBITS, int LT, int DBITS, int DT, int RING, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
     inflate_indexed_kernel(const bitar_chunk* __restrict__ ops, bitar_result* __restrict__ results,
-                           const Task* __restrict__ tasks, Counters* __restrict__ pc) {
+                           const Task* __restrict__ tasks, Counters* __restrict__ pc, CkAcc* __restrict__ acc,
+                           int checksum_type) {
   using Lane = fl::FastLane<LBITS, LT, DBITS, DT, RING, true>;
   using WS = WarpSmem<LT, DT, RING>;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   fl::CtaTables* cta = reinterpret_cast<fl::CtaTables*>(smem_raw + (size_t)WARPS * sizeof(WS));
   if (threadIdx.x < 32) cta->dinfo[threadIdx.x] = fl::dist_info((int)threadIdx.x);
+  if (checksum_type & BITAR_CHECKSUM_CRC32) {
+    for (unsigned i = threadIdx.x; i < 256; i += WARPS * 32) cta->crc[0][i] = cks::crc_table_entry(i);
+    if (threadIdx.x == 0) cks::crc_x2n_init(cta->x2n);
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < 256; i += WARPS * 32) {
+      uint32_t c = cta->crc[0][i];
+      for (int k = 1; k < 4; ++k) {
+        c = (c >> 8) ^ cta->crc[0][c & 0xFFu];
+        cta->crc[k][i] = c;
+      }
+    }
+  }
   __syncthreads();
 
   const int lane = (int)(threadIdx.x & 31u);
   WS& ws = *reinterpret_cast<WS*>(smem_raw + (size_t)(threadIdx.x >> 5) * sizeof(WS));
   Lane L;
-  L.bind_parts(ws.lt, ws.dt, ws.ring + lane * WS::kRingStride, cta, &ws.sc, 0u);
+  L.bind_parts(ws.lt, ws.dt, ws.ring + lane * WS::kRingStride, cta, &ws.sc, (uint32_t)checksum_type);
   const uint32_t n_tasks = pc->n_tasks;
   constexpr unsigned kFull = 0xFFFFFFFFu;
 
@@ -203,6 +223,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
     const uint32_t block_end = b + 1u < nb ? fl::index_word(ix, (b + 1u) * 33u) : ix.end_bit;
     uint8_t* out = static_cast<uint8_t*>(op.dst) + ((size_t)b << 16);
     uint32_t status = fl::kStatusOk;
+    // this lane's share of the block's checksum: (crc register, sum of bytes, weighted sum) of `ck_len` bytes
+    // that are followed by `ck_tail` more bytes of the chunk
+    uint32_t ck_crc = 0, ck_s1 = 0, ck_s2 = 0, ck_len = 0, ck_tail = 0;
 
     // ---- block header: every lane reads the same bits ----
     L.in = src;
@@ -225,6 +248,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
         at += 4u;
         if ((len ^ 0xFFFFu) != nlen || done + len > blen || (uint64_t)at + len > ix.stream_bytes) { status = fl::kStatusDataError; break; }
         for (uint32_t i = (uint32_t)lane; i < len; i += 32u) out[done + i] = src[at + i];
+        if (checksum_type != BITAR_CHECKSUM_NONE && ck_len == 0) {   // stored pieces: lane j sums the j-th slice of the block
+          const uint32_t per = (blen + 31u) / 32u, lo = min(blen, per * (uint32_t)lane), hi = min(blen, lo + per);
+          // (the payload of a two-piece block is contiguous in the output, which the warp reads back below)
+          ck_len = hi - lo;
+          ck_tail = lo;   // temporarily: the slice's offset inside the block
+        }
         done += len;
         at += len;
         if (done == blen) {
@@ -303,14 +332,67 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
           const uint32_t ebit = s + 1u < ns ? fl::index_word(ix, b * 33u + 2u + s) : block_end;
           const uint32_t len = min(dfl::kSub, blen - s * dfl::kSub);
           if (sbit < hdr || sbit > ebit || ebit > block_end) L.status = fl::kStatusDataError;
-          else L.start_sub(src, ix.stream_bytes, sbit, ebit, s + 1u == ns, out + (size_t)s * dfl::kSub, len);
+          else {
+            L.start_sub(src, ix.stream_bytes, sbit, ebit, s + 1u == ns, out + (size_t)s * dfl::kSub, len, b == 0u && s == 0u);
+            ck_len = len;
+            ck_tail = ix.total_out - ((b << 16) + s * dfl::kSub + len);
+          }
         }
         while (L.state != Lane::kDone) L.step();
         status = L.status;
+        if (ck_len) {
+          ck_crc = L.crc;
+          ck_s1 = L.ad_a % cks::kAdlerMod;
+          ck_s2 = (uint32_t)(L.ad_b % cks::kAdlerMod);
+        }
       }
     }
     __syncwarp();
     if (status != fl::kStatusOk) atomicMax(&results[tk.op].status, status);
+    if (checksum_type != BITAR_CHECKSUM_NONE) {
+      if (type == 0u && ck_len) {   // stored block: sum this lane's slice of what the warp just wrote
+        const uint32_t lo = ck_tail;
+        const uint8_t* p = out + lo;
+        uint32_t state = (b == 0u && lo == 0u) ? 0xFFFFFFFFu : 0u, s1 = 0;
+        uint64_t s2 = 0;
+        for (uint32_t i = 0; i < ck_len; ++i) {
+          const uint32_t byte = *reinterpret_cast<const volatile uint8_t*>(p + i);
+          if (checksum_type & BITAR_CHECKSUM_CRC32) state = cta->crc[0][(state ^ byte) & 0xFFu] ^ (state >> 8);
+          s1 += byte;
+          s2 += (uint64_t)(ck_len - i) * byte;
+        }
+        ck_crc = state;
+        ck_s1 = s1 % cks::kAdlerMod;
+        ck_s2 = (uint32_t)(s2 % cks::kAdlerMod);
+        ck_tail = ix.total_out - ((b << 16) + lo + ck_len);
+      }
+      uint32_t c = 0, a = 0, bb = 0;
+      if (ck_len) {
+        if (checksum_type & BITAR_CHECKSUM_CRC32) c = cks::crc_contrib(ck_crc, ck_tail, cta->x2n);
+        a = ck_s1;
+        bb = cks::adler_b_contrib(ck_s1, ck_s2, ck_tail % cks::kAdlerMod);
+      }
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) {
+        c ^= __shfl_xor_sync(kFull, c, o2);
+        a += __shfl_xor_sync(kFull, a, o2);
+        bb += __shfl_xor_sync(kFull, bb, o2);
+      }
+      if (lane == 0) {
+        CkAcc* k = acc + tk.op;
+        atomicXor(&k->crc, c);
+        atomicAdd(&k->a, a % cks::kAdlerMod);
+        atomicAdd(&k->b, bb % cks::kAdlerMod);
+        __threadfence();
+        if (atomicSub(&k->remaining, 1u) == 1u) {   // the chunk's last block: publish
+          __threadfence();
+          const uint32_t crc = (checksum_type & BITAR_CHECKSUM_CRC32) ? (atomicXor(&k->crc, 0u) ^ 0xFFFFFFFFu) : 0u;
+          const uint32_t adler = (checksum_type & BITAR_CHECKSUM_ADLER32)
+                                     ? cks::adler_finish(atomicAdd(&k->a, 0u), atomicAdd(&k->b, 0u), ix.total_out) : 0u;
+          results[tk.op].checksum = cks::pack(crc, adler);
+        }
+      }
+    }
   }
 }
 
@@ -329,15 +411,15 @@ struct IndexedConfig {
     return c;
   }
   // n_blocks_max: upper bound of the task count (the real count lives on the device)
-  static cudaError_t launch(const bitar_chunk* ops, bitar_result* res, const Task* tasks, Counters* pc, uint32_t n_blocks_max,
-                            int device, int sm_count, cudaStream_t stream) {
+  static cudaError_t launch(const bitar_chunk* ops, bitar_result* res, const Task* tasks, Counters* pc, CkAcc* acc,
+                            int checksum_type, uint32_t n_blocks_max, int device, int sm_count, cudaStream_t stream) {
     const int c = ctas_per_sm(device);
     if (c < 1) return cudaErrorLaunchOutOfResources;
     uint32_t grid = (uint32_t)(sm_count * c);
     const uint32_t want = (n_blocks_max + WARPS - 1) / WARPS;
     if (want < grid) grid = want;
     if (grid == 0) return cudaSuccess;
-    inflate_indexed_kernel<LBITS, LT, DBITS, DT, RING, WARPS><<<grid, kThreads, kSmem, stream>>>(ops, res, tasks, pc);
+    inflate_indexed_kernel<LBITS, LT, DBITS, DT, RING, WARPS><<<grid, kThreads, kSmem, stream>>>(ops, res, tasks, pc, acc, checksum_type);
     return cudaGetLastError();
   }
 };

@@ -185,15 +185,26 @@ def test_inflate_error_statuses(cuda_device):
         dev.close()
 
 
-def test_inflate_checksums(cuda_device):
-    dev = G.open_device(SEG, checksum_type=capi.CHECKSUM_CRC32_ADLER32)
+@pytest.mark.parametrize("ck", [capi.CHECKSUM_CRC32_ADLER32, capi.CHECKSUM_CRC32, capi.CHECKSUM_ADLER32])
+def test_inflate_checksums(cuda_device, ck):
+    """Checksums of the inflated bytes == zlib's, for zlib streams (whole-stream kernel) and for the deflate
+    kernel's own streams (sub-range kernel: per-lane partial sums combined per block and per chunk), including
+    multi-block chunks and a chunk that mixes a stored and a coded block."""
+    dev = G.open_device(3 * 65536 + 5000, checksum_type=ck)
     try:
         chunks = [c for _, c in corpus()][:40]
-        comps = [zraw(c, 1) for c in chunks]
-        outs, res, err = G.gpu_inflate_chunks(dev, comps, [max(c.size, 1) for c in chunks])
+        chunks += [synth.lineitem_like(3 * 65536 + 5000), synth.lineitem_like(65536 + 1),
+                   np.concatenate([np.frombuffer(np.random.default_rng(9).bytes(65536), np.uint8), synth.lineitem_like(30000)])]
+        gpu_comps, _, err = G.gpu_deflate_chunks(dev, chunks)
         assert err is None
-        for c, r in zip(chunks, res):
-            assert int(r["checksum"]) & 0xFFFFFFFF == O.crc32(c)
-            assert int(r["checksum"]) >> 32 == O.adler32(c)
+        for comps in ([zraw(c, 1) for c in chunks], gpu_comps):
+            outs, res, err = G.gpu_inflate_chunks(dev, comps, [max(c.size, 1) for c in chunks])
+            assert err is None
+            for c, o, r in zip(chunks, outs, res):
+                assert np.array_equal(o, c)
+                want_crc = O.crc32(c) if ck & capi.CHECKSUM_CRC32 else 0
+                want_adler = O.adler32(c) if ck & capi.CHECKSUM_ADLER32 else 0
+                assert int(r["checksum"]) & 0xFFFFFFFF == want_crc, c.size
+                assert int(r["checksum"]) >> 32 == want_adler, c.size
     finally:
         dev.close()
