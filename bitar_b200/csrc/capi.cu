@@ -336,7 +336,7 @@ int inflate_variant() {
   int v = g_inflate_variant.load();
   if (v < 0) {
     const char* s = getenv("BITAR_INFLATE_VARIANT");
-    v = s ? atoi(s) : 20;
+    v = s ? atoi(s) : 22;
     g_inflate_variant.store(v);
   }
   return v;
@@ -569,12 +569,14 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) return e;
       g_launches.fetch_add(2);
-      switch (variant) {
-        default:
+      switch (variant) {   // default = 22: 24 warps / SM, 9-bit litlen root (measured best on the columnar mix)
         case 20: e = IndexedConfig<10, 1344, 8, 512, 128, 20>::launch(q->d_ops, q->d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
         case 21: e = IndexedConfig<10, 1344, 8, 512, 128, 16>::launch(q->d_ops, q->d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
+        default:
         case 22: e = IndexedConfig<9, 864, 7, 256, 128, 24>::launch(q->d_ops, q->d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
         case 23: e = IndexedConfig<10, 1344, 8, 512, 256, 14>::launch(q->d_ops, q->d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
+        case 24: e = IndexedConfig<10, 1344, 7, 256, 128, 24>::launch(q->d_ops, q->d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
+        case 25: e = IndexedConfig<10, 1344, 8, 512, 128, 22>::launch(q->d_ops, q->d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
       }
       if (e != cudaSuccess) return e;
       return InflateConfig<32, 10, 8, 1024, 4>::launch(q->d_ops, n, q->d_res, &pc->generic_next, ck, id, sms, q->stream,

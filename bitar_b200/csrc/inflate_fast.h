@@ -242,7 +242,8 @@ struct LaneLayout {
 //               (deflate_common.h): the decode tables belong to the warp (built once per block by
 //               inflate_indexed_kernel.cuh), the lane starts at a given bit offset, must produce exactly
 //               the sub-range and must end exactly where the index says the next sub-range starts.
-template <int LBITS, int LT, int DBITS, int DT, int RING, bool SUB = false>
+// CK = false compiles the checksum folding out (the kernels pick it when no checksum is configured).
+template <int LBITS, int LT, int DBITS, int DT, int RING, bool SUB = false, bool CK = true>
 struct FastLane {
   static_assert(DBITS >= 7, "the distance table also hosts the 7-bit code-length code");
   static_assert(RING >= 128 && (RING & (RING - 1)) == 0, "ring: power of two >= 128");
@@ -434,7 +435,7 @@ struct FastLane {
         for (uint32_t v = vflushed; v < a; ++v) {
           const uint32_t b = s_ld8(ring_s + (v & RM));
           vbase[v] = (uint8_t)b;
-          if (ck_type) ck_byte(b);
+          if (CK && ck_type) ck_byte(b);
         }
         vflushed = a;
         continue;
@@ -447,7 +448,7 @@ struct FastLane {
       uint32_t* o32 = reinterpret_cast<uint32_t*>(vbase + vflushed);
       o32[0] = w0; o32[1] = w1; o32[2] = w2; o32[3] = w3;
 #endif
-      if (ck_type) {
+      if (CK && ck_type) {
         ck_word(w0); ck_word(w1); ck_word(w2); ck_word(w3);
       }
       vflushed += 16u;
@@ -459,7 +460,7 @@ struct FastLane {
     for (uint32_t v = vflushed; v < vpos; ++v) {
       const uint32_t b = s_ld8(ring_s + (v & RM));
       vbase[v] = (uint8_t)b;
-      if (ck_type) ck_byte(b);
+      if (CK && ck_type) ck_byte(b);
     }
     vflushed = vpos;
     state = kDone;

@@ -176,13 +176,14 @@ __device__ __forceinline__ uint32_t warp_build_table(const uint8_t* lens, int n,
   return fl::kStatusOk;
 }
 
-template <int LBITS, int LT, int DBITS, int DT, int RING, int WARPS>
+template <int LBITS, int LT, int DBITS, int DT, int RING, int WARPS, bool CK>
 __global__ void __launch_bounds__(WARPS * 32, 1)
     inflate_indexed_kernel(const bitar_chunk* __restrict__ ops, bitar_result* __restrict__ results,
                            const Task* __restrict__ tasks, Counters* __restrict__ pc, CkAcc* __restrict__ acc,
                            int checksum_type) {
-  using Lane = fl::FastLane<LBITS, LT, DBITS, DT, RING, true>;
+  using Lane = fl::FastLane<LBITS, LT, DBITS, DT, RING, true, CK>;
   using WS = WarpSmem<LT, DT, RING>;
+  if (!CK) checksum_type = BITAR_CHECKSUM_NONE;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   fl::CtaTables* cta = reinterpret_cast<fl::CtaTables*>(smem_raw + (size_t)WARPS * sizeof(WS));
   if (threadIdx.x < 32) cta->dinfo[threadIdx.x] = fl::dist_info((int)threadIdx.x);
@@ -404,9 +405,11 @@ struct IndexedConfig {
     static int per_device[64] = {0};
     int& c = per_device[device & 63];
     if (c == 0) {
-      auto kern = inflate_indexed_kernel<LBITS, LT, DBITS, DT, RING, WARPS>;
+      auto kern = inflate_indexed_kernel<LBITS, LT, DBITS, DT, RING, WARPS, false>;
+      auto kern_ck = inflate_indexed_kernel<LBITS, LT, DBITS, DT, RING, WARPS, true>;
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem) != cudaSuccess) return 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, kern, kThreads, kSmem) != cudaSuccess) return 0;
+      if (cudaFuncSetAttribute(kern_ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem) != cudaSuccess) return 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, kern_ck, kThreads, kSmem) != cudaSuccess) return 0;
     }
     return c;
   }
@@ -419,7 +422,10 @@ struct IndexedConfig {
     const uint32_t want = (n_blocks_max + WARPS - 1) / WARPS;
     if (want < grid) grid = want;
     if (grid == 0) return cudaSuccess;
-    inflate_indexed_kernel<LBITS, LT, DBITS, DT, RING, WARPS><<<grid, kThreads, kSmem, stream>>>(ops, res, tasks, pc, acc, checksum_type);
+    if (checksum_type == BITAR_CHECKSUM_NONE)
+      inflate_indexed_kernel<LBITS, LT, DBITS, DT, RING, WARPS, false><<<grid, kThreads, kSmem, stream>>>(ops, res, tasks, pc, acc, 0);
+    else
+      inflate_indexed_kernel<LBITS, LT, DBITS, DT, RING, WARPS, true><<<grid, kThreads, kSmem, stream>>>(ops, res, tasks, pc, acc, checksum_type);
     return cudaGetLastError();
   }
 };

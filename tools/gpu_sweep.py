@@ -54,7 +54,7 @@ def main():
                 best = min(best, k)
             ok = bool((out[:data.size] == src).all().item()) and int(ires["produced"].sum()) == data.size
             print(f"[{wname}] inflate variant={v} kernel={best:.3f} ms  {data.size / best / 1e6:.1f} GB/s ok={ok}", flush=True)
-        capi.lib().bitar_tune_inflate_variant(20)
+        capi.lib().bitar_tune_inflate_variant(22)
         dev.close()
         del src, out
 
