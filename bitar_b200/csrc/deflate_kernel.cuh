@@ -75,6 +75,8 @@ struct __align__(16) Smem {
     EncodeArea enc;
   } u;
   uint32_t keep[4];                  // the partially filled 16-byte unit of the stage while the tables use its space
+  uint8_t len_sym_lut[256];          // match length - 3 -> length symbol index (dfl::len_sym)
+  uint8_t dist_sym_lut[512];         // zlib's two-level map: d < 256 ? lut[d] : lut[256 + (d >> 7)], d = dist - 1
   uint32_t ll_freq[288];
   uint32_t d_freq[32];
   uint32_t ll_enc[288];              // code | (length << 16) under the chosen block type
@@ -143,14 +145,22 @@ __device__ __forceinline__ uint32_t ld32u(uint32_t saddr) {
   return __funnelshift_r(lds_u32(a), lds_u32(a + 4), (saddr & 3u) * 8u);
 }
 
+// Length of the common prefix of the bytes at p and c (both in the block held in shared memory), at most maxl.
+// Both streams are read as aligned words, one new word per stream and step; the previous word is carried.
 __device__ __forceinline__ int match_len(uint32_t ds, int p, int c, int maxl) {
+  const uint32_t ap = (ds + (uint32_t)p) & ~3u, ac = (ds + (uint32_t)c) & ~3u;
+  const uint32_t sp = ((ds + (uint32_t)p) & 3u) * 8u, sc = ((ds + (uint32_t)c) & 3u) * 8u;
+  uint32_t wp = lds_u32(ap), wc = lds_u32(ac);
   int l = 0;
   while (l < maxl) {
-    uint32_t x = ld32u(ds + p + l) ^ ld32u(ds + c + l);
+    const uint32_t np = lds_u32(ap + (uint32_t)l + 4u), nc = lds_u32(ac + (uint32_t)l + 4u);
+    const uint32_t x = __funnelshift_r(wp, np, sp) ^ __funnelshift_r(wc, nc, sc);
     if (x) {
       l += (__ffs((int)x) - 1) >> 3;
       break;
     }
+    wp = np;
+    wc = nc;
     l += 4;
   }
   return min(l, maxl);
@@ -297,32 +307,39 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
         dist = p - (int)cand;
       }
     }
-    // transfer function of the window: e_r = lane + (2^r hops), frozen once it leaves the window
-    int e0 = lane + adv, e1, e2, e3, e4, e5;
-    {
-      int t;
-      t = __shfl_sync(kFull, e0, e0 & 31); e1 = e0 < 32 ? t : e0;
-      t = __shfl_sync(kFull, e1, e1 & 31); e2 = e1 < 32 ? t : e1;
-      t = __shfl_sync(kFull, e2, e2 & 31); e3 = e2 < 32 ? t : e2;
-      t = __shfl_sync(kFull, e3, e3 & 31); e4 = e3 < 32 ? t : e3;
-      t = __shfl_sync(kFull, e4, e4 & 31); e5 = e4 < 32 ? t : e4;
+    unsigned reach;
+    if (!__any_sync(kFull, adv > 1)) {                // literals only: every position from a on starts a token
+      reach = 0xFFFFFFFFu << a;
+      carry = base + 32;
+    } else {
+      // transfer function of the window: e_r = lane + (2^r hops), frozen once it leaves the window
+      int e0 = lane + adv, e1, e2, e3, e4, e5;
+      {
+        int t;
+        t = __shfl_sync(kFull, e0, e0 & 31); e1 = e0 < 32 ? t : e0;
+        t = __shfl_sync(kFull, e1, e1 & 31); e2 = e1 < 32 ? t : e1;
+        t = __shfl_sync(kFull, e2, e2 & 31); e3 = e2 < 32 ? t : e2;
+        t = __shfl_sync(kFull, e3, e3 & 31); e4 = e3 < 32 ? t : e3;
+        t = __shfl_sync(kFull, e4, e4 & 31); e5 = e4 < 32 ? t : e4;
+      }
+      reach = 1u << a;
+      unsigned contrib;
+      contrib = ((reach >> lane) & 1u) && e0 < 32 ? (1u << e0) : 0u; reach |= __reduce_or_sync(kFull, contrib);
+      contrib = ((reach >> lane) & 1u) && e1 < 32 ? (1u << e1) : 0u; reach |= __reduce_or_sync(kFull, contrib);
+      contrib = ((reach >> lane) & 1u) && e2 < 32 ? (1u << e2) : 0u; reach |= __reduce_or_sync(kFull, contrib);
+      contrib = ((reach >> lane) & 1u) && e3 < 32 ? (1u << e3) : 0u; reach |= __reduce_or_sync(kFull, contrib);
+      contrib = ((reach >> lane) & 1u) && e4 < 32 ? (1u << e4) : 0u; reach |= __reduce_or_sync(kFull, contrib);
+      carry = base + __shfl_sync(kFull, e5, a);       // where the chain entering at lane a leaves the window
     }
-    unsigned reach = 1u << a;
-    unsigned contrib;
-    contrib = ((reach >> lane) & 1u) && e0 < 32 ? (1u << e0) : 0u; reach |= __reduce_or_sync(kFull, contrib);
-    contrib = ((reach >> lane) & 1u) && e1 < 32 ? (1u << e1) : 0u; reach |= __reduce_or_sync(kFull, contrib);
-    contrib = ((reach >> lane) & 1u) && e2 < 32 ? (1u << e2) : 0u; reach |= __reduce_or_sync(kFull, contrib);
-    contrib = ((reach >> lane) & 1u) && e3 < 32 ? (1u << e3) : 0u; reach |= __reduce_or_sync(kFull, contrib);
-    contrib = ((reach >> lane) & 1u) && e4 < 32 ? (1u << e4) : 0u; reach |= __reduce_or_sync(kFull, contrib);
-    carry = base + __shfl_sync(kFull, e5, a);         // where the chain entering at lane a leaves the window
     const bool start = ((reach >> lane) & 1u) && p < n;
     const unsigned starts = __ballot_sync(kFull, start);
     if (start) {
       uint32_t tok;
       if (adv > 1) {
         tok = dfl::tok_match(adv, dist);
-        atomicAdd(&sm.ll_freq[257 + dfl::len_sym(adv)], 1u);
-        atomicAdd(&sm.d_freq[dfl::dist_sym(dist)], 1u);
+        const uint32_t d1 = (uint32_t)dist - 1u;
+        atomicAdd(&sm.ll_freq[257u + sm.len_sym_lut[adv - 3]], 1u);
+        atomicAdd(&sm.d_freq[sm.dist_sym_lut[d1 < 256u ? d1 : 256u + (d1 >> 7)]], 1u);
       } else {
         tok = lds_u8(ds + p);
         atomicAdd(&sm.ll_freq[tok], 1u);
@@ -584,6 +601,8 @@ __global__ void __launch_bounds__(kThreads, 2)
     if (tid == 0) cks::crc_x2n_init(sm.x2n);
   }
   for (int i = tid; i < kStageWords; i += kThreads) sm.u.enc.stage[i] = 0;
+  for (int i = tid; i < 256; i += kThreads) sm.len_sym_lut[i] = (uint8_t)dfl::len_sym(i + 3);
+  for (int i = tid; i < 512; i += kThreads) sm.dist_sym_lut[i] = (uint8_t)dfl::dist_sym(i < 256 ? i + 1 : ((i - 256) << 7) + 1);
   __syncthreads();
   uint32_t tma_parity = 0;
   // optional phase timers (cycles, thread 0): 0 load, 1 match, 2 sort, 3 plan, 4 tables+header, 5 encode, 6 finish
