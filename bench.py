@@ -27,8 +27,8 @@ sys.path.insert(0, ROOT)
 METRIC = "deflate+inflate round-trip throughput, uncompressed bytes (bitar Compress->Decompress)"
 SEG_DEFAULT = 59460          # apps/app_common.h:39 kDecompressedSegSize
 # DRAM bytes moved per uncompressed byte, from ncu (dram__bytes_read.sum + dram__bytes_write.sum, 256 MiB launch)
-DEFLATE_DRAM_BYTES_PER_BYTE = (379.004672e6 + 782.062592e6) / 268435456
-INFLATE_DRAM_BYTES_PER_BYTE = (142.796032e6 + 240.311040e6) / 268435456
+DEFLATE_DRAM_BYTES_PER_BYTE = (273.783552e6 + 101.975040e6) / 268435456
+INFLATE_DRAM_BYTES_PER_BYTE = (154.528256e6 + 255.910400e6) / 268435456
 
 
 def peaks():
@@ -253,13 +253,13 @@ def main():
             "deflate_gbps": world * U / (td_ms * 1e-3) / 1e9, "inflate_gbps": world * U / (ti_ms * 1e-3) / 1e9,
             "deflate_kernel_ms": kd_ms, "inflate_kernel_ms": ki_ms, "wall_ms_per_step": wall_ms,
             "ratio": U / Cbytes, "zlib_level1_ratio": zratio,
-            # dominant kernel = deflate_kernel (79 % of the step's GPU time, profiles/r01_launches_bench_1GiB_c.csv).
+            # dominant kernel = deflate_kernel (78 % of the device-resident step's GPU time, profiles/r01_launches_bench_1GiB_f.csv).
             # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture at 256 MiB
-            # (profiles/r01_ncu_full_deflate_and_indexed_inflate_256MiB.txt), scaled linearly to this launch's bytes.
+            # (profiles/r01_ncu_full_deflate_and_indexed_inflate_256MiB_f.txt), scaled linearly to this launch's bytes.
             "roofline": {"bound": "hbm", "kernel": "deflate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": DEFLATE_DRAM_BYTES_PER_BYTE * U, "peak_source": which,
                          "algorithmic_bytes": "U + C per launch (read input once, write the stream once)",
-                         "note": "issue- and latency-bound integer kernel: 55 % issue-slot utilisation, 2.9 % DRAM throughput (ncu)",
+                         "note": "issue- and latency-bound integer kernel: 61 % issue-slot utilisation, 1.4 % DRAM throughput (ncu)",
                          "inflate": {"kernel": "inflate_indexed_kernel", "achieved": (U + Cbytes) / (ki_ms * 1e-3) / 1e9,
                                      "frac": (U + Cbytes) / (ki_ms * 1e-3) / 1e9 / peak,
                                      "traffic": INFLATE_DRAM_BYTES_PER_BYTE * U}},
@@ -326,13 +326,29 @@ def run_e2e(args, L, capi, C, torch, dist, world, local_rank, data, seg, n, U):
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     dt = float(dt.cpu()[0])
+    # PCIe roofline of this leg, measured in the same run: plain pinned <-> device copies of U bytes
+    d_tmp = torch.empty(U, dtype=torch.uint8, device="cuda")
+    pcie = {}
+    for name, dst, src in (("h2d_gbps", d_tmp.data_ptr(), h_in.value), ("d2h_gbps", h_out.value, d_tmp.data_ptr())):
+        best = 1e9
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            capi.check(L.bitar_qp_memcpy(dev._h, 0, dst, src, U))
+            dev.wait(0)
+            best = min(best, time.perf_counter() - t1)
+        pcie[name] = U / best / 1e9
+    del d_tmp
+    # each step moves U + C bytes in each direction; with both directions overlapped the floor is max(dir) / bw
+    floor = max((U + h2d) / (pcie["h2d_gbps"] * 1e9), (cbytes + U) / (pcie["d2h_gbps"] * 1e9))
+    pcie["frac_of_pcie_floor"] = floor / dt
     for b in (h_in, h_out):
         capi.check(L.bitar_mem_free(capi.MEM_PINNED, local_rank, b))
     for s in slots[::-1]:
         dev.put_slot(s)
     dev.close()
     return {"value": world * U / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(U + h2d),
-            "d2h_bytes_per_step": int(cbytes + U), "ms_per_step": dt * 1e3, "queue_pairs": len(parts),
+            "d2h_bytes_per_step": int(cbytes + U), "ms_per_step": dt * 1e3, "queue_pairs": len(parts), "pcie": pcie,
             "path": "pinned host in/out through the C-ABI: compress reads and writes host memory in place (zero-copy over "
                     "PCIe), decompress is staged through device memory by the library (gather kernel, inflate, scatter kernel)"}
 
