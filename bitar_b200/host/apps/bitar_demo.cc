@@ -6,15 +6,21 @@
 // synthetic columnar mix (--bytes).  Buffers live in the pinned-host pool (the Rtememzone analogue:
 // zero-copy for the device) or, with --device, in the device pool.
 #include <arrow/buffer.h>
+#include <arrow/io/file.h>
+#include <arrow/io/memory.h>
+#include <arrow/ipc/feather.h>
+#include <arrow/ipc/reader.h>
+#include <arrow/ipc/writer.h>
 #include <arrow/memory_pool.h>
 #include <arrow/result.h>
 #include <arrow/status.h>
+#include <arrow/table.h>
+#include <parquet/arrow/reader.h>
 
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <fstream>
 #include <string>
 #include <vector>
 
@@ -55,6 +61,51 @@ void FillSynthetic(std::uint8_t* p, std::size_t n) {
   for (std::size_t i = 2 * third; i + 8 <= n; i += 8) { double v = (double)(90000 + rnd() % 10410000) / 100.0; std::memcpy(p + i, &v, 8); }
 }
 
+// "content mode" of the reference (apps/demo_app.cc:144-247, 297-330): a Parquet / Feather file is read into an
+// arrow::Table and serialised to Arrow IPC stream bytes -- straight into the pinned-host pool, so the
+// compressor reads them in place; anything else is taken as raw bytes.
+bool EndsWith(const std::string& s, const std::string& suffix) {
+  return s.size() >= suffix.size() && s.compare(s.size() - suffix.size(), suffix.size(), suffix) == 0;
+}
+
+arrow::Result<std::shared_ptr<arrow::Buffer>> SerializeTable(const std::shared_ptr<arrow::Table>& table, arrow::MemoryPool* pool) {
+  const auto options = arrow::ipc::IpcWriteOptions::Defaults();
+  ARROW_ASSIGN_OR_RAISE(auto sink, arrow::io::BufferOutputStream::Create(1 << 20, pool));
+  ARROW_ASSIGN_OR_RAISE(auto writer, arrow::ipc::MakeStreamWriter(sink, table->schema(), options));
+  ARROW_RETURN_NOT_OK(writer->WriteTable(*table));
+  ARROW_RETURN_NOT_OK(writer->Close());
+  return sink->Finish();
+}
+
+arrow::Result<std::shared_ptr<arrow::Buffer>> ReadFile(const std::string& path, arrow::MemoryPool* pool, bool* is_table) {
+  ARROW_ASSIGN_OR_RAISE(auto file, arrow::io::MemoryMappedFile::Open(path, arrow::io::FileMode::READ));
+  std::shared_ptr<arrow::Table> table;
+  *is_table = true;
+  if (EndsWith(path, ".parquet")) {
+    ARROW_ASSIGN_OR_RAISE(auto reader, parquet::arrow::OpenFile(file, arrow::default_memory_pool()));
+    ARROW_RETURN_NOT_OK(reader->ReadTable(&table));
+  } else if (EndsWith(path, ".feather") || EndsWith(path, ".arrow")) {
+    ARROW_ASSIGN_OR_RAISE(auto reader, arrow::ipc::feather::Reader::Open(file, arrow::ipc::IpcReadOptions::Defaults()));
+    ARROW_RETURN_NOT_OK(reader->Read(&table));
+  } else {
+    *is_table = false;
+    ARROW_ASSIGN_OR_RAISE(auto size, file->GetSize());
+    ARROW_ASSIGN_OR_RAISE(auto buffer, arrow::AllocateBuffer(size, pool));
+    ARROW_ASSIGN_OR_RAISE(auto got, file->ReadAt(0, size, buffer->mutable_data()));
+    if (got != size) return arrow::Status::IOError("Unable to read ", size, " bytes from file");
+    return std::shared_ptr<arrow::Buffer>(std::move(buffer));
+  }
+  std::printf("table: %lld rows x %d columns\n", (long long)table->num_rows(), table->num_columns());
+  return SerializeTable(table, pool);
+}
+
+// DeserializeTable of the reference (apps/demo_app.cc:225-243): the round-tripped bytes must still be an IPC stream
+arrow::Result<std::shared_ptr<arrow::Table>> DeserializeTable(const std::shared_ptr<arrow::Buffer>& buffer) {
+  arrow::io::BufferReader reader(buffer);
+  ARROW_ASSIGN_OR_RAISE(auto batches, arrow::ipc::RecordBatchStreamReader::Open(&reader));
+  return batches->ToTable();
+}
+
 bool SameBytes(const std::uint8_t* a, const std::uint8_t* b, std::size_t n, bool on_device) {
   if (!on_device) return std::memcmp(a, b, n) == 0;
   std::vector<std::uint8_t> ha(n), hb(n);
@@ -69,11 +120,11 @@ int main(int argc, char** argv) {
   std::size_t bytes = 64u << 20;
   std::uint32_t seg = 59460, qps_per_device = 2;
   std::string file, mode = "both";
-  bool on_device = false;
+  bool on_device = false, bytes_given = false;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     auto next = [&]() { return i + 1 < argc ? std::string(argv[++i]) : std::string(); };
-    if (a == "--bytes") bytes = std::stoull(next());
+    if (a == "--bytes") { bytes = std::stoull(next()); bytes_given = true; }
     else if (a == "--seg") seg = (std::uint32_t)std::stoul(next());
     else if (a == "--qps") qps_per_device = (std::uint32_t)std::stoul(next());
     else if (a == "--file") file = next();
@@ -95,19 +146,29 @@ int main(int argc, char** argv) {
     if (on_device) return bitar::AllocateDeviceBuffer(size, device);
     return arrow::AllocateResizableBuffer(size, pool);
   };
-  std::vector<std::uint8_t> host;
+  std::shared_ptr<arrow::Buffer> input;
+  bool is_table = false;
   if (!file.empty()) {
-    std::ifstream f(file, std::ios::binary);
-    host.assign(std::istreambuf_iterator<char>(f), std::istreambuf_iterator<char>());
-    bytes = host.size();
+    auto host_r = ReadFile(file, pool, &is_table);   // pinned host memory, device-accessible in place
+    CHECK_OK(host_r.status());
+    if (bytes_given && (std::int64_t)bytes < (*host_r)->size()) *host_r = arrow::SliceBuffer(*host_r, 0, (std::int64_t)bytes);
+    bytes = (std::size_t)(*host_r)->size();
+    if (on_device) {
+      auto in_r = allocate((std::int64_t)bytes, ids[0]);
+      CHECK_OK(in_r.status());
+      input = std::move(*in_r);
+      bitar_mem_copy(const_cast<std::uint8_t*>(input->data()), (*host_r)->data(), bytes);
+    } else {
+      input = *host_r;
+    }
   } else {
-    host.resize(bytes);
+    std::vector<std::uint8_t> host(bytes);
     FillSynthetic(host.data(), bytes);
+    auto in_r = allocate((std::int64_t)bytes, ids[0]);
+    CHECK_OK(in_r.status());
+    input = std::move(*in_r);
+    bitar_mem_copy(const_cast<std::uint8_t*>(input->data()), host.data(), bytes);
   }
-  auto in_r = allocate((std::int64_t)bytes, ids[0]);
-  CHECK_OK(in_r.status());
-  std::shared_ptr<arrow::Buffer> input = std::move(*in_r);
-  bitar_mem_copy(const_cast<std::uint8_t*>(input->data()), host.data(), bytes);
 
   const std::size_t n_chunks = (bytes + seg - 1) / seg;
   std::size_t total_qps = 0;
@@ -145,6 +206,12 @@ int main(int argc, char** argv) {
       const bool ok = (std::size_t)output->size() == bytes && SameBytes(output->data(), input->data(), bytes, on_device);
       std::printf("  ratio %.3f  round trip %s\n", (double)bytes / (double)csize, ok ? "OK" : "MISMATCH");
       failures += !ok;
+      if (ok && is_table && !on_device && !bytes_given && t == 0) {   // the inflated bytes are an Arrow IPC stream again
+        auto table_r = DeserializeTable(std::shared_ptr<arrow::Buffer>(std::move(output)));
+        std::printf("  deserialised table: %s\n", table_r.ok() ? "OK" : table_r.status().ToString().c_str());
+        failures += !table_r.ok();
+        if (table_r.ok()) std::printf("  %lld rows x %d columns\n", (long long)(*table_r)->num_rows(), (*table_r)->num_columns());
+      }
       if (dev->Recycle(compressed) != compressed.size()) { std::printf("  recycle count mismatch\n"); ++failures; }
     }
   }

@@ -39,3 +39,36 @@ def test_demo_app_flow(args):
     r = subprocess.run([DEMO] + args, capture_output=True, text=True, timeout=600)
     print(r.stdout[-3000:], r.stderr[-2000:])
     assert r.returncode == 0 and "PASSED" in r.stdout and "MISMATCH" not in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["parquet", "feather", "raw"])
+def test_demo_app_content_mode(tmp_path, fmt):
+    """The reference's content mode (apps/demo_app.cc:144-247): a Parquet / Feather file becomes Arrow IPC stream
+    bytes in the pinned-host pool, is compressed and decompressed on the GPU, and must still deserialise."""
+    import numpy as np
+    import pyarrow as pa
+    import pyarrow.feather as feather
+    import pyarrow.parquet as pq
+    _build()
+    rng = np.random.default_rng(7)
+    n = 400_000
+    table = pa.table({
+        "l_orderkey": np.cumsum(rng.integers(0, 4, n)).astype(np.int64),
+        "l_returnflag": pa.array(rng.choice(["A", "N", "R"], n)).dictionary_encode(),
+        "l_extendedprice": rng.integers(90000, 10500000, n) / 100.0,
+        "l_comment": pa.array([f"row {i % 977} of the synthetic lineitem table" for i in range(n)]),
+    })
+    path = str(tmp_path / f"lineitem.{fmt}")
+    if fmt == "parquet":
+        pq.write_table(table, path)
+    elif fmt == "feather":
+        feather.write_feather(table, path, compression="uncompressed")
+    else:
+        with open(path, "wb") as f:
+            f.write(table.column("l_orderkey").chunk(0).buffers()[1].to_pybytes())
+    r = subprocess.run([DEMO, "--file", path, "--mode", "sync"], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "PASSED" in r.stdout and "MISMATCH" not in r.stdout
+    if fmt != "raw":
+        assert "deserialised table: OK" in r.stdout and f"{n} rows x 4 columns" in r.stdout
