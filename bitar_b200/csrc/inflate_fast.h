@@ -218,6 +218,23 @@ BITAR_HD bool parse_index(const uint8_t* src, uint32_t src_len, IndexInfo* ix) {
 }
 BITAR_HD uint32_t index_word(const IndexInfo& ix, uint32_t k) { return load_u32le(ix.words + 4u * k); }
 
+// Bit offsets of block b / of its sub-range s as the index gives them, checked against each other and against
+// the stream: nothing derived from a damaged index may point outside the DEFLATE stream.
+struct BlockBits {
+  uint32_t hdr, end;   // first bit of the block header; first bit after the block
+};
+BITAR_HD bool index_block_bits(const IndexInfo& ix, uint32_t b, uint32_t n_blocks, BlockBits* bb) {
+  bb->hdr = index_word(ix, b * 33u);
+  bb->end = b + 1u < n_blocks ? index_word(ix, (b + 1u) * 33u) : ix.end_bit;
+  return bb->hdr < bb->end && bb->end <= ix.end_bit;
+}
+BITAR_HD bool index_sub_bits(const IndexInfo& ix, uint32_t b, uint32_t s, uint32_t n_subs, const BlockBits& bb, uint32_t* sbit,
+                             uint32_t* ebit) {
+  *sbit = index_word(ix, b * 33u + 1u + s);
+  *ebit = s + 1u < n_subs ? index_word(ix, b * 33u + 2u + s) : bb.end;
+  return *sbit >= bb.hdr && *sbit <= *ebit && *ebit <= bb.end;
+}
+
 // CTA-shared constants: distance symbol info and (when checksums are on) four CRC-32 slicing tables
 struct CtaTables {
   uint32_t dinfo[32];
@@ -354,7 +371,7 @@ struct FastLane {
     start_off = off;
     const uint32_t mis = (uint32_t)((uintptr_t)a & 3u);
     words = reinterpret_cast<const uint32_t*>(a - mis);
-    const uint32_t bytes = in_len - off;
+    const uint32_t bytes = off < in_len ? in_len - off : 0u;
     nwords = bytes ? (mis + bytes + 3u) >> 2 : 0u;
     const uint32_t w0 = nwords ? inf::ld_in32(words) : 0u;
     lo = w0 >> (8u * mis);
@@ -384,7 +401,7 @@ struct FastLane {
     return v;
   }
   BITAR_HD int64_t consumed_bits() const { return 32ll * ((int64_t)wpos - 1) - (int64_t)skip - (int64_t)cnt; }
-  BITAR_HD bool overrun() const { return consumed_bits() > 8ll * (int64_t)(in_len - start_off); }
+  BITAR_HD bool overrun() const { return consumed_bits() > 8ll * ((int64_t)in_len - (int64_t)start_off); }
   BITAR_HD uint32_t consumed_bytes() const {
     const int64_t used = (int64_t)start_off + ((consumed_bits() + 7) >> 3);
     return used > (int64_t)in_len ? in_len : (uint32_t)used;

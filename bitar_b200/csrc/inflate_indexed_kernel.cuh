@@ -220,10 +220,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
     fl::parse_index(src, op.src_len, &ix);   // validated by the plan kernel
     const uint32_t nb = dfl::idx_blocks(ix.total_out), b = tk.block;
     const uint32_t blen = min(65536u, ix.total_out - (b << 16)), ns = dfl::idx_subs(blen);
-    const uint32_t hdr = fl::index_word(ix, b * 33u);
-    const uint32_t block_end = b + 1u < nb ? fl::index_word(ix, (b + 1u) * 33u) : ix.end_bit;
+    fl::BlockBits bb;
+    uint32_t status = fl::index_block_bits(ix, b, nb, &bb) ? fl::kStatusOk : fl::kStatusDataError;
+    const uint32_t hdr = status == fl::kStatusOk ? bb.hdr : 0u, block_end = bb.end;
     uint8_t* out = static_cast<uint8_t*>(op.dst) + ((size_t)b << 16);
-    uint32_t status = fl::kStatusOk;
     // this lane's share of the block's checksum: (crc register, sum of bytes, weighted sum) of `ck_len` bytes
     // that are followed by `ck_tail` more bytes of the chunk
     uint32_t ck_crc = 0, ck_s1 = 0, ck_s2 = 0, ck_len = 0, ck_tail = 0;
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
     const uint32_t last = L.take(1);
     const uint32_t type = L.take(2);
     const uint32_t want_last = b + 1u == nb ? 1u : 0u;
-    if ((type != 0u && last != want_last) || type == 3u || hdr >= block_end || block_end > ix.end_bit) status = fl::kStatusDataError;
+    if ((type != 0u && last != want_last) || type == 3u) status = fl::kStatusDataError;
     if (status == fl::kStatusOk && type == 0u) {
       // stored block: one or two pieces (65535 + 1; only the last carries the block's BFINAL), copied by the whole warp
       uint32_t done = 0, at = ((hdr + 3u + 7u) >> 3), piece_last = last;
@@ -329,10 +329,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
         L.state = Lane::kDone;
         if ((uint32_t)lane < ns) {
           const uint32_t s = (uint32_t)lane;
-          const uint32_t sbit = fl::index_word(ix, b * 33u + 1u + s);
-          const uint32_t ebit = s + 1u < ns ? fl::index_word(ix, b * 33u + 2u + s) : block_end;
+          uint32_t sbit, ebit;
           const uint32_t len = min(dfl::kSub, blen - s * dfl::kSub);
-          if (sbit < hdr || sbit > ebit || ebit > block_end) L.status = fl::kStatusDataError;
+          if (!fl::index_sub_bits(ix, b, s, ns, bb, &sbit, &ebit)) L.status = fl::kStatusDataError;
           else {
             L.start_sub(src, ix.stream_bytes, sbit, ebit, s + 1u == ns, out + (size_t)s * dfl::kSub, len, b == 0u && s == 0u);
             ck_len = len;

@@ -163,6 +163,30 @@ def test_indexed_inflate_of_model_streams(huffman):
     assert info["indexed"] and info["status"] == 0 and np.array_equal(out, mixed)
 
 
+def test_corrupted_streams_never_write_out_of_bounds():
+    """Random damage to the stream or to the index: every decoder (whole-stream lane, indexed sub-range path)
+    must report something and keep its writes inside [dst, dst + cap) -- DEFLATE carries no integrity check, so
+    a damaged stream may also decode 'successfully' to other bytes; what must never happen is a hang or a write
+    outside the destination."""
+    rng = np.random.default_rng(11)
+    ch = synth.lineitem_like(SEG)
+    m = M.model_deflate(ch, 2)
+    z = np.frombuffer(zlib.compress(ch.tobytes(), 1)[2:-4], np.uint8)
+    for trial in range(300):
+        for stream, fn in ((m, M.host_inflate_indexed), (m, M.host_inflate_fast), (z, M.host_inflate_fast)):
+            bad = stream.copy()
+            for _ in range(int(rng.integers(1, 4))):
+                if trial % 3 == 0 and stream is m:
+                    k = stream.size - 1 - int(rng.integers(0, 140))      # inside the index
+                else:
+                    k = int(rng.integers(0, stream.size))
+                bad[k] ^= 1 << int(rng.integers(0, 8))
+            out, info = fn(bad, SEG)
+            assert info["guard_ok"] and info["status"] in (0, 1, 2, 3), (trial, info)
+            if fn is M.host_inflate_indexed and info["indexed"] and info["status"] == 0:
+                assert out.size == SEG
+
+
 def test_deflate_model_large_chunks_multi_block():
     data = synth.lineitem_like(3 * 65536 + 1000)
     m = M.model_deflate(data, 2)

@@ -92,6 +92,31 @@ def test_gpu_streams_inflate_through_the_index(cuda_device, variant, huffman):
         capi.lib().bitar_tune_inflate_variant(22)
 
 
+def test_corrupted_streams_fuzz(cuda_device):
+    """600 randomly damaged chunks (GPU streams with their index, zlib streams) in one call: every op reports a
+    status, nothing is written outside the destinations (guard bytes), the queue pair stays usable."""
+    rng = np.random.default_rng(5)
+    ch = synth.lineitem_like(SEG)
+    dev = G.open_device(SEG)
+    try:
+        comps, _, _ = G.gpu_deflate_chunks(dev, [ch])
+        good = [comps[0], zraw(ch, 1)]
+        bad = []
+        for t in range(600):
+            s = good[t & 1].copy()
+            for _ in range(int(rng.integers(1, 4))):
+                k = s.size - 1 - int(rng.integers(0, 140)) if (t % 6 == 0) else int(rng.integers(0, s.size))
+                s[k] ^= 1 << int(rng.integers(0, 8))
+            bad.append(s)
+        outs, res, err = G.gpu_inflate_chunks(dev, bad, [SEG] * len(bad))     # asserts the guard bytes
+        assert set(int(x) for x in res["status"]) <= {0, 1, 2, 3}
+        assert (res["produced"] <= SEG).all()
+        outs, res, err = G.gpu_inflate_chunks(dev, good, [SEG, SEG])
+        assert err is None and all(np.array_equal(o, ch) for o in outs)
+    finally:
+        dev.close()
+
+
 def test_host_resident_buffers_are_staged(cuda_device):
     """Compressed slots and the destination in PINNED HOST memory: the inflate call gathers / scatters through
     device memory (capi.cu stage_copy_kernel); results and guard bytes as for device buffers."""

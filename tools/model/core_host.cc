@@ -104,8 +104,10 @@ API int host_inflate_indexed(const uint8_t* in, uint32_t in_len, uint8_t* out, u
   uint32_t status = kStatusOk;
   for (uint32_t b = 0; b < nb && status == kStatusOk; ++b) {
     const uint32_t blen = ix.total_out - (b << 16) < 65536u ? ix.total_out - (b << 16) : 65536u;
-    const uint32_t ns = dfl::idx_subs(blen), hdr = index_word(ix, b * 33u);
-    const uint32_t block_end = b + 1 < nb ? index_word(ix, (b + 1) * 33u) : ix.end_bit;
+    const uint32_t ns = dfl::idx_subs(blen);
+    BlockBits bb;
+    if (!index_block_bits(ix, b, nb, &bb)) { status = kStatusDataError; break; }
+    const uint32_t hdr = bb.hdr, block_end = bb.end;
     Gen g;
     g.bind(smem, &cta, &scratch, 0);
     g.start(in, ix.stream_bytes, out + (b << 16), blen);
@@ -125,8 +127,8 @@ API int host_inflate_indexed(const uint8_t* in, uint32_t in_len, uint8_t* out, u
       Sub l;
       l.bind_parts(g.lt, g.dt, smem + 2 * LT + 2 * DT, &cta, &scratch, 0);
       const uint32_t len = blen - s * dfl::kSub < dfl::kSub ? blen - s * dfl::kSub : dfl::kSub;
-      const uint32_t sbit = index_word(ix, b * 33u + 1u + s);
-      const uint32_t ebit = s + 1 < ns ? index_word(ix, b * 33u + 2u + s) : block_end;
+      uint32_t sbit, ebit;
+      if (!index_sub_bits(ix, b, s, ns, bb, &sbit, &ebit)) { status = kStatusDataError; break; }
       l.start_sub(in, ix.stream_bytes, sbit, ebit, s + 1 == ns, out + (b << 16) + s * dfl::kSub, len);
       uint64_t steps = 0;
       while (l.state != Sub::kDone && ++steps < (1ull << 30)) l.step();
