@@ -268,7 +268,7 @@ __device__ void sort512(Smem& sm) {
 
 // ---- match phase -------------------------------------------------------------------------------------
 // One warp, one 2 KiB sub-range [s0, s1) of the block: windows of 32 positions in order.
-// Semantics == tools/model Params{step = 32, cand_mode = 1, hash_bits = 10, sub_log2 = 11}: candidate = nearest
+// Semantics == tools/model Params{step = 32, cand_mode = 1, hash_bits = 10, lazy = 1, sub_log2 = 11}: candidate = nearest
 // previous position with the same 4-byte hash -- a lower lane of the window if there is one, else the most
 // recent earlier position of this sub-range from the table; greedy parse in position order.
 __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int s0, int s1, int warp, int lane,
@@ -305,6 +305,13 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
       if (len >= dfl::kMinMatch) {
         adv = len;
         dist = p - (int)cand;
+      }
+    }
+    {   // lazy step: a match yields to a strictly longer match that starts at the next position of the window
+      const int next_adv = __shfl_down_sync(kFull, adv, 1);
+      if (lane < 31 && adv > 1 && next_adv > adv) {
+        adv = 1;
+        dist = 0;
       }
     }
     unsigned reach;

@@ -27,6 +27,7 @@ struct Params {
   int far3 = 4096;      // reject length-3 matches farther than this (0 = keep all)
   int huffman = 2;      // 1 fixed only, 2 dynamic (min of stored/fixed/dynamic)
   int block = 65536;    // sub-block size inside a chunk (window restarts at sub-block start)
+  int lazy = 1;         // 1: a match yields to a strictly longer match starting at the next position of its window
   int sub_log2 = kSubLog2;  // matches stay inside the 2^sub_log2-byte sub-range of their position and the
                         // parallel-inflate index is appended (deflate_common.h); 0 = off
 };
@@ -119,6 +120,9 @@ inline void find_tokens(const uint8_t* d, int n, const Params& P, std::vector<ui
         mdist[t] = bdist;
       }
     }
+    if (P.lazy)   // decided on the matches as found (not on already reduced neighbours): one pass, in place is fine going up
+      for (int t = 0; t + 1 < P.step; ++t)
+        if (adv[t] > 1 && adv[t + 1] > adv[t] + (P.lazy - 1)) adv[t] = 1, mdist[t] = 0;
     int lim = std::min(n, base + P.step);
     int pos = carry;
     while (pos < lim) {
