@@ -446,6 +446,9 @@ int bitar_dev_open(int device_id, uint16_t n_qps, const bitar_cfg* cfg_in, bitar
     }
   }
   cudaError_t e = bitar::dk::deflate_grid(device_id, dev->sm_count, &dev->deflate_grid);
+  if (const char* g = getenv("BITAR_DEBUG_DEFLATE_GRID")) {   // tuning experiments only
+    if (atoi(g) > 0) dev->deflate_grid = atoi(g);
+  }
   if (e != cudaSuccess) {
     delete dev;
     return fail(BITAR_E_INVALID, "deflate kernel cannot be configured on device %d: %s", device_id, cudaGetErrorString(e));
