@@ -115,3 +115,94 @@ def test_pinned_host_zero_copy(cuda_device):
         capi.check(capi.lib().bitar_mem_free(capi.MEM_PINNED, 0, q))
     finally:
         dev.close()
+
+
+def _crc32_combine(crc1, crc2, len2):
+    """zlib's crc32_combine(): CRC of A||B from CRC(A), CRC(B), len(B) (GF(2) matrix method)."""
+    def times(mat, vec):
+        s, i = 0, 0
+        while vec:
+            if vec & 1:
+                s ^= mat[i]
+            vec >>= 1
+            i += 1
+        return s
+
+    def square(mat):
+        return [times(mat, mat[n]) for n in range(32)]
+
+    if len2 == 0:
+        return crc1
+    odd = [0xEDB88320] + [1 << n for n in range(31)]
+    even = square(odd)
+    odd = square(even)
+    while True:
+        even = square(odd)
+        if len2 & 1:
+            crc1 = times(even, crc1)
+        len2 >>= 1
+        if not len2:
+            break
+        odd = square(even)
+        if len2 & 1:
+            crc1 = times(odd, crc1)
+        len2 >>= 1
+        if not len2:
+            break
+    return crc1 ^ crc2
+
+
+def _adler32_combine(a1, a2, len2):
+    base = 65521
+    rem = len2 % base
+    s1 = a1 & 0xFFFF
+    s2 = (rem * s1) % base
+    s1 += (a2 & 0xFFFF) + base - 1
+    s2 += ((a1 >> 16) & 0xFFFF) + ((a2 >> 16) & 0xFFFF) + base - rem
+    if s1 >= base:
+        s1 -= base
+    if s1 >= base:
+        s1 -= base
+    if s2 >= (base << 1):
+        s2 -= (base << 1)
+    if s2 >= base:
+        s2 -= base
+    return s1 | (s2 << 16)
+
+
+def test_full_size_round_trip_and_checksum_of_checksums(cuda_device):
+    """BASELINE config 2 at full size (1 GiB, 18 059 segments of 59 460 bytes), checked through size-independent
+    properties: Compress -> Decompress is the identity; the per-segment CRC-32 / Adler-32 the deflate kernel
+    returns, combined in segment order, equal zlib's checksum of the whole buffer; the inflate kernel returns
+    the same per-segment checksums; total compressed size within the tolerance of zlib level 1 (sample)."""
+    import zlib
+    import oracle_lib as O
+    U = 1 << 30
+    data = synth.lineitem_like(U)
+    n = (U + SEG - 1) // SEG
+    dev = G.open_device(SEG, max_preallocate_memzones=n + 8, checksum_type=capi.CHECKSUM_CRC32_ADLER32)
+    try:
+        src = torch.from_numpy(data).cuda()
+        out = torch.empty(n * SEG + 64, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        ops, slots = dev.compress_ops(src.data_ptr(), U)
+        res = dev.enqueue("deflate", 0, ops)
+        dev.wait(0)
+        assert (res["status"] == 0).all()
+        crc, adler = 0, 1
+        for c, ln in zip(res["checksum"], ops["src_len"]):
+            crc = _crc32_combine(crc, int(c) & 0xFFFFFFFF, int(ln))
+            adler = _adler32_combine(adler, int(c) >> 32, int(ln))
+        assert crc == zlib.crc32(data) and adler == zlib.adler32(data)
+        ires = dev.enqueue("inflate", 0, dev.decompress_ops(slots, res["produced"], out.data_ptr()))
+        dev.wait(0)
+        assert int(ires["produced"].sum()) == U and bool(torch.equal(out[:U], src))
+        assert np.array_equal(ires["checksum"], res["checksum"])
+        third, part = U // 3, (8 << 20) // SEG * SEG
+        zs = np.concatenate([data[i * third:i * third + part] for i in range(3)])
+        _, zp = O.compress_buffer(zs, SEG, threads=8)
+        gpu_ratio, zlib_ratio = U / float(res["produced"].sum()), zs.size / float(zp.sum())
+        assert gpu_ratio >= zlib_ratio / 1.05, (gpu_ratio, zlib_ratio)
+        assert sum(dev.put_slot(s) for s in slots[::-1]) == n
+    finally:
+        dev.close()
