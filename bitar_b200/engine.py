@@ -252,6 +252,38 @@ class CompressDriver:
         return [CompressDevice(d, base + (1 if i < rem else 0)) for i, d in enumerate(device_ids)]
 
 
+# -- framing: the chunks as members of a gzip file --------------------------------------
+INDEX_MAGIC = 0xB17A0B01
+
+
+def stream_length(chunk):
+    """Bytes of the raw DEFLATE stream at the start of a compressed chunk (numpy uint8 array): the chunk minus the
+    parallel-inflate index, when it carries one (bitar_b200/csrc/deflate_common.h)."""
+    c = np.ascontiguousarray(chunk, dtype=np.uint8)
+    if c.size >= 16 and int(c[-4:].view("<u4")[0]) == INDEX_MAGIC:
+        total, end_bit = int(c[-8:-4].view("<u4")[0]), int(c[-12:-8].view("<u4")[0])
+        full, rem = divmod(total, 65536)
+        entries = full * 33 + ((1 + (rem + 2047) // 2048) if rem else 0)
+        if (end_bit + 7) // 8 + 4 * (entries + 3) == c.size:
+            return (end_bit + 7) // 8
+    return c.size
+
+
+def gzip_members(chunks, results, sizes):
+    """RFC 1952 framing: every compressed chunk becomes one gzip member (header, raw DEFLATE stream, CRC-32,
+    ISIZE); the concatenation is a valid multi-member gzip file that gzip / zlib tools decompress to the original
+    buffer.  `results` are the Compress() results of a device configured with a CRC-32 checksum, `sizes` the
+    uncompressed segment sizes."""
+    import struct
+    out = bytearray()
+    for c, r, n in zip(chunks, results, sizes):
+        c = np.ascontiguousarray(c, dtype=np.uint8)
+        out += b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\xff"
+        out += c[:stream_length(c)].tobytes()
+        out += struct.pack("<II", int(r["checksum"]) & 0xFFFFFFFF, int(n) & 0xFFFFFFFF)
+    return bytes(out)
+
+
 def shard_range(n_chunks, rank, world):
     """Chunk range [first, last) of rank `rank` out of `world`: contiguous ranges of
     ceil(n / world) chunks, so that concatenating the ranks' outputs in rank order is the output of one

@@ -187,6 +187,21 @@ def test_corrupted_streams_never_write_out_of_bounds():
                 assert out.size == SEG
 
 
+def test_gzip_member_framing_of_model_streams():
+    """engine.gzip_members(): kernel-format chunks (index stripped) + CRC-32 / ISIZE per member form a
+    multi-member gzip file that Python's gzip module decompresses to the original buffer."""
+    import gzip
+    from bitar_b200 import engine as E
+    data = synth.lineitem_like(3 * SEG + 100)
+    chunks = [data[o:o + SEG] for o in range(0, data.size, SEG)]
+    comps = [M.model_deflate(c, 2) for c in chunks]
+    res = np.zeros(len(chunks), dtype=[("produced", "<u4"), ("status", "<u4"), ("checksum", "<u8")])
+    for i, c in enumerate(chunks):
+        res["checksum"][i] = O.crc32(c)
+        assert E.stream_length(comps[i]) == M.split_index(comps[i])[0].size
+    assert gzip.decompress(E.gzip_members(comps, res, [c.size for c in chunks])) == data.tobytes()
+
+
 def test_deflate_model_large_chunks_multi_block():
     data = synth.lineitem_like(3 * 65536 + 1000)
     m = M.model_deflate(data, 2)

@@ -117,6 +117,22 @@ def test_pinned_host_zero_copy(cuda_device):
         dev.close()
 
 
+def test_chunks_frame_as_gzip_members(cuda_device):
+    """the deflate kernel's chunks (index stripped) + its CRC-32s framed as gzip members are a
+    multi-member gzip file that Python's gzip module (zlib) decompresses to the original buffer."""
+    import gzip
+    data = synth.lineitem_like(9 * SEG + 4321)
+    dev = G.open_device(SEG, checksum_type=capi.CHECKSUM_CRC32)
+    try:
+        chunks = [data[o:o + SEG] for o in range(0, data.size, SEG)]
+        comps, res, err = G.gpu_deflate_chunks(dev, chunks)
+        assert err is None
+        blob = E.gzip_members(comps, res, [c.size for c in chunks])
+        assert gzip.decompress(blob) == data.tobytes()
+    finally:
+        dev.close()
+
+
 def _crc32_combine(crc1, crc2, len2):
     """zlib's crc32_combine(): CRC of A||B from CRC(A), CRC(B), len(B) (GF(2) matrix method)."""
     def times(mat, vec):
