@@ -8,8 +8,8 @@
 //             also independent for the compressor: every WARP owns one sub-range at a time, with its own
 //             1024-entry hash table in shared memory, and walks it in windows of 32 positions:
 //             4-byte hash, nearest earlier position with that hash (inside the window through
-//             __match_any_sync, else the table), match extension, greedy parse of the window by a
-//             transfer function (5 shuffle-doubling rounds) with the carry in a register.  No CTA-wide
+//             __match_any_sync, else the table), match extension, greedy parse of the window (a walk
+//             over its match lanes, one shuffle each) with the carry in a register.  No CTA-wide
 //             barrier, no atomics on the tables, deterministic.
 //   count   : literal/length and distance frequencies with shared-memory atomics.
 //   plan    : CTA-wide bitonic sort of the used symbols, then length-limited Huffman code
@@ -314,29 +314,27 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
         dist = 0;
       }
     }
-    unsigned reach;
-    if (!__any_sync(kFull, adv > 1)) {                // literals only: every position from a on starts a token
-      reach = 0xFFFFFFFFu << a;
-      carry = base + 32;
-    } else {
-      // transfer function of the window: e_r = lane + (2^r hops), frozen once it leaves the window
-      int e0 = lane + adv, e1, e2, e3, e4, e5;
-      {
-        int t;
-        t = __shfl_sync(kFull, e0, e0 & 31); e1 = e0 < 32 ? t : e0;
-        t = __shfl_sync(kFull, e1, e1 & 31); e2 = e1 < 32 ? t : e1;
-        t = __shfl_sync(kFull, e2, e2 & 31); e3 = e2 < 32 ? t : e2;
-        t = __shfl_sync(kFull, e3, e3 & 31); e4 = e3 < 32 ? t : e3;
-        t = __shfl_sync(kFull, e4, e4 & 31); e5 = e4 < 32 ? t : e4;
+    // Greedy parse of the window from a: literal lanes hand the parse to their neighbour, so only the match lanes
+    // on the way cost a step (one shuffle each); every lane walks redundantly.
+    unsigned reach = 0;
+    {
+      const unsigned matches = __ballot_sync(kFull, adv > 1);
+      int pos = a;
+      for (;;) {
+        const unsigned ahead = matches & (0xFFFFFFFFu << pos);
+        if (!ahead) {                                 // literals to the end of the window
+          reach |= 0xFFFFFFFFu << pos;
+          carry = base + 32;
+          break;
+        }
+        const int q = __ffs((int)ahead) - 1;          // next match start: pos..q all start tokens
+        reach |= (0xFFFFFFFFu << pos) & (0xFFFFFFFFu >> (31 - q));
+        pos = q + __shfl_sync(kFull, adv, q);
+        if (pos >= 32) {
+          carry = base + pos;
+          break;
+        }
       }
-      reach = 1u << a;
-      unsigned contrib;
-      contrib = ((reach >> lane) & 1u) && e0 < 32 ? (1u << e0) : 0u; reach |= __reduce_or_sync(kFull, contrib);
-      contrib = ((reach >> lane) & 1u) && e1 < 32 ? (1u << e1) : 0u; reach |= __reduce_or_sync(kFull, contrib);
-      contrib = ((reach >> lane) & 1u) && e2 < 32 ? (1u << e2) : 0u; reach |= __reduce_or_sync(kFull, contrib);
-      contrib = ((reach >> lane) & 1u) && e3 < 32 ? (1u << e3) : 0u; reach |= __reduce_or_sync(kFull, contrib);
-      contrib = ((reach >> lane) & 1u) && e4 < 32 ? (1u << e4) : 0u; reach |= __reduce_or_sync(kFull, contrib);
-      carry = base + __shfl_sync(kFull, e5, a);       // where the chain entering at lane a leaves the window
     }
     const bool start = ((reach >> lane) & 1u) && p < n;
     const unsigned starts = __ballot_sync(kFull, start);
