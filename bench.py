@@ -138,7 +138,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--mib", type=int, default=1024, help="uncompressed MiB per GPU (BASELINE config 2: 1 GiB)")
     ap.add_argument("--seg", type=int, default=SEG_DEFAULT)
-    ap.add_argument("--qps", type=int, default=4, help="queue pairs used by the end-to-end leg")
+    ap.add_argument("--qps", type=int, default=8, help="queue pairs used by the end-to-end leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

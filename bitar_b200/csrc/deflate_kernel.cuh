@@ -87,6 +87,7 @@ struct __align__(16) Smem {
   uint32_t x2n[32];
   uint32_t cks_crc, cks_a, cks_b;    // checksum accumulators
   uint32_t ll_m, d_m;
+  uint32_t next_idx;                 // the chunk this CTA compresses next (fetched early, its input is prefetched)
   uint32_t sub_cnt[32];              // tokens of each sub-range of the block (compact, at tokens + sub * 2048)
   uint32_t sub_voff[34];             // encode: first slot of each sub-range (counts rounded up to kTokPerThread)
   uint32_t index[(BITAR_MAX_SEG_SIZE >> dfl::kIdxBlockLog2) * 33 + 4];   // parallel-inflate index of the chunk (deflate_common.h)
@@ -125,6 +126,13 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
           smem_u32(dst_smem)),
       "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
+}
+
+// L2 prefetch of a global range (16-byte aligned address, size a multiple of 16): the next chunk's first block is
+// requested while the current chunk is being compressed, so that its TMA load -- over PCIe when the input lives
+// in pinned host memory -- does not start from cold
+__device__ __forceinline__ void tma_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 
 // Shared-memory reads of the input block go through explicit 32-bit shared addresses (`ds` = shared
@@ -663,6 +671,16 @@ __global__ void __launch_bounds__(kThreads, 2)
       if (tid == 0) {
         mbar_expect_tx(&sm.mbar, bytes);
         tma_load_1d(sm.raw, g0 - gmis, bytes, &sm.mbar);
+        if (off == 0) {   // claim the next chunk now and ask L2 for its first block
+          const uint32_t nx = gridDim.x + atomicAdd(counter, 1u);
+          sm.next_idx = nx;
+          if (nx < n_ops) {
+            const uint8_t* ns = static_cast<const uint8_t*>(ops[nx].src);
+            const uint32_t nl = min(ops[nx].src_len, (uint32_t)kBlockMax);
+            const uint32_t nmis = (uint32_t)(reinterpret_cast<uintptr_t>(ns) & 15u);
+            if (nl) tma_prefetch_l2(ns - nmis, (nmis + nl + 15u) & ~15u);
+          }
+        }
       }
       // the hash tables take the space of the bit stage for the duration of the match phase: park the
       // partially filled 16-byte unit at its front
@@ -1043,9 +1061,9 @@ __global__ void __launch_bounds__(kThreads, 2)
     // reset the stage for the next chunk and fetch its index
     __syncthreads();
     for (int i = tid; i < kStageWords; i += kThreads) sm.u.enc.stage[i] = 0;
-    if (tid == 0) sm.tile_bits = gridDim.x + atomicAdd(counter, 1u);
+    if (tid == 0 && total == 0) sm.next_idx = gridDim.x + atomicAdd(counter, 1u);   // (an empty chunk loaded nothing)
     __syncthreads();
-    idx = sm.tile_bits;
+    idx = sm.next_idx;
     __syncthreads();
     BITAR_PHASE(6)
   }
