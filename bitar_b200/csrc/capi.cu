@@ -70,6 +70,7 @@ struct QueuePair {
   uint8_t* d_stage_out = nullptr;
   size_t stage_out_cap = 0;
   bool stage_src = false, stage_dst = false;
+  bool stage_dst_contig = false;        // destinations form one range of equal-capacity segments (Decompress())
   bitar_result* user_out = nullptr;
   uint32_t pending_n = 0;
   std::atomic<int> busy{0};
@@ -260,6 +261,13 @@ int inflate_prepare_staging(QueuePair* q, uint32_t n) {
     CU_TRY(cudaMalloc((void**)&q->d_stage_out, need_out), BITAR_E_OUT_OF_MEMORY);
     q->stage_out_cap = need_out;
   }
+  // Decompress() lays segment i at out + i * S (src/memory.cc:482-493): then the staged output mirrors that
+  // layout and goes back with ONE copy-engine transfer (which, unlike a kernel, runs beside the inflate kernels of
+  // the other queue pairs); only the last segment, the one that may be short, is copied by produced size.
+  q->stage_dst_contig = q->stage_dst && n > 1;
+  for (uint32_t i = 1; i < n && q->stage_dst_contig; ++i)
+    q->stage_dst_contig = q->h_orig[i].dst_cap == q->h_orig[0].dst_cap &&
+                          static_cast<uint8_t*>(q->h_orig[i].dst) == static_cast<uint8_t*>(q->h_orig[0].dst) + (size_t)i * q->h_orig[0].dst_cap;
   size_t at_in = 0, at_out = 0;
   for (uint32_t i = 0; i < n; ++i) {
     bitar_chunk& c = q->h_ops[i];
@@ -268,7 +276,9 @@ int inflate_prepare_staging(QueuePair* q, uint32_t n) {
       c.src = q->d_stage_in + at_in + mis;
       at_in += (((size_t)c.src_len + 15u) & ~(size_t)15u) + 32u;
     }
-    if (q->stage_dst) {
+    if (q->stage_dst_contig) {
+      c.dst = q->d_stage_out + (reinterpret_cast<uintptr_t>(q->h_orig[0].dst) & 15u) + (size_t)i * c.dst_cap;
+    } else if (q->stage_dst) {
       const size_t mis = reinterpret_cast<uintptr_t>(c.dst) & 15u;
       c.dst = q->d_stage_out + at_out + mis;
       at_out += (((size_t)c.dst_cap + 15u) & ~(size_t)15u) + 32u;
@@ -294,7 +304,7 @@ int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, b
   int rc = qp_reserve(dev, q, n);
   if (rc) return rc;
   memcpy(q->h_ops, ops, (size_t)n * sizeof(bitar_chunk));
-  q->stage_src = q->stage_dst = false;
+  q->stage_src = q->stage_dst = q->stage_dst_contig = false;
   if (inflate) {
     rc = inflate_prepare_staging(q, n);
     if (rc) return rc;
@@ -315,7 +325,14 @@ int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, b
   if (e == cudaSuccess) e = cudaEventRecord(q->ev_k0, q->stream);
   if (e == cudaSuccess) e = launch(q);
   if (e == cudaSuccess) e = cudaEventRecord(q->ev_k1, q->stream);
-  if (e == cudaSuccess && q->stage_dst) {
+  if (e == cudaSuccess && q->stage_dst_contig) {
+    e = cudaMemcpyAsync(q->h_orig[0].dst, q->h_ops[0].dst, (size_t)(n - 1) * q->h_orig[0].dst_cap, cudaMemcpyDeviceToHost, q->stream);
+    if (e == cudaSuccess) {
+      stage_copy_kernel<<<1, 256, 0, q->stream>>>(q->d_ops + (n - 1), q->d_orig + (n - 1), q->d_res + (n - 1), 1);
+      e = cudaGetLastError();
+      g_launches.fetch_add(1);
+    }
+  } else if (e == cudaSuccess && q->stage_dst) {
     stage_copy_kernel<<<n, 256, 0, q->stream>>>(q->d_ops, q->d_orig, q->d_res, 1);
     e = cudaGetLastError();
     g_launches.fetch_add(1);
