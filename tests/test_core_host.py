@@ -214,3 +214,50 @@ def test_deflate_model_large_chunks_multi_block():
     m = M.model_deflate(rnd, 2)
     assert np.array_equal(O.inflate_chunk(m, rnd.size), rnd)
     assert m.size <= rnd.size + 5 * 3              # never worse than three stored pieces (65535 + 1 + 10 bytes)
+
+
+def _structured(rng, n):
+    """Random bytes with random structure: runs, periodic patterns, small alphabets, copies from far back."""
+    out = np.empty(n, np.uint8)
+    at = 0
+    while at < n:
+        kind = int(rng.integers(0, 6))
+        ln = int(min(n - at, rng.integers(1, 700)))
+        if kind == 0:
+            out[at:at + ln] = rng.integers(0, 256, ln, dtype=np.uint8)
+        elif kind == 1:
+            out[at:at + ln] = int(rng.integers(0, 256))
+        elif kind == 2:
+            per = rng.integers(0, 256, int(rng.integers(1, 40)), dtype=np.uint8)
+            out[at:at + ln] = np.resize(per, ln)
+        elif kind == 3:
+            out[at:at + ln] = rng.integers(0, int(rng.integers(2, 17)), ln, dtype=np.uint8)
+        elif at > 0:
+            back = int(rng.integers(1, min(at, 40000) + 1))
+            for k in range(ln):            # overlapping copy semantics
+                out[at + k] = out[at + k - back]
+        else:
+            out[at:at + ln] = 7
+        at += ln
+    return out
+
+
+def test_random_structured_inputs_round_trip_on_the_cpu_builds():
+    """200 random inputs of ragged sizes (1 .. 70 000 bytes, crossing the 2 KiB sub-range and 64 KiB block
+    boundaries): model stream -> zlib, -> independent RFC 1951 decoder, -> whole-stream lane, -> indexed path."""
+    rng = np.random.default_rng(2026)
+    sizes = [1, 2, 3, 2047, 2048, 2049, 4095, 4097, 65535, 65536, 65537] + [int(rng.integers(1, 70000)) for _ in range(189)]
+    for i, n in enumerate(sizes):
+        d = _structured(rng, n)
+        for huffman in ((2,) if i % 4 else (1, 2)):
+            m = M.model_deflate(d, huffman)
+            assert np.array_equal(O.inflate_chunk(m, n), d), (i, n)
+            body, index = M.split_index(m)
+            out, info = O.rfc_inflate(m, n)
+            assert np.array_equal(out, d) and info["consumed"] == body.size
+            out, info = M.host_inflate_fast(m, n, 9, i % 7)
+            assert info["status"] == 0 and info["guard_ok"] and np.array_equal(out, d)
+            out, info = M.host_inflate_indexed(m, n, i % 5)
+            assert info["indexed"] == (index is not None)
+            if index is not None:
+                assert info["status"] == 0 and info["guard_ok"] and np.array_equal(out, d), (i, n, info)

@@ -111,3 +111,29 @@ def test_ratio_and_roundtrip_by_segment_size(cuda_device, seg):
         assert sum(dev.put_slot(s) for s in slots[::-1]) == len(slots)
     finally:
         dev.close()
+
+
+def test_random_structured_ragged_batch(cuda_device):
+    """One call, 300 ops of ragged sizes (1 .. 200 000 bytes: below a sub-range, across sub-range and 64 KiB block
+    boundaries) and random structure: every GPU stream equals the sequential model, inflates under zlib, and the
+    GPU inflates the whole batch back (sub-range kernel and whole-stream kernel mixed in one call)."""
+    from test_core_host import _structured
+    rng = np.random.default_rng(77)
+    sizes = [1, 2, 3, 2047, 2048, 2049, 4095, 4097, 65535, 65536, 65537, 131072, 200000] + \
+            [int(rng.integers(1, 70000)) for _ in range(287)]
+    chunks = [_structured(rng, n) for n in sizes]
+    dev = G.open_device(200000, checksum_type=capi.CHECKSUM_CRC32_ADLER32)
+    try:
+        comps, res, err = G.gpu_deflate_chunks(dev, chunks, src_shift=1, dst_shift=2)
+        assert err is None and (res["status"] == 0).all()
+        for i, (c, z, r) in enumerate(zip(chunks, comps, res)):
+            assert np.array_equal(z, M.model_deflate(c, capi.HUFFMAN_DYNAMIC)), (i, c.size)
+            if i % 5 == 0:
+                assert np.array_equal(O.inflate_chunk(z, c.size), c)
+            assert int(r["checksum"]) & 0xFFFFFFFF == O.crc32(c) and int(r["checksum"]) >> 32 == O.adler32(c)
+        outs, ires, err = G.gpu_inflate_chunks(dev, comps, [c.size for c in chunks], src_shift=3, dst_shift=1)
+        assert err is None
+        for c, o, r, r0 in zip(chunks, outs, ires, res):
+            assert np.array_equal(o, c) and int(r["checksum"]) == int(r0["checksum"])
+    finally:
+        dev.close()
