@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libbitar_cuda.so")
+LIB_PATH = os.environ.get("BITAR_CUDA_LIB") or os.path.join(_HERE, "csrc", "libbitar_cuda.so")   # env: A/B runs of two builds
 
 # struct bitar_chunk / bitar_result as numpy record dtypes (layout-identical to the C structs)
 CHUNK_DTYPE = np.dtype([("src", "<u8"), ("dst", "<u8"), ("src_len", "<u4"), ("dst_cap", "<u4")])

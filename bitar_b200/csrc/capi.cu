@@ -560,18 +560,24 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
       // 64 KiB block; everything else (zlib streams, stored chunks) to the whole-stream kernel.
       using namespace bitar::xk;
       size_t blocks = 0;
+      uint32_t max_cap = 0;
       for (uint32_t i = 0; i < n; ++i) {
         const uint32_t cap = q->h_ops[i].dst_cap < BITAR_MAX_SEG_SIZE ? q->h_ops[i].dst_cap : BITAR_MAX_SEG_SIZE;
         blocks += (cap + 65535u) >> 16;
+        max_cap = cap > max_cap ? cap : max_cap;
       }
-      if (q->tasks_cap < blocks) {
+      // segments of at most 8 sub-ranges (16 KiB) are decoded four to a warp by their own kernel; calls with larger
+      // segments keep everything (including a short last segment) on the warp-per-block kernel
+      const bool small_mode = max_cap <= bitar::xk::kSmallSubs * bitar::dfl::kSub;
+      if (q->tasks_cap < blocks + n) {   // block tasks, then room for one small task per op
         if (q->d_tasks) cudaFree(q->d_tasks);
         q->d_tasks = nullptr;
         q->tasks_cap = 0;
-        cudaError_t e = cudaMalloc((void**)&q->d_tasks, blocks * sizeof(Task));
+        cudaError_t e = cudaMalloc((void**)&q->d_tasks, (blocks + n) * sizeof(Task));
         if (e != cudaSuccess) return e;
-        q->tasks_cap = blocks;
+        q->tasks_cap = blocks + n;
       }
+      Task* small_tasks = q->d_tasks + blocks;
       if (q->generic_cap < n) {
         if (q->d_generic) cudaFree(q->d_generic);
         q->d_generic = nullptr;
@@ -585,7 +591,8 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
       }
       Counters* pc = reinterpret_cast<Counters*>(q->d_counter);
       CkAcc* acc = ck != BITAR_CHECKSUM_NONE ? q->d_ck : nullptr;
-      inflate_plan_kernel<<<(n + 127) / 128, 128, 0, q->stream>>>(q->d_ops, n, q->d_res, q->d_tasks, q->d_generic, pc, acc, 1);
+      inflate_plan_kernel<<<(n + 127) / 128, 128, 0, q->stream>>>(q->d_ops, n, q->d_res, q->d_tasks, small_tasks, q->d_generic, pc, acc, 1,
+                                                                  small_mode ? 1 : 0);
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) return e;
       g_launches.fetch_add(2);
@@ -599,6 +606,11 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
         case 25: e = IndexedConfig<10, 1344, 8, 512, 128, 22>::launch(q->d_ops, q->d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
       }
       if (e != cudaSuccess) return e;
+      if (small_mode) {   // blocks of at most 8 sub-ranges: four to a warp
+        e = IndexedConfig<9, 864, 7, 256, 128, 11, 8>::launch(q->d_ops, q->d_res, small_tasks, pc, acc, ck, n, id, sms, q->stream);
+        if (e != cudaSuccess) return e;
+        g_launches.fetch_add(1);
+      }
       return InflateConfig<32, 10, 8, 1024, 4>::launch(q->d_ops, n, q->d_res, &pc->generic_next, ck, id, sms, q->stream,
                                                        q->d_generic, &pc->n_generic);
     }

@@ -92,6 +92,33 @@ def test_gpu_streams_inflate_through_the_index(cuda_device, variant, huffman):
         capi.lib().bitar_tune_inflate_variant(22)
 
 
+@pytest.mark.parametrize("seg", [2049, 4096, 5000, 16384])
+def test_small_segments_four_blocks_per_warp(cuda_device, seg):
+    """Segments of at most 8 sub-ranges take the GROUP = 8 kernel (four blocks per warp, tables per group):
+    round trip, checksums, a tiny last segment, single-sub-range and stored segments in the same call, and
+    damaged chunks reported per op."""
+    data = np.concatenate([synth.lineitem_like(40 * seg + 77), np.frombuffer(np.random.default_rng(4).bytes(2 * seg), np.uint8),
+                           np.zeros(3 * seg + 5, np.uint8)])
+    chunks = [data[o:o + seg] for o in range(0, data.size, seg)]
+    dev = G.open_device(seg, checksum_type=capi.CHECKSUM_CRC32_ADLER32)
+    try:
+        comps, res, err = G.gpu_deflate_chunks(dev, chunks)
+        assert err is None
+        for shift in (0, 5):
+            outs, ires, err = G.gpu_inflate_chunks(dev, comps, [seg] * len(chunks), src_shift=shift % 4, dst_shift=shift)
+            assert err is None and (ires["status"] == 0).all()
+            for c, o, r in zip(chunks, outs, ires):
+                assert np.array_equal(o, c)
+                assert int(r["checksum"]) & 0xFFFFFFFF == O.crc32(c) and int(r["checksum"]) >> 32 == O.adler32(c)
+        bad = [c.copy() for c in comps[:8]]
+        for k, b in enumerate(bad):
+            b[b.size - 13 - 4 * (k % 3)] ^= 0x20          # index words of the first chunks
+        outs, ires, err = G.gpu_inflate_chunks(dev, bad + comps[8:12], [seg] * 12)
+        assert err is not None and (ires["status"][:8] != 0).all() and (ires["status"][8:] == 0).all()
+    finally:
+        dev.close()
+
+
 def test_corrupted_streams_fuzz(cuda_device):
     """600 randomly damaged chunks (GPU streams with their index, zlib streams) in one call: every op reports a
     status, nothing is written outside the destinations (guard bytes), the queue pair stays usable."""
