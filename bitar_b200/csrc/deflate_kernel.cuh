@@ -61,6 +61,7 @@ struct PlanPar {                      // scratch of the parallel half of the pla
   unsigned long long dyn_bits, fix_bits;
   uint32_t d_node_freq[64];
   uint16_t d_parent[64];
+  uint8_t seq[328];                  // litlen lengths then distance lengths, as the code-length RLE scans them
 };
 struct EncodeArea {
   uint32_t stage[kStageWords];       // output bit stage, stage[0] is virtual byte `sbase`
@@ -375,27 +376,29 @@ __device__ void huff_merge(const uint32_t* __restrict__ key, int m, uint32_t* no
   constexpr uint32_t kInf = 0xFFFFFFFFu;
   uint32_t lf = key[0] >> 9, lf2 = key[1] >> 9, nf = kInf, nf2 = kInf;   // heads of the leaf / internal queues
   int leaf = 0, inode = m, next = m;
+  // branch-free picks (a taken branch costs this single thread ~20 cycles, a select 2): both queues' next entries
+  // are loaded unconditionally from clamped addresses and chosen by the comparison
   for (int k = 0; k < m - 1; ++k) {
     uint32_t f = 0;
 #pragma unroll
     for (int pick = 0; pick < 2; ++pick) {
-      if (lf <= nf) {
-        f += lf;
-        parent[leaf] = (uint16_t)next;
-        ++leaf;
-        lf = lf2;
-        lf2 = leaf + 1 < m ? key[leaf + 1] >> 9 : kInf;
-      } else {
-        f += nf;
-        parent[inode] = (uint16_t)next;
-        ++inode;
-        nf = nf2;
-        nf2 = inode + 1 < next ? node_freq[inode + 1] : kInf;
-      }
+      const bool tl = lf <= nf;                       // ties prefer leaves
+      f += tl ? lf : nf;
+      parent[tl ? leaf : inode] = (uint16_t)next;
+      leaf += tl ? 1 : 0;
+      inode += tl ? 0 : 1;
+      const uint32_t load_l = key[min(leaf + 1, m - 1)] >> 9;
+      const uint32_t load_n = node_freq[min(inode + 1, 2 * m - 2)];
+      const uint32_t new_lf2 = leaf + 1 < m ? load_l : kInf;
+      const uint32_t new_nf2 = inode + 1 < next ? load_n : kInf;
+      lf = tl ? lf2 : lf;
+      nf = tl ? nf : nf2;
+      lf2 = tl ? new_lf2 : lf2;
+      nf2 = tl ? nf2 : new_nf2;
     }
     node_freq[next] = f;
-    if (inode == next) nf = f;
-    else if (inode + 1 == next) nf2 = f;
+    nf = inode == next ? f : nf;
+    nf2 = inode + 1 == next ? f : nf2;
     ++next;
   }
 }
@@ -495,16 +498,23 @@ __device__ __forceinline__ void cl_rle_parallel(Smem& sm, int tid, int lane, int
   dfl::BlockPlan& pl = sm.plan;
   const int hlit = pl.hlit, total_syms = pl.hlit + pl.hdist;
   if (tid < dfl::kNumCl) sm.u.enc.scratch.cl_freq[tid] = 0;
+  uint8_t* seq = sm.u.enc.pp.seq;
+  if (tid < total_syms) seq[tid] = tid < hlit ? pl.ll_len[tid] : pl.d_len[tid - hlit];
+  __syncthreads();
   int v = 0, run = 0;
   uint32_t ntok = 0;
   if (tid < total_syms) {
-    const auto at = [&](int i) -> int { return i < hlit ? pl.ll_len[i] : pl.d_len[i - hlit]; };
-    v = at(tid);
-    const bool start = tid == 0 || tid == hlit || at(tid - 1) != v;
+    v = seq[tid];
+    const bool start = tid == 0 || tid == hlit || seq[tid - 1] != v;
     if (start) {
       const int end = tid < hlit ? hlit : total_syms;
       run = 1;
-      while (tid + run < end && at(tid + run) == v) ++run;
+      while (tid + run < end && ((tid + run) & 3) && seq[tid + run] == v) ++run;   // to a word boundary
+      if (((tid + run) & 3) == 0) {                                                 // then four lengths per step
+        const uint32_t pat = (uint32_t)v * 0x01010101u;
+        while (tid + run + 4 <= end && *reinterpret_cast<const uint32_t*>(seq + tid + run) == pat) run += 4;
+      }
+      while (tid + run < end && seq[tid + run] == v) ++run;
       if (v == 0) {
         const int rem = run % 138;
         ntok = (uint32_t)(run / 138 + (rem >= 3 ? 1 : rem));
