@@ -45,9 +45,9 @@ constexpr int kWarps = 16;
 constexpr int kThreads = kWarps * 32;
 constexpr int kBlockMax = 65536;                 // sub-block size (positions fit 16 bits)
 constexpr int kHashBits = 10;                    // per-warp table: 1024 entries for a 2048-position sub-range
-constexpr int kTokPerThread = 4;                 // encode: consecutive tokens per thread
-constexpr int kTile = kThreads * kTokPerThread;  // encode: tokens per tile (2048, at most 48 bits each)
-constexpr int kStageWords = 3584;                // 14 KiB bit stage (a tile emits <= 12 KiB + the partial unit)
+constexpr int kTokPerThread = 8;                 // encode: consecutive tokens per thread
+constexpr int kTile = kThreads * kTokPerThread;  // encode: tokens per tile (4096, at most 48 bits each)
+constexpr int kStageWords = 6400;                // 25 KiB bit stage (a tile emits <= 24 KiB + the partial unit)
 constexpr uint32_t kTokNone = 0x100u;            // compact token stream: padding (emits nothing)
 constexpr uint32_t kTokEob = 0x101u;             //                       end of block
 // other compact tokens: < 0x100 literal byte; >= 0x200 match, (dist << 9) | len (dfl::tok_match)
@@ -969,11 +969,16 @@ __global__ void __launch_bounds__(kThreads, 2)
           for (int j = 0; j < kTokPerThread; ++j) tk[j] = j == 0 ? kTokEob : kTokNone;
         } else {
           const uint4 v = *reinterpret_cast<const uint4*>(tokens + sr * (int)dfl::kSub + l);
+          const uint4 w = *reinterpret_cast<const uint4*>(tokens + sr * (int)dfl::kSub + l + 4);
           const int have = (int)sm.sub_cnt[sr] - l;
           tk[0] = v.x;
           tk[1] = have > 1 ? v.y : kTokNone;
           tk[2] = have > 2 ? v.z : kTokNone;
           tk[3] = have > 3 ? v.w : kTokNone;
+          tk[4] = have > 4 ? w.x : kTokNone;
+          tk[5] = have > 5 ? w.y : kTokNone;
+          tk[6] = have > 6 ? w.z : kTokNone;
+          tk[7] = have > 7 ? w.w : kTokNone;
         }
         uint32_t mybits = 0;
 #pragma unroll
