@@ -159,18 +159,25 @@ __device__ __forceinline__ uint32_t ld32u(uint32_t saddr) {
 __device__ __forceinline__ int match_len(uint32_t ds, int p, int c, int maxl) {
   const uint32_t ap = (ds + (uint32_t)p) & ~3u, ac = (ds + (uint32_t)c) & ~3u;
   const uint32_t sp = ((ds + (uint32_t)p) & 3u) * 8u, sc = ((ds + (uint32_t)c) & 3u) * 8u;
-  uint32_t wp = lds_u32(ap), wc = lds_u32(ac);
-  int l = 0;
-  while (l < maxl) {
-    const uint32_t np = lds_u32(ap + (uint32_t)l + 4u), nc = lds_u32(ac + (uint32_t)l + 4u);
-    const uint32_t x = __funnelshift_r(wp, np, sp) ^ __funnelshift_r(wc, nc, sc);
-    if (x) {
-      l += (__ffs((int)x) - 1) >> 3;
-      break;
+  // the first 8 bytes without a branch (six independent loads, one latency): most matches of columnar data end here
+  const uint32_t p0 = lds_u32(ap), p1 = lds_u32(ap + 4u), c0 = lds_u32(ac), c1 = lds_u32(ac + 4u);
+  uint32_t wp = lds_u32(ap + 8u), wc = lds_u32(ac + 8u);
+  const uint32_t x0 = __funnelshift_r(p0, p1, sp) ^ __funnelshift_r(c0, c1, sc);
+  const uint32_t x1 = __funnelshift_r(p1, wp, sp) ^ __funnelshift_r(c1, wc, sc);
+  int l = x0 ? (__ffs((int)x0) - 1) >> 3 : 4 + ((__ffs((int)x1) - 1) >> 3);
+  if ((x0 | x1) == 0) {
+    l = 8;
+    while (l < maxl) {
+      const uint32_t np = lds_u32(ap + (uint32_t)l + 4u), nc = lds_u32(ac + (uint32_t)l + 4u);
+      const uint32_t x = __funnelshift_r(wp, np, sp) ^ __funnelshift_r(wc, nc, sc);
+      if (x) {
+        l += (__ffs((int)x) - 1) >> 3;
+        break;
+      }
+      wp = np;
+      wc = nc;
+      l += 4;
     }
-    wp = np;
-    wc = nc;
-    l += 4;
   }
   return min(l, maxl);
 }
