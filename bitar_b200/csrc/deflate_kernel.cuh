@@ -354,18 +354,17 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
     }
     const bool start = ((reach >> lane) & 1u) && p < n;
     const unsigned starts = __ballot_sync(kFull, start);
-    if (start) {
-      uint32_t tok;
-      if (adv > 1) {
-        tok = dfl::tok_match(adv, dist);
-        const uint32_t d1 = (uint32_t)dist - 1u;
-        atomicAdd(&sm.ll_freq[257u + sm.len_sym_lut[adv - 3]], 1u);
-        atomicAdd(&sm.d_freq[sm.dist_sym_lut[d1 < 256u ? d1 : 256u + (d1 >> 7)]], 1u);
-      } else {
-        tok = lds_u8(ds + p);
-        atomicAdd(&sm.ll_freq[tok], 1u);
+    {   // token + symbol counts, without a literal / match branch (the loads are harmless for the other kind)
+      const bool is_match = adv > 1;
+      const uint32_t byte = lds_u8(ds + p);
+      const uint32_t d1 = is_match ? (uint32_t)dist - 1u : 0u;
+      const uint32_t len_sym = sm.len_sym_lut[is_match ? adv - 3 : 0];
+      const uint32_t dist_sym = sm.dist_sym_lut[d1 < 256u ? d1 : 256u + (d1 >> 7)];
+      if (start) {
+        atomicAdd(&sm.ll_freq[is_match ? 257u + len_sym : byte], 1u);
+        if (is_match) atomicAdd(&sm.d_freq[dist_sym], 1u);
+        out[cnt + (uint32_t)__popc(starts & lt_mask)] = is_match ? dfl::tok_match(adv, dist) : byte;
       }
-      out[cnt + (uint32_t)__popc(starts & lt_mask)] = tok;
     }
     cnt += (uint32_t)__popc(starts);
   }
