@@ -164,9 +164,8 @@ __device__ __forceinline__ int match_len(uint32_t ds, int p, int c, int maxl) {
   uint32_t wp = lds_u32(ap + 8u), wc = lds_u32(ac + 8u);
   const uint32_t x0 = __funnelshift_r(p0, p1, sp) ^ __funnelshift_r(c0, c1, sc);
   const uint32_t x1 = __funnelshift_r(p1, wp, sp) ^ __funnelshift_r(c1, wc, sc);
-  int l = x0 ? (__ffs((int)x0) - 1) >> 3 : 4 + ((__ffs((int)x1) - 1) >> 3);
-  if ((x0 | x1) == 0) {
-    l = 8;
+  int l = x0 ? (__ffs((int)x0) - 1) >> 3 : x1 ? 4 + ((__ffs((int)x1) - 1) >> 3) : 8;
+  if ((x0 | x1) == 0 && maxl > 8) {
     while (l < maxl) {
       const uint32_t np = lds_u32(ap + (uint32_t)l + 4u), nc = lds_u32(ac + (uint32_t)l + 4u);
       const uint32_t x = __funnelshift_r(wp, np, sp) ^ __funnelshift_r(wc, nc, sc);
@@ -315,14 +314,13 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
     if (lower) cand = (uint32_t)(base + 31 - __clz((int)lower));
     const int a = carry - base;                       // where the parse enters this window (>= 0)
     if (a >= 32) continue;                            // the whole window lies inside the previous match
-    int adv = 1, dist = 0;
-    if (cand != kNoCand && p >= carry) {
-      const int len = match_len(ds, p, (int)cand, min(dfl::kMaxMatch, sub_end - p));
-      if (len >= dfl::kMinMatch) {
-        adv = len;
-        dist = p - (int)cand;
-      }
-    }
+    // every lane runs the (branch-free) first 8 bytes of the match extension; lanes without a usable candidate
+    // compare their position with itself under a length limit of 0
+    const bool has_cand = cand != kNoCand && p >= carry;
+    const int c = has_cand ? (int)cand : p;
+    const int len = match_len(ds, p, c, has_cand ? min(dfl::kMaxMatch, sub_end - p) : 0);
+    const bool hit = len >= dfl::kMinMatch;
+    int adv = hit ? len : 1, dist = hit ? p - c : 0;
     {   // lazy step: a match yields to a strictly longer match that starts at the next position of the window
       const int next_adv = __shfl_down_sync(kFull, adv, 1);
       if (lane < 31 && adv > 1 && next_adv > adv) {
