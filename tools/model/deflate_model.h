@@ -27,6 +27,7 @@ struct Params {
   int far3 = 4096;      // reject length-3 matches farther than this (0 = keep all)
   int huffman = 2;      // 1 fixed only, 2 dynamic (min of stored/fixed/dynamic)
   int block = 65536;    // sub-block size inside a chunk (window restarts at sub-block start)
+  int near_mode = 0;    // 0: nearest lower lane of the window with the same HASH; 1..: same 4-byte WORD at a distance of set #near_mode
   int lazy = 1;         // 1: a match yields to a strictly longer match starting at the next position of its window
   int sub_log2 = kSubLog2;  // matches stay inside the 2^sub_log2-byte sub-range of their position and the
                         // parallel-inflate index is appended (deflate_common.h); 0 = off
@@ -82,14 +83,23 @@ inline void find_tokens(const uint8_t* d, int n, const Params& P, std::vector<ui
       old[t] = valid[t] ? head[h[t]] : 0;
       near[t] = -1;
     }
+    static const int kSets[4][16] = {{0}, {1, 2, 3, 4, 6, 8, 12, 16, 24, 0}, {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 20, 24, 28, 0}, {1, 2, 4, 8, 16, 0}};
     for (int w0 = 0; w0 < P.step; w0 += 32)
       for (int l = 1; l < 32 && w0 + l < P.step; ++l) {
         if (!valid[w0 + l]) continue;
-        for (int k = l - 1; k >= 0; --k)
-          if (valid[w0 + k] && h[w0 + k] == h[w0 + l]) {
-            near[w0 + l] = base + w0 + k;
-            break;
-          }
+        if (P.near_mode == 0) {
+          for (int k = l - 1; k >= 0; --k)
+            if (valid[w0 + k] && h[w0 + k] == h[w0 + l]) {
+              near[w0 + l] = base + w0 + k;
+              break;
+            }
+        } else {
+          for (const int* dd = kSets[P.near_mode]; *dd; ++dd)
+            if (*dd <= l && load32(d, (size_t)n, (size_t)(base + w0 + l)) == load32(d, (size_t)n, (size_t)(base + w0 + l - *dd))) {
+              near[w0 + l] = base + w0 + l - *dd;
+              break;
+            }
+        }
       }
     for (int t = 0; t < P.step; ++t)
       if (valid[t]) head[h[t]] = std::max(head[h[t]], (uint32_t)(base + t + 1));
