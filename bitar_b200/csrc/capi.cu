@@ -44,6 +44,16 @@ int fail(int code, const char* fmt, ...) {
     if (e_ != cudaSuccess) return fail(code, "%s: %s", #expr, cudaGetErrorString(e_));       \
   } while (0)
 
+// Up to 16 streams per device (8 queue pairs, each with a copy-back stream for staged calls): more hardware queues
+// than the driver's default 8, or streams sharing one serialise.  Takes effect when the library is loaded before the
+// process initialises CUDA (the env var is read then); an existing setting is left alone.
+struct ConnectionsDefault {
+  ConnectionsDefault() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+} g_connections_default;
+
+constexpr uint32_t kMaxStageBatches = 16;
+constexpr size_t kStageBatchBytes = (size_t)16 << 20;   // inflated bytes per batch of a staged call
+
 struct QueuePair {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_start = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_stop = nullptr;
@@ -71,6 +81,11 @@ struct QueuePair {
   size_t stage_out_cap = 0;
   bool stage_src = false, stage_dst = false;
   bool stage_dst_contig = false;        // destinations form one range of equal-capacity segments (Decompress())
+  size_t stage_out_bytes = 0;           // sum of the call's destination capacities
+  // staged calls run in batches: batch b's copy-back (copy_stream) overlaps batch b+1's gather + inflate (stream)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_batch[kMaxStageBatches] = {};
+  cudaEvent_t ev_copied = nullptr;
   bitar_result* user_out = nullptr;
   uint32_t pending_n = 0;
   std::atomic<int> busy{0};
@@ -264,6 +279,13 @@ int inflate_prepare_staging(QueuePair* q, uint32_t n) {
   // Decompress() lays segment i at out + i * S (src/memory.cc:482-493): then the staged output mirrors that
   // layout and goes back with ONE copy-engine transfer (which, unlike a kernel, runs beside the inflate kernels of
   // the other queue pairs); only the last segment, the one that may be short, is copied by produced size.
+  q->stage_out_bytes = need_out;
+  if (q->stage_dst && !q->copy_stream) {
+    CU_TRY(cudaStreamCreateWithFlags(&q->copy_stream, cudaStreamNonBlocking), BITAR_E_OUT_OF_MEMORY);
+    for (uint32_t b = 0; b < kMaxStageBatches; ++b)
+      CU_TRY(cudaEventCreateWithFlags(&q->ev_batch[b], cudaEventDisableTiming), BITAR_E_OUT_OF_MEMORY);
+    CU_TRY(cudaEventCreateWithFlags(&q->ev_copied, cudaEventDisableTiming), BITAR_E_OUT_OF_MEMORY);
+  }
   q->stage_dst_contig = q->stage_dst && n > 1;
   for (uint32_t i = 1; i < n && q->stage_dst_contig; ++i)
     q->stage_dst_contig = q->h_orig[i].dst_cap == q->h_orig[0].dst_cap &&
@@ -317,25 +339,55 @@ int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, b
   if (e == cudaSuccess) e = cudaMemsetAsync(q->d_counter, 0, 8 * sizeof(unsigned int), q->stream);
   if (e == cudaSuccess && (q->stage_src || q->stage_dst))
     e = cudaMemcpyAsync(q->d_orig, q->h_orig, (size_t)n * sizeof(bitar_chunk), cudaMemcpyHostToDevice, q->stream);
-  if (e == cudaSuccess && q->stage_src) {
-    stage_copy_kernel<<<n, 256, 0, q->stream>>>(q->d_orig, q->d_ops, nullptr, 0);
-    e = cudaGetLastError();
-    g_launches.fetch_add(1);
+  // Staged inflate calls (host-resident buffers) run in batches so that the copy-back of one batch (PCIe device ->
+  // host) overlaps the gather (PCIe host -> device) and the kernels of the next one; everything else is one batch.
+  uint32_t nb = 1;
+  if (q->stage_dst && n > 1) {
+    const size_t want = q->stage_out_bytes / kStageBatchBytes;
+    nb = (uint32_t)(want < 1 ? 1 : want > kMaxStageBatches ? kMaxStageBatches : want);
+    if (nb > n) nb = n;
   }
-  if (e == cudaSuccess) e = cudaEventRecord(q->ev_k0, q->stream);
-  if (e == cudaSuccess) e = launch(q);
-  if (e == cudaSuccess) e = cudaEventRecord(q->ev_k1, q->stream);
-  if (e == cudaSuccess && q->stage_dst_contig) {
-    e = cudaMemcpyAsync(q->h_orig[0].dst, q->h_ops[0].dst, (size_t)(n - 1) * q->h_orig[0].dst_cap, cudaMemcpyDeviceToHost, q->stream);
-    if (e == cudaSuccess) {
-      stage_copy_kernel<<<1, 256, 0, q->stream>>>(q->d_ops + (n - 1), q->d_orig + (n - 1), q->d_res + (n - 1), 1);
+  const uint32_t per = (n + nb - 1) / nb;
+  for (uint32_t b = 0, first = 0; first < n && e == cudaSuccess; ++b, first += per) {
+    const uint32_t count = n - first < per ? n - first : per;
+    const bool last = first + count == n;
+    if (q->stage_src) {
+      stage_copy_kernel<<<count, 256, 0, q->stream>>>(q->d_orig + first, q->d_ops + first, nullptr, 0);
       e = cudaGetLastError();
       g_launches.fetch_add(1);
     }
-  } else if (e == cudaSuccess && q->stage_dst) {
-    stage_copy_kernel<<<n, 256, 0, q->stream>>>(q->d_ops, q->d_orig, q->d_res, 1);
-    e = cudaGetLastError();
-    g_launches.fetch_add(1);
+    if (e == cudaSuccess && b == 0) e = cudaEventRecord(q->ev_k0, q->stream);
+    if (e == cudaSuccess && b > 0) e = cudaMemsetAsync(q->d_counter, 0, 8 * sizeof(unsigned int), q->stream);
+    if (e == cudaSuccess) e = launch(q, first, count);
+    if (e == cudaSuccess && last) e = cudaEventRecord(q->ev_k1, q->stream);
+    if (e != cudaSuccess || !q->stage_dst) continue;
+    cudaStream_t cs = q->stream;
+    if (nb > 1) {
+      cs = q->copy_stream;
+      e = cudaEventRecord(q->ev_batch[b], q->stream);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, q->ev_batch[b], 0);
+      if (e != cudaSuccess) continue;
+    }
+    if (q->stage_dst_contig) {
+      // one copy-engine transfer for the batch's full segments; the call's last segment, the one that may be
+      // short, goes by its produced size
+      const uint32_t full = last ? count - 1 : count;
+      if (full)
+        e = cudaMemcpyAsync(q->h_orig[first].dst, q->h_ops[first].dst, (size_t)full * q->h_orig[0].dst_cap, cudaMemcpyDeviceToHost, cs);
+      if (e == cudaSuccess && last) {
+        stage_copy_kernel<<<1, 256, 0, cs>>>(q->d_ops + (n - 1), q->d_orig + (n - 1), q->d_res + (n - 1), 1);
+        e = cudaGetLastError();
+        g_launches.fetch_add(1);
+      }
+    } else {
+      stage_copy_kernel<<<count, 256, 0, cs>>>(q->d_ops + first, q->d_orig + first, q->d_res + first, 1);
+      e = cudaGetLastError();
+      g_launches.fetch_add(1);
+    }
+    if (e == cudaSuccess && nb > 1 && last) {
+      e = cudaEventRecord(q->ev_copied, cs);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(q->stream, q->ev_copied, 0);
+    }
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(q->h_res, q->d_res, (size_t)n * sizeof(bitar_result), cudaMemcpyDeviceToHost, q->stream);
   if (e == cudaSuccess) e = cudaEventRecord(q->ev_stop, q->stream);
@@ -462,6 +514,9 @@ int bitar_dev_open(int device_id, uint16_t n_qps, const bitar_cfg* cfg_in, bitar
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
   }
+  // same carve-out for the small helper kernels as for the codec kernels (see inflate_kernel.cuh)
+  cudaFuncSetAttribute(stage_copy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(bitar::xk::inflate_plan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaError_t e = bitar::dk::deflate_grid(device_id, dev->sm_count, &dev->deflate_grid);
   if (const char* g = getenv("BITAR_DEBUG_DEFLATE_GRID")) {   // tuning experiments only
     if (atoi(g) > 0) dev->deflate_grid = atoi(g);
@@ -523,6 +578,10 @@ int bitar_dev_close(bitar_dev* dev) {
     if (q->ev_k0) cudaEventDestroy(q->ev_k0);
     if (q->ev_k1) cudaEventDestroy(q->ev_k1);
     if (q->ev_stop) cudaEventDestroy(q->ev_stop);
+    for (uint32_t b = 0; b < kMaxStageBatches; ++b)
+      if (q->ev_batch[b]) cudaEventDestroy(q->ev_batch[b]);
+    if (q->ev_copied) cudaEventDestroy(q->ev_copied);
+    if (q->copy_stream) cudaStreamDestroy(q->copy_stream);
     if (q->stream) cudaStreamDestroy(q->stream);
     delete q;
   }
@@ -540,19 +599,22 @@ int bitar_dev_config(const bitar_dev* dev, bitar_cfg* cfg_out) {
 uint16_t bitar_dev_num_qps(const bitar_dev* dev) { return dev ? (uint16_t)dev->qps.size() : 0; }
 
 int bitar_qp_deflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, bitar_result* results) {
-  return qp_submit(dev, qp, ops, n, results, [&](QueuePair* q) -> cudaError_t {
+  return qp_submit(dev, qp, ops, n, results, [&](QueuePair* q, uint32_t first, uint32_t count) -> cudaError_t {
     if (!q->d_tokens) {
       cudaError_t e = cudaMalloc((void**)&q->d_tokens, bitar::dk::deflate_scratch_bytes(dev->deflate_grid));
       if (e != cudaSuccess) return e;
     }
-    return bitar::dk::deflate_launch(q->d_ops, n, q->d_res, q->d_counter, q->d_tokens, dev->deflate_grid,
+    return bitar::dk::deflate_launch(q->d_ops + first, count, q->d_res + first, q->d_counter, q->d_tokens, dev->deflate_grid,
                                      dev->cfg.huffman_enc, dev->cfg.checksum_type, g_deflate_prof.load(), q->stream);
   });
 }
 
 int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, bitar_result* results) {
-  return qp_submit(dev, qp, ops, n, results, [&](QueuePair* q) -> cudaError_t {
+  return qp_submit(dev, qp, ops, n, results, [&](QueuePair* q, uint32_t first, uint32_t n) -> cudaError_t {
     using namespace bitar::ik;
+    bitar_chunk* const d_ops = q->d_ops + first;       // this batch of the call (one batch unless staged)
+    bitar_result* const d_res = q->d_res + first;
+    const bitar_chunk* const h_ops = q->h_ops + first;
     const int ck = dev->cfg.checksum_type, id = dev->id, sms = dev->sm_count;
     const int variant = inflate_variant();
     if (variant >= 20) {
@@ -562,7 +624,7 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
       size_t blocks = 0;
       uint32_t max_cap = 0;
       for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t cap = q->h_ops[i].dst_cap < BITAR_MAX_SEG_SIZE ? q->h_ops[i].dst_cap : BITAR_MAX_SEG_SIZE;
+        const uint32_t cap = h_ops[i].dst_cap < BITAR_MAX_SEG_SIZE ? h_ops[i].dst_cap : BITAR_MAX_SEG_SIZE;
         blocks += (cap + 65535u) >> 16;
         max_cap = cap > max_cap ? cap : max_cap;
       }
@@ -591,27 +653,27 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
       }
       Counters* pc = reinterpret_cast<Counters*>(q->d_counter);
       CkAcc* acc = ck != BITAR_CHECKSUM_NONE ? q->d_ck : nullptr;
-      inflate_plan_kernel<<<(n + 127) / 128, 128, 0, q->stream>>>(q->d_ops, n, q->d_res, q->d_tasks, small_tasks, q->d_generic, pc, acc, 1,
+      inflate_plan_kernel<<<(n + 127) / 128, 128, 0, q->stream>>>(d_ops, n, d_res, q->d_tasks, small_tasks, q->d_generic, pc, acc, 1,
                                                                   small_mode ? 1 : 0);
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) return e;
       g_launches.fetch_add(2);
       switch (variant) {   // default = 22: 24 warps / SM, 9-bit litlen root (measured best on the columnar mix)
-        case 20: e = IndexedConfig<10, 1344, 8, 512, 128, 20>::launch(q->d_ops, q->d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
-        case 21: e = IndexedConfig<10, 1344, 8, 512, 128, 16>::launch(q->d_ops, q->d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
+        case 20: e = IndexedConfig<10, 1344, 8, 512, 128, 20>::launch(d_ops, d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
+        case 21: e = IndexedConfig<10, 1344, 8, 512, 128, 16>::launch(d_ops, d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
         default:
-        case 22: e = IndexedConfig<9, 864, 7, 256, 128, 24>::launch(q->d_ops, q->d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
-        case 23: e = IndexedConfig<10, 1344, 8, 512, 256, 14>::launch(q->d_ops, q->d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
-        case 24: e = IndexedConfig<10, 1344, 7, 256, 128, 24>::launch(q->d_ops, q->d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
-        case 25: e = IndexedConfig<10, 1344, 8, 512, 128, 22>::launch(q->d_ops, q->d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
+        case 22: e = IndexedConfig<9, 864, 7, 256, 128, 24>::launch(d_ops, d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
+        case 23: e = IndexedConfig<10, 1344, 8, 512, 256, 14>::launch(d_ops, d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
+        case 24: e = IndexedConfig<10, 1344, 7, 256, 128, 24>::launch(d_ops, d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
+        case 25: e = IndexedConfig<10, 1344, 8, 512, 128, 22>::launch(d_ops, d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
       }
       if (e != cudaSuccess) return e;
       if (small_mode) {   // blocks of at most 8 sub-ranges: four to a warp
-        e = IndexedConfig<9, 864, 7, 256, 128, 11, 8>::launch(q->d_ops, q->d_res, small_tasks, pc, acc, ck, n, id, sms, q->stream);
+        e = IndexedConfig<9, 864, 7, 256, 128, 11, 8>::launch(d_ops, d_res, small_tasks, pc, acc, ck, n, id, sms, q->stream);
         if (e != cudaSuccess) return e;
         g_launches.fetch_add(1);
       }
-      return InflateConfig<32, 10, 8, 1024, 4>::launch(q->d_ops, n, q->d_res, &pc->generic_next, ck, id, sms, q->stream,
+      return InflateConfig<32, 10, 8, 1024, 4>::launch(d_ops, n, d_res, &pc->generic_next, ck, id, sms, q->stream,
                                                        q->d_generic, &pc->n_generic);
     }
     if (variant >= 12) {   // lane-per-stream kernels (inflate_fast.h)
@@ -627,7 +689,7 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
           if (e != cudaSuccess) return e;
           q->lane_scratch_bytes = need;
         }
-        return Cfg::launch(q->d_ops, n, q->d_res, q->d_counter, q->d_lane_scratch, ck, id, sms, q->stream);
+        return Cfg::launch(d_ops, n, d_res, q->d_counter, q->d_lane_scratch, ck, id, sms, q->stream);
       };
       switch (variant) {
         default:
@@ -638,14 +700,14 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
     }
     switch (variant) {
       default:
-      case 0: return InflateConfig<8, 10, 8, 1024, 2>::launch(q->d_ops, n, q->d_res, q->d_counter, ck, id, sms, q->stream);
-      case 1: return InflateConfig<8, 9, 7, 1024, 2>::launch(q->d_ops, n, q->d_res, q->d_counter, ck, id, sms, q->stream);
-      case 2: return InflateConfig<4, 10, 8, 1024, 1>::launch(q->d_ops, n, q->d_res, q->d_counter, ck, id, sms, q->stream);
-      case 3: return InflateConfig<4, 9, 7, 1024, 1>::launch(q->d_ops, n, q->d_res, q->d_counter, ck, id, sms, q->stream);
-      case 4: return InflateConfig<16, 10, 8, 1024, 4>::launch(q->d_ops, n, q->d_res, q->d_counter, ck, id, sms, q->stream);
-      case 5: return InflateConfig<32, 10, 8, 1024, 4>::launch(q->d_ops, n, q->d_res, q->d_counter, ck, id, sms, q->stream);
-      case 6: return InflateConfig<2, 9, 7, 1024, 1>::launch(q->d_ops, n, q->d_res, q->d_counter, ck, id, sms, q->stream);
-      case 7: return InflateConfig<8, 10, 8, 1024, 1>::launch(q->d_ops, n, q->d_res, q->d_counter, ck, id, sms, q->stream);
+      case 0: return InflateConfig<8, 10, 8, 1024, 2>::launch(d_ops, n, d_res, q->d_counter, ck, id, sms, q->stream);
+      case 1: return InflateConfig<8, 9, 7, 1024, 2>::launch(d_ops, n, d_res, q->d_counter, ck, id, sms, q->stream);
+      case 2: return InflateConfig<4, 10, 8, 1024, 1>::launch(d_ops, n, d_res, q->d_counter, ck, id, sms, q->stream);
+      case 3: return InflateConfig<4, 9, 7, 1024, 1>::launch(d_ops, n, d_res, q->d_counter, ck, id, sms, q->stream);
+      case 4: return InflateConfig<16, 10, 8, 1024, 4>::launch(d_ops, n, d_res, q->d_counter, ck, id, sms, q->stream);
+      case 5: return InflateConfig<32, 10, 8, 1024, 4>::launch(d_ops, n, d_res, q->d_counter, ck, id, sms, q->stream);
+      case 6: return InflateConfig<2, 9, 7, 1024, 1>::launch(d_ops, n, d_res, q->d_counter, ck, id, sms, q->stream);
+      case 7: return InflateConfig<8, 10, 8, 1024, 1>::launch(d_ops, n, d_res, q->d_counter, ck, id, sms, q->stream);
     }
   }, /*inflate=*/true);
 }

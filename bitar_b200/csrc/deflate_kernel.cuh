@@ -1097,6 +1097,7 @@ inline cudaError_t deflate_grid(int device, int sm_count, int* grid_out) {
   if (ctas == 0) {
     cudaError_t e = cudaFuncSetAttribute(deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(deflate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, deflate_kernel, kThreads, sizeof(Smem));
     if (e != cudaSuccess) return e;
     if (ctas < 1) return cudaErrorLaunchOutOfResources;

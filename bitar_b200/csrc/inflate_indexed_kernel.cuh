@@ -426,6 +426,8 @@ struct IndexedConfig {
       auto kern_ck = inflate_indexed_kernel<LBITS, LT, DBITS, DT, RING, WARPS, true, GROUP>;
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem) != cudaSuccess) return 0;
       if (cudaFuncSetAttribute(kern_ck, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem) != cudaSuccess) return 0;
+      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      cudaFuncSetAttribute(kern_ck, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, kern_ck, kThreads, kSmem) != cudaSuccess) return 0;
     }
     return c;

@@ -127,6 +127,9 @@ struct InflateConfig {
     if (ctas_per_sm == 0) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
       if (e != cudaSuccess) return e;
+      // every kernel of the library asks for the same shared-memory carve-out: an SM has to drain before it can
+      // change the split, which serialises kernels of different queue pairs (and of one stream) otherwise
+      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kThreads, kSmem);
       if (e != cudaSuccess) return e;
       if (ctas_per_sm < 1) return cudaErrorLaunchOutOfResources;

@@ -72,8 +72,14 @@ def main():
     mib = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     qps_list = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1, 4]
     data = synth.lineitem_like(mib << 20)
+    # SWEEP_BUFFERS=device|pinned and SWEEP_SEGS=4096,65536,... restrict the sweep
+    only = os.environ.get("SWEEP_BUFFERS", "")
+    segs = [int(x) for x in os.environ.get("SWEEP_SEGS", "").split(",") if x] or \
+        [4096, 8192, 16384, 32768, 65536, 131072, 262144, 524288, 1048576]
     for pinned in (False, True):
-        for seg in (4096, 8192, 16384, 32768, 65536, 131072, 262144, 524288, 1048576):
+        if only and only != ("pinned" if pinned else "device"):
+            continue
+        for seg in segs:
             for qps in qps_list:
                 print(json.dumps(run(data, seg, qps, pinned)), flush=True)
 
