@@ -19,6 +19,11 @@
 #include <vector>
 
 #include "../../include/bitar_cuda.h"
+#include "deflate_kernel.cuh"      // bitar::dk: 16 warps per CTA, 2 CTAs per SM, chunks up to 1 MiB
+#define BITAR_DK_NS dks            // bitar::dks: 4 warps per CTA, 6 CTAs per SM, chunks up to 16 KiB
+#define BITAR_DK_WARPS 4
+#define BITAR_DK_BLOCK_MAX 16384
+#define BITAR_DK_MIN_CTAS 6
 #include "deflate_kernel.cuh"
 #include "inflate_kernel.cuh"
 #include "inflate_fast_kernel.cuh"
@@ -101,6 +106,7 @@ struct bitar_dev {
   bitar_cfg cfg{};
   std::vector<QueuePair*> qps;
   int deflate_grid = 0;
+  int deflate_grid_small = 0;       // grid of the small-chunk instance (bitar::dks)
   // slot pool
   std::mutex mu;
   std::vector<void*> slabs;
@@ -518,6 +524,7 @@ int bitar_dev_open(int device_id, uint16_t n_qps, const bitar_cfg* cfg_in, bitar
   cudaFuncSetAttribute(stage_copy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(bitar::xk::inflate_plan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaError_t e = bitar::dk::deflate_grid(device_id, dev->sm_count, &dev->deflate_grid);
+  if (e == cudaSuccess) e = bitar::dks::deflate_grid(device_id, dev->sm_count, &dev->deflate_grid_small);
   if (const char* g = getenv("BITAR_DEBUG_DEFLATE_GRID")) {   // tuning experiments only
     if (atoi(g) > 0) dev->deflate_grid = atoi(g);
   }
@@ -601,9 +608,18 @@ uint16_t bitar_dev_num_qps(const bitar_dev* dev) { return dev ? (uint16_t)dev->q
 int bitar_qp_deflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, bitar_result* results) {
   return qp_submit(dev, qp, ops, n, results, [&](QueuePair* q, uint32_t first, uint32_t count) -> cudaError_t {
     if (!q->d_tokens) {
-      cudaError_t e = cudaMalloc((void**)&q->d_tokens, bitar::dk::deflate_scratch_bytes(dev->deflate_grid));
+      const size_t a = bitar::dk::deflate_scratch_bytes(dev->deflate_grid), b = bitar::dks::deflate_scratch_bytes(dev->deflate_grid_small);
+      cudaError_t e = cudaMalloc((void**)&q->d_tokens, a > b ? a : b);
       if (e != cudaSuccess) return e;
     }
+    // calls whose chunks all fit 16 KiB (8 sub-ranges: half of a 16-warp CTA would idle) go to the instance with
+    // 4 warps per CTA and three times the CTAs per SM; same output
+    uint32_t max_len = 0;
+    for (uint32_t i = 0; i < count; ++i) max_len = q->h_ops[first + i].src_len > max_len ? q->h_ops[first + i].src_len : max_len;
+    static const int small_mode = getenv("BITAR_DEFLATE_SMALL") ? atoi(getenv("BITAR_DEFLATE_SMALL")) : 1;   // 0: off (A/B runs)
+    if (small_mode && max_len <= (uint32_t)bitar::dks::kBlockMax)
+      return bitar::dks::deflate_launch(q->d_ops + first, count, q->d_res + first, q->d_counter, q->d_tokens, dev->deflate_grid_small,
+                                        dev->cfg.huffman_enc, dev->cfg.checksum_type, g_deflate_prof.load(), q->stream);
     return bitar::dk::deflate_launch(q->d_ops + first, count, q->d_res + first, q->d_counter, q->d_tokens, dev->deflate_grid,
                                      dev->cfg.huffman_enc, dev->cfg.checksum_type, g_deflate_prof.load(), q->stream);
   });

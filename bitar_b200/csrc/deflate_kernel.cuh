@@ -30,7 +30,15 @@
 //
 // Replaces: the compress ops assembled at /root/reference/src/memory.cc:350-430 and executed behind
 // src/device.cc:464-535 with the xform of src/config.cc:83-91 (DEFLATE, level 1, fixed | dynamic).
-#pragma once
+//
+// This header is a template over four macros and may be included once per configuration (capi.cu includes it twice):
+//   BITAR_DK_NS        namespace of the instance                     default dk    small chunks: dks
+//   BITAR_DK_WARPS     warps per CTA                                         16                  4
+//   BITAR_DK_BLOCK_MAX bytes per block (= largest chunk when < 64 KiB)       65536               16384
+//   BITAR_DK_MIN_CTAS  resident CTAs per SM the kernel is compiled for       2                   6
+// The output does not depend on the configuration (the match phase works per 2 KiB sub-range, the plan per block);
+// the small instance exists because a 4 KiB chunk keeps 2 of a CTA's warps busy: it trades warps per CTA for
+// CTAs per SM.  It is only valid for chunks of at most BITAR_DK_BLOCK_MAX bytes.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -38,16 +46,26 @@
 #include "checksum.h"
 #include "deflate_common.h"
 
-namespace bitar {
-namespace dk {
+#ifndef BITAR_DK_NS
+#define BITAR_DK_NS dk
+#define BITAR_DK_WARPS 16
+#define BITAR_DK_BLOCK_MAX 65536
+#define BITAR_DK_MIN_CTAS 2
+#endif
 
-constexpr int kWarps = 16;
+namespace bitar {
+namespace BITAR_DK_NS {
+
+constexpr int kWarps = BITAR_DK_WARPS;
 constexpr int kThreads = kWarps * 32;
-constexpr int kBlockMax = 65536;                 // sub-block size (positions fit 16 bits)
+constexpr int kBlockMax = BITAR_DK_BLOCK_MAX;    // sub-block size (positions fit 16 bits)
+constexpr uint32_t kMaxSeg = kBlockMax < 65536 ? (uint32_t)kBlockMax : (uint32_t)BITAR_MAX_SEG_SIZE;   // largest chunk
 constexpr int kHashBits = 10;                    // per-warp table: 1024 entries for a 2048-position sub-range
 constexpr int kTokPerThread = 8;                 // encode: consecutive tokens per thread
-constexpr int kTile = kThreads * kTokPerThread;  // encode: tokens per tile (4096, at most 48 bits each)
-constexpr int kStageWords = 6400;                // 25 KiB bit stage (a tile emits <= 24 KiB + the partial unit)
+constexpr int kTile = kThreads * kTokPerThread;  // encode: tokens per tile (4096 with 16 warps, at most 48 bits each)
+constexpr int kStageWords = kTile * 3 / 2 + 160; // bit stage: a tile's 6 bytes per token + the block header (<= 141 words) + the partial unit
+constexpr int kSeqPerThread = (328 + kThreads - 1) / kThreads;   // plan: code lengths (<= 316) per thread
+constexpr int kHdrPerThread = (19 + 316 + kThreads - 1) / kThreads;   // header: code-length items per thread
 constexpr uint32_t kTokNone = 0x100u;            // compact token stream: padding (emits nothing)
 constexpr uint32_t kTokEob = 0x101u;             //                       end of block
 // other compact tokens: < 0x100 literal byte; >= 0x200 match, (dist << 9) | len (dfl::tok_match)
@@ -72,12 +90,14 @@ struct EncodeArea {
 struct __align__(16) Smem {
   uint8_t raw[kBlockMax + 48];       // input block, shifted so that raw + (src & 15) is the first byte
   union {                            // the match phase and the plan/encode phases never overlap in time
-    uint16_t head[kWarps][(1 << kHashBits) + 32];   // per warp: hash -> most recent position (kNoCand = empty) + 32 dummy slots
+    struct {
+      uint16_t head[kWarps][(1 << kHashBits) + 32];   // per warp: hash -> most recent position (kNoCand = empty) + 32 dummy slots
+      uint8_t len_sym_lut[256];      // match length - 3 -> length symbol index (dfl::len_sym)
+      uint8_t dist_sym_lut[512];     // zlib's two-level map: d < 256 ? lut[d] : lut[256 + (d >> 7)], d = dist - 1
+    } m;                             // (the tables are longer than the bit stage: the look-up tables lie behind it)
     EncodeArea enc;
   } u;
   uint32_t keep[4];                  // the partially filled 16-byte unit of the stage while the tables use its space
-  uint8_t len_sym_lut[256];          // match length - 3 -> length symbol index (dfl::len_sym)
-  uint8_t dist_sym_lut[512];         // zlib's two-level map: d < 256 ? lut[d] : lut[256 + (d >> 7)], d = dist - 1
   uint32_t ll_freq[288];
   uint32_t d_freq[32];
   uint32_t ll_enc[288];              // code | (length << 16) under the chosen block type
@@ -91,7 +111,7 @@ struct __align__(16) Smem {
   uint32_t next_idx;                 // the chunk this CTA compresses next (fetched early, its input is prefetched)
   uint32_t sub_cnt[32];              // tokens of each sub-range of the block (compact, at tokens + sub * 2048)
   uint32_t sub_voff[34];             // encode: first slot of each sub-range (counts rounded up to kTokPerThread)
-  uint32_t index[(BITAR_MAX_SEG_SIZE >> dfl::kIdxBlockLog2) * 33 + 4];   // parallel-inflate index of the chunk (deflate_common.h)
+  uint32_t index[((kMaxSeg + 65535u) >> dfl::kIdxBlockLog2) * 33 + 4];   // parallel-inflate index of the chunk (deflate_common.h)
   uint32_t any_coded;                // some Huffman-coded block spans more than one sub-range
   uint32_t block_type;
   uint32_t tile_bits;
@@ -264,8 +284,7 @@ __device__ void sort512(Smem& sm) {
   for (uint32_t k = 2; k <= 512; k <<= 1) {
     for (uint32_t j = k >> 1; j > 0; j >>= 1) {
       __syncthreads();
-      uint32_t i = threadIdx.x;
-      if (i < 512) {
+      for (uint32_t i = threadIdx.x; i < 512; i += kThreads) {
         uint32_t ixj = i ^ j;
         if (ixj > i) {
           uint32_t a = sm.u.enc.sort_keys[i], b = sm.u.enc.sort_keys[ixj];
@@ -289,9 +308,9 @@ __device__ void sort512(Smem& sm) {
 __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int s0, int s1, int warp, int lane,
                                                uint32_t* __restrict__ tokens) {
   constexpr unsigned kFull = 0xFFFFFFFFu;
-  volatile uint16_t* head = sm.u.head[warp];          // head[1024..1055]: per-lane dummy slots, always empty
+  volatile uint16_t* head = sm.u.m.head[warp];          // head[1024..1055]: per-lane dummy slots, always empty
   {
-    uint32_t* h32 = reinterpret_cast<uint32_t*>(sm.u.head[warp]);
+    uint32_t* h32 = reinterpret_cast<uint32_t*>(sm.u.m.head[warp]);
     for (int i = lane; i < ((1 << kHashBits) + 32) / 2; i += 32) h32[i] = 0xFFFFFFFFu;
   }
   __syncwarp();
@@ -356,8 +375,8 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
       const bool is_match = adv > 1;
       const uint32_t byte = lds_u8(ds + p);
       const uint32_t d1 = is_match ? (uint32_t)dist - 1u : 0u;
-      const uint32_t len_sym = sm.len_sym_lut[is_match ? adv - 3 : 0];
-      const uint32_t dist_sym = sm.dist_sym_lut[d1 < 256u ? d1 : 256u + (d1 >> 7)];
+      const uint32_t len_sym = sm.u.m.len_sym_lut[is_match ? adv - 3 : 0];
+      const uint32_t dist_sym = sm.u.m.dist_sym_lut[d1 < 256u ? d1 : 256u + (d1 >> 7)];
       if (start) {
         atomicAdd(&sm.ll_freq[is_match ? 257u + len_sym : byte], 1u);
         if (is_match) atomicAdd(&sm.d_freq[dist_sym], 1u);
@@ -496,66 +515,77 @@ __device__ __forceinline__ uint32_t block_excl_scan(Smem& sm, uint32_t v, uint32
 }
 
 // Code-length RLE (dfl::cl_rle over the litlen lengths, then over the distance lengths) with one run per
-// thread: thread i owns position i of the concatenated length sequence and emits the tokens of the run that
-// starts there.  Same tokens, in the same order, as the serial function.
+// position: thread t owns positions [t * kSeqPerThread, +kSeqPerThread) of the concatenated length sequence (one
+// position per thread with 16 warps) and emits the tokens of the runs that start there.  Same tokens, in the same
+// order, as the serial function.
 __device__ __forceinline__ void cl_rle_parallel(Smem& sm, int tid, int lane, int warp) {
   dfl::BlockPlan& pl = sm.plan;
   const int hlit = pl.hlit, total_syms = pl.hlit + pl.hdist;
   if (tid < dfl::kNumCl) sm.u.enc.scratch.cl_freq[tid] = 0;
   uint8_t* seq = sm.u.enc.pp.seq;
-  if (tid < total_syms) seq[tid] = tid < hlit ? pl.ll_len[tid] : pl.d_len[tid - hlit];
+  for (int i = tid; i < total_syms; i += kThreads) seq[i] = i < hlit ? pl.ll_len[i] : pl.d_len[i - hlit];
   __syncthreads();
-  int v = 0, run = 0;
+  int v[kSeqPerThread], run[kSeqPerThread];
   uint32_t ntok = 0;
-  if (tid < total_syms) {
-    v = seq[tid];
-    const bool start = tid == 0 || tid == hlit || seq[tid - 1] != v;
-    if (start) {
-      const int end = tid < hlit ? hlit : total_syms;
-      run = 1;
-      while (tid + run < end && ((tid + run) & 3) && seq[tid + run] == v) ++run;   // to a word boundary
-      if (((tid + run) & 3) == 0) {                                                 // then four lengths per step
-        const uint32_t pat = (uint32_t)v * 0x01010101u;
-        while (tid + run + 4 <= end && *reinterpret_cast<const uint32_t*>(seq + tid + run) == pat) run += 4;
-      }
-      while (tid + run < end && seq[tid + run] == v) ++run;
-      if (v == 0) {
-        const int rem = run % 138;
-        ntok = (uint32_t)(run / 138 + (rem >= 3 ? 1 : rem));
-      } else {
-        const int rem = (run - 1) % 6;
-        ntok = (uint32_t)(1 + (run - 1) / 6 + (rem >= 3 ? 1 : rem));
+#pragma unroll
+  for (int k = 0; k < kSeqPerThread; ++k) {
+    const int pos = tid * kSeqPerThread + k;
+    v[k] = 0;
+    run[k] = 0;
+    if (pos < total_syms) {
+      v[k] = seq[pos];
+      const bool start = pos == 0 || pos == hlit || seq[pos - 1] != v[k];
+      if (start) {
+        const int end = pos < hlit ? hlit : total_syms;
+        int r = 1;
+        while (pos + r < end && ((pos + r) & 3) && seq[pos + r] == v[k]) ++r;   // to a word boundary
+        if (((pos + r) & 3) == 0) {                                             // then four lengths per step
+          const uint32_t pat = (uint32_t)v[k] * 0x01010101u;
+          while (pos + r + 4 <= end && *reinterpret_cast<const uint32_t*>(seq + pos + r) == pat) r += 4;
+        }
+        while (pos + r < end && seq[pos + r] == v[k]) ++r;
+        run[k] = r;
+        if (v[k] == 0) {
+          const int rem = r % 138;
+          ntok += (uint32_t)(r / 138 + (rem >= 3 ? 1 : rem));
+        } else {
+          const int rem = (r - 1) % 6;
+          ntok += (uint32_t)(1 + (r - 1) / 6 + (rem >= 3 ? 1 : rem));
+        }
       }
     }
   }
   uint32_t total = 0;
   uint32_t o = block_excl_scan(sm, ntok, &total, lane, warp);
-  if (run > 0) {
-    uint32_t* cl_freq = sm.u.enc.scratch.cl_freq;
-    const auto emit = [&](int sym, int extra) {
-      pl.cl_tok[o++] = (uint16_t)(sym | (extra << 5));
-      atomicAdd(&cl_freq[sym], 1u);
-    };
-    if (v == 0) {
-      while (run >= 11) {
-        const int r = run > 138 ? 138 : run;
-        emit(18, r - 11);
-        run -= r;
+  uint32_t* cl_freq = sm.u.enc.scratch.cl_freq;
+  const auto emit = [&](int sym, int extra) {
+    pl.cl_tok[o++] = (uint16_t)(sym | (extra << 5));
+    atomicAdd(&cl_freq[sym], 1u);
+  };
+#pragma unroll
+  for (int k = 0; k < kSeqPerThread; ++k) {
+    int r = run[k];
+    if (r <= 0) continue;
+    if (v[k] == 0) {
+      while (r >= 11) {
+        const int c = r > 138 ? 138 : r;
+        emit(18, c - 11);
+        r -= c;
       }
-      if (run >= 3) {
-        emit(17, run - 3);
-        run = 0;
+      if (r >= 3) {
+        emit(17, r - 3);
+        r = 0;
       }
-      while (run-- > 0) emit(0, 0);
+      while (r-- > 0) emit(0, 0);
     } else {
-      emit(v, 0);
-      run--;
-      while (run >= 3) {
-        const int r = run > 6 ? 6 : run;
-        emit(16, r - 3);
-        run -= r;
+      emit(v[k], 0);
+      r--;
+      while (r >= 3) {
+        const int c = r > 6 ? 6 : r;
+        emit(16, c - 3);
+        r -= c;
       }
-      while (run-- > 0) emit(v, 0);
+      while (r-- > 0) emit(v[k], 0);
     }
   }
   if (tid == 0) pl.n_cl_tok = (int)total;
@@ -610,7 +640,7 @@ __device__ __forceinline__ int token_bits(const Smem& sm, uint32_t tok, uint32_t
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
     deflate_kernel(const bitar_chunk* __restrict__ ops, uint32_t n_ops, bitar_result* __restrict__ results,
                    unsigned int* __restrict__ counter, uint32_t* __restrict__ token_scratch, int huffman,
                    int checksum_type, unsigned long long* __restrict__ prof) {
@@ -628,8 +658,6 @@ __global__ void __launch_bounds__(kThreads, 2)
     if (tid == 0) cks::crc_x2n_init(sm.x2n);
   }
   for (int i = tid; i < kStageWords; i += kThreads) sm.u.enc.stage[i] = 0;
-  for (int i = tid; i < 256; i += kThreads) sm.len_sym_lut[i] = (uint8_t)dfl::len_sym(i + 3);
-  for (int i = tid; i < 512; i += kThreads) sm.dist_sym_lut[i] = (uint8_t)dfl::dist_sym(i < 256 ? i + 1 : ((i - 256) << 7) + 1);
   __syncthreads();
   uint32_t tma_parity = 0;
   // optional phase timers (cycles, thread 0): 0 load, 1 match, 2 sort, 3 plan, 4 tables+header, 5 encode, 6 finish
@@ -699,6 +727,9 @@ __global__ void __launch_bounds__(kThreads, 2)
       // the hash tables take the space of the bit stage for the duration of the match phase: park the
       // partially filled 16-byte unit at its front
       if (tid < 4) sm.keep[tid] = sm.u.enc.stage[tid];
+      static_assert(sizeof(sm.u.m.head) >= sizeof(sm.u.enc.stage), "the look-up tables must lie behind the bit stage");
+      for (int i = tid; i < 256; i += kThreads) sm.u.m.len_sym_lut[i] = (uint8_t)dfl::len_sym(i + 3);
+      for (int i = tid; i < 512; i += kThreads) sm.u.m.dist_sym_lut[i] = (uint8_t)dfl::dist_sym(i < 256 ? i + 1 : ((i - 256) << 7) + 1);
       for (int i = tid; i < 288; i += kThreads) sm.ll_freq[i] = 0;
       if (tid < 32) sm.d_freq[tid] = 0;
       mbar_wait(&sm.mbar, tma_parity);
@@ -715,14 +746,21 @@ __global__ void __launch_bounds__(kThreads, 2)
       for (int i = tid; i < kStageWords; i += kThreads) sm.u.enc.stage[i] = tid < 4 && i < 4 ? sm.keep[i] : 0u;
       BITAR_PHASE(1)
       // ---- plan: sort used symbols, Huffman lengths, header; checksums in parallel ----
-      if (tid == 0) sm.ll_freq[dfl::kEob] = 1;
+      if (tid == 0) {
+        sm.ll_freq[dfl::kEob] = 1;
+        sm.ll_m = 0;
+      }
       __syncthreads();
       {
-        uint32_t key = 0xFFFFFFFFu;
-        if (tid < dfl::kNumLitLen && sm.ll_freq[tid]) key = (sm.ll_freq[tid] << 9) | (uint32_t)tid;
-        if (tid < 512) sm.u.enc.sort_keys[tid] = key;
-        int used = __syncthreads_count(key != 0xFFFFFFFFu);
-        if (tid == 0) sm.ll_m = (uint32_t)used;
+        uint32_t used = 0;
+        for (int i = tid; i < 512; i += kThreads) {
+          uint32_t key = 0xFFFFFFFFu;
+          if (i < dfl::kNumLitLen && sm.ll_freq[i]) key = (sm.ll_freq[i] << 9) | (uint32_t)i;
+          sm.u.enc.sort_keys[i] = key;
+          used += key != 0xFFFFFFFFu;
+        }
+        used = __reduce_add_sync(0xFFFFFFFFu, used);
+        if (lane == 0 && used) atomicAdd(&sm.ll_m, used);
       }
       sort512(sm);
       BITAR_PHASE(2)
@@ -774,21 +812,22 @@ __global__ void __launch_bounds__(kThreads, 2)
         else if (warp == 1) huff_codes_warp(sm.plan.d_len, dfl::kNumDist, pp.d_bl, pp.d_at, sm.plan.d_code, lane);
         else {
           // body sizes under the dynamic and the fixed code, highest used symbols: one symbol per thread
-          const int i = tid - 64;
           unsigned long long dyn = 0, fix = 0;
-          if (i < dfl::kNumLitLen) {
-            const uint32_t f = sm.ll_freq[i];
-            const int eb = i > 256 ? dfl::len_extra_bits(i - 257) : 0;
-            dyn = (unsigned long long)f * (uint32_t)(sm.plan.ll_len[i] + eb);
-            fix = (unsigned long long)f * (uint32_t)(dfl::fixed_ll_len(i) + eb);
-            if (sm.plan.ll_len[i]) atomicMax(&pp.hlit_max, (uint32_t)i);
-          } else if (i < dfl::kNumLitLen + dfl::kNumDist) {
-            const int j = i - dfl::kNumLitLen;
-            const uint32_t f = sm.d_freq[j];
-            const int eb = dfl::dist_extra_bits(j);
-            dyn = (unsigned long long)f * (uint32_t)(sm.plan.d_len[j] + eb);
-            fix = (unsigned long long)f * (uint32_t)(5 + eb);
-            if (sm.plan.d_len[j]) atomicMax(&pp.hdist_max, (uint32_t)j);
+          for (int i = tid - 64; i < dfl::kNumLitLen + dfl::kNumDist; i += kThreads - 64) {
+            if (i < dfl::kNumLitLen) {
+              const uint32_t f = sm.ll_freq[i];
+              const int eb = i > 256 ? dfl::len_extra_bits(i - 257) : 0;
+              dyn += (unsigned long long)f * (uint32_t)(sm.plan.ll_len[i] + eb);
+              fix += (unsigned long long)f * (uint32_t)(dfl::fixed_ll_len(i) + eb);
+              if (sm.plan.ll_len[i]) atomicMax(&pp.hlit_max, (uint32_t)i);
+            } else {
+              const int j = i - dfl::kNumLitLen;
+              const uint32_t f = sm.d_freq[j];
+              const int eb = dfl::dist_extra_bits(j);
+              dyn += (unsigned long long)f * (uint32_t)(sm.plan.d_len[j] + eb);
+              fix += (unsigned long long)f * (uint32_t)(5 + eb);
+              if (sm.plan.d_len[j]) atomicMax(&pp.hdist_max, (uint32_t)j);
+            }
           }
 #pragma unroll
           for (int o2 = 16; o2 > 0; o2 >>= 1) {
@@ -922,18 +961,30 @@ __global__ void __launch_bounds__(kThreads, 2)
       }
       if (type == dfl::kDynamic) {
         const dfl::BlockPlan& pl = sm.plan;
-        uint32_t bits = 0, nb = 0;
-        if (tid < pl.hclen) {
-          bits = pl.cl_len[dfl::cl_order(tid)];
-          nb = 3;
-        } else if (tid < pl.hclen + pl.n_cl_tok) {
-          const int t = pl.cl_tok[tid - pl.hclen], sym = t & 31, ev = t >> 5;
-          bits = (uint32_t)pl.cl_code[sym] | ((uint32_t)ev << pl.cl_len[sym]);
-          nb = (uint32_t)pl.cl_len[sym] + (uint32_t)dfl::cl_extra_bits(sym);
+        // item i: the i-th code-length-code length (3 bits), then the RLE tokens; thread t owns items
+        // [t * kHdrPerThread, +kHdrPerThread) (one item per thread with 16 warps)
+        uint32_t bits[kHdrPerThread], nb[kHdrPerThread], mine = 0;
+#pragma unroll
+        for (int k = 0; k < kHdrPerThread; ++k) {
+          const int i = tid * kHdrPerThread + k;
+          bits[k] = nb[k] = 0;
+          if (i < pl.hclen) {
+            bits[k] = pl.cl_len[dfl::cl_order(i)];
+            nb[k] = 3;
+          } else if (i < pl.hclen + pl.n_cl_tok) {
+            const int t = pl.cl_tok[i - pl.hclen], sym = t & 31, ev = t >> 5;
+            bits[k] = (uint32_t)pl.cl_code[sym] | ((uint32_t)ev << pl.cl_len[sym]);
+            nb[k] = (uint32_t)pl.cl_len[sym] + (uint32_t)dfl::cl_extra_bits(sym);
+          }
+          mine += nb[k];
         }
         uint32_t total = 0;
-        const uint32_t off2 = block_excl_scan(sm, nb, &total, lane, warp);
-        stage_or(sm, o, o.bit + 17u + off2, bits, (int)nb);
+        uint32_t off2 = block_excl_scan(sm, mine, &total, lane, warp);
+#pragma unroll
+        for (int k = 0; k < kHdrPerThread; ++k) {
+          stage_or(sm, o, o.bit + 17u + off2, bits[k], (int)nb[k]);
+          off2 += nb[k];
+        }
       }
       o.bit += hdr_bits;
       __syncthreads();
@@ -1115,5 +1166,10 @@ inline cudaError_t deflate_launch(const bitar_chunk* ops, uint32_t n, bitar_resu
   return cudaGetLastError();
 }
 
-}  // namespace dk
+}  // namespace BITAR_DK_NS
 }  // namespace bitar
+
+#undef BITAR_DK_NS
+#undef BITAR_DK_WARPS
+#undef BITAR_DK_BLOCK_MAX
+#undef BITAR_DK_MIN_CTAS

@@ -137,3 +137,32 @@ def test_random_structured_ragged_batch(cuda_device):
             assert np.array_equal(o, c) and int(r["checksum"]) == int(r0["checksum"])
     finally:
         dev.close()
+
+
+@pytest.mark.parametrize("huffman", [capi.HUFFMAN_DYNAMIC, capi.HUFFMAN_FIXED])
+def test_small_chunk_instance_matches_model(cuda_device, huffman):
+    """Calls whose chunks all fit 16 KiB run on the 4-warp instance of the deflate kernel (bitar::dks): same bytes as
+    the sequential model, valid under zlib, checksums equal zlib's; empty, 1-byte, incompressible and all-zero chunks
+    and every sub-range boundary included."""
+    from test_core_host import _structured
+    rng = np.random.default_rng(99)
+    sizes = [0, 1, 2, 3, 7, 8, 2047, 2048, 2049, 4095, 4096, 4097, 8192, 12288, 16383, 16384] + \
+            [int(rng.integers(1, 16385)) for _ in range(240)]
+    chunks = [_structured(rng, n) for n in sizes]
+    chunks += [np.frombuffer(rng.bytes(n), np.uint8) for n in (100, 4096, 16384)]          # stored
+    chunks += [np.zeros(n, np.uint8) for n in (4096, 16384)]                               # long matches
+    chunks += [synth.lineitem_like(3 * 16384)[i * 16384:(i + 1) * 16384] for i in range(3)]
+    dev = G.open_device(16384, huffman_enc=huffman, checksum_type=capi.CHECKSUM_CRC32_ADLER32)
+    try:
+        comps, res, err = G.gpu_deflate_chunks(dev, chunks, src_shift=5, dst_shift=9)
+        assert err is None and (res["status"] == 0).all()
+        for i, (c, z, r) in enumerate(zip(chunks, comps, res)):
+            assert np.array_equal(z, M.model_deflate(c, huffman)), (i, c.size)
+            assert np.array_equal(O.inflate_chunk(z, max(c.size, 1)), c)
+            assert int(r["checksum"]) & 0xFFFFFFFF == O.crc32(c) and int(r["checksum"]) >> 32 == O.adler32(c)
+        outs, ires, err = G.gpu_inflate_chunks(dev, comps, [c.size for c in chunks])
+        assert err is None
+        for c, o in zip(chunks, outs):
+            assert np.array_equal(o, c)
+    finally:
+        dev.close()
