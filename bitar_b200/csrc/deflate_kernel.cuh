@@ -46,6 +46,9 @@
 #include "checksum.h"
 #include "deflate_common.h"
 
+#ifndef BITAR_DK_RANK_SORT
+#define BITAR_DK_RANK_SORT 0       // experiments: rank sort in the 16-warp instance too
+#endif
 #ifndef BITAR_DK_NS
 #define BITAR_DK_NS dk
 #define BITAR_DK_WARPS 16
@@ -297,6 +300,30 @@ __device__ void sort512(Smem& sm) {
       }
     }
   }
+  __syncthreads();
+}
+
+// The same order by rank: a key's place is the number of smaller keys (keys are distinct: the symbol is part of the
+// key).  Every thread scans all 288 keys for each of its own with broadcast 16-byte reads; no barrier per step,
+// which is what the bitonic network costs a small CTA.  sm.ll_m (the number of used symbols) must be complete.
+__device__ void sort_rank(Smem& sm) {
+  uint32_t* tmp = sm.u.enc.scratch.sorted;
+  const uint4* k4 = reinterpret_cast<const uint4*>(sm.u.enc.sort_keys);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 288; i += kThreads) {
+    const uint32_t k = sm.u.enc.sort_keys[i];
+    if (k == 0xFFFFFFFFu) continue;
+    uint32_t r = 0;
+#pragma unroll 8
+    for (int j = 0; j < 288 / 4; ++j) {
+      const uint4 v = k4[j];
+      r += (uint32_t)(v.x < k) + (uint32_t)(v.y < k) + (uint32_t)(v.z < k) + (uint32_t)(v.w < k);
+    }
+    tmp[r] = k;
+  }
+  __syncthreads();
+  const int m = (int)sm.ll_m;
+  for (int i = threadIdx.x; i < 288; i += kThreads) sm.u.enc.sort_keys[i] = i < m ? tmp[i] : 0xFFFFFFFFu;
   __syncthreads();
 }
 
@@ -660,7 +687,8 @@ __global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
   for (int i = tid; i < kStageWords; i += kThreads) sm.u.enc.stage[i] = 0;
   __syncthreads();
   uint32_t tma_parity = 0;
-  // optional phase timers (cycles, thread 0): 0 load, 1 match, 2 sort, 3 plan, 4 tables+header, 5 encode, 6 finish
+  // optional phase timers (cycles, thread 0): 0 load, 1 match, 2 sort, 3 Huffman merge (serial), 4 tables+header, 5 encode,
+  // 6 finish, 7 depths / lengths / codes / sizes, 8 code-length RLE, 9 code-length code + block type (serial)
   long long t_prev = prof ? clock64() : 0;
 #define BITAR_PHASE(k)                                          \
   if (prof && tid == 0) {                                       \
@@ -762,7 +790,8 @@ __global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
         used = __reduce_add_sync(0xFFFFFFFFu, used);
         if (lane == 0 && used) atomicAdd(&sm.ll_m, used);
       }
-      sort512(sm);
+      if (kThreads >= 512 && !BITAR_DK_RANK_SORT) sort512(sm);
+      else sort_rank(sm);
       BITAR_PHASE(2)
       PlanPar& pp = sm.u.enc.pp;
       dfl::HuffScratch& hs = sm.u.enc.scratch.hs;
@@ -797,6 +826,7 @@ __global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
                        kThreads - 64);
       }
       __syncthreads();
+      BITAR_PHASE(3)
       {
         const int ll_m = (int)sm.ll_m, d_m = (int)sm.d_m;
         if (tid < kThreads - 64) huff_depths(hs.parent, ll_m, dfl::kMaxBits, pp.ll_bl, &pp.ll_over, tid, kThreads - 64);
@@ -848,7 +878,9 @@ __global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
         sm.plan.fixed_body_bits = pp.fix_bits;
       }
       __syncthreads();
+      BITAR_PHASE(7)
       cl_rle_parallel(sm, tid, lane, warp);            // code-length RLE, one run per thread
+      BITAR_PHASE(8)
       if (tid == 0) {
         dfl::plan_cl_tree(&sm.plan, &sm.u.enc.scratch);   // code-length code, header size (serial, 19 symbols)
         // choose the block type (same rule as the model)
@@ -878,7 +910,7 @@ __global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
         sm.tile_bits = (uint32_t)best;
       }
       __syncthreads();
-      BITAR_PHASE(3)
+      BITAR_PHASE(9)
       const uint32_t type = sm.block_type;
       {
         uint64_t end_bit = o.bit + sm.tile_bits;
