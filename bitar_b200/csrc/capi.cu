@@ -20,10 +20,10 @@
 
 #include "../../include/bitar_cuda.h"
 #include "deflate_kernel.cuh"      // bitar::dk: 16 warps per CTA, 2 CTAs per SM, chunks up to 1 MiB
-#define BITAR_DK_NS dks            // bitar::dks: 4 warps per CTA, 6 CTAs per SM, chunks up to 16 KiB
+#define BITAR_DK_NS dks            // bitar::dks: 4 warps per CTA, 6 .. 8 CTAs per SM, chunks up to 16 KiB
 #define BITAR_DK_WARPS 4
 #define BITAR_DK_BLOCK_MAX 16384
-#define BITAR_DK_MIN_CTAS 6
+#define BITAR_DK_MIN_CTAS 8
 #include "deflate_kernel.cuh"
 #include "inflate_kernel.cuh"
 #include "inflate_fast_kernel.cuh"
@@ -106,7 +106,8 @@ struct bitar_dev {
   bitar_cfg cfg{};
   std::vector<QueuePair*> qps;
   int deflate_grid = 0;
-  int deflate_grid_small = 0;       // grid of the small-chunk instance (bitar::dks)
+  int deflate_grid_small = 0;       // largest grid of the small-chunk instance (bitar::dks)
+  int deflate_grid_override = 0;    // BITAR_DEBUG_DEFLATE_GRID (16-warp instance only)
   // slot pool
   std::mutex mu;
   std::vector<void*> slabs;
@@ -526,7 +527,7 @@ int bitar_dev_open(int device_id, uint16_t n_qps, const bitar_cfg* cfg_in, bitar
   cudaError_t e = bitar::dk::deflate_grid(device_id, dev->sm_count, &dev->deflate_grid);
   if (e == cudaSuccess) e = bitar::dks::deflate_grid(device_id, dev->sm_count, &dev->deflate_grid_small);
   if (const char* g = getenv("BITAR_DEBUG_DEFLATE_GRID")) {   // tuning experiments only
-    if (atoi(g) > 0) dev->deflate_grid = atoi(g);
+    if (atoi(g) > 0) dev->deflate_grid_override = atoi(g);
   }
   if (e != cudaSuccess) {
     delete dev;
@@ -618,10 +619,11 @@ int bitar_qp_deflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
     for (uint32_t i = 0; i < count; ++i) max_len = q->h_ops[first + i].src_len > max_len ? q->h_ops[first + i].src_len : max_len;
     static const int small_mode = getenv("BITAR_DEFLATE_SMALL") ? atoi(getenv("BITAR_DEFLATE_SMALL")) : 1;   // 0: off (A/B runs)
     if (small_mode && max_len <= (uint32_t)bitar::dks::kBlockMax)
-      return bitar::dks::deflate_launch(q->d_ops + first, count, q->d_res + first, q->d_counter, q->d_tokens, dev->deflate_grid_small,
-                                        dev->cfg.huffman_enc, dev->cfg.checksum_type, g_deflate_prof.load(), q->stream);
-    return bitar::dk::deflate_launch(q->d_ops + first, count, q->d_res + first, q->d_counter, q->d_tokens, dev->deflate_grid,
-                                     dev->cfg.huffman_enc, dev->cfg.checksum_type, g_deflate_prof.load(), q->stream);
+      return bitar::dks::deflate_launch(q->d_ops + first, count, q->d_res + first, q->d_counter, q->d_tokens, dev->id, dev->sm_count, 0,
+                                        max_len, dev->cfg.huffman_enc, dev->cfg.checksum_type, g_deflate_prof.load(), q->stream);
+    return bitar::dk::deflate_launch(q->d_ops + first, count, q->d_res + first, q->d_counter, q->d_tokens, dev->id, dev->sm_count,
+                                     dev->deflate_grid_override, (uint32_t)bitar::dk::kBlockMax, dev->cfg.huffman_enc,
+                                     dev->cfg.checksum_type, g_deflate_prof.load(), q->stream);
   });
 }
 

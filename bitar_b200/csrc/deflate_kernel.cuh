@@ -91,7 +91,6 @@ struct EncodeArea {
   PlanPar pp;
 };
 struct __align__(16) Smem {
-  uint8_t raw[kBlockMax + 48];       // input block, shifted so that raw + (src & 15) is the first byte
   union {                            // the match phase and the plan/encode phases never overlap in time
     struct {
       uint16_t head[kWarps][(1 << kHashBits) + 32];   // per warp: hash -> most recent position (kNoCand = empty) + 32 dummy slots
@@ -120,7 +119,14 @@ struct __align__(16) Smem {
   uint32_t tile_bits;
   unsigned long long mbar;           // TMA completion barrier
   dfl::BlockPlan plan;
+  // input block, shifted so that raw + (src & 15) is the first byte.  Last member: a launch whose chunks are all
+  // shorter than kBlockMax allocates only what they need (smem_bytes), which raises the CTAs per SM.
+  __align__(16) uint8_t raw[kBlockMax + 48];
 };
+inline size_t smem_bytes(uint32_t max_len) {
+  const uint32_t len = max_len < (uint32_t)kBlockMax ? (max_len + 15u) & ~15u : (uint32_t)kBlockMax;
+  return sizeof(Smem) - (size_t)kBlockMax + len;
+}
 
 // ---- small helpers -----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -1174,27 +1180,39 @@ __global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
 
 inline size_t deflate_scratch_bytes(int grid) { return (size_t)grid * kBlockMax * sizeof(uint32_t); }
 
-inline cudaError_t deflate_grid(int device, int sm_count, int* grid_out) {
-  static int per_device[64] = {0};
-  int& ctas = per_device[device & 63];
-  if (ctas == 0) {
+// resident CTAs per SM for chunks of at most max_len bytes (the shared-memory footprint follows the chunk size)
+inline cudaError_t deflate_ctas_per_sm(int device, uint32_t max_len, int* ctas_out) {
+  static bool configured[64] = {false};
+  if (!configured[device & 63]) {
     cudaError_t e = cudaFuncSetAttribute(deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return e;
     cudaFuncSetAttribute(deflate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, deflate_kernel, kThreads, sizeof(Smem));
-    if (e != cudaSuccess) return e;
-    if (ctas < 1) return cudaErrorLaunchOutOfResources;
+    configured[device & 63] = true;
   }
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_out, deflate_kernel, kThreads, smem_bytes(max_len));
+  if (e != cudaSuccess) return e;
+  return *ctas_out < 1 ? cudaErrorLaunchOutOfResources : cudaSuccess;
+}
+
+// largest grid any launch on this device can use (sizes the token scratch)
+inline cudaError_t deflate_grid(int device, int sm_count, int* grid_out) {
+  int ctas = 0;
+  cudaError_t e = deflate_ctas_per_sm(device, kBlockMax < 65536 ? 1u : (uint32_t)kBlockMax, &ctas);
+  if (e != cudaSuccess) return e;
   *grid_out = sm_count * ctas;
   return cudaSuccess;
 }
 
 inline cudaError_t deflate_launch(const bitar_chunk* ops, uint32_t n, bitar_result* res, unsigned int* counter,
-                                  uint32_t* scratch, int grid_max, int huffman, int checksum_type,
-                                  unsigned long long* prof, cudaStream_t stream) {
+                                  uint32_t* scratch, int device, int sm_count, int grid_override, uint32_t max_len, int huffman,
+                                  int checksum_type, unsigned long long* prof, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
-  int grid = (int)min((uint32_t)grid_max, n);
-  deflate_kernel<<<grid, kThreads, sizeof(Smem), stream>>>(ops, n, res, counter, scratch, huffman, checksum_type, prof);
+  int ctas = 0;
+  cudaError_t e = deflate_ctas_per_sm(device, max_len, &ctas);
+  if (e != cudaSuccess) return e;
+  int grid = grid_override > 0 ? grid_override : sm_count * ctas;
+  if ((uint32_t)grid > n) grid = (int)n;
+  deflate_kernel<<<grid, kThreads, smem_bytes(max_len), stream>>>(ops, n, res, counter, scratch, huffman, checksum_type, prof);
   return cudaGetLastError();
 }
 
