@@ -625,6 +625,54 @@ __device__ __forceinline__ void cl_rle_parallel(Smem& sm, int tid, int lane, int
   __syncthreads();
 }
 
+// The code-length code (19 symbols) and the header size by one warp: dfl::plan_cl_tree() with the symbol-parallel
+// steps of the big trees (rank sort through shuffles, depths, length assignment, canonical codes); only the merge
+// stays serial.  cl_freq comes from cl_rle_parallel.  Same results as the serial function (the model uses that one).
+__device__ __forceinline__ void plan_cl_tree_warp(Smem& sm, int lane) {
+  constexpr unsigned kFull = 0xFFFFFFFFu;
+  dfl::BlockPlan& pl = sm.plan;
+  PlanPar& pp = sm.u.enc.pp;                       // the big trees are done: their counters and the distance
+  uint32_t* sorted = sm.u.enc.scratch.sorted;      // tree's node arrays are free
+  const uint32_t f = lane < dfl::kNumCl ? sm.u.enc.scratch.cl_freq[lane] : 0u;
+  uint32_t fs = f;
+  {
+    const unsigned used = __ballot_sync(kFull, f != 0);
+    if (__popc(used) == 1) {   // complete the code: a second symbol gets a 1-bit code too
+      const int other = (__ffs((int)used) - 1) == 0 ? 1 : 0;
+      if (lane == other) fs = 1;
+    }
+  }
+  const int cm = __popc(__ballot_sync(kFull, fs != 0));
+  const uint32_t key = fs ? (fs << 9) | (uint32_t)lane : 0xFFFFFFFFu;
+  uint32_t rank = 0;
+#pragma unroll
+  for (int j = 0; j < dfl::kNumCl; ++j) rank += (uint32_t)(__shfl_sync(kFull, key, j) < key);
+  if (fs) sorted[rank] = key;
+  if (lane < 16) pp.ll_bl[lane] = 0;
+  if (lane < dfl::kNumCl) pl.cl_len[lane] = 0;
+  if (lane == 0) pp.ll_over = 0;
+  __syncwarp();
+  if (lane == 0) huff_merge(sorted, cm, pp.d_node_freq, pp.d_parent);
+  __syncwarp();
+  huff_depths(pp.d_parent, cm, dfl::kMaxClBits, pp.ll_bl, &pp.ll_over, lane, 32);
+  __syncwarp();
+  if (lane == 0) huff_repair(pp.ll_bl, (int)pp.ll_over, dfl::kMaxClBits);
+  __syncwarp();
+  huff_assign(sorted, cm, dfl::kMaxClBits, pp.ll_bl, pl.cl_len, lane, 32);
+  __syncwarp();
+  huff_codes_warp(pl.cl_len, dfl::kNumCl, pp.ll_bl, pp.ll_at, pl.cl_code, lane);
+  const uint32_t my_len = lane < dfl::kNumCl ? pl.cl_len[lane] : 0u;
+  const unsigned nz = __ballot_sync(kFull, lane < dfl::kNumCl && pl.cl_len[dfl::cl_order(lane)] != 0);
+  const int hclen = max(4, 32 - __clz((int)nz));
+  uint32_t hb = lane < dfl::kNumCl ? f * (my_len + (uint32_t)dfl::cl_extra_bits(lane)) : 0u;
+  hb = __reduce_add_sync(kFull, hb);
+  if (lane == 0) {
+    pl.hclen = hclen;
+    pl.header_bits = 3 + 5 + 5 + 4 + 3 * (uint32_t)hclen + hb;
+  }
+  __syncwarp();
+}
+
 // ---- checksum of the block held in shared memory (threads tid0..tid0+nthr) ---------------------------
 __device__ __forceinline__ void block_checksum(Smem& sm, const uint8_t* d, uint32_t n, uint32_t tail_after,
                                                bool first_block, int type, int t, int nthr) {
@@ -887,8 +935,8 @@ __global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
       BITAR_PHASE(7)
       cl_rle_parallel(sm, tid, lane, warp);            // code-length RLE, one run per thread
       BITAR_PHASE(8)
+      if (warp == 0) plan_cl_tree_warp(sm, lane);          // code-length code, header size
       if (tid == 0) {
-        dfl::plan_cl_tree(&sm.plan, &sm.u.enc.scratch);   // code-length code, header size (serial, 19 symbols)
         // choose the block type (same rule as the model)
         uint64_t dyn_bits = (uint64_t)sm.plan.header_bits + sm.plan.dyn_body_bits;
         uint64_t fix_bits = 3 + sm.plan.fixed_body_bits;

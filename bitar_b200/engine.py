@@ -284,6 +284,19 @@ def gzip_members(chunks, results, sizes):
     return bytes(out)
 
 
+def zlib_streams(chunks, results):
+    """RFC 1950 framing: every compressed chunk becomes one zlib stream (CMF/FLG 78 01: 32 KiB window, fastest
+    level, no dictionary; raw DEFLATE stream; Adler-32 big-endian) -- what Arrow's / Parquet's ZLIB-format readers
+    and `zlib.decompress` expect per buffer.  `results` are the Compress() results of a device configured with an
+    Adler-32 checksum.  Returns a list of bytes objects, one per chunk."""
+    import struct
+    out = []
+    for c, r in zip(chunks, results):
+        c = np.ascontiguousarray(c, dtype=np.uint8)
+        out.append(b"\x78\x01" + c[:stream_length(c)].tobytes() + struct.pack(">I", int(r["checksum"]) >> 32))
+    return out
+
+
 def shard_range(n_chunks, rank, world):
     """Chunk range [first, last) of rank `rank` out of `world`: contiguous ranges of
     ceil(n / world) chunks, so that concatenating the ranks' outputs in rank order is the output of one

@@ -202,6 +202,25 @@ def test_gzip_member_framing_of_model_streams():
     assert gzip.decompress(E.gzip_members(comps, res, [c.size for c in chunks])) == data.tobytes()
 
 
+def test_zlib_stream_framing_of_model_streams():
+    """engine.zlib_streams(): 78 01 + stream (index stripped) + Adler-32 is what zlib.decompress() accepts
+    (RFC 1950; it verifies the Adler-32)."""
+    import zlib
+    from bitar_b200 import engine as E
+    data = synth.lineitem_like(2 * SEG + 77)
+    chunks = [data[o:o + SEG] for o in range(0, data.size, SEG)]
+    comps = [M.model_deflate(c, 2) for c in chunks]
+    res = np.zeros(len(chunks), dtype=[("produced", "<u4"), ("status", "<u4"), ("checksum", "<u8")])
+    for i, c in enumerate(chunks):
+        res["checksum"][i] = np.uint64(O.adler32(c)) << np.uint64(32)
+    for c, z in zip(chunks, E.zlib_streams(comps, res)):
+        assert zlib.decompress(z) == c.tobytes()
+    bad = bytearray(E.zlib_streams(comps, res)[0])
+    bad[-1] ^= 1
+    with pytest.raises(zlib.error):
+        zlib.decompress(bytes(bad))
+
+
 def test_deflate_model_large_chunks_multi_block():
     data = synth.lineitem_like(3 * 65536 + 1000)
     m = M.model_deflate(data, 2)

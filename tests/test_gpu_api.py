@@ -133,6 +133,21 @@ def test_chunks_frame_as_gzip_members(cuda_device):
         dev.close()
 
 
+def test_chunks_frame_as_zlib_streams(cuda_device):
+    """chunk + the kernel's Adler-32 framed per RFC 1950 is accepted (and verified) by zlib.decompress."""
+    import zlib
+    data = synth.lineitem_like(5 * SEG + 99)
+    dev = G.open_device(SEG, checksum_type=capi.CHECKSUM_CRC32_ADLER32)
+    try:
+        chunks = [data[o:o + SEG] for o in range(0, data.size, SEG)]
+        comps, res, err = G.gpu_deflate_chunks(dev, chunks)
+        assert err is None
+        for c, z in zip(chunks, E.zlib_streams(comps, res)):
+            assert zlib.decompress(z) == c.tobytes()
+    finally:
+        dev.close()
+
+
 def _crc32_combine(crc1, crc2, len2):
     """zlib's crc32_combine(): CRC of A||B from CRC(A), CRC(B), len(B) (GF(2) matrix method)."""
     def times(mat, vec):
