@@ -57,6 +57,7 @@ struct ConnectionsDefault {
 } g_connections_default;
 
 constexpr uint32_t kMaxStageBatches = 16;
+constexpr uint32_t kStageLanes = 3;                     // + the queue pair's own stream: 8 queue pairs fit 32 hardware queues
 constexpr size_t kStageBatchBytes = (size_t)16 << 20;   // inflated bytes per batch of a staged call
 
 struct QueuePair {
@@ -87,10 +88,11 @@ struct QueuePair {
   bool stage_src = false, stage_dst = false;
   bool stage_dst_contig = false;        // destinations form one range of equal-capacity segments (Decompress())
   size_t stage_out_bytes = 0;           // sum of the call's destination capacities
-  // staged calls run in batches: batch b's copy-back (copy_stream) overlaps batch b+1's gather + inflate (stream)
-  cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_batch[kMaxStageBatches] = {};
-  cudaEvent_t ev_copied = nullptr;
+  // staged calls run in batches spread over kStageLanes extra streams: one batch is gather -> inflate -> copy-back
+  // in order on its lane, the lanes overlap each other (PCIe both ways and the SMs busy at once)
+  cudaStream_t lane[kStageLanes] = {};
+  cudaEvent_t ev_lane[kStageLanes] = {};
+  cudaEvent_t ev_fork = nullptr;
   bitar_result* user_out = nullptr;
   uint32_t pending_n = 0;
   std::atomic<int> busy{0};
@@ -242,6 +244,10 @@ __global__ void __launch_bounds__(256) stage_copy_kernel(const bitar_chunk* __re
   if (threadIdx.x < n - done) dst[done + threadIdx.x] = src[done + threadIdx.x];
 }
 
+// Resets a queue pair's work counters.  A kernel of our own rather than cudaMemsetAsync: the driver's memset kernel
+// runs with the default shared-memory carve-out, and switching the carve-out back and forth drains the SMs.
+__global__ void zero_counters_kernel(unsigned int* c) { c[threadIdx.x] = 0; }
+
 bool is_host_memory(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -287,11 +293,12 @@ int inflate_prepare_staging(QueuePair* q, uint32_t n) {
   // layout and goes back with ONE copy-engine transfer (which, unlike a kernel, runs beside the inflate kernels of
   // the other queue pairs); only the last segment, the one that may be short, is copied by produced size.
   q->stage_out_bytes = need_out;
-  if (q->stage_dst && !q->copy_stream) {
-    CU_TRY(cudaStreamCreateWithFlags(&q->copy_stream, cudaStreamNonBlocking), BITAR_E_OUT_OF_MEMORY);
-    for (uint32_t b = 0; b < kMaxStageBatches; ++b)
-      CU_TRY(cudaEventCreateWithFlags(&q->ev_batch[b], cudaEventDisableTiming), BITAR_E_OUT_OF_MEMORY);
-    CU_TRY(cudaEventCreateWithFlags(&q->ev_copied, cudaEventDisableTiming), BITAR_E_OUT_OF_MEMORY);
+  if (q->stage_dst && !q->ev_fork) {
+    for (uint32_t k = 0; k < kStageLanes; ++k) {
+      CU_TRY(cudaStreamCreateWithFlags(&q->lane[k], cudaStreamNonBlocking), BITAR_E_OUT_OF_MEMORY);
+      CU_TRY(cudaEventCreateWithFlags(&q->ev_lane[k], cudaEventDisableTiming), BITAR_E_OUT_OF_MEMORY);
+    }
+    CU_TRY(cudaEventCreateWithFlags(&q->ev_fork, cudaEventDisableTiming), BITAR_E_OUT_OF_MEMORY);
   }
   q->stage_dst_contig = q->stage_dst && n > 1;
   for (uint32_t i = 1; i < n && q->stage_dst_contig; ++i)
@@ -316,9 +323,14 @@ int inflate_prepare_staging(QueuePair* q, uint32_t n) {
   return BITAR_OK;
 }
 
-template <typename Launch>
-int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, bitar_result* results, Launch&& launch,
-              bool inflate = false) {
+enum { kSubmitDeflate = 0, kSubmitInflate = 1, kSubmitInflateOneBatch = 2 };
+
+// prepare(q, n): allocations for the whole call, before anything is enqueued;
+// launch(q, first, count, counters, stream): the kernels of ops [first, first + count) on `stream`.
+template <typename Prepare, typename Launch>
+int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, bitar_result* results, Prepare&& prepare,
+              Launch&& launch, int mode) {
+  const bool inflate = mode != kSubmitDeflate;
   if (!dev) return fail(BITAR_E_INVALID, "null device");
   if (qp >= dev->qps.size()) return fail(BITAR_E_INVALID, "queue_pair_id must be in the range of [0, %zu)", dev->qps.size());
   QueuePair* q = dev->qps[qp];
@@ -343,58 +355,69 @@ int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, b
   q->busy.store(1, std::memory_order_release);
   cudaError_t e = cudaEventRecord(q->ev_start, q->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(q->d_ops, q->h_ops, (size_t)n * sizeof(bitar_chunk), cudaMemcpyHostToDevice, q->stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(q->d_counter, 0, 8 * sizeof(unsigned int), q->stream);
   if (e == cudaSuccess && (q->stage_src || q->stage_dst))
     e = cudaMemcpyAsync(q->d_orig, q->h_orig, (size_t)n * sizeof(bitar_chunk), cudaMemcpyHostToDevice, q->stream);
-  // Staged inflate calls (host-resident buffers) run in batches so that the copy-back of one batch (PCIe device ->
-  // host) overlaps the gather (PCIe host -> device) and the kernels of the next one; everything else is one batch.
+  // Staged inflate calls (host-resident buffers) run in batches: gather (PCIe host -> device), inflate and copy-back
+  // (PCIe device -> host) of one batch in order on one of kStageLanes streams, the lanes side by side.  One batch
+  // alone is latency-bound (a 2 KiB sub-range takes a lane ~0.8 ms whatever the batch size), hence several in flight.
+  // Everything else is one batch on the queue pair's own stream.
   uint32_t nb = 1;
-  if (q->stage_dst && n > 1) {
-    const size_t want = q->stage_out_bytes / kStageBatchBytes;
+  if (q->stage_dst && n > 1 && mode == kSubmitInflate) {
+    static const size_t batch_bytes = getenv("BITAR_STAGE_BATCH_MIB") ? (size_t)atoi(getenv("BITAR_STAGE_BATCH_MIB")) << 20 : kStageBatchBytes;
+    const size_t want = q->stage_out_bytes / (batch_bytes ? batch_bytes : 1);
     nb = (uint32_t)(want < 1 ? 1 : want > kMaxStageBatches ? kMaxStageBatches : want);
     if (nb > n) nb = n;
   }
+  const bool lanes = nb > 1;
+  if (e == cudaSuccess) e = prepare(q, n);     // buffers sized for the whole call: batches in flight share them
+  if (e == cudaSuccess && lanes) e = cudaEventRecord(q->ev_fork, q->stream);
+  if (e == cudaSuccess && lanes) e = cudaEventRecord(q->ev_k0, q->stream);
   const uint32_t per = (n + nb - 1) / nb;
   for (uint32_t b = 0, first = 0; first < n && e == cudaSuccess; ++b, first += per) {
     const uint32_t count = n - first < per ? n - first : per;
     const bool last = first + count == n;
+    cudaStream_t st = lanes ? q->lane[b % kStageLanes] : q->stream;
+    if (lanes && b < kStageLanes) {
+      e = cudaStreamWaitEvent(st, q->ev_fork, 0);
+      if (e != cudaSuccess) continue;
+    }
     if (q->stage_src) {
-      stage_copy_kernel<<<count, 256, 0, q->stream>>>(q->d_orig + first, q->d_ops + first, nullptr, 0);
+      stage_copy_kernel<<<count, 256, 0, st>>>(q->d_orig + first, q->d_ops + first, nullptr, 0);
       e = cudaGetLastError();
       g_launches.fetch_add(1);
     }
-    if (e == cudaSuccess && b == 0) e = cudaEventRecord(q->ev_k0, q->stream);
-    if (e == cudaSuccess && b > 0) e = cudaMemsetAsync(q->d_counter, 0, 8 * sizeof(unsigned int), q->stream);
-    if (e == cudaSuccess) e = launch(q, first, count);
-    if (e == cudaSuccess && last) e = cudaEventRecord(q->ev_k1, q->stream);
-    if (e != cudaSuccess || !q->stage_dst) continue;
-    cudaStream_t cs = q->stream;
-    if (nb > 1) {
-      cs = q->copy_stream;
-      e = cudaEventRecord(q->ev_batch[b], q->stream);
-      if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, q->ev_batch[b], 0);
-      if (e != cudaSuccess) continue;
+    if (e == cudaSuccess && !lanes) e = cudaEventRecord(q->ev_k0, st);
+    unsigned int* counters = q->d_counter + 8 * b;
+    if (e == cudaSuccess) {
+      zero_counters_kernel<<<1, 8, 0, st>>>(counters);
+      e = cudaGetLastError();
     }
+    if (e == cudaSuccess) e = launch(q, first, count, counters, st);
+    if (e == cudaSuccess && !lanes) e = cudaEventRecord(q->ev_k1, st);
+    if (e != cudaSuccess || !q->stage_dst) continue;
     if (q->stage_dst_contig) {
       // one copy-engine transfer for the batch's full segments; the call's last segment, the one that may be
       // short, goes by its produced size
       const uint32_t full = last ? count - 1 : count;
       if (full)
-        e = cudaMemcpyAsync(q->h_orig[first].dst, q->h_ops[first].dst, (size_t)full * q->h_orig[0].dst_cap, cudaMemcpyDeviceToHost, cs);
+        e = cudaMemcpyAsync(q->h_orig[first].dst, q->h_ops[first].dst, (size_t)full * q->h_orig[0].dst_cap, cudaMemcpyDeviceToHost, st);
       if (e == cudaSuccess && last) {
-        stage_copy_kernel<<<1, 256, 0, cs>>>(q->d_ops + (n - 1), q->d_orig + (n - 1), q->d_res + (n - 1), 1);
+        stage_copy_kernel<<<1, 256, 0, st>>>(q->d_ops + (n - 1), q->d_orig + (n - 1), q->d_res + (n - 1), 1);
         e = cudaGetLastError();
         g_launches.fetch_add(1);
       }
     } else {
-      stage_copy_kernel<<<count, 256, 0, cs>>>(q->d_ops + first, q->d_orig + first, q->d_res + first, 1);
+      stage_copy_kernel<<<count, 256, 0, st>>>(q->d_ops + first, q->d_orig + first, q->d_res + first, 1);
       e = cudaGetLastError();
       g_launches.fetch_add(1);
     }
-    if (e == cudaSuccess && nb > 1 && last) {
-      e = cudaEventRecord(q->ev_copied, cs);
-      if (e == cudaSuccess) e = cudaStreamWaitEvent(q->stream, q->ev_copied, 0);
+  }
+  if (lanes) {   // join
+    for (uint32_t k = 0; k < kStageLanes && k < nb && e == cudaSuccess; ++k) {
+      e = cudaEventRecord(q->ev_lane[k], q->lane[k]);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(q->stream, q->ev_lane[k], 0);
     }
+    if (e == cudaSuccess) e = cudaEventRecord(q->ev_k1, q->stream);
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(q->h_res, q->d_res, (size_t)n * sizeof(bitar_result), cudaMemcpyDeviceToHost, q->stream);
   if (e == cudaSuccess) e = cudaEventRecord(q->ev_stop, q->stream);
@@ -523,6 +546,7 @@ int bitar_dev_open(int device_id, uint16_t n_qps, const bitar_cfg* cfg_in, bitar
   }
   // same carve-out for the small helper kernels as for the codec kernels (see inflate_kernel.cuh)
   cudaFuncSetAttribute(stage_copy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(zero_counters_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(bitar::xk::inflate_plan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaError_t e = bitar::dk::deflate_grid(device_id, dev->sm_count, &dev->deflate_grid);
   if (e == cudaSuccess) e = bitar::dks::deflate_grid(device_id, dev->sm_count, &dev->deflate_grid_small);
@@ -545,7 +569,7 @@ int bitar_dev_open(int device_id, uint16_t n_qps, const bitar_cfg* cfg_in, bitar
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&q->ev_k0);
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&q->ev_k1);
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&q->ev_stop);
-    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&q->d_counter, 8 * sizeof(unsigned int));
+    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&q->d_counter, 8 * kMaxStageBatches * sizeof(unsigned int));
     if (e2 != cudaSuccess) {
       bitar_dev_close(dev);
       return fail(BITAR_E_INVALID, "Failed to setup queue pair %u for device %d: %s", (unsigned)i, device_id, cudaGetErrorString(e2));
@@ -586,10 +610,11 @@ int bitar_dev_close(bitar_dev* dev) {
     if (q->ev_k0) cudaEventDestroy(q->ev_k0);
     if (q->ev_k1) cudaEventDestroy(q->ev_k1);
     if (q->ev_stop) cudaEventDestroy(q->ev_stop);
-    for (uint32_t b = 0; b < kMaxStageBatches; ++b)
-      if (q->ev_batch[b]) cudaEventDestroy(q->ev_batch[b]);
-    if (q->ev_copied) cudaEventDestroy(q->ev_copied);
-    if (q->copy_stream) cudaStreamDestroy(q->copy_stream);
+    for (uint32_t k = 0; k < kStageLanes; ++k) {
+      if (q->ev_lane[k]) cudaEventDestroy(q->ev_lane[k]);
+      if (q->lane[k]) cudaStreamDestroy(q->lane[k]);
+    }
+    if (q->ev_fork) cudaEventDestroy(q->ev_fork);
     if (q->stream) cudaStreamDestroy(q->stream);
     delete q;
   }
@@ -607,127 +632,148 @@ int bitar_dev_config(const bitar_dev* dev, bitar_cfg* cfg_out) {
 uint16_t bitar_dev_num_qps(const bitar_dev* dev) { return dev ? (uint16_t)dev->qps.size() : 0; }
 
 int bitar_qp_deflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, bitar_result* results) {
-  return qp_submit(dev, qp, ops, n, results, [&](QueuePair* q, uint32_t first, uint32_t count) -> cudaError_t {
-    if (!q->d_tokens) {
-      const size_t a = bitar::dk::deflate_scratch_bytes(dev->deflate_grid), b = bitar::dks::deflate_scratch_bytes(dev->deflate_grid_small);
-      cudaError_t e = cudaMalloc((void**)&q->d_tokens, a > b ? a : b);
-      if (e != cudaSuccess) return e;
-    }
-    // calls whose chunks all fit 16 KiB (8 sub-ranges: half of a 16-warp CTA would idle) go to the instance with
-    // 4 warps per CTA and three times the CTAs per SM; same output
-    uint32_t max_len = 0;
-    for (uint32_t i = 0; i < count; ++i) max_len = q->h_ops[first + i].src_len > max_len ? q->h_ops[first + i].src_len : max_len;
-    static const int small_mode = getenv("BITAR_DEFLATE_SMALL") ? atoi(getenv("BITAR_DEFLATE_SMALL")) : 1;   // 0: off (A/B runs)
-    if (small_mode && max_len <= (uint32_t)bitar::dks::kBlockMax)
-      return bitar::dks::deflate_launch(q->d_ops + first, count, q->d_res + first, q->d_counter, q->d_tokens, dev->id, dev->sm_count, 0,
-                                        max_len, dev->cfg.huffman_enc, dev->cfg.checksum_type, g_deflate_prof.load(), q->stream);
-    return bitar::dk::deflate_launch(q->d_ops + first, count, q->d_res + first, q->d_counter, q->d_tokens, dev->id, dev->sm_count,
-                                     dev->deflate_grid_override, (uint32_t)bitar::dk::kBlockMax, dev->cfg.huffman_enc,
-                                     dev->cfg.checksum_type, g_deflate_prof.load(), q->stream);
-  });
+  return qp_submit(
+      dev, qp, ops, n, results,
+      [&](QueuePair* q, uint32_t) -> cudaError_t {
+        if (q->d_tokens) return cudaSuccess;
+        const size_t a = bitar::dk::deflate_scratch_bytes(dev->deflate_grid), b = bitar::dks::deflate_scratch_bytes(dev->deflate_grid_small);
+        return cudaMalloc((void**)&q->d_tokens, a > b ? a : b);
+      },
+      [&](QueuePair* q, uint32_t first, uint32_t count, unsigned int* counters, cudaStream_t st) -> cudaError_t {
+        // calls whose chunks all fit 16 KiB (8 sub-ranges: half of a 16-warp CTA would idle) go to the instance with
+        // 4 warps per CTA and three to four times the CTAs per SM; same output
+        uint32_t max_len = 0;
+        for (uint32_t i = 0; i < count; ++i) max_len = q->h_ops[first + i].src_len > max_len ? q->h_ops[first + i].src_len : max_len;
+        static const int small_mode = getenv("BITAR_DEFLATE_SMALL") ? atoi(getenv("BITAR_DEFLATE_SMALL")) : 1;   // 0: off (A/B runs)
+        if (small_mode && max_len <= (uint32_t)bitar::dks::kBlockMax)
+          return bitar::dks::deflate_launch(q->d_ops + first, count, q->d_res + first, counters, q->d_tokens, dev->id, dev->sm_count, 0,
+                                            max_len, dev->cfg.huffman_enc, dev->cfg.checksum_type, g_deflate_prof.load(), st);
+        return bitar::dk::deflate_launch(q->d_ops + first, count, q->d_res + first, counters, q->d_tokens, dev->id, dev->sm_count,
+                                         dev->deflate_grid_override, (uint32_t)bitar::dk::kBlockMax, dev->cfg.huffman_enc,
+                                         dev->cfg.checksum_type, g_deflate_prof.load(), st);
+      },
+      kSubmitDeflate);
 }
 
+namespace {
+inline uint32_t op_blocks(const bitar_chunk& c) {   // 64 KiB blocks an op's output can span
+  const uint32_t cap = c.dst_cap < BITAR_MAX_SEG_SIZE ? c.dst_cap : BITAR_MAX_SEG_SIZE;
+  return (cap + 65535u) >> 16;
+}
+}  // namespace
+
 int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, bitar_result* results) {
-  return qp_submit(dev, qp, ops, n, results, [&](QueuePair* q, uint32_t first, uint32_t n) -> cudaError_t {
-    using namespace bitar::ik;
-    bitar_chunk* const d_ops = q->d_ops + first;       // this batch of the call (one batch unless staged)
-    bitar_result* const d_res = q->d_res + first;
-    const bitar_chunk* const h_ops = q->h_ops + first;
-    const int ck = dev->cfg.checksum_type, id = dev->id, sms = dev->sm_count;
-    const int variant = inflate_variant();
-    if (variant >= 20) {
-      // default: chunks carrying the parallel-inflate index go to the sub-range kernel, one warp per
-      // 64 KiB block; everything else (zlib streams, stored chunks) to the whole-stream kernel.
-      using namespace bitar::xk;
-      size_t blocks = 0;
-      uint32_t max_cap = 0;
-      for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t cap = h_ops[i].dst_cap < BITAR_MAX_SEG_SIZE ? h_ops[i].dst_cap : BITAR_MAX_SEG_SIZE;
-        blocks += (cap + 65535u) >> 16;
-        max_cap = cap > max_cap ? cap : max_cap;
-      }
-      // segments of at most 8 sub-ranges (16 KiB) are decoded four to a warp by their own kernel; calls with larger
-      // segments keep everything (including a short last segment) on the warp-per-block kernel
-      const bool small_mode = max_cap <= bitar::xk::kSmallSubs * bitar::dfl::kSub;
-      if (q->tasks_cap < blocks + n) {   // block tasks, then room for one small task per op
-        if (q->d_tasks) cudaFree(q->d_tasks);
-        q->d_tasks = nullptr;
-        q->tasks_cap = 0;
-        cudaError_t e = cudaMalloc((void**)&q->d_tasks, (blocks + n) * sizeof(Task));
-        if (e != cudaSuccess) return e;
-        q->tasks_cap = blocks + n;
-      }
-      Task* small_tasks = q->d_tasks + blocks;
-      if (q->generic_cap < n) {
-        if (q->d_generic) cudaFree(q->d_generic);
-        q->d_generic = nullptr;
-        q->generic_cap = 0;
-        if (q->d_ck) cudaFree(q->d_ck);
-        q->d_ck = nullptr;
-        cudaError_t e = cudaMalloc((void**)&q->d_generic, (size_t)n * sizeof(uint32_t));
-        if (e == cudaSuccess) e = cudaMalloc((void**)&q->d_ck, (size_t)n * sizeof(CkAcc));
-        if (e != cudaSuccess) return e;
-        q->generic_cap = n;
-      }
-      Counters* pc = reinterpret_cast<Counters*>(q->d_counter);
-      CkAcc* acc = ck != BITAR_CHECKSUM_NONE ? q->d_ck : nullptr;
-      inflate_plan_kernel<<<(n + 127) / 128, 128, 0, q->stream>>>(d_ops, n, d_res, q->d_tasks, small_tasks, q->d_generic, pc, acc, 1,
-                                                                  small_mode ? 1 : 0);
-      cudaError_t e = cudaGetLastError();
-      if (e != cudaSuccess) return e;
-      g_launches.fetch_add(2);
-      switch (variant) {   // default = 22: 24 warps / SM, 9-bit litlen root (measured best on the columnar mix)
-        case 20: e = IndexedConfig<10, 1344, 8, 512, 128, 20>::launch(d_ops, d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
-        case 21: e = IndexedConfig<10, 1344, 8, 512, 128, 16>::launch(d_ops, d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
-        default:
-        case 22: e = IndexedConfig<9, 864, 7, 256, 128, 24>::launch(d_ops, d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
-        case 23: e = IndexedConfig<10, 1344, 8, 512, 256, 14>::launch(d_ops, d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
-        case 24: e = IndexedConfig<10, 1344, 7, 256, 128, 24>::launch(d_ops, d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
-        case 25: e = IndexedConfig<10, 1344, 8, 512, 128, 22>::launch(d_ops, d_res, q->d_tasks, pc, acc, ck, (uint32_t)blocks, id, sms, q->stream); break;
-      }
-      if (e != cudaSuccess) return e;
-      if (small_mode) {   // blocks of at most 8 sub-ranges: four to a warp
-        e = IndexedConfig<9, 864, 7, 256, 128, 11, 8>::launch(d_ops, d_res, small_tasks, pc, acc, ck, n, id, sms, q->stream);
-        if (e != cudaSuccess) return e;
-        g_launches.fetch_add(1);
-      }
-      return InflateConfig<32, 10, 8, 1024, 4>::launch(d_ops, n, d_res, &pc->generic_next, ck, id, sms, q->stream,
-                                                       q->d_generic, &pc->n_generic);
-    }
-    if (variant >= 12) {   // lane-per-stream kernels (inflate_fast.h)
-      auto run = [&](auto cfg) -> cudaError_t {
-        using Cfg = decltype(cfg);
-        const size_t need = Cfg::scratch_bytes(id, sms);
-        if (need == 0) return cudaErrorLaunchOutOfResources;
-        if (q->lane_scratch_bytes < need) {
-          if (q->d_lane_scratch) cudaFree(q->d_lane_scratch);
-          q->d_lane_scratch = nullptr;
-          q->lane_scratch_bytes = 0;
-          cudaError_t e = cudaMalloc(&q->d_lane_scratch, need);
+  const int variant = inflate_variant();
+  const int ck = dev ? dev->cfg.checksum_type : 0, id = dev ? dev->id : 0, sms = dev ? dev->sm_count : 0;
+  size_t total_blocks = 0;
+  return qp_submit(
+      dev, qp, ops, n, results,
+      [&](QueuePair* q, uint32_t n_all) -> cudaError_t {
+        // buffers of the indexed path, sized for the whole call (its batches run side by side, each on its own slice)
+        using namespace bitar::xk;
+        for (uint32_t i = 0; i < n_all; ++i) total_blocks += op_blocks(q->h_ops[i]);
+        if (variant < 20) return cudaSuccess;
+        if (q->tasks_cap < total_blocks + n_all) {   // block tasks, then room for one small task per op
+          if (q->d_tasks) cudaFree(q->d_tasks);
+          q->d_tasks = nullptr;
+          q->tasks_cap = 0;
+          cudaError_t e = cudaMalloc((void**)&q->d_tasks, (total_blocks + n_all) * sizeof(Task));
           if (e != cudaSuccess) return e;
-          q->lane_scratch_bytes = need;
+          q->tasks_cap = total_blocks + n_all;
         }
-        return Cfg::launch(d_ops, n, d_res, q->d_counter, q->d_lane_scratch, ck, id, sms, q->stream);
-      };
-      switch (variant) {
-        default:
-        case 12: return run(bitar::fk::FastConfig<9, 576, 7, 128, 256, 4>{});
-        case 13: return run(bitar::fk::FastConfig<9, 640, 7, 160, 512, 3>{});
-        case 14: return run(bitar::fk::FastConfig<10, 1152, 8, 288, 512, 2>{});
-      }
-    }
-    switch (variant) {
-      default:
-      case 0: return InflateConfig<8, 10, 8, 1024, 2>::launch(d_ops, n, d_res, q->d_counter, ck, id, sms, q->stream);
-      case 1: return InflateConfig<8, 9, 7, 1024, 2>::launch(d_ops, n, d_res, q->d_counter, ck, id, sms, q->stream);
-      case 2: return InflateConfig<4, 10, 8, 1024, 1>::launch(d_ops, n, d_res, q->d_counter, ck, id, sms, q->stream);
-      case 3: return InflateConfig<4, 9, 7, 1024, 1>::launch(d_ops, n, d_res, q->d_counter, ck, id, sms, q->stream);
-      case 4: return InflateConfig<16, 10, 8, 1024, 4>::launch(d_ops, n, d_res, q->d_counter, ck, id, sms, q->stream);
-      case 5: return InflateConfig<32, 10, 8, 1024, 4>::launch(d_ops, n, d_res, q->d_counter, ck, id, sms, q->stream);
-      case 6: return InflateConfig<2, 9, 7, 1024, 1>::launch(d_ops, n, d_res, q->d_counter, ck, id, sms, q->stream);
-      case 7: return InflateConfig<8, 10, 8, 1024, 1>::launch(d_ops, n, d_res, q->d_counter, ck, id, sms, q->stream);
-    }
-  }, /*inflate=*/true);
+        if (q->generic_cap < n_all) {
+          if (q->d_generic) cudaFree(q->d_generic);
+          q->d_generic = nullptr;
+          q->generic_cap = 0;
+          if (q->d_ck) cudaFree(q->d_ck);
+          q->d_ck = nullptr;
+          cudaError_t e = cudaMalloc((void**)&q->d_generic, (size_t)n_all * sizeof(uint32_t));
+          if (e == cudaSuccess) e = cudaMalloc((void**)&q->d_ck, (size_t)n_all * sizeof(CkAcc));
+          if (e != cudaSuccess) return e;
+          q->generic_cap = n_all;
+        }
+        return cudaSuccess;
+      },
+      [&](QueuePair* q, uint32_t first, uint32_t n, unsigned int* counters, cudaStream_t st) -> cudaError_t {
+        using namespace bitar::ik;
+        bitar_chunk* const d_ops = q->d_ops + first;       // this batch of the call (one batch unless staged)
+        bitar_result* const d_res = q->d_res + first;
+        const bitar_chunk* const h_ops = q->h_ops + first;
+        if (variant >= 20) {
+          // default: chunks carrying the parallel-inflate index go to the sub-range kernel, one warp per
+          // 64 KiB block; everything else (zlib streams, stored chunks) to the whole-stream kernel.
+          using namespace bitar::xk;
+          size_t before = 0, blocks = 0;
+          uint32_t max_cap = 0;
+          for (uint32_t i = 0; i < first; ++i) before += op_blocks(q->h_ops[i]);
+          for (uint32_t i = 0; i < n; ++i) {
+            blocks += op_blocks(h_ops[i]);
+            max_cap = h_ops[i].dst_cap > max_cap ? h_ops[i].dst_cap : max_cap;
+          }
+          // segments of at most 8 sub-ranges (16 KiB) are decoded four to a warp by their own kernel; calls with larger
+          // segments keep everything (including a short last segment) on the warp-per-block kernel
+          const bool small_mode = max_cap <= bitar::xk::kSmallSubs * bitar::dfl::kSub;
+          Task* const tasks = q->d_tasks + before;
+          Task* const small_tasks = q->d_tasks + total_blocks + first;
+          uint32_t* const generic = q->d_generic + first;
+          Counters* pc = reinterpret_cast<Counters*>(counters);
+          CkAcc* acc = ck != BITAR_CHECKSUM_NONE ? q->d_ck + first : nullptr;
+          inflate_plan_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_ops, n, d_res, tasks, small_tasks, generic, pc, acc, 1, small_mode ? 1 : 0);
+          cudaError_t e = cudaGetLastError();
+          if (e != cudaSuccess) return e;
+          g_launches.fetch_add(2);
+          switch (variant) {   // default = 22: 24 warps / SM, 9-bit litlen root (measured best on the columnar mix)
+            case 20: e = IndexedConfig<10, 1344, 8, 512, 128, 20>::launch(d_ops, d_res, tasks, pc, acc, ck, (uint32_t)blocks, id, sms, st); break;
+            case 21: e = IndexedConfig<10, 1344, 8, 512, 128, 16>::launch(d_ops, d_res, tasks, pc, acc, ck, (uint32_t)blocks, id, sms, st); break;
+            default:
+            case 22: e = IndexedConfig<9, 864, 7, 256, 128, 24>::launch(d_ops, d_res, tasks, pc, acc, ck, (uint32_t)blocks, id, sms, st); break;
+            case 23: e = IndexedConfig<10, 1344, 8, 512, 256, 14>::launch(d_ops, d_res, tasks, pc, acc, ck, (uint32_t)blocks, id, sms, st); break;
+            case 24: e = IndexedConfig<10, 1344, 7, 256, 128, 24>::launch(d_ops, d_res, tasks, pc, acc, ck, (uint32_t)blocks, id, sms, st); break;
+            case 25: e = IndexedConfig<10, 1344, 8, 512, 128, 22>::launch(d_ops, d_res, tasks, pc, acc, ck, (uint32_t)blocks, id, sms, st); break;
+          }
+          if (e != cudaSuccess) return e;
+          if (small_mode) {   // blocks of at most 8 sub-ranges: four to a warp
+            e = IndexedConfig<9, 864, 7, 256, 128, 11, 8>::launch(d_ops, d_res, small_tasks, pc, acc, ck, n, id, sms, st);
+            if (e != cudaSuccess) return e;
+            g_launches.fetch_add(1);
+          }
+          return InflateConfig<32, 10, 8, 1024, 4>::launch(d_ops, n, d_res, &pc->generic_next, ck, id, sms, st, generic, &pc->n_generic);
+        }
+        if (variant >= 12) {   // lane-per-stream kernels (inflate_fast.h); experiments, never batched
+          auto run = [&](auto cfg) -> cudaError_t {
+            using Cfg = decltype(cfg);
+            const size_t need = Cfg::scratch_bytes(id, sms);
+            if (need == 0) return cudaErrorLaunchOutOfResources;
+            if (q->lane_scratch_bytes < need) {
+              if (q->d_lane_scratch) cudaFree(q->d_lane_scratch);
+              q->d_lane_scratch = nullptr;
+              q->lane_scratch_bytes = 0;
+              cudaError_t e = cudaMalloc(&q->d_lane_scratch, need);
+              if (e != cudaSuccess) return e;
+              q->lane_scratch_bytes = need;
+            }
+            return Cfg::launch(d_ops, n, d_res, counters, q->d_lane_scratch, ck, id, sms, st);
+          };
+          switch (variant) {
+            default:
+            case 12: return run(bitar::fk::FastConfig<9, 576, 7, 128, 256, 4>{});
+            case 13: return run(bitar::fk::FastConfig<9, 640, 7, 160, 512, 3>{});
+            case 14: return run(bitar::fk::FastConfig<10, 1152, 8, 288, 512, 2>{});
+          }
+        }
+        switch (variant) {
+          default:
+          case 0: return InflateConfig<8, 10, 8, 1024, 2>::launch(d_ops, n, d_res, counters, ck, id, sms, st);
+          case 1: return InflateConfig<8, 9, 7, 1024, 2>::launch(d_ops, n, d_res, counters, ck, id, sms, st);
+          case 2: return InflateConfig<4, 10, 8, 1024, 1>::launch(d_ops, n, d_res, counters, ck, id, sms, st);
+          case 3: return InflateConfig<4, 9, 7, 1024, 1>::launch(d_ops, n, d_res, counters, ck, id, sms, st);
+          case 4: return InflateConfig<16, 10, 8, 1024, 4>::launch(d_ops, n, d_res, counters, ck, id, sms, st);
+          case 5: return InflateConfig<32, 10, 8, 1024, 4>::launch(d_ops, n, d_res, counters, ck, id, sms, st);
+          case 6: return InflateConfig<2, 9, 7, 1024, 1>::launch(d_ops, n, d_res, counters, ck, id, sms, st);
+          case 7: return InflateConfig<8, 10, 8, 1024, 1>::launch(d_ops, n, d_res, counters, ck, id, sms, st);
+        }
+      },
+      variant >= 20 ? kSubmitInflate : kSubmitInflateOneBatch);
 }
 
 int bitar_qp_wait(bitar_dev* dev, uint16_t qp) {
