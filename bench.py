@@ -27,8 +27,8 @@ sys.path.insert(0, ROOT)
 METRIC = "deflate+inflate round-trip throughput, uncompressed bytes (bitar Compress->Decompress)"
 SEG_DEFAULT = 59460          # apps/app_common.h:39 kDecompressedSegSize
 # DRAM bytes moved per uncompressed byte, from ncu (dram__bytes_read.sum + dram__bytes_write.sum, 256 MiB launch)
-DEFLATE_DRAM_BYTES_PER_BYTE = (289.293824e6 + 105.449472e6) / 268435456
-INFLATE_DRAM_BYTES_PER_BYTE = (157.800192e6 + 253.604096e6) / 268435456
+DEFLATE_DRAM_BYTES_PER_BYTE = (290.577408e6 + 113.426688e6) / 268435456
+INFLATE_DRAM_BYTES_PER_BYTE = (159.259904e6 + 256.195072e6) / 268435456
 
 
 def peaks():
@@ -253,13 +253,13 @@ def main():
             "deflate_gbps": world * U / (td_ms * 1e-3) / 1e9, "inflate_gbps": world * U / (ti_ms * 1e-3) / 1e9,
             "deflate_kernel_ms": kd_ms, "inflate_kernel_ms": ki_ms, "wall_ms_per_step": wall_ms,
             "ratio": U / Cbytes, "zlib_level1_ratio": zratio,
-            # dominant kernel = deflate_kernel (78 % of the device-resident step's GPU time, profiles/r01_launches_bench_1GiB_j.csv).
+            # dominant kernel = deflate_kernel (76 % of the device-resident step's GPU time, profiles/r01_launches_bench_1GiB_k.csv).
             # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture at 256 MiB
-            # (profiles/r01_ncu_full_deflate_and_indexed_inflate_256MiB_j.txt), scaled linearly to this launch's bytes.
+            # (profiles/r01_ncu_full_deflate_and_indexed_inflate_256MiB_k.txt), scaled linearly to this launch's bytes.
             "roofline": {"bound": "hbm", "kernel": "deflate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": DEFLATE_DRAM_BYTES_PER_BYTE * U, "peak_source": which,
                          "algorithmic_bytes": "U + C per launch (read input once, write the stream once)",
-                         "note": "issue- and latency-bound integer kernel: 65 % issue-slot utilisation, 1.8 % DRAM throughput (ncu)",
+                         "note": "issue- and latency-bound integer kernel: 66 % issue-slot utilisation, 1.5 % DRAM throughput (ncu)",
                          "inflate": {"kernel": "inflate_indexed_kernel", "achieved": (U + Cbytes) / (ki_ms * 1e-3) / 1e9,
                                      "frac": (U + Cbytes) / (ki_ms * 1e-3) / 1e9 / peak,
                                      "traffic": INFLATE_DRAM_BYTES_PER_BYTE * U}},

@@ -56,9 +56,9 @@ struct ConnectionsDefault {
   ConnectionsDefault() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
 } g_connections_default;
 
-constexpr uint32_t kMaxStageBatches = 16;
+constexpr uint32_t kMaxStageBatches = 8;               // measured: ~8 batches of >= 16 MiB per call, whatever its size
 constexpr uint32_t kStageLanes = 3;                     // + the queue pair's own stream: 8 queue pairs fit 32 hardware queues
-constexpr size_t kStageBatchBytes = (size_t)16 << 20;   // inflated bytes per batch of a staged call
+constexpr size_t kStageBatchBytes = (size_t)16 << 20;   // least inflated bytes per batch of a staged call
 
 struct QueuePair {
   cudaStream_t stream = nullptr;
