@@ -47,7 +47,7 @@
 #include "deflate_common.h"
 
 #ifndef BITAR_DK_RANK_SORT
-#define BITAR_DK_RANK_SORT 0       // experiments: rank sort in the 16-warp instance too
+#define BITAR_DK_RANK_SORT 1       // 0: the bitonic network in the 16-warp instance (A/B)
 #endif
 #ifndef BITAR_DK_NS
 #define BITAR_DK_NS dk
@@ -428,12 +428,15 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
 
 // Two-queue merge over leaves sorted ascending by (freq << 9 | symbol); same picks (ties prefer leaves) as
 // dfl::huff_lengths_from_sorted.  Leaves 0..m-1, internal nodes m..2m-2, parent[] for every node but the root.
+// Sentinels instead of bounds checks (this one thread is bound by its instruction count, ~30 per pick): the caller
+// sets key[m] = 0xFFFFFFFF (as a frequency: 2^23 - 1, above every real sum) and node_freq[m .. 2m-1] = 0xFFFFFFFF
+// (a node that does not exist yet).
 __device__ void huff_merge(const uint32_t* __restrict__ key, int m, uint32_t* node_freq, uint16_t* parent) {
   constexpr uint32_t kInf = 0xFFFFFFFFu;
   uint32_t lf = key[0] >> 9, lf2 = key[1] >> 9, nf = kInf, nf2 = kInf;   // heads of the leaf / internal queues
   int leaf = 0, inode = m, next = m;
   // branch-free picks (a taken branch costs this single thread ~20 cycles, a select 2): both queues' next entries
-  // are loaded unconditionally from clamped addresses and chosen by the comparison
+  // are loaded unconditionally and chosen by the comparison
   for (int k = 0; k < m - 1; ++k) {
     uint32_t f = 0;
 #pragma unroll
@@ -443,10 +446,8 @@ __device__ void huff_merge(const uint32_t* __restrict__ key, int m, uint32_t* no
       parent[tl ? leaf : inode] = (uint16_t)next;
       leaf += tl ? 1 : 0;
       inode += tl ? 0 : 1;
-      const uint32_t load_l = key[min(leaf + 1, m - 1)] >> 9;
-      const uint32_t load_n = node_freq[min(inode + 1, 2 * m - 2)];
-      const uint32_t new_lf2 = leaf + 1 < m ? load_l : kInf;
-      const uint32_t new_nf2 = inode + 1 < next ? load_n : kInf;
+      const uint32_t new_lf2 = key[leaf + 1] >> 9;
+      const uint32_t new_nf2 = node_freq[inode + 1];
       lf = tl ? lf2 : lf;
       nf = tl ? nf : nf2;
       lf2 = tl ? new_lf2 : lf2;
@@ -648,6 +649,8 @@ __device__ __forceinline__ void plan_cl_tree_warp(Smem& sm, int lane) {
 #pragma unroll
   for (int j = 0; j < dfl::kNumCl; ++j) rank += (uint32_t)(__shfl_sync(kFull, key, j) < key);
   if (fs) sorted[rank] = key;
+  if (lane == 0) sorted[cm] = 0xFFFFFFFFu;                     // sentinels of the merge
+  pp.d_node_freq[lane] = pp.d_node_freq[32 + lane] = 0xFFFFFFFFu;
   if (lane < 16) pp.ll_bl[lane] = 0;
   if (lane < dfl::kNumCl) pl.cl_len[lane] = 0;
   if (lane == 0) pp.ll_over = 0;
@@ -844,6 +847,9 @@ __global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
         used = __reduce_add_sync(0xFFFFFFFFu, used);
         if (lane == 0 && used) atomicAdd(&sm.ll_m, used);
       }
+      // sentinels of the Huffman merge: nodes that do not exist yet
+      for (int i = tid; i < 2 * 288; i += kThreads) sm.u.enc.scratch.hs.node_freq[i] = 0xFFFFFFFFu;
+      if (tid < 64) sm.u.enc.pp.d_node_freq[tid] = 0xFFFFFFFFu;
       if (kThreads >= 512 && !BITAR_DK_RANK_SORT) sort512(sm);
       else sort_rank(sm);
       BITAR_PHASE(2)
@@ -873,6 +879,7 @@ __global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
             used++;
           }
         const int dm = dfl::sort_used_small(df, dfl::kNumDist, sm.d_sorted);
+        sm.d_sorted[dm < 31 ? dm : 31] = 0xFFFFFFFFu;   // sentinel (30 distance symbols at most)
         sm.d_m = (uint32_t)dm;
         huff_merge(sm.d_sorted, dm, pp.d_node_freq, pp.d_parent);
       } else if (warp >= 2 && checksum_type != BITAR_CHECKSUM_NONE) {

@@ -146,6 +146,7 @@ inline void find_tokens(const uint8_t* d, int n, const Params& P, std::vector<ui
 
 struct BlockStats {
   uint64_t literals = 0, matches = 0, match_bytes = 0;
+  uint64_t far128 = 0, far128_bytes = 0, far256 = 0, far256_bytes = 0, far512 = 0, far512_bytes = 0;   // matches by distance (inflate ring sizes)
   int type = 0;
   uint64_t bits = 0;
 };
@@ -172,6 +173,9 @@ inline void encode_block(const uint8_t* d, int n, const std::vector<uint32_t>& t
       if (st) {
         st->matches++;
         st->match_bytes += (uint64_t)tok_len(t);
+        if (tok_dist(t) > 128) st->far128++, st->far128_bytes += (uint64_t)tok_len(t);
+        if (tok_dist(t) > 256) st->far256++, st->far256_bytes += (uint64_t)tok_len(t);
+        if (tok_dist(t) > 512) st->far512++, st->far512_bytes += (uint64_t)tok_len(t);
       }
     }
   }

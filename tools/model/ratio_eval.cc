@@ -64,7 +64,7 @@ int main(int argc, char** argv) {
     else if (k == "sub_log2") P.sub_log2 = v;
     else return fprintf(stderr, "unknown key %s\n", k.c_str()), 2;
   }
-  uint64_t zsum = 0, msum = 0, lits = 0, matches = 0, mbytes = 0;
+  uint64_t zsum = 0, msum = 0, lits = 0, matches = 0, mbytes = 0, fr[6] = {0, 0, 0, 0, 0, 0};
   int types[3] = {0, 0, 0};
   for (size_t off = 0; off < data.size(); off += seg) {
     size_t n = std::min(seg, data.size() - off);
@@ -81,6 +81,7 @@ int main(int argc, char** argv) {
       lits += s.literals;
       matches += s.matches;
       mbytes += s.match_bytes;
+      fr[0] += s.far128; fr[1] += s.far128_bytes; fr[2] += s.far256; fr[3] += s.far256_bytes; fr[4] += s.far512; fr[5] += s.far512_bytes;
       types[s.type]++;
     }
   }
@@ -89,5 +90,7 @@ int main(int argc, char** argv) {
          (double)data.size() / msum, (double)msum / zsum, (unsigned long long)lits,
          (unsigned long long)matches, matches ? (double)mbytes / matches : 0.0,
          (double)data.size() / (double)(lits + matches), types[0], types[1], types[2]);
+  printf("matches farther than 128 / 256 / 512 B: %.1f%% / %.1f%% / %.1f%% of matches, %.1f%% / %.1f%% / %.1f%% of all bytes\n", 100.0 * fr[0] / matches, 100.0 * fr[2] / matches,
+         100.0 * fr[4] / matches, 100.0 * fr[1] / data.size(), 100.0 * fr[3] / data.size(), 100.0 * fr[5] / data.size());
   return 0;
 }

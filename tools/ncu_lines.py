@@ -38,6 +38,7 @@ def main():
             continue
         if r[0] == "Line No":
             hdr = {n: i for i, n in enumerate(r)}
+            ncol = len(r)
             ri = [(n, i) for i, n in enumerate(r) if n.startswith("stall_") and "Not Issued" not in n]
             continue
         if skip or hdr is None:
@@ -46,11 +47,12 @@ def main():
             continue          # the SASS rows under a line (listed twice); the line's own row carries the sums
         line = (cur_file.split("/")[-1], int(r[0]))
         text[line] = r[1].strip()
+        sh = len(r) - ncol      # ncu does not escape quotes inside the source text: such rows have extra columns
         try:
-            inst[line] += int(r[hdr["Instructions Executed"]])
-            samp[line] += int(r[hdr["# Samples"]])
+            inst[line] += int(r[hdr["Instructions Executed"] + sh])
+            samp[line] += int(r[hdr["# Samples"] + sh])
             for n, i in ri:
-                v = int(r[i])
+                v = int(r[i + sh])
                 if v:
                     reasons[line][n[6:]] += v
         except (ValueError, IndexError):
