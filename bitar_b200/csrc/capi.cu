@@ -34,6 +34,7 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_inflate_variant{-1};
+std::atomic<size_t> g_stage_batch_bytes{0};                 // tests: least bytes per batch of a staged inflate call (0 = default)
 std::atomic<unsigned long long*> g_deflate_prof{nullptr};  // device buffer of 8 phase counters (debug)
 
 int fail(int code, const char* fmt, ...) {
@@ -363,7 +364,9 @@ int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, b
   // Everything else is one batch on the queue pair's own stream.
   uint32_t nb = 1;
   if (q->stage_dst && n > 1 && mode == kSubmitInflate) {
-    static const size_t batch_bytes = getenv("BITAR_STAGE_BATCH_MIB") ? (size_t)atoi(getenv("BITAR_STAGE_BATCH_MIB")) << 20 : kStageBatchBytes;
+    static const size_t env_bytes = getenv("BITAR_STAGE_BATCH_MIB") ? (size_t)atoi(getenv("BITAR_STAGE_BATCH_MIB")) << 20 : kStageBatchBytes;
+    const size_t tuned = g_stage_batch_bytes.load();
+    const size_t batch_bytes = tuned ? tuned : env_bytes;
     const size_t want = q->stage_out_bytes / (batch_bytes ? batch_bytes : 1);
     nb = (uint32_t)(want < 1 ? 1 : want > kMaxStageBatches ? kMaxStageBatches : want);
     if (nb > n) nb = n;
@@ -974,5 +977,7 @@ BITAR_API int bitar_debug_lane(unsigned int* out16) {
 
 // not part of the public header: selects the inflate kernel instantiation for tuning sweeps
 BITAR_API void bitar_tune_inflate_variant(int v) { g_inflate_variant.store(v); }
+// not part of the public header: least inflated bytes per batch of a staged (host-buffer) inflate call; 0 = default
+BITAR_API void bitar_tune_stage_batch(unsigned long long bytes) { g_stage_batch_bytes.store((size_t)bytes); }
 
 }  // extern "C"

@@ -189,6 +189,79 @@ def test_host_resident_buffers_are_staged(cuda_device):
         dev.close()
 
 
+@pytest.mark.parametrize("ck", [capi.CHECKSUM_NONE, capi.CHECKSUM_CRC32_ADLER32])
+def test_staged_calls_in_batches_on_lane_streams(cuda_device, ck):
+    """A staged inflate call large enough for several batches runs them on the queue pair's lane streams, each batch
+    with its own slice of the task / counter / checksum buffers.  Forced here on a small buffer (1 MiB per batch):
+    contiguous destination (copy-engine copy-back), scattered destination (scatter kernel), foreign streams mixed in
+    (whole-stream kernel), checksums, two queue pairs at once."""
+    import ctypes as C
+    L = capi.lib()
+    L.bitar_tune_stage_batch.argtypes = [C.c_ulonglong]
+    data = synth.lineitem_like(160 * SEG + 777)
+    n = (data.size + SEG - 1) // SEG
+    dev = G.open_device(SEG, qps=2, slot_mem_kind=capi.MEM_PINNED, max_preallocate_memzones=n + 8, checksum_type=ck)
+    bufs = []
+
+    def pinned(nbytes):
+        p = C.c_void_p()
+        capi.check(L.bitar_mem_alloc(capi.MEM_PINNED, 0, nbytes, 64, C.byref(p)))
+        bufs.append(p)
+        return p.value
+
+    try:
+        L.bitar_tune_stage_batch(1 << 20)
+        h_in, h_out = pinned(data.size), pinned(n * SEG + 64)
+        C.memmove(h_in, data.ctypes.data, data.size)
+        ops, slots = dev.compress_ops(h_in, data.size)
+        res = dev.enqueue("deflate", 0, ops)
+        dev.wait(0)
+        # every fifth chunk replaced by a zlib-produced stream (no index -> whole-stream kernel inside the batches)
+        zs, zp = O.compress_buffer(data, SEG)
+        h_z = pinned(zs.size)
+        C.memmove(h_z, zs.ctypes.data, zs.size)
+        src = np.array(slots, dtype=np.uint64)
+        produced = res["produced"].copy()
+        for i in range(0, n, 5):
+            src[i] = h_z + i * zs.shape[1]
+            produced[i] = zp[i]
+        want_ck = [(O.adler32(data[i * SEG:(i + 1) * SEG]) << 32) | O.crc32(data[i * SEG:(i + 1) * SEG]) for i in range(n)]
+        back = np.ctypeslib.as_array(C.cast(h_out, C.POINTER(C.c_uint8)), shape=(n * SEG + 64,))
+        # (a) contiguous destination, both queue pairs at once on halves of the buffer
+        C.memset(h_out, 0xA5, n * SEG + 64)
+        half = n // 2
+        r0 = dev.enqueue("inflate", 0, dev.decompress_ops(src[:half], produced[:half], h_out))
+        r1 = dev.enqueue("inflate", 1, dev.decompress_ops(src[half:], produced[half:], h_out + half * SEG))
+        dev.wait(0)
+        dev.wait(1)
+        ires = np.concatenate([r0, r1])
+        assert (ires["status"] == 0).all() and int(ires["produced"].sum()) == data.size
+        assert np.array_equal(back[:data.size], data) and (back[data.size:] == 0xA5).all()
+        if ck:
+            assert [int(c) for c in ires["checksum"]] == want_ck
+        # (b) scattered destination: segment i at a stride of SEG + 48 (not the Decompress() layout)
+        stride = SEG + 48
+        h_sc = pinned(n * stride + 64)
+        C.memset(h_sc, 0x5A, n * stride + 64)
+        iops = dev.decompress_ops(src, produced, h_sc)
+        iops["dst"] = np.uint64(h_sc) + np.arange(n, dtype=np.uint64) * np.uint64(stride) + np.uint64(1)
+        ires = dev.enqueue("inflate", 0, iops)
+        dev.wait(0)
+        sc = np.ctypeslib.as_array(C.cast(h_sc, C.POINTER(C.c_uint8)), shape=(n * stride + 64,))
+        assert (ires["status"] == 0).all()
+        for i in range(n):
+            c = data[i * SEG:(i + 1) * SEG]
+            assert np.array_equal(sc[i * stride + 1:i * stride + 1 + c.size], c), i
+            assert (sc[i * stride + 1 + c.size:(i + 1) * stride + 1] == 0x5A).all(), i
+        if ck:
+            assert [int(c) for c in ires["checksum"]] == want_ck
+    finally:
+        L.bitar_tune_stage_batch(0)
+        for b in bufs:
+            L.bitar_mem_free(capi.MEM_PINNED, 0, b)
+        dev.close()
+
+
 def test_bitar_decompress_contract(cuda_device):
     """Decompress(): op i lands at out + i*S, total = sum(produced) (src/device.cc:240-318); checked
     against oracle_decompress_buffer on the oracle's own compressed slots."""
