@@ -34,6 +34,7 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_inflate_variant{-1};
+std::atomic<int> g_stage_strided{1};                        // tests / A-B runs: 0 = always gather with the kernel
 std::atomic<size_t> g_stage_batch_bytes{0};                 // tests: least bytes per batch of a staged inflate call (0 = default)
 std::atomic<unsigned long long*> g_deflate_prof{nullptr};  // device buffer of 8 phase counters (debug)
 
@@ -89,6 +90,13 @@ struct QueuePair {
   bool stage_src = false, stage_dst = false;
   bool stage_dst_contig = false;        // destinations form one range of equal-capacity segments (Decompress())
   size_t stage_out_bytes = 0;           // sum of the call's destination capacities
+  uint32_t nb = 1, per = 0;             // batches of the call, ops per batch
+  // compressed inputs at a constant stride (pool slots handed out by take_n: Compress() -> Decompress()): a batch's
+  // gather is one strided copy-engine transfer instead of a kernel reading host memory
+  bool stage_src_strided = false;
+  size_t src_stride = 0;
+  uint32_t batch_pitch[kMaxStageBatches] = {};
+  size_t batch_in_off[kMaxStageBatches] = {};
   // staged calls run in batches spread over kStageLanes extra streams: one batch is gather -> inflate -> copy-back
   // in order on its lane, the lanes overlap each other (PCIe both ways and the SMs busy at once)
   cudaStream_t lane[kStageLanes] = {};
@@ -260,7 +268,9 @@ bool is_host_memory(const void* p) {
 
 // Rewrites q->h_ops to staged device addresses when the call's buffers are host memory (caller's ops are
 // kept in q->h_orig).  Called with the queue pair idle, before the descriptors are uploaded.
-int inflate_prepare_staging(QueuePair* q, uint32_t n) {
+int inflate_prepare_staging(QueuePair* q, uint32_t n, bool allow_batches) {
+  q->nb = 1;
+  q->per = n;
   q->stage_src = q->h_ops[0].src != nullptr && q->h_ops[0].src_len > 0 && is_host_memory(q->h_ops[0].src);
   q->stage_dst = q->h_ops[0].dst != nullptr && is_host_memory(q->h_ops[0].dst);
   if (!q->stage_src && !q->stage_dst) return BITAR_OK;
@@ -274,9 +284,47 @@ int inflate_prepare_staging(QueuePair* q, uint32_t n) {
   }
   memcpy(q->h_orig, q->h_ops, (size_t)n * sizeof(bitar_chunk));
   size_t need_in = 0, need_out = 0;
+  uint32_t max_len = 0;
   for (uint32_t i = 0; i < n; ++i) {
     need_in += (((size_t)q->h_ops[i].src_len + 15u) & ~(size_t)15u) + 32u;
     need_out += (((size_t)q->h_ops[i].dst_cap + 15u) & ~(size_t)15u) + 32u;
+    max_len = q->h_ops[i].src_len > max_len ? q->h_ops[i].src_len : max_len;
+  }
+  q->stage_out_bytes = need_out;
+  // Staged calls with a host-resident destination run in batches (qp_submit): at most kMaxStageBatches, each of at
+  // least kStageBatchBytes of output.
+  if (q->stage_dst && n > 1 && allow_batches) {
+    static const size_t env_bytes = getenv("BITAR_STAGE_BATCH_MIB") ? (size_t)atoi(getenv("BITAR_STAGE_BATCH_MIB")) << 20 : kStageBatchBytes;
+    const size_t tuned = g_stage_batch_bytes.load();
+    const size_t batch_bytes = tuned ? tuned : env_bytes;
+    const size_t want = need_out / (batch_bytes ? batch_bytes : 1);
+    q->nb = (uint32_t)(want < 1 ? 1 : want > kMaxStageBatches ? kMaxStageBatches : want);
+    if (q->nb > n) q->nb = n;
+    q->per = (n + q->nb - 1) / q->nb;
+    q->nb = (n + q->per - 1) / q->per;
+  }
+  // sources at a constant stride with room for the widest row?
+  const size_t mis0 = reinterpret_cast<uintptr_t>(q->h_orig[0].src) & 15u;
+  q->stage_src_strided = false;
+  if (q->stage_src && n > 1 && g_stage_strided.load()) {
+    const uint8_t* s0 = static_cast<const uint8_t*>(q->h_orig[0].src);
+    const uint8_t* s1 = static_cast<const uint8_t*>(q->h_orig[1].src);
+    const size_t stride = s1 > s0 ? (size_t)(s1 - s0) : 0;
+    bool ok = stride > 0 && (stride & 15u) == 0 && ((mis0 + max_len + 15u) & ~(size_t)15u) <= stride;
+    for (uint32_t i = 2; i < n && ok; ++i) ok = static_cast<const uint8_t*>(q->h_orig[i].src) == s0 + (size_t)i * stride;
+    q->stage_src_strided = ok;
+    q->src_stride = stride;
+    if (ok) {   // a batch's rows share the pitch of its widest one
+      need_in = 0;
+      for (uint32_t b = 0, first = 0; first < n; ++b, first += q->per) {
+        const uint32_t count = n - first < q->per ? n - first : q->per;
+        uint32_t widest = 0;
+        for (uint32_t i = first; i < first + count; ++i) widest = q->h_orig[i].src_len > widest ? q->h_orig[i].src_len : widest;
+        q->batch_pitch[b] = (uint32_t)((mis0 + widest + 15u) & ~(size_t)15u);
+        q->batch_in_off[b] = need_in;
+        need_in += (size_t)count * q->batch_pitch[b] + 32u;
+      }
+    }
   }
   if (q->stage_src && q->stage_in_cap < need_in) {
     if (q->d_stage_in) cudaFree(q->d_stage_in);
@@ -290,10 +338,6 @@ int inflate_prepare_staging(QueuePair* q, uint32_t n) {
     CU_TRY(cudaMalloc((void**)&q->d_stage_out, need_out), BITAR_E_OUT_OF_MEMORY);
     q->stage_out_cap = need_out;
   }
-  // Decompress() lays segment i at out + i * S (src/memory.cc:482-493): then the staged output mirrors that
-  // layout and goes back with ONE copy-engine transfer (which, unlike a kernel, runs beside the inflate kernels of
-  // the other queue pairs); only the last segment, the one that may be short, is copied by produced size.
-  q->stage_out_bytes = need_out;
   if (q->stage_dst && !q->ev_fork) {
     for (uint32_t k = 0; k < kStageLanes; ++k) {
       CU_TRY(cudaStreamCreateWithFlags(&q->lane[k], cudaStreamNonBlocking), BITAR_E_OUT_OF_MEMORY);
@@ -301,6 +345,10 @@ int inflate_prepare_staging(QueuePair* q, uint32_t n) {
     }
     CU_TRY(cudaEventCreateWithFlags(&q->ev_fork, cudaEventDisableTiming), BITAR_E_OUT_OF_MEMORY);
   }
+  // Decompress() lays segment i at out + i * S (src/memory.cc:482-493): then the staged output mirrors that
+  // layout and a batch goes back with ONE copy-engine transfer (which, unlike a kernel, runs beside the inflate
+  // kernels of the other batches and queue pairs); only the call's last segment, the one that may be short, is
+  // copied by produced size.
   q->stage_dst_contig = q->stage_dst && n > 1;
   for (uint32_t i = 1; i < n && q->stage_dst_contig; ++i)
     q->stage_dst_contig = q->h_orig[i].dst_cap == q->h_orig[0].dst_cap &&
@@ -308,7 +356,10 @@ int inflate_prepare_staging(QueuePair* q, uint32_t n) {
   size_t at_in = 0, at_out = 0;
   for (uint32_t i = 0; i < n; ++i) {
     bitar_chunk& c = q->h_ops[i];
-    if (q->stage_src) {
+    if (q->stage_src_strided) {
+      const uint32_t b = i / q->per;
+      c.src = q->d_stage_in + q->batch_in_off[b] + (size_t)(i - b * q->per) * q->batch_pitch[b] + mis0;
+    } else if (q->stage_src) {
       const size_t mis = reinterpret_cast<uintptr_t>(c.src) & 15u;
       c.src = q->d_stage_in + at_in + mis;
       at_in += (((size_t)c.src_len + 15u) & ~(size_t)15u) + 32u;
@@ -346,9 +397,11 @@ int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, b
   int rc = qp_reserve(dev, q, n);
   if (rc) return rc;
   memcpy(q->h_ops, ops, (size_t)n * sizeof(bitar_chunk));
-  q->stage_src = q->stage_dst = q->stage_dst_contig = false;
+  q->stage_src = q->stage_dst = q->stage_dst_contig = q->stage_src_strided = false;
+  q->nb = 1;
+  q->per = n;
   if (inflate) {
-    rc = inflate_prepare_staging(q, n);
+    rc = inflate_prepare_staging(q, n, mode == kSubmitInflate);
     if (rc) return rc;
   }
   q->user_out = results;
@@ -362,20 +415,12 @@ int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, b
   // (PCIe device -> host) of one batch in order on one of kStageLanes streams, the lanes side by side.  One batch
   // alone is latency-bound (a 2 KiB sub-range takes a lane ~0.8 ms whatever the batch size), hence several in flight.
   // Everything else is one batch on the queue pair's own stream.
-  uint32_t nb = 1;
-  if (q->stage_dst && n > 1 && mode == kSubmitInflate) {
-    static const size_t env_bytes = getenv("BITAR_STAGE_BATCH_MIB") ? (size_t)atoi(getenv("BITAR_STAGE_BATCH_MIB")) << 20 : kStageBatchBytes;
-    const size_t tuned = g_stage_batch_bytes.load();
-    const size_t batch_bytes = tuned ? tuned : env_bytes;
-    const size_t want = q->stage_out_bytes / (batch_bytes ? batch_bytes : 1);
-    nb = (uint32_t)(want < 1 ? 1 : want > kMaxStageBatches ? kMaxStageBatches : want);
-    if (nb > n) nb = n;
-  }
+  const uint32_t nb = q->nb;
   const bool lanes = nb > 1;
   if (e == cudaSuccess) e = prepare(q, n);     // buffers sized for the whole call: batches in flight share them
   if (e == cudaSuccess && lanes) e = cudaEventRecord(q->ev_fork, q->stream);
   if (e == cudaSuccess && lanes) e = cudaEventRecord(q->ev_k0, q->stream);
-  const uint32_t per = (n + nb - 1) / nb;
+  const uint32_t per = q->per;
   for (uint32_t b = 0, first = 0; first < n && e == cudaSuccess; ++b, first += per) {
     const uint32_t count = n - first < per ? n - first : per;
     const bool last = first + count == n;
@@ -384,7 +429,19 @@ int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, b
       e = cudaStreamWaitEvent(st, q->ev_fork, 0);
       if (e != cudaSuccess) continue;
     }
-    if (q->stage_src) {
+    if (q->stage_src_strided) {
+      // one strided transfer for the batch's rows; the call's last op by its exact length (a row is read to the
+      // batch's pitch, which stays inside the source range only while another row follows)
+      const size_t mis0 = reinterpret_cast<uintptr_t>(q->h_orig[0].src) & 15u;
+      const uint32_t rows = last ? count - 1 : count;
+      uint8_t* const stage = q->d_stage_in + q->batch_in_off[b];
+      if (rows)
+        e = cudaMemcpy2DAsync(stage, q->batch_pitch[b], static_cast<const uint8_t*>(q->h_orig[first].src) - mis0, q->src_stride,
+                              q->batch_pitch[b], rows, cudaMemcpyHostToDevice, st);
+      if (e == cudaSuccess && last)
+        e = cudaMemcpyAsync(stage + (size_t)(count - 1) * q->batch_pitch[b] + mis0, q->h_orig[n - 1].src, q->h_orig[n - 1].src_len,
+                            cudaMemcpyHostToDevice, st);
+    } else if (q->stage_src) {
       stage_copy_kernel<<<count, 256, 0, st>>>(q->d_orig + first, q->d_ops + first, nullptr, 0);
       e = cudaGetLastError();
       g_launches.fetch_add(1);
@@ -979,5 +1036,7 @@ BITAR_API int bitar_debug_lane(unsigned int* out16) {
 BITAR_API void bitar_tune_inflate_variant(int v) { g_inflate_variant.store(v); }
 // not part of the public header: least inflated bytes per batch of a staged (host-buffer) inflate call; 0 = default
 BITAR_API void bitar_tune_stage_batch(unsigned long long bytes) { g_stage_batch_bytes.store((size_t)bytes); }
+// not part of the public header: 0 = gather staged inputs with the kernel even when they lie at a constant stride
+BITAR_API void bitar_tune_stage_strided(int on) { g_stage_strided.store(on); }
 
 }  // extern "C"

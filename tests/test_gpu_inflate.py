@@ -255,6 +255,14 @@ def test_staged_calls_in_batches_on_lane_streams(cuda_device, ck):
             assert (sc[i * stride + 1 + c.size:(i + 1) * stride + 1] == 0x5A).all(), i
         if ck:
             assert [int(c) for c in ires["checksum"]] == want_ck
+        # (c) every source a pool slot (constant stride): the batches gather with strided copy-engine transfers
+        C.memset(h_out, 0xA5, n * SEG + 64)
+        ires = dev.enqueue("inflate", 1, dev.decompress_ops(np.array(slots, dtype=np.uint64), res["produced"], h_out + 5))
+        dev.wait(1)
+        assert (ires["status"] == 0).all() and int(ires["produced"].sum()) == data.size
+        assert np.array_equal(back[5:5 + data.size], data) and (back[5 + data.size:] == 0xA5).all()
+        if ck:
+            assert [int(c) for c in ires["checksum"]] == want_ck
     finally:
         L.bitar_tune_stage_batch(0)
         for b in bufs:

@@ -17,13 +17,13 @@ from bitar_b200 import synth  # noqa: E402
 from bitar_b200.engine import CompressDevice, Configuration  # noqa: E402
 
 
-def run(data, seg, qps, pinned, reps=3):
+def run(data, seg, qps, pinned, reps=3, device_slots=False):
     L = capi.lib()
     U = data.size
     n = (U + seg - 1) // seg
     dev = CompressDevice(0, qps).Initialize(Configuration(
         decompressed_seg_size=seg, max_preallocate_memzones=n + 64,
-        slot_mem_kind=capi.MEM_PINNED if pinned else capi.MEM_DEVICE))
+        slot_mem_kind=capi.MEM_PINNED if pinned and not device_slots else capi.MEM_DEVICE))
     if pinned:
         h_in, h_out = C.c_void_p(), C.c_void_p()
         capi.check(L.bitar_mem_alloc(capi.MEM_PINNED, 0, U, 64, C.byref(h_in)))
@@ -63,7 +63,7 @@ def run(data, seg, qps, pinned, reps=3):
     for s in slots[::-1]:
         dev.put_slot(s)
     dev.close()
-    return {"seg": seg, "qps": qps, "buffers": "pinned_host" if pinned else "device", "chunks": n,
+    return {"seg": seg, "qps": qps, "buffers": ("pinned_host+device_slots" if device_slots else "pinned_host") if pinned else "device", "chunks": n,
             "compress_gbps": round(U / best_c / 1e9, 2), "decompress_gbps": round(U / best_d / 1e9, 2),
             "ratio": round(U / float(produced.sum()), 3), "ok": ok}
 
@@ -76,6 +76,11 @@ def main():
     only = os.environ.get("SWEEP_BUFFERS", "")
     segs = [int(x) for x in os.environ.get("SWEEP_SEGS", "").split(",") if x] or \
         [4096, 8192, 16384, 32768, 65536, 131072, 262144, 524288, 1048576]
+    if only == "mixed":    # experiment: input / output buffers pinned, compressed slots in device memory
+        for seg in segs:
+            for qps in qps_list:
+                print(json.dumps(run(data, seg, qps, True, device_slots=True)), flush=True)
+        return
     for pinned in (False, True):
         if only and only != ("pinned" if pinned else "device"):
             continue
