@@ -319,8 +319,11 @@ def run_e2e(args, L, capi, C, torch, dist, world, local_rank, data, seg, n, U):
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    step_ms = []
     for _ in range(args.steps):
+        t_step = time.perf_counter()
         cbytes, h2d, total = step()
+        step_ms.append(round((time.perf_counter() - t_step) * 1e3, 3))
     torch.cuda.synchronize()
     dt = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -348,9 +351,9 @@ def run_e2e(args, L, capi, C, torch, dist, world, local_rank, data, seg, n, U):
         dev.put_slot(s)
     dev.close()
     return {"value": world * U / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(U + h2d),
-            "d2h_bytes_per_step": int(cbytes + U), "ms_per_step": dt * 1e3, "queue_pairs": len(parts), "pcie": pcie,
+            "d2h_bytes_per_step": int(cbytes + U), "ms_per_step": dt * 1e3, "step_ms": step_ms, "queue_pairs": len(parts), "pcie": pcie,
             "path": "pinned host in/out through the C-ABI: compress reads and writes host memory in place (zero-copy over "
-                    "PCIe), decompress is staged through device memory by the library in batches (gather kernel and inflate of batch b+1 overlap the copy-back of batch b)"}
+                    "PCIe), decompress is staged through device memory by the library in batches on three extra streams per queue pair (strided copy-engine gather, inflate, copy-engine copy-back)"}
 
 
 if __name__ == "__main__":

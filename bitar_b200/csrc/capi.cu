@@ -95,6 +95,7 @@ struct QueuePair {
   // gather is one strided copy-engine transfer instead of a kernel reading host memory
   bool stage_src_strided = false;
   size_t src_stride = 0;
+
   uint32_t batch_pitch[kMaxStageBatches] = {};
   size_t batch_in_off[kMaxStageBatches] = {};
   // staged calls run in batches spread over kStageLanes extra streams: one batch is gather -> inflate -> copy-back
@@ -202,8 +203,8 @@ int qp_reserve(bitar_dev* dev, QueuePair* q, uint32_t n) {
   if (q->d_res) cudaFree(q->d_res);
   q->h_ops = nullptr; q->h_res = nullptr; q->d_ops = nullptr; q->d_res = nullptr;
   q->cap = 0;
-  CU_TRY(cudaHostAlloc((void**)&q->h_ops, (size_t)cap * sizeof(bitar_chunk), cudaHostAllocPortable), BITAR_E_OUT_OF_MEMORY);
-  CU_TRY(cudaHostAlloc((void**)&q->h_res, (size_t)cap * sizeof(bitar_result), cudaHostAllocPortable), BITAR_E_OUT_OF_MEMORY);
+  CU_TRY(cudaHostAlloc((void**)&q->h_ops, (size_t)cap * sizeof(bitar_chunk), cudaHostAllocPortable | cudaHostAllocMapped), BITAR_E_OUT_OF_MEMORY);
+  CU_TRY(cudaHostAlloc((void**)&q->h_res, (size_t)cap * sizeof(bitar_result), cudaHostAllocPortable | cudaHostAllocMapped), BITAR_E_OUT_OF_MEMORY);
   CU_TRY(cudaMalloc((void**)&q->d_ops, (size_t)cap * sizeof(bitar_chunk)), BITAR_E_OUT_OF_MEMORY);
   CU_TRY(cudaMalloc((void**)&q->d_res, (size_t)cap * sizeof(bitar_result)), BITAR_E_OUT_OF_MEMORY);
   q->cap = cap;
@@ -257,6 +258,23 @@ __global__ void __launch_bounds__(256) stage_copy_kernel(const bitar_chunk* __re
 // runs with the default shared-memory carve-out, and switching the carve-out back and forth drains the SMs.
 __global__ void zero_counters_kernel(unsigned int* c) { c[threadIdx.x] = 0; }
 
+// Descriptor upload / result download by the SMs (8-byte words between pinned host memory and device memory).  The
+// copy engines serve their requests in order across ALL streams: a 400 KB descriptor upload issued after another
+// queue pair's (or batch's) 128 MiB staging copy waits for it, and so does every kernel behind the upload
+// (measured: a deflate call enqueued after a 1 GiB host-to-device copy on another stream started 19 ms late).
+__global__ void __launch_bounds__(256) words_copy_kernel(uint2* __restrict__ dst, const uint2* __restrict__ src, uint32_t n) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+static_assert(sizeof(bitar_chunk) % 8 == 0 && sizeof(bitar_result) % 8 == 0, "descriptors move as 8-byte words");
+inline cudaError_t words_copy(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  const uint32_t n = (uint32_t)(bytes / 8);
+  if (n == 0) return cudaSuccess;
+  uint32_t blocks = (n + 255u) / 256u;
+  if (blocks > 64u) blocks = 64u;
+  words_copy_kernel<<<blocks, 256, 0, st>>>(static_cast<uint2*>(dst), static_cast<const uint2*>(src), n);
+  return cudaGetLastError();
+}
+
 bool is_host_memory(const void* p) {
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -278,7 +296,7 @@ int inflate_prepare_staging(QueuePair* q, uint32_t n, bool allow_batches) {
     if (q->h_orig) cudaFreeHost(q->h_orig);
     if (q->d_orig) cudaFree(q->d_orig);
     q->h_orig = nullptr; q->d_orig = nullptr; q->orig_cap = 0;
-    CU_TRY(cudaHostAlloc((void**)&q->h_orig, (size_t)q->cap * sizeof(bitar_chunk), cudaHostAllocPortable), BITAR_E_OUT_OF_MEMORY);
+    CU_TRY(cudaHostAlloc((void**)&q->h_orig, (size_t)q->cap * sizeof(bitar_chunk), cudaHostAllocPortable | cudaHostAllocMapped), BITAR_E_OUT_OF_MEMORY);
     CU_TRY(cudaMalloc((void**)&q->d_orig, (size_t)q->cap * sizeof(bitar_chunk)), BITAR_E_OUT_OF_MEMORY);
     q->orig_cap = q->cap;
   }
@@ -408,9 +426,9 @@ int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, b
   q->pending_n = n;
   q->busy.store(1, std::memory_order_release);
   cudaError_t e = cudaEventRecord(q->ev_start, q->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(q->d_ops, q->h_ops, (size_t)n * sizeof(bitar_chunk), cudaMemcpyHostToDevice, q->stream);
+  if (e == cudaSuccess) e = words_copy(q->d_ops, q->h_ops, (size_t)n * sizeof(bitar_chunk), q->stream);
   if (e == cudaSuccess && (q->stage_src || q->stage_dst))
-    e = cudaMemcpyAsync(q->d_orig, q->h_orig, (size_t)n * sizeof(bitar_chunk), cudaMemcpyHostToDevice, q->stream);
+    e = words_copy(q->d_orig, q->h_orig, (size_t)n * sizeof(bitar_chunk), q->stream);
   // Staged inflate calls (host-resident buffers) run in batches: gather (PCIe host -> device), inflate and copy-back
   // (PCIe device -> host) of one batch in order on one of kStageLanes streams, the lanes side by side.  One batch
   // alone is latency-bound (a 2 KiB sub-range takes a lane ~0.8 ms whatever the batch size), hence several in flight.
@@ -446,7 +464,7 @@ int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, b
       e = cudaGetLastError();
       g_launches.fetch_add(1);
     }
-    if (e == cudaSuccess && !lanes) e = cudaEventRecord(q->ev_k0, st);
+    if (e == cudaSuccess && !lanes && b == 0) e = cudaEventRecord(q->ev_k0, st);
     unsigned int* counters = q->d_counter + 8 * b;
     if (e == cudaSuccess) {
       zero_counters_kernel<<<1, 8, 0, st>>>(counters);
@@ -479,7 +497,7 @@ int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, b
     }
     if (e == cudaSuccess) e = cudaEventRecord(q->ev_k1, q->stream);
   }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(q->h_res, q->d_res, (size_t)n * sizeof(bitar_result), cudaMemcpyDeviceToHost, q->stream);
+  if (e == cudaSuccess) e = words_copy(q->h_res, q->d_res, (size_t)n * sizeof(bitar_result), q->stream);
   if (e == cudaSuccess) e = cudaEventRecord(q->ev_stop, q->stream);
   if (e == cudaSuccess) e = cudaLaunchHostFunc(q->stream, qp_finish, q);
   if (e != cudaSuccess) {
@@ -607,6 +625,7 @@ int bitar_dev_open(int device_id, uint16_t n_qps, const bitar_cfg* cfg_in, bitar
   // same carve-out for the small helper kernels as for the codec kernels (see inflate_kernel.cuh)
   cudaFuncSetAttribute(stage_copy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(zero_counters_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(words_copy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(bitar::xk::inflate_plan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaError_t e = bitar::dk::deflate_grid(device_id, dev->sm_count, &dev->deflate_grid);
   if (e == cudaSuccess) e = bitar::dks::deflate_grid(device_id, dev->sm_count, &dev->deflate_grid_small);
@@ -675,6 +694,7 @@ int bitar_dev_close(bitar_dev* dev) {
       if (q->lane[k]) cudaStreamDestroy(q->lane[k]);
     }
     if (q->ev_fork) cudaEventDestroy(q->ev_fork);
+
     if (q->stream) cudaStreamDestroy(q->stream);
     delete q;
   }
