@@ -135,7 +135,11 @@ BITAR_API uint16_t bitar_dev_num_qps(const bitar_dev* dev);
  *     Both calls ENQUEUE n ops on the queue pair's stream and return; `results` (host memory, n
  *     entries) is filled when the work completes and is valid after bitar_qp_wait() returns 0.
  *     Returns BITAR_E_CANCELLED when the queue pair still has pending ops (EntryGuard,
- *     src/device.cc:456-459). --- */
+ *     src/device.cc:456-459).
+ *     Buffers in pinned / registered host memory: deflate reads and writes them in place over PCIe;
+ *     inflate stages them through device memory inside the call, in batches on up to three further
+ *     streams of the queue pair that join its stream before the results are published (everything a
+ *     caller orders after the call on bitar_qp_stream() still runs after it). --- */
 BITAR_API int bitar_qp_deflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n,
                                bitar_result* results);
 BITAR_API int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n,
