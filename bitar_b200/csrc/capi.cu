@@ -272,6 +272,7 @@ inline cudaError_t words_copy(void* dst, const void* src, size_t bytes, cudaStre
   uint32_t blocks = (n + 255u) / 256u;
   if (blocks > 64u) blocks = 64u;
   words_copy_kernel<<<blocks, 256, 0, st>>>(static_cast<uint2*>(dst), static_cast<const uint2*>(src), n);
+  g_launches.fetch_add(1);
   return cudaGetLastError();
 }
 
@@ -471,6 +472,7 @@ int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, b
       e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = launch(q, first, count, counters, st);
+    g_launches.fetch_add(2);   // the counter reset + the batch's last codec kernel (the others are counted where they launch)
     if (e == cudaSuccess && !lanes) e = cudaEventRecord(q->ev_k1, st);
     if (e != cudaSuccess || !q->stage_dst) continue;
     if (q->stage_dst_contig) {
@@ -505,7 +507,6 @@ int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, b
     return fail(BITAR_E_IO_ERROR, "enqueue on queue pair %u of device %d failed: %s", (unsigned)qp, dev->id, cudaGetErrorString(e));
   }
   q->timed = true;
-  g_launches.fetch_add(1);
   return BITAR_OK;
 }
 
