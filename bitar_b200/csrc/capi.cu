@@ -805,12 +805,10 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
           g_launches.fetch_add(2);
           switch (variant) {   // default = 22: 24 warps / SM, 9-bit litlen root (measured best on the columnar mix)
             case 20: e = IndexedConfig<10, 1344, 8, 512, 128, 20>::launch(d_ops, d_res, tasks, pc, acc, ck, (uint32_t)blocks, id, sms, st); break;
-            case 21: e = IndexedConfig<10, 1344, 8, 512, 128, 16>::launch(d_ops, d_res, tasks, pc, acc, ck, (uint32_t)blocks, id, sms, st); break;
             default:
             case 22: e = IndexedConfig<9, 864, 7, 256, 128, 24>::launch(d_ops, d_res, tasks, pc, acc, ck, (uint32_t)blocks, id, sms, st); break;
             case 23: e = IndexedConfig<10, 1344, 8, 512, 256, 14>::launch(d_ops, d_res, tasks, pc, acc, ck, (uint32_t)blocks, id, sms, st); break;
             case 24: e = IndexedConfig<10, 1344, 7, 256, 128, 24>::launch(d_ops, d_res, tasks, pc, acc, ck, (uint32_t)blocks, id, sms, st); break;
-            case 25: e = IndexedConfig<10, 1344, 8, 512, 128, 22>::launch(d_ops, d_res, tasks, pc, acc, ck, (uint32_t)blocks, id, sms, st); break;
           }
           if (e != cudaSuccess) return e;
           if (small_mode) {   // blocks of at most 8 sub-ranges: four to a warp
@@ -845,13 +843,7 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
         switch (variant) {
           default:
           case 0: return InflateConfig<8, 10, 8, 1024, 2>::launch(d_ops, n, d_res, counters, ck, id, sms, st);
-          case 1: return InflateConfig<8, 9, 7, 1024, 2>::launch(d_ops, n, d_res, counters, ck, id, sms, st);
-          case 2: return InflateConfig<4, 10, 8, 1024, 1>::launch(d_ops, n, d_res, counters, ck, id, sms, st);
-          case 3: return InflateConfig<4, 9, 7, 1024, 1>::launch(d_ops, n, d_res, counters, ck, id, sms, st);
-          case 4: return InflateConfig<16, 10, 8, 1024, 4>::launch(d_ops, n, d_res, counters, ck, id, sms, st);
           case 5: return InflateConfig<32, 10, 8, 1024, 4>::launch(d_ops, n, d_res, counters, ck, id, sms, st);
-          case 6: return InflateConfig<2, 9, 7, 1024, 1>::launch(d_ops, n, d_res, counters, ck, id, sms, st);
-          case 7: return InflateConfig<8, 10, 8, 1024, 1>::launch(d_ops, n, d_res, counters, ck, id, sms, st);
         }
       },
       variant >= 20 ? kSubmitInflate : kSubmitInflateOneBatch);

@@ -44,7 +44,7 @@ def main():
         print(f"[{wname}] deflate seg={seg} n={n} U={data.size} C={comp} ratio={data.size / comp:.3f} "
               f"kernel={best:.3f} ms  {data.size / best / 1e6:.1f} GB/s", flush=True)
         iops = dev.decompress_ops(slots, res["produced"], out.data_ptr())
-        for v in [int(x) for x in os.environ.get("SWEEP_VARIANTS", "5,20,21,22,23").split(",")]:
+        for v in [int(x) for x in os.environ.get("SWEEP_VARIANTS", "5,20,22,23,24").split(",")]:
             capi.lib().bitar_tune_inflate_variant(v)
             best = 1e9
             for _ in range(reps + 1):
