@@ -353,7 +353,7 @@ def run_e2e(args, L, capi, C, torch, dist, world, local_rank, data, seg, n, U):
     return {"value": world * U / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(U + h2d),
             "d2h_bytes_per_step": int(cbytes + U), "ms_per_step": dt * 1e3, "step_ms": step_ms, "queue_pairs": len(parts), "pcie": pcie,
             "path": "pinned host in/out through the C-ABI: compress reads and writes host memory in place (zero-copy over "
-                    "PCIe), decompress is staged through device memory by the library in batches on three extra streams per queue pair (strided copy-engine gather, inflate, copy-engine copy-back)"}
+                    "PCIe), decompress is staged through device memory by the library in batches on three extra streams per queue pair (strided copy-engine gather -- rows go at the pitch of the batch's widest stream, so somewhat more than C bytes cross PCIe --, inflate, copy-engine copy-back)"}
 
 
 if __name__ == "__main__":
