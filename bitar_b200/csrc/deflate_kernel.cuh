@@ -1,6 +1,6 @@
 // deflate_kernel.cuh -- K1 + K2 + K3 + K5: one CTA compresses one chunk into one raw DEFLATE stream.
 //
-// Pipeline inside a CTA (16 warps), per <=64 KiB sub-block:
+// Pipeline inside a CTA (16 warps; 4 in the small-chunk instance), per <=64 KiB sub-block:
 //   load    : the sub-block is pulled into shared memory with a 1-D TMA bulk copy (cp.async.bulk +
 //             mbarrier), so match extension and literal look-ups never touch HBM again.
 //   match   : matches never leave the 2 KiB SUB-RANGE of their position (deflate_common.h: that is what
@@ -12,10 +12,12 @@
 //             over its match lanes, one shuffle each) with the carry in a register.  No CTA-wide
 //             barrier, no atomics on the tables, deterministic.
 //   count   : literal/length and distance frequencies with shared-memory atomics.
-//   plan    : CTA-wide bitonic sort of the used symbols, then length-limited Huffman code
-//             construction, code-length RLE and header costing (deflate_common.h, serial, thread 0)
-//             while the other warps compute CRC-32 / Adler-32 of the block in parallel.
-//   encode  : cheapest of stored / fixed / dynamic; every thread encodes 4 consecutive tokens,
+//   plan    : rank sort of the used symbols, two-queue Huffman merge (the one serial step: thread 0 for the
+//             literal/length tree, thread 32 for the distance tree, CRC-32 / Adler-32 of the block on the
+//             other warps meanwhile), then in parallel: node depths, zlib's over-long-tree repair, length
+//             assignment, canonical codes, body sizes, code-length RLE (one run per thread) and the 19-symbol
+//             code-length code (one warp).  Same results as dfl::build_dynamic_plan (deflate_common.h).
+//   encode  : cheapest of stored / fixed / dynamic; every thread encodes 8 consecutive tokens,
 //             a block-wide prefix sum of code lengths (warp shuffles) gives each thread its bit
 //             offset, codes are packed into a shared-memory stage and leave the SM as aligned
 //             16-byte vector stores.  The bit offsets of the sub-range starts are collected on the way
