@@ -297,6 +297,48 @@ def zlib_streams(chunks, results):
     return out
 
 
+def unframe(buf):
+    """The other direction of zlib_streams() / gzip_members(): locate the raw DEFLATE stream inside ONE RFC 1950
+    (zlib) stream or ONE RFC 1952 (gzip) member, as Arrow's / Parquet's GZIP pages and `zlib.compress` produce them,
+    so that Decompress() can be pointed at it.  Returns (offset, length, kind, expected): `kind` is "zlib" or "gzip",
+    `expected` the trailer's checksum (Adler-32 for zlib, CRC-32 for gzip; plus ISIZE for gzip as a second element) to
+    compare with the checksum the inflate kernel returns.  Raises ValueError for anything else (preset dictionaries,
+    unknown methods, truncated framing).  The DEFLATE stream's own end is found by the decoder, not here: `length`
+    spans up to the trailer."""
+    import struct
+    b = np.ascontiguousarray(buf, dtype=np.uint8)
+    n = b.size
+    if n >= 18 and b[0] == 0x1F and b[1] == 0x8B:
+        if b[2] != 8:
+            raise ValueError("gzip member: method is not DEFLATE")
+        flg, at = int(b[3]), 10
+        if flg & 0xE0:
+            raise ValueError("gzip member: reserved flag bits set")
+        if flg & 4:                                   # FEXTRA
+            if at + 2 > n:
+                raise ValueError("gzip member: truncated header")
+            at += 2 + int(b[at]) + 256 * int(b[at + 1])
+        for bit in (8, 16):                           # FNAME, FCOMMENT: zero-terminated
+            if flg & bit:
+                while at < n and b[at] != 0:
+                    at += 1
+                at += 1
+        if flg & 2:                                   # FHCRC
+            at += 2
+        if at + 8 > n:
+            raise ValueError("gzip member: truncated")
+        crc, isize = struct.unpack("<II", b[n - 8:].tobytes())
+        return at, n - 8 - at, "gzip", (crc, isize)
+    if n >= 6 and (int(b[0]) & 0x0F) == 8 and ((int(b[0]) << 8) | int(b[1])) % 31 == 0:
+        if (int(b[0]) >> 4) > 7:
+            raise ValueError("zlib stream: window larger than 32 KiB")
+        if int(b[1]) & 0x20:
+            raise ValueError("zlib stream: preset dictionary")
+        (adler,) = struct.unpack(">I", b[n - 4:].tobytes())
+        return 2, n - 6, "zlib", (adler,)
+    raise ValueError("neither a zlib stream nor a gzip member")
+
+
 def shard_range(n_chunks, rank, world):
     """Chunk range [first, last) of rank `rank` out of `world`: contiguous ranges of
     ceil(n / world) chunks, so that concatenating the ranks' outputs in rank order is the output of one

@@ -202,6 +202,28 @@ def test_gzip_member_framing_of_model_streams():
     assert gzip.decompress(E.gzip_members(comps, res, [c.size for c in chunks])) == data.tobytes()
 
 
+def test_unframe_locates_the_raw_stream():
+    """engine.unframe(): offsets / lengths / trailers of zlib streams and gzip members (with optional header fields)."""
+    import gzip
+    import io
+    from bitar_b200 import engine as E
+    data = synth.lineitem_like(20000).tobytes()
+    z = np.frombuffer(zlib.compress(data, 6), np.uint8)
+    off, ln, kind, exp = E.unframe(z)
+    assert (off, kind) == (2, "zlib") and exp == (zlib.adler32(data),)
+    assert zlib.decompress(z[off:off + ln].tobytes(), -15) == data
+    bio = io.BytesIO()
+    with gzip.GzipFile(filename="some-name.bin", mode="wb", fileobj=bio, compresslevel=1, mtime=7) as f:   # FNAME set
+        f.write(data)
+    g = np.frombuffer(bio.getvalue(), np.uint8)
+    off, ln, kind, exp = E.unframe(g)
+    assert kind == "gzip" and exp == (zlib.crc32(data), len(data)) and off == 10 + len("some-name.bin") + 1
+    assert zlib.decompress(g[off:off + ln].tobytes(), -15) == data
+    for bad in (b"\x78\x20" + bytes(10), b"\x1f\x8b\x07" + bytes(20), b"hello world, not framed"):
+        with pytest.raises(ValueError):
+            E.unframe(np.frombuffer(bad, np.uint8))
+
+
 def test_zlib_stream_framing_of_model_streams():
     """engine.zlib_streams(): 78 01 + stream (index stripped) + Adler-32 is what zlib.decompress() accepts
     (RFC 1950; it verifies the Adler-32)."""

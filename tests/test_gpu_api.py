@@ -1,5 +1,6 @@
 """GPU: the reference's object-level flow (apps/demo_app.cc:332-357, 487-548, 550-693) through the
 host-side mirror: Compress -> Decompress -> memcmp -> Recycle, sync and async, multi queue pair."""
+import zlib
 import numpy as np
 import pytest
 import torch
@@ -144,6 +145,34 @@ def test_chunks_frame_as_zlib_streams(cuda_device):
         assert err is None
         for c, z in zip(chunks, E.zlib_streams(comps, res)):
             assert zlib.decompress(z) == c.tobytes()
+    finally:
+        dev.close()
+
+
+def test_framed_foreign_streams_inflate_on_gpu(cuda_device):
+    """zlib.compress() output (RFC 1950) and gzip members (RFC 1952) -- what Arrow's GZIP codec and
+    Parquet pages hold -- inflate on the GPU once engine.unframe() has located the raw stream; the kernel's Adler-32 /
+    CRC-32 equal the trailers."""
+    import gzip
+    data = synth.lineitem_like(7 * SEG + 1234)
+    chunks = [data[o:o + SEG] for o in range(0, data.size, SEG)]
+    framed = [np.frombuffer(zlib.compress(c.tobytes(), 6) if i % 2 else gzip.compress(c.tobytes(), 1), np.uint8)
+              for i, c in enumerate(chunks)]
+    raw, expect = [], []
+    for f in framed:
+        off, ln, kind, exp = E.unframe(f)
+        raw.append(f[off:off + ln])
+        expect.append((kind, exp))
+    dev = G.open_device(SEG, checksum_type=capi.CHECKSUM_CRC32_ADLER32)
+    try:
+        outs, res, err = G.gpu_inflate_chunks(dev, raw, [c.size for c in chunks])
+        assert err is None and (res["status"] == 0).all()
+        for c, o, r, (kind, exp) in zip(chunks, outs, res, expect):
+            assert np.array_equal(o, c)
+            if kind == "zlib":
+                assert int(r["checksum"]) >> 32 == exp[0]
+            else:
+                assert int(r["checksum"]) & 0xFFFFFFFF == exp[0] and c.size == exp[1]
     finally:
         dev.close()
 
