@@ -212,6 +212,30 @@ int main(int argc, char** argv) {
         failures += !table_r.ok();
         if (table_r.ok()) std::printf("  %lld rows x %d columns\n", (long long)(*table_r)->num_rows(), (*table_r)->num_columns());
       }
+      if (t == 0 && !on_device) {
+        // the same compressed segments from ordinary heap memory (as if read back from storage): Decompress()
+        // stages them itself
+        bitar::BufferVector heap;
+        std::vector<std::shared_ptr<arrow::Buffer>> keep;
+        for (auto& b : compressed) {
+          auto copy_r = arrow::AllocateBuffer(b->size());
+          CHECK_OK(copy_r.status());
+          std::shared_ptr<arrow::Buffer> copy = std::move(*copy_r);
+          if (b->size()) std::memcpy(copy->mutable_data(), b->data(), (std::size_t)b->size());
+          heap.emplace_back(std::make_unique<arrow::Buffer>(copy->data(), copy->size()));
+          keep.push_back(std::move(copy));
+        }
+        auto out2_r = allocate((std::int64_t)(heap.size() * (std::size_t)seg), dev->device_id());
+        CHECK_OK(out2_r.status());
+        auto output2 = std::move(*out2_r);
+        auto t4 = Clock::now();
+        CHECK_OK(dev->Decompress(0, heap, output2));
+        auto t5 = Clock::now();
+        PrintPerf("Decompress (pageable input)", (std::int64_t)bytes, t4, t5);
+        const bool ok2 = (std::size_t)output2->size() == bytes && SameBytes(output2->data(), input->data(), bytes, on_device);
+        std::printf("  pageable compressed input: %s\n", ok2 ? "OK" : "MISMATCH");
+        failures += !ok2;
+      }
       if (dev->Recycle(compressed) != compressed.size()) { std::printf("  recycle count mismatch\n"); ++failures; }
     }
   }

@@ -96,6 +96,8 @@ class CompressDevice {
     std::vector<bitar_result> results;
     std::vector<void*> slots;
     void* registered = nullptr;   // pageable input registered for the duration of a call
+    void* staged = nullptr;       // pinned copy of compressed buffers that arrived in pageable memory (Decompress)
+    std::size_t staged_cap = 0;
   };
 
   const std::uint8_t device_id_;

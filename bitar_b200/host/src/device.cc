@@ -8,6 +8,7 @@
 #include <arrow/util/logging.h>
 
 #include <algorithm>
+#include <cstring>
 #include <string>
 
 namespace bitar {
@@ -40,6 +41,8 @@ CompressDevice<Class>::~CompressDevice() {   // stop / close, src/device.cc:329-
     for (std::uint16_t q = 0; q < num_qps_; ++q) {
       bitar_qp_wait(handle_, q);
       Unregister(q);
+      if (qp_state_[q].staged != nullptr) bitar_mem_free(BITAR_MEM_PINNED, device_id_, qp_state_[q].staged);
+      qp_state_[q].staged = nullptr;
     }
     bitar_dev_close(handle_);
   }
@@ -212,16 +215,36 @@ arrow::Status CompressDevice<Class>::EnqueueDecompress(std::uint16_t queue_pair_
     return arrow::Status::CapacityError("The decompressed_buffer is required to be >= ", n * seg, " bytes");   // src/device.cc:248-254
   ARROW_RETURN_NOT_OK(EntryGuard(queue_pair_id));
   Unregister(queue_pair_id);
-  for (const auto& b : compressed_buffers)
-    if (b == nullptr || (b->size() > 0 && bitar_ptr_kind(b->data(), nullptr) == 0))
-      return arrow::Status::Invalid("compressed buffers must live in device-accessible memory (pool slots, device memory or "
-                                    "pinned / registered host memory)");
+  // Compressed buffers in pageable memory (read from a file into heap buffers, say) are copied into a pinned stage
+  // of this queue pair, one buffer per row of a constant stride, which is the layout the library gathers with one
+  // strided copy-engine transfer per batch (pool slots look the same).  Device-accessible buffers are used in place.
+  std::size_t widest = 0;
+  bool pageable = false;
+  for (const auto& b : compressed_buffers) {
+    if (b == nullptr) return arrow::Status::Invalid("null compressed buffer");
+    widest = std::max(widest, static_cast<std::size_t>(b->size()));
+    pageable = pageable || (b->size() > 0 && bitar_ptr_kind(b->data(), nullptr) == 0);
+  }
+  const std::size_t stride = (widest + 16 + 255) & ~static_cast<std::size_t>(255);
+  if (pageable && q.staged_cap < n * stride) {
+    if (q.staged != nullptr) bitar_mem_free(BITAR_MEM_PINNED, device_id_, q.staged);
+    q.staged = nullptr;
+    q.staged_cap = 0;
+    ARROW_RETURN_NOT_OK(internal::StatusFromC(bitar_mem_alloc(BITAR_MEM_PINNED, device_id_, n * stride, 256, &q.staged)));
+    q.staged_cap = n * stride;
+  }
   ARROW_RETURN_NOT_OK(MakeAccessible(decompressed_buffer->mutable_data(), n * seg, &q.registered));
   q.ops.resize(n);
   q.results.assign(n, bitar_result{0, BITAR_OP_NOT_RUN, 0});
   for (std::size_t i = 0; i < n; ++i) {   // AssembleFrom(buffers, index, span, offset), src/memory.cc:432-505
-    q.ops[i].src = compressed_buffers[i]->data();
-    q.ops[i].src_len = static_cast<std::uint32_t>(compressed_buffers[i]->size());
+    const auto& b = compressed_buffers[i];
+    if (b->size() > 0 && bitar_ptr_kind(b->data(), nullptr) == 0) {
+      std::memcpy(static_cast<std::uint8_t*>(q.staged) + i * stride, b->data(), static_cast<std::size_t>(b->size()));
+      q.ops[i].src = static_cast<std::uint8_t*>(q.staged) + i * stride;
+    } else {
+      q.ops[i].src = b->data();
+    }
+    q.ops[i].src_len = static_cast<std::uint32_t>(b->size());
     q.ops[i].dst = decompressed_buffer->mutable_data() + i * seg;
     q.ops[i].dst_cap = static_cast<std::uint32_t>(seg);
   }

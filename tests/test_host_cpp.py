@@ -39,6 +39,8 @@ def test_demo_app_flow(args):
     r = subprocess.run([DEMO] + args, capture_output=True, text=True, timeout=600)
     print(r.stdout[-3000:], r.stderr[-2000:])
     assert r.returncode == 0 and "PASSED" in r.stdout and "MISMATCH" not in r.stdout
+    if "--device" not in args:   # Decompress() stages heap-resident compressed buffers itself
+        assert "pageable compressed input: OK" in r.stdout
 
 
 @pytest.mark.gpu
