@@ -249,6 +249,11 @@ __device__ __forceinline__ void stage_or(Smem& sm, const OutStream& o, uint64_t 
 __device__ void stream_flush(Smem& sm, OutStream& o, uint32_t upto, bool slide) {
   __syncthreads();
   const uint8_t* sbytes = reinterpret_cast<const uint8_t*>(sm.u.enc.stage);
+  // when the stage slides: the 4 words of the partial unit move to its front (read now, written after the barrier)
+  const uint32_t new_base = upto & ~15u;
+  const uint32_t shift_words = slide ? (new_base - o.sbase) >> 2 : 0u;
+  uint32_t keep = 0;
+  if (shift_words && threadIdx.x < 4) keep = sm.u.enc.stage[shift_words + threadIdx.x];
   uint32_t lo = o.vflushed, hi = upto;
   if (hi > lo) {
     uint32_t a = (lo + 15u) & ~15u, b = hi & ~15u;
@@ -262,19 +267,11 @@ __device__ void stream_flush(Smem& sm, OutStream& o, uint32_t upto, bool slide) 
     }
     o.vflushed = hi;
   }
-  if (!slide) return;
-  __syncthreads();
-  uint32_t new_base = upto & ~15u;
-  uint32_t shift_words = (new_base - o.sbase) >> 2;
   if (shift_words == 0) return;
-  // keep the 4 words of the partial unit, clear everything else that was used
-  uint32_t keep = 0;
-  if (threadIdx.x < 4) keep = sm.u.enc.stage[shift_words + threadIdx.x];
-  __syncthreads();
-  uint32_t used_words = min((uint32_t)kStageWords, shift_words + 8u);
-  for (uint32_t i = threadIdx.x; i < used_words; i += kThreads) sm.u.enc.stage[i] = 0;
-  __syncthreads();
-  if (threadIdx.x < 4) sm.u.enc.stage[threadIdx.x] = keep;
+  __syncthreads();   // every read of the stage is done
+  // clear everything that was used; words 0..3 (first iteration of threads 0..3) receive the partial unit instead
+  const uint32_t used_words = min((uint32_t)kStageWords, shift_words + 8u);
+  for (uint32_t i = threadIdx.x; i < used_words; i += kThreads) sm.u.enc.stage[i] = i < 4u ? keep : 0u;
   o.sbase = new_base;
   __syncthreads();
 }
