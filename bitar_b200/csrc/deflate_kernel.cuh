@@ -73,7 +73,14 @@ constexpr int kSeqPerThread = (328 + kThreads - 1) / kThreads;   // plan: code l
 constexpr int kHdrPerThread = (19 + 316 + kThreads - 1) / kThreads;   // header: code-length items per thread
 constexpr uint32_t kTokNone = 0x100u;            // compact token stream: padding (emits nothing)
 constexpr uint32_t kTokEob = 0x101u;             //                       end of block
-// other compact tokens: < 0x100 literal byte; >= 0x200 match, (dist << 9) | len (dfl::tok_match)
+// other compact tokens: < 0x100 literal byte; bit 31 set: a match with its symbols already worked out by the match
+// phase (which needs them for the frequency counts anyway), so that the encode phase is table look-ups only:
+//   bits 0..7 length - 3, 9..19 distance - 1 (a match never leaves its 2 KiB sub-range), 21..25 distance symbol,
+//   26..30 length symbol index
+static_assert(dfl::kSub <= 2048, "compact match tokens hold an 11-bit distance");
+__device__ __forceinline__ uint32_t tok_pack(uint32_t len3, uint32_t d1, uint32_t len_sym, uint32_t dist_sym) {
+  return 0x80000000u | (len_sym << 26) | (dist_sym << 21) | (d1 << 9) | len3;
+}
 constexpr uint32_t kNoCand = 0xFFFFu;
 
 struct PlanPar {                      // scratch of the parallel half of the plan
@@ -412,7 +419,7 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
       if (start) {
         atomicAdd(&sm.ll_freq[is_match ? 257u + len_sym : byte], 1u);
         if (is_match) atomicAdd(&sm.d_freq[dist_sym], 1u);
-        out[cnt + (uint32_t)__popc(starts & lt_mask)] = is_match ? dfl::tok_match(adv, dist) : byte;
+        out[cnt + (uint32_t)__popc(starts & lt_mask)] = is_match ? tok_pack((uint32_t)adv - 3u, d1, len_sym, dist_sym) : byte;
       }
     }
     cnt += (uint32_t)__popc(starts);
@@ -709,16 +716,16 @@ __device__ __forceinline__ int token_bits(const Smem& sm, uint32_t tok, uint32_t
     lo_n = (int)(e >> 16);
     return lo_n;
   }
-  int len = dfl::tok_len(tok), dist = dfl::tok_dist(tok);
-  int ls = dfl::len_sym(len), dsym = dfl::dist_sym(dist);
-  uint32_t e = sm.ll_enc[257 + ls];
-  int cl = (int)(e >> 16), leb = dfl::len_extra_bits(ls);
-  lo_bits = (e & 0xFFFFu) | ((uint32_t)dfl::len_extra_val(len, ls) << cl);
-  lo_n = cl + leb;  // <= 20
-  uint32_t f = sm.d_enc[dsym];
-  int dl = (int)(f >> 16), deb = dfl::dist_extra_bits(dsym);
-  hi_bits = (f & 0xFFFFu) | ((uint32_t)dfl::dist_extra_val(dist, dsym) << dl);
-  hi_n = dl + deb;  // <= 28
+  // ll_enc / d_enc entries of length and distance symbols carry their number of extra bits in bits 24..;
+  // the extra value is the low bits of length - 3 / distance - 1 (RFC 1951's bases are aligned that way)
+  const uint32_t e = sm.ll_enc[257u + ((tok >> 26) & 31u)];
+  const uint32_t cl = (e >> 16) & 0xFFu, leb = e >> 24;
+  lo_bits = (e & 0xFFFFu) | (((tok & 0xFFu) & ((1u << leb) - 1u)) << cl);
+  lo_n = (int)(cl + leb);  // <= 20
+  const uint32_t f = sm.d_enc[(tok >> 21) & 31u];
+  const uint32_t dl = (f >> 16) & 0xFFu, deb = f >> 24;
+  hi_bits = (f & 0xFFFFu) | ((((tok >> 9) & 0x7FFu) & ((1u << deb) - 1u)) << dl);
+  hi_n = (int)(dl + deb);  // <= 28
   return lo_n + hi_n;
 }
 
@@ -1030,12 +1037,14 @@ __global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
           uint32_t code = i < 144 ? 0x30u + i : i < 256 ? 0x190u + (i - 144) : i < 280 ? (uint32_t)(i - 256) : 0xC0u + (i - 280);
           e = dfl::bitrev(code, l) | ((uint32_t)l << 16);
         }
+        if (i > 256 && i < 257 + 29) e |= (uint32_t)dfl::len_extra_bits(i - 257) << 24;
         sm.ll_enc[i] = e;
       }
       if (tid < 32) {
         uint32_t e;
         if (type == dfl::kDynamic) e = (uint32_t)sm.plan.d_code[tid] | ((uint32_t)sm.plan.d_len[tid] << 16);
         else e = dfl::bitrev((uint32_t)tid, 5) | (5u << 16);
+        if (tid < dfl::kNumDist) e |= (uint32_t)dfl::dist_extra_bits(tid) << 24;
         sm.d_enc[tid] = e;
       }
       // ---- header: fixed fields by thread 0, then one code-length-code length / RLE token per thread at the bit
