@@ -78,9 +78,7 @@ constexpr uint32_t kTokEob = 0x101u;             //                       end of
 //   bits 0..7 length - 3, 9..19 distance - 1 (a match never leaves its 2 KiB sub-range), 21..25 distance symbol,
 //   26..30 length symbol index
 static_assert(dfl::kSub <= 2048, "compact match tokens hold an 11-bit distance");
-__device__ __forceinline__ uint32_t tok_pack(uint32_t len3, uint32_t d1, uint32_t len_sym, uint32_t dist_sym) {
-  return 0x80000000u | (len_sym << 26) | (dist_sym << 21) | (d1 << 9) | len3;
-}
+// (the match phase ORs them together from pre-shifted look-up tables)
 constexpr uint32_t kNoCand = 0xFFFFu;
 
 struct PlanPar {                      // scratch of the parallel half of the plan
@@ -103,8 +101,10 @@ struct __align__(16) Smem {
   union {                            // the match phase and the plan/encode phases never overlap in time
     struct {
       uint16_t head[kWarps][(1 << kHashBits) + 32];   // per warp: hash -> most recent position (kNoCand = empty) + 32 dummy slots
-      uint8_t len_sym_lut[256];      // match length - 3 -> length symbol index (dfl::len_sym)
-      uint8_t dist_sym_lut[512];     // zlib's two-level map: d < 256 ? lut[d] : lut[256 + (d >> 7)], d = dist - 1
+      // pre-shifted token fields (tok_pack): length - 3 -> (length symbol index << 26) | (length - 3);
+      // distance - 1 -> distance symbol << 21 through zlib's two-level map d < 256 ? lut[d] : lut[256 + (d >> 7)]
+      uint32_t len_sym_lut[256];
+      uint32_t dist_sym_lut[512];
     } m;                             // (the tables are longer than the bit stage: the look-up tables lie behind it)
     EncodeArea enc;
   } u;
@@ -202,7 +202,9 @@ __device__ __forceinline__ int match_len(uint32_t ds, int p, int c, int maxl) {
   uint32_t wp = lds_u32(ap + 8u), wc = lds_u32(ac + 8u);
   const uint32_t x0 = __funnelshift_r(p0, p1, sp) ^ __funnelshift_r(c0, c1, sc);
   const uint32_t x1 = __funnelshift_r(p1, wp, sp) ^ __funnelshift_r(c1, wc, sc);
-  int l = x0 ? (__ffs((int)x0) - 1) >> 3 : x1 ? 4 + ((__ffs((int)x1) - 1) >> 3) : 8;
+  // equal leading bytes of each word: clz(brev(x)) >> 3 is 0..3, or 4 when the words are equal -- no branch
+  const int l0 = __clz((int)__brev(x0)) >> 3, l1 = __clz((int)__brev(x1)) >> 3;
+  int l = l0 + (l0 == 4 ? l1 : 0);
   if ((x0 | x1) == 0 && maxl > 8) {
     while (l < maxl) {
       const uint32_t np = lds_u32(ap + (uint32_t)l + 4u), nc = lds_u32(ac + (uint32_t)l + 4u);
@@ -414,12 +416,12 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
       const bool is_match = adv > 1;
       const uint32_t byte = lds_u8(ds + p);
       const uint32_t d1 = is_match ? (uint32_t)dist - 1u : 0u;
-      const uint32_t len_sym = sm.u.m.len_sym_lut[is_match ? adv - 3 : 0];
-      const uint32_t dist_sym = sm.u.m.dist_sym_lut[d1 < 256u ? d1 : 256u + (d1 >> 7)];
+      const uint32_t len_f = sm.u.m.len_sym_lut[is_match ? adv - 3 : 0];                  // symbol << 26 | length - 3
+      const uint32_t dist_f = sm.u.m.dist_sym_lut[d1 < 256u ? d1 : 256u + (d1 >> 7)];     // symbol << 21
       if (start) {
-        atomicAdd(&sm.ll_freq[is_match ? 257u + len_sym : byte], 1u);
-        if (is_match) atomicAdd(&sm.d_freq[dist_sym], 1u);
-        out[cnt + (uint32_t)__popc(starts & lt_mask)] = is_match ? tok_pack((uint32_t)adv - 3u, d1, len_sym, dist_sym) : byte;
+        atomicAdd(&sm.ll_freq[is_match ? 257u + (len_f >> 26) : byte], 1u);
+        if (is_match) atomicAdd(&sm.d_freq[dist_f >> 21], 1u);
+        out[cnt + (uint32_t)__popc(starts & lt_mask)] = is_match ? (0x80000000u | len_f | dist_f | (d1 << 9)) : byte;
       }
     }
     cnt += (uint32_t)__popc(starts);
@@ -819,8 +821,9 @@ __global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
       // partially filled 16-byte unit at its front
       if (tid < 4) sm.keep[tid] = sm.u.enc.stage[tid];
       static_assert(sizeof(sm.u.m.head) >= sizeof(sm.u.enc.stage), "the look-up tables must lie behind the bit stage");
-      for (int i = tid; i < 256; i += kThreads) sm.u.m.len_sym_lut[i] = (uint8_t)dfl::len_sym(i + 3);
-      for (int i = tid; i < 512; i += kThreads) sm.u.m.dist_sym_lut[i] = (uint8_t)dfl::dist_sym(i < 256 ? i + 1 : ((i - 256) << 7) + 1);
+      for (int i = tid; i < 256; i += kThreads) sm.u.m.len_sym_lut[i] = ((uint32_t)dfl::len_sym(i + 3) << 26) | (uint32_t)i;
+      for (int i = tid; i < 512; i += kThreads)
+        sm.u.m.dist_sym_lut[i] = (uint32_t)dfl::dist_sym(i < 256 ? i + 1 : ((i - 256) << 7) + 1) << 21;
       for (int i = tid; i < 288; i += kThreads) sm.ll_freq[i] = 0;
       if (tid < 32) sm.d_freq[tid] = 0;
       mbar_wait(&sm.mbar, tma_parity);
