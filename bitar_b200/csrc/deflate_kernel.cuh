@@ -359,7 +359,7 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
   const uint32_t dummy = (1u << kHashBits) + (uint32_t)lane;
   const int sub_end = min(n, s0 + (int)dfl::kSub);
   int carry = s0;                                     // next token start
-  uint32_t* out = tokens + s0;                        // this sub-range's tokens, compact and in order
+  // this sub-range's tokens go to tokens[s0 ..], compact and in order
   uint32_t cnt = 0;
   for (int base = s0; base < s1; base += 32) {
     const int p = base + lane;
@@ -410,7 +410,7 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
         }
       }
     }
-    const bool start = ((reach >> lane) & 1u) && p < n;
+    const bool start = (reach & (lt_mask + 1u)) != 0u && p < n;   // lt_mask + 1 == this lane's bit
     const unsigned starts = __ballot_sync(kFull, start);
     {   // token + symbol counts, without a literal / match branch (the loads are harmless for the other kind)
       const bool is_match = adv > 1;
@@ -421,7 +421,8 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
       if (start) {
         atomicAdd(&sm.ll_freq[is_match ? 257u + (len_f >> 26) : byte], 1u);
         if (is_match) atomicAdd(&sm.d_freq[dist_f >> 21], 1u);
-        out[cnt + (uint32_t)__popc(starts & lt_mask)] = is_match ? (0x80000000u | len_f | dist_f | (d1 << 9)) : byte;
+        // (one 32-bit index from the scratch base: a single wide multiply-add forms the address)
+        tokens[(uint32_t)s0 + cnt + (uint32_t)__popc(starts & lt_mask)] = is_match ? (0x80000000u | len_f | dist_f | (d1 << 9)) : byte;
       }
     }
     cnt += (uint32_t)__popc(starts);
