@@ -27,8 +27,8 @@ sys.path.insert(0, ROOT)
 METRIC = "deflate+inflate round-trip throughput, uncompressed bytes (bitar Compress->Decompress)"
 SEG_DEFAULT = 59460          # apps/app_common.h:39 kDecompressedSegSize
 # DRAM bytes moved per uncompressed byte, from ncu (dram__bytes_read.sum + dram__bytes_write.sum, 256 MiB launch)
-DEFLATE_DRAM_BYTES_PER_BYTE = (288.350208e6 + 108.836352e6) / 268435456
-INFLATE_DRAM_BYTES_PER_BYTE = (158.810112e6 + 256.509440e6) / 268435456
+DEFLATE_DRAM_BYTES_PER_BYTE = (289.780736e6 + 109.076992e6) / 268435456
+INFLATE_DRAM_BYTES_PER_BYTE = (161.789440e6 + 255.810048e6) / 268435456
 
 
 def peaks():
@@ -256,9 +256,9 @@ def main():
             "deflate_gbps": world * U / (td_ms * 1e-3) / 1e9, "inflate_gbps": world * U / (ti_ms * 1e-3) / 1e9,
             "deflate_kernel_ms": kd_ms, "inflate_kernel_ms": ki_ms, "wall_ms_per_step": wall_ms,
             "ratio": U / Cbytes, "zlib_level1_ratio": zratio,
-            # dominant kernel = deflate_kernel (75 % of the device-resident step's GPU time, profiles/r01_launches_bench_1GiB_p.csv).
+            # dominant kernel = deflate_kernel (74 % of the device-resident step's GPU time, profiles/r01_launches_bench_1GiB_q.csv).
             # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture at 256 MiB
-            # (profiles/r01_ncu_full_deflate_and_indexed_inflate_256MiB_p.txt), scaled linearly to this launch's bytes.
+            # (profiles/r01_ncu_full_deflate_and_indexed_inflate_256MiB_q.txt), scaled linearly to this launch's bytes.
             "roofline": {"bound": "hbm", "kernel": "deflate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": DEFLATE_DRAM_BYTES_PER_BYTE * U, "peak_source": which,
                          "algorithmic_bytes": "U + C per launch (read input once, write the stream once)",
