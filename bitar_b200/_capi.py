@@ -40,7 +40,8 @@ class Cfg(C.Structure):
     _fields_ = [("decompressed_seg_size", C.c_uint32), ("compressed_seg_size", C.c_uint32),
                 ("max_preallocate_slots", C.c_uint32), ("burst_size", C.c_uint16),
                 ("max_sgl_segs", C.c_uint16), ("window_size", C.c_uint8), ("huffman_enc", C.c_uint8),
-                ("checksum_type", C.c_uint8), ("slot_mem_kind", C.c_uint8)]
+                ("checksum_type", C.c_uint8), ("slot_mem_kind", C.c_uint8), ("no_index", C.c_uint8),
+                ("reserved", C.c_uint8 * 3)]
 
 
 # every symbol include/bitar_cuda.h declares (tests check that the library exports all of them)

@@ -26,8 +26,7 @@
 #define BITAR_DK_MIN_CTAS 8
 #include "deflate_kernel.cuh"
 #include "inflate_kernel.cuh"
-#include "inflate_fast_kernel.cuh"
-#include "inflate_indexed_kernel.cuh"
+#include "inflate_tok_kernel.cuh"
 
 namespace {
 
@@ -72,13 +71,17 @@ struct QueuePair {
   uint32_t cap = 0;
   unsigned int* d_counter = nullptr;
   uint32_t* d_tokens = nullptr;    // deflate token scratch (grid * 64 Ki u32), allocated on first use
-  void* d_lane_scratch = nullptr;  // inflate per-lane scratch, allocated on first use
-  size_t lane_scratch_bytes = 0;
+  uint16_t* d_far = nullptr;       // deflate far-candidate scratch (grid * 64 Ki u16)
   bitar::xk::Task* d_tasks = nullptr;   // indexed inflate: one task per 64 KiB block
+  uint32_t* d_block_state = nullptr;    //   what phase A left of the block (coded / done / bad)
   size_t tasks_cap = 0;
+  uint8_t* d_units = nullptr;           //   token units between the two phases: `subs` slots per task
+  size_t units_cap = 0;
+  uint16_t* d_unit_cnt = nullptr;       //   units per slot
+  size_t unit_cnt_cap = 0;
   uint32_t* d_generic = nullptr;        // ops left to the whole-stream kernel
+  uint32_t* d_indexed = nullptr;        // ops on the two-phase path
   size_t generic_cap = 0;
-  bitar::xk::CkAcc* d_ck = nullptr;     // per-op checksum accumulators of the indexed path
   // inflate with host (pinned / registered) buffers: stage through device memory
   bitar_chunk* h_orig = nullptr;        // the caller's pointers (pinned), n entries
   bitar_chunk* d_orig = nullptr;
@@ -412,6 +415,10 @@ int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, b
     return BITAR_OK;
   }
   if (!ops || !results) return fail(BITAR_E_INVALID, "null ops/results");
+  if (!inflate)   // a chunk is at most one segment (src/device.cc:168-170 cuts the buffer); the kernels' block index is sized for it
+    for (uint32_t i = 0; i < n; ++i)
+      if (ops[i].src_len > BITAR_MAX_SEG_SIZE)
+        return fail(BITAR_E_INVALID, "op %u: src_len %u above the largest segment (%u)", i, ops[i].src_len, BITAR_MAX_SEG_SIZE);
   CU_TRY(cudaSetDevice(dev->id), BITAR_E_INVALID);
   int rc = qp_reserve(dev, q, n);
   if (rc) return rc;
@@ -514,10 +521,22 @@ int inflate_variant() {
   int v = g_inflate_variant.load();
   if (v < 0) {
     const char* s = getenv("BITAR_INFLATE_VARIANT");
-    v = s ? atoi(s) : 22;
+    v = s ? atoi(s) : 0;
     g_inflate_variant.store(v);
   }
   return v;
+}
+
+// (re)allocate a device buffer of the queue pair that only ever grows
+template <typename T>
+cudaError_t grow(T** p, size_t* cap, size_t need) {
+  if (*cap >= need) return cudaSuccess;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  cudaError_t e = cudaMalloc((void**)p, need * sizeof(T));
+  if (e == cudaSuccess) *cap = need;
+  return e;
 }
 
 }  // namespace
@@ -628,6 +647,7 @@ int bitar_dev_open(int device_id, uint16_t n_qps, const bitar_cfg* cfg_in, bitar
   cudaFuncSetAttribute(zero_counters_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(words_copy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(bitar::xk::inflate_plan_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  cudaFuncSetAttribute(bitar::xk::inflate_checksum_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaError_t e = bitar::dk::deflate_grid(device_id, dev->sm_count, &dev->deflate_grid);
   if (e == cudaSuccess) e = bitar::dks::deflate_grid(device_id, dev->sm_count, &dev->deflate_grid_small);
   if (const char* g = getenv("BITAR_DEBUG_DEFLATE_GRID")) {   // tuning experiments only
@@ -678,10 +698,13 @@ int bitar_dev_close(bitar_dev* dev) {
     if (q->d_res) cudaFree(q->d_res);
     if (q->d_counter) cudaFree(q->d_counter);
     if (q->d_tokens) cudaFree(q->d_tokens);
-    if (q->d_lane_scratch) cudaFree(q->d_lane_scratch);
+    if (q->d_far) cudaFree(q->d_far);
     if (q->d_tasks) cudaFree(q->d_tasks);
+    if (q->d_block_state) cudaFree(q->d_block_state);
+    if (q->d_units) cudaFree(q->d_units);
+    if (q->d_unit_cnt) cudaFree(q->d_unit_cnt);
     if (q->d_generic) cudaFree(q->d_generic);
-    if (q->d_ck) cudaFree(q->d_ck);
+    if (q->d_indexed) cudaFree(q->d_indexed);
     if (q->h_orig) cudaFreeHost(q->h_orig);
     if (q->d_orig) cudaFree(q->d_orig);
     if (q->d_stage_in) cudaFree(q->d_stage_in);
@@ -718,6 +741,9 @@ int bitar_qp_deflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
       [&](QueuePair* q, uint32_t) -> cudaError_t {
         if (q->d_tokens) return cudaSuccess;
         const size_t a = bitar::dk::deflate_scratch_bytes(dev->deflate_grid), b = bitar::dks::deflate_scratch_bytes(dev->deflate_grid_small);
+        const size_t fa = bitar::dk::deflate_far_bytes(dev->deflate_grid), fb = bitar::dks::deflate_far_bytes(dev->deflate_grid_small);
+        cudaError_t e = cudaMalloc((void**)&q->d_far, fa > fb ? fa : fb);
+        if (e != cudaSuccess) return e;
         return cudaMalloc((void**)&q->d_tokens, a > b ? a : b);
       },
       [&](QueuePair* q, uint32_t first, uint32_t count, unsigned int* counters, cudaStream_t st) -> cudaError_t {
@@ -725,13 +751,15 @@ int bitar_qp_deflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
         // 4 warps per CTA and three to four times the CTAs per SM; same output
         uint32_t max_len = 0;
         for (uint32_t i = 0; i < count; ++i) max_len = q->h_ops[first + i].src_len > max_len ? q->h_ops[first + i].src_len : max_len;
+        const int max_dist = 1 << dev->cfg.window_size, emit_index = dev->cfg.no_index ? 0 : 1;
         static const int small_mode = getenv("BITAR_DEFLATE_SMALL") ? atoi(getenv("BITAR_DEFLATE_SMALL")) : 1;   // 0: off (A/B runs)
         if (small_mode && max_len <= (uint32_t)bitar::dks::kBlockMax)
-          return bitar::dks::deflate_launch(q->d_ops + first, count, q->d_res + first, counters, q->d_tokens, dev->id, dev->sm_count, 0,
-                                            max_len, dev->cfg.huffman_enc, dev->cfg.checksum_type, g_deflate_prof.load(), st);
-        return bitar::dk::deflate_launch(q->d_ops + first, count, q->d_res + first, counters, q->d_tokens, dev->id, dev->sm_count,
+          return bitar::dks::deflate_launch(q->d_ops + first, count, q->d_res + first, counters, q->d_tokens, q->d_far, dev->id, dev->sm_count, 0,
+                                            max_len, dev->cfg.huffman_enc, dev->cfg.checksum_type, max_dist, emit_index,
+                                            g_deflate_prof.load(), st);
+        return bitar::dk::deflate_launch(q->d_ops + first, count, q->d_res + first, counters, q->d_tokens, q->d_far, dev->id, dev->sm_count,
                                          dev->deflate_grid_override, (uint32_t)bitar::dk::kBlockMax, dev->cfg.huffman_enc,
-                                         dev->cfg.checksum_type, g_deflate_prof.load(), st);
+                                         dev->cfg.checksum_type, max_dist, emit_index, g_deflate_prof.load(), st);
       },
       kSubmitDeflate);
 }
@@ -747,106 +775,71 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
   const int variant = inflate_variant();
   const int ck = dev ? dev->cfg.checksum_type : 0, id = dev ? dev->id : 0, sms = dev ? dev->sm_count : 0;
   size_t total_blocks = 0;
+  uint32_t subs = 32;          // unit slots per task: 32 sub-ranges of a 64 KiB block, fewer when every segment is small
+  bool small_mode = false;
   return qp_submit(
       dev, qp, ops, n, results,
       [&](QueuePair* q, uint32_t n_all) -> cudaError_t {
-        // buffers of the indexed path, sized for the whole call (its batches run side by side, each on its own slice)
+        // buffers of the two-phase path, sized for the whole call (its batches run side by side, each on its own slice)
         using namespace bitar::xk;
-        for (uint32_t i = 0; i < n_all; ++i) total_blocks += op_blocks(q->h_ops[i]);
-        if (variant < 20) return cudaSuccess;
-        if (q->tasks_cap < total_blocks + n_all) {   // block tasks, then room for one small task per op
-          if (q->d_tasks) cudaFree(q->d_tasks);
-          q->d_tasks = nullptr;
-          q->tasks_cap = 0;
-          cudaError_t e = cudaMalloc((void**)&q->d_tasks, (total_blocks + n_all) * sizeof(Task));
-          if (e != cudaSuccess) return e;
-          q->tasks_cap = total_blocks + n_all;
+        uint32_t max_cap = 0;
+        for (uint32_t i = 0; i < n_all; ++i) {
+          total_blocks += op_blocks(q->h_ops[i]);
+          max_cap = q->h_ops[i].dst_cap > max_cap ? q->h_ops[i].dst_cap : max_cap;
         }
-        if (q->generic_cap < n_all) {
-          if (q->d_generic) cudaFree(q->d_generic);
-          q->d_generic = nullptr;
-          q->generic_cap = 0;
-          if (q->d_ck) cudaFree(q->d_ck);
-          q->d_ck = nullptr;
-          cudaError_t e = cudaMalloc((void**)&q->d_generic, (size_t)n_all * sizeof(uint32_t));
-          if (e == cudaSuccess) e = cudaMalloc((void**)&q->d_ck, (size_t)n_all * sizeof(CkAcc));
-          if (e != cudaSuccess) return e;
-          q->generic_cap = n_all;
-        }
-        return cudaSuccess;
+        if (variant == 5) return cudaSuccess;
+        // segments of at most 8 sub-ranges (16 KiB) are decoded four to a warp, with as many unit slots as they need
+        small_mode = max_cap <= kSmallSubs * bitar::dfl::kSub;
+        if (small_mode) subs = max_cap ? (max_cap + bitar::dfl::kSub - 1u) >> bitar::dfl::kSubLog2 : 1u;
+        size_t cap2 = q->tasks_cap;
+        cudaError_t e = grow(&q->d_tasks, &q->tasks_cap, total_blocks);
+        if (e == cudaSuccess) e = grow(&q->d_block_state, &cap2, total_blocks);
+        if (e == cudaSuccess) e = grow(&q->d_units, &q->units_cap, total_blocks * subs * (size_t)bitar::tk::kSlotBytes);
+        if (e == cudaSuccess) e = grow(&q->d_unit_cnt, &q->unit_cnt_cap, total_blocks * subs);
+        cap2 = q->generic_cap;
+        if (e == cudaSuccess) e = grow(&q->d_generic, &q->generic_cap, (size_t)n_all);
+        if (e == cudaSuccess) e = grow(&q->d_indexed, &cap2, (size_t)n_all);
+        return e;
       },
       [&](QueuePair* q, uint32_t first, uint32_t n, unsigned int* counters, cudaStream_t st) -> cudaError_t {
         using namespace bitar::ik;
         bitar_chunk* const d_ops = q->d_ops + first;       // this batch of the call (one batch unless staged)
         bitar_result* const d_res = q->d_res + first;
         const bitar_chunk* const h_ops = q->h_ops + first;
-        if (variant >= 20) {
-          // default: chunks carrying the parallel-inflate index go to the sub-range kernel, one warp per
-          // 64 KiB block; everything else (zlib streams, stored chunks) to the whole-stream kernel.
-          using namespace bitar::xk;
-          size_t before = 0, blocks = 0;
-          uint32_t max_cap = 0;
-          for (uint32_t i = 0; i < first; ++i) before += op_blocks(q->h_ops[i]);
-          for (uint32_t i = 0; i < n; ++i) {
-            blocks += op_blocks(h_ops[i]);
-            max_cap = h_ops[i].dst_cap > max_cap ? h_ops[i].dst_cap : max_cap;
-          }
-          // segments of at most 8 sub-ranges (16 KiB) are decoded four to a warp by their own kernel; calls with larger
-          // segments keep everything (including a short last segment) on the warp-per-block kernel
-          const bool small_mode = max_cap <= bitar::xk::kSmallSubs * bitar::dfl::kSub;
-          Task* const tasks = q->d_tasks + before;
-          Task* const small_tasks = q->d_tasks + total_blocks + first;
-          uint32_t* const generic = q->d_generic + first;
-          Counters* pc = reinterpret_cast<Counters*>(counters);
-          CkAcc* acc = ck != BITAR_CHECKSUM_NONE ? q->d_ck + first : nullptr;
-          inflate_plan_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_ops, n, d_res, tasks, small_tasks, generic, pc, acc, 1, small_mode ? 1 : 0);
-          cudaError_t e = cudaGetLastError();
+        if (variant == 5)   // tests: everything through the whole-stream kernel
+          return InflateConfig<32, 10, 8, 1024, 4>::launch(d_ops, n, d_res, counters, ck, id, sms, st);
+        // default: chunks carrying the parallel-inflate index take the two-phase path (a warp Huffman-decodes the 32
+        // sub-ranges of a 64 KiB block into token units, a group of 8 lanes resolves the block's copies in order);
+        // everything else (zlib streams, stored chunks) goes to the whole-stream kernel.
+        using namespace bitar::xk;
+        size_t before = 0, blocks = 0;
+        for (uint32_t i = 0; i < first; ++i) before += op_blocks(q->h_ops[i]);
+        for (uint32_t i = 0; i < n; ++i) blocks += op_blocks(h_ops[i]);
+        Task* const tasks = q->d_tasks + before;
+        uint32_t* const state = q->d_block_state + before;
+        uint8_t* const units = q->d_units + before * subs * (size_t)bitar::tk::kSlotBytes;
+        uint16_t* const unit_cnt = q->d_unit_cnt + before * subs;
+        uint32_t* const generic = q->d_generic + first;
+        uint32_t* const indexed = q->d_indexed + first;
+        Counters* pc = reinterpret_cast<Counters*>(counters);
+        inflate_plan_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_ops, n, d_res, tasks, indexed, generic, pc, 1);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (small_mode) e = TokConfig<9, 864, 7, 256, 8, 8, 4>::launch(d_ops, d_res, tasks, pc, units, unit_cnt, state, subs, (uint32_t)blocks, id, sms, st);
+        else e = TokConfig<9, 864, 7, 256, 16, 32>::launch(d_ops, d_res, tasks, pc, units, unit_cnt, state, subs, (uint32_t)blocks, id, sms, st);
+        if (e != cudaSuccess) return e;
+        e = ResolveConfig<8, 1024, 8>::launch(d_ops, d_res, tasks, pc, units, unit_cnt, state, subs, (uint32_t)blocks, id, sms, st);
+        if (e != cudaSuccess) return e;
+        g_launches.fetch_add(3);
+        if (ck != BITAR_CHECKSUM_NONE) {
+          inflate_checksum_kernel<<<(n + 3) / 4 < (uint32_t)(8 * sms) ? (n + 3) / 4 : (uint32_t)(8 * sms), 128, 0, st>>>(d_ops, d_res, indexed, pc, ck);
+          e = cudaGetLastError();
           if (e != cudaSuccess) return e;
-          g_launches.fetch_add(2);
-          switch (variant) {   // default = 22: 24 warps / SM, 9-bit litlen root (measured best on the columnar mix)
-            case 20: e = IndexedConfig<10, 1344, 8, 512, 128, 20>::launch(d_ops, d_res, tasks, pc, acc, ck, (uint32_t)blocks, id, sms, st); break;
-            default:
-            case 22: e = IndexedConfig<9, 864, 7, 256, 128, 24>::launch(d_ops, d_res, tasks, pc, acc, ck, (uint32_t)blocks, id, sms, st); break;
-            case 23: e = IndexedConfig<10, 1344, 8, 512, 256, 14>::launch(d_ops, d_res, tasks, pc, acc, ck, (uint32_t)blocks, id, sms, st); break;
-            case 24: e = IndexedConfig<10, 1344, 7, 256, 128, 24>::launch(d_ops, d_res, tasks, pc, acc, ck, (uint32_t)blocks, id, sms, st); break;
-          }
-          if (e != cudaSuccess) return e;
-          if (small_mode) {   // blocks of at most 8 sub-ranges: four to a warp
-            e = IndexedConfig<9, 864, 7, 256, 128, 11, 8>::launch(d_ops, d_res, small_tasks, pc, acc, ck, n, id, sms, st);
-            if (e != cudaSuccess) return e;
-            g_launches.fetch_add(1);
-          }
-          return InflateConfig<32, 10, 8, 1024, 4>::launch(d_ops, n, d_res, &pc->generic_next, ck, id, sms, st, generic, &pc->n_generic);
+          g_launches.fetch_add(1);
         }
-        if (variant >= 12) {   // lane-per-stream kernels (inflate_fast.h); experiments, never batched
-          auto run = [&](auto cfg) -> cudaError_t {
-            using Cfg = decltype(cfg);
-            const size_t need = Cfg::scratch_bytes(id, sms);
-            if (need == 0) return cudaErrorLaunchOutOfResources;
-            if (q->lane_scratch_bytes < need) {
-              if (q->d_lane_scratch) cudaFree(q->d_lane_scratch);
-              q->d_lane_scratch = nullptr;
-              q->lane_scratch_bytes = 0;
-              cudaError_t e = cudaMalloc(&q->d_lane_scratch, need);
-              if (e != cudaSuccess) return e;
-              q->lane_scratch_bytes = need;
-            }
-            return Cfg::launch(d_ops, n, d_res, counters, q->d_lane_scratch, ck, id, sms, st);
-          };
-          switch (variant) {
-            default:
-            case 12: return run(bitar::fk::FastConfig<9, 576, 7, 128, 256, 4>{});
-            case 13: return run(bitar::fk::FastConfig<9, 640, 7, 160, 512, 3>{});
-            case 14: return run(bitar::fk::FastConfig<10, 1152, 8, 288, 512, 2>{});
-          }
-        }
-        switch (variant) {
-          default:
-          case 0: return InflateConfig<8, 10, 8, 1024, 2>::launch(d_ops, n, d_res, counters, ck, id, sms, st);
-          case 5: return InflateConfig<32, 10, 8, 1024, 4>::launch(d_ops, n, d_res, counters, ck, id, sms, st);
-        }
+        return InflateConfig<32, 10, 8, 1024, 4>::launch(d_ops, n, d_res, &pc->generic_next, ck, id, sms, st, generic, &pc->n_generic);
       },
-      variant >= 20 ? kSubmitInflate : kSubmitInflateOneBatch);
+      kSubmitInflate);
 }
 
 int bitar_qp_wait(bitar_dev* dev, uint16_t qp) {

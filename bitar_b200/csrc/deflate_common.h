@@ -355,32 +355,40 @@ BITAR_HD uint32_t tok_match(int len, int dist) { return ((uint32_t)dist << 9) | 
 BITAR_HD int tok_len(uint32_t t) { return (int)(t & 511u); }
 BITAR_HD int tok_dist(uint32_t t) { return (int)(t >> 9); }
 
-// hash of the 4 input bytes at a position (little-endian word w); min_match 3 ignores the top byte
-BITAR_HD uint32_t hash_word(uint32_t w, int hash_bits, int min_match) {
-  if (min_match == 3) w &= 0x00FFFFFFu;
-  return (w * 0x9E3779B1u) >> (32 - hash_bits);
+// Hashes of the 4 input bytes at a position (little-endian word w): one multiply serves both tables of the match finder.
+// near: bucket of the per-sub-range 2-way table; far: slot of the block-wide "last position before this sub-range" table,
+// whose size follows the block length n (2^9 .. 2^13 entries) so that small chunks need little shared memory.
+BITAR_HD uint32_t hash_mul(uint32_t w) { return w * 0x9E3779B1u; }
+BITAR_HD uint32_t hash_near(uint32_t w, int near_bits) { return hash_mul(w) >> (32 - near_bits); }
+BITAR_HD uint32_t hash_far(uint32_t w, int far_bits) { return hash_mul(w) >> (32 - far_bits); }
+BITAR_HD int far_hash_bits(uint32_t n) {
+  const int b = n > 1u ? ilog2(n - 1u) - 2 : 0;
+  return b < 9 ? 9 : b > 13 ? 13 : b;
 }
 
 enum BlockType { kStored = 0, kFixed = 1, kDynamic = 2 };
 
 // ---- parallel-inflate index ------------------------------------------------------------------------
-// The compressor never lets a match start, end or reach outside the 2 KiB SUB-RANGE of its position, so
-// every sub-range of a block can be decoded on its own once the decoder knows (a) the block's Huffman
-// code and (b) the bit offset of the sub-range's first symbol.  (b) is appended to the chunk AFTER the
-// final block's end-of-block symbol and byte padding: a stock RFC 1951 decoder stops at the final block
-// and never looks at it (zlib returns Z_STREAM_END with the trailer left in avail_in), the sm_100a inflate
-// kernel finds it from the end of the buffer and decodes 32 sub-ranges per warp.  All values are
-// little-endian u32, bit offsets count from the first bit of the chunk's stream:
+// The compressor never lets a TOKEN straddle the boundary of a 2 KiB SUB-RANGE (a match starts and ends inside the
+// sub-range of its position; its SOURCE may lie anywhere in the preceding 32 KiB of the same 64 KiB block), so the
+// symbols of every sub-range can be Huffman-decoded on their own once the decoder knows (a) the block's Huffman code and
+// (b) the bit offset of the sub-range's first symbol.  (b) is appended to the chunk AFTER the final block's end-of-block
+// symbol and byte padding: a stock RFC 1951 decoder stops at the final block and never looks at it (zlib returns
+// Z_STREAM_END with the trailer left in avail_in).  The sm_100a inflate path finds it from the end of the buffer, decodes
+// the symbols of 32 sub-ranges per warp into tokens (inflate_tok_kernel.cuh) and then resolves each block's back-references
+// in stream order (inflate_resolve_kernel.cuh).  All values are little-endian u32, bit offsets count from the first bit
+// of the chunk's stream:
 //     for each 64 KiB block b:  hdr_bit[b], then sub_bit[b][s] for each sub-range s (0 for stored blocks)
 //     end_bit      bit offset just past the final end-of-block symbol
 //     total_out    uncompressed bytes of the chunk
 //     kIndexMagic
-// The index is omitted when no Huffman-coded block is longer than one sub-range, or when it does not fit
-// the output slot.
+// The index is omitted when no Huffman-coded block is longer than one sub-range, when it does not fit the output slot,
+// or when the device was opened with emit_index = 0 (the chunk is then bare RFC 1951 and inflates through the
+// whole-stream kernel).
 constexpr int kSubLog2 = 11;
 constexpr uint32_t kSub = 1u << kSubLog2;
 constexpr int kIdxBlockLog2 = 16;                  // == the compressor's sub-block size (kBlockMax)
-constexpr uint32_t kIndexMagic = 0xB17A0B01u;      // "bitar", sub-range log2, version
+constexpr uint32_t kIndexMagic = 0xB17A0B02u;      // "bitar", sub-range log2, version (2: match sources leave the sub-range)
 BITAR_HD uint32_t idx_blocks(uint32_t total) { return (total + 65535u) >> kIdxBlockLog2; }
 BITAR_HD uint32_t idx_subs(uint32_t block_len) { return (block_len + kSub - 1u) >> kSubLog2; }
 BITAR_HD uint32_t idx_entry(uint32_t block, uint32_t sub) { return block * 33u + 1u + sub; }   // hdr_bit at block * 33

@@ -3,14 +3,18 @@
 // Pipeline inside a CTA (16 warps; 4 in the small-chunk instance), per <=64 KiB sub-block:
 //   load    : the sub-block is pulled into shared memory with a 1-D TMA bulk copy (cp.async.bulk +
 //             mbarrier), so match extension and literal look-ups never touch HBM again.
-//   match   : matches never leave the 2 KiB SUB-RANGE of their position (deflate_common.h: that is what
-//             lets the inflate kernel decode 32 sub-ranges of a block in parallel), so the sub-ranges are
-//             also independent for the compressor: every WARP owns one sub-range at a time, with its own
-//             1024-entry hash table in shared memory, and walks it in windows of 32 positions:
-//             4-byte hash, nearest earlier position with that hash (inside the window through
-//             __match_any_sync, else the table), match extension, greedy parse of the window (a walk
-//             over its match lanes, one shuffle each) with the carry in a register.  No CTA-wide
-//             barrier, no atomics on the tables, deterministic.
+//   far     : for every position the last earlier position BEFORE ITS 2 KiB SUB-RANGE that holds the same 4 bytes
+//             (a block-wide table of up to 8192 u16 entries keyed by a 13-bit hash; the CTA walks the sub-ranges in
+//             order: look up, barrier, insert, barrier), written as one u16 per position to an L2-resident scratch.
+//             These FAR candidates give the match finder the 32 KiB window of the reference's level-1 zlib.
+//   match   : a token never straddles a sub-range boundary (deflate_common.h: that is what lets the inflate kernels
+//             Huffman-decode the 32 sub-ranges of a block in parallel), so the parse of each sub-range is
+//             independent: every WARP owns one sub-range at a time, with its own 2-way table of 512 buckets in
+//             shared memory (the two most recent positions of a hash), and walks it in windows of 32 positions:
+//             4-byte hash, the two most recent earlier positions with that hash (inside the window through
+//             __match_any_sync, else the table), both matches extended, the far candidate extended where the near
+//             match is shorter than 8 bytes, greedy parse of the window (a walk over its match lanes, one shuffle
+//             each) with the carry in a register.  No CTA-wide barrier, no atomics on the tables, deterministic.
 //   count   : literal/length and distance frequencies with shared-memory atomics.
 //   plan    : rank sort of the used symbols, two-queue Huffman merge (the one serial step: thread 0 for the
 //             literal/length tree, thread 32 for the distance tree, CRC-32 / Adler-32 of the block on the
@@ -38,7 +42,8 @@
 //   BITAR_DK_WARPS     warps per CTA                                         16                  4
 //   BITAR_DK_BLOCK_MAX bytes per block (= largest chunk when < 64 KiB)       65536               16384
 //   BITAR_DK_MIN_CTAS  resident CTAs per SM the kernel is compiled for       2                   6
-// The output does not depend on the configuration (the match phase works per 2 KiB sub-range, the plan per block);
+// The output does not depend on the configuration (the far pass and the plan work per block, the match phase per 2 KiB
+// sub-range; the far table's size follows the block length, not the instance);
 // the small instance exists because a 4 KiB chunk keeps 2 of a CTA's warps busy: it trades warps per CTA for
 // CTAs per SM.  It is only valid for chunks of at most BITAR_DK_BLOCK_MAX bytes.
 #include <cuda_runtime.h>
@@ -65,7 +70,12 @@ constexpr int kWarps = BITAR_DK_WARPS;
 constexpr int kThreads = kWarps * 32;
 constexpr int kBlockMax = BITAR_DK_BLOCK_MAX;    // sub-block size (positions fit 16 bits)
 constexpr uint32_t kMaxSeg = kBlockMax < 65536 ? (uint32_t)kBlockMax : (uint32_t)BITAR_MAX_SEG_SIZE;   // largest chunk
-constexpr int kHashBits = 10;                    // per-warp table: 1024 entries for a 2048-position sub-range
+constexpr int kNearBits = 9;                     // per-warp 2-way table: 512 buckets for a 2048-position sub-range
+constexpr int kNearSlots = (1 << kNearBits) + 32;  // + one always-empty dummy slot per lane
+constexpr int kFarTabMax = 1 << (kBlockMax >= 65536 ? 13 : 11);   // dfl::far_hash_bits(kBlockMax) entries at most
+constexpr int kFarNeed = 8;                      // the far candidate is tried where the near match is shorter (model: far_need)
+constexpr int kFarMin = 4;                       // shortest far match (model: far_min)
+constexpr uint32_t kNoFar = 0xFFFFu;
 constexpr int kTokPerThread = 8;                 // encode: consecutive tokens per thread
 constexpr int kTile = kThreads * kTokPerThread;  // encode: tokens per tile (4096 with 16 warps, at most 48 bits each)
 constexpr int kStageWords = kTile * 3 / 2 + 160; // bit stage: a tile's 6 bytes per token + the block header (<= 141 words) + the partial unit
@@ -73,12 +83,10 @@ constexpr int kSeqPerThread = (328 + kThreads - 1) / kThreads;   // plan: code l
 constexpr int kHdrPerThread = (19 + 316 + kThreads - 1) / kThreads;   // header: code-length items per thread
 constexpr uint32_t kTokNone = 0x100u;            // compact token stream: padding (emits nothing)
 constexpr uint32_t kTokEob = 0x101u;             //                       end of block
-// other compact tokens: < 0x100 literal byte; bit 31 set: a match with its symbols already worked out by the match
-// phase (which needs them for the frequency counts anyway), so that the encode phase is table look-ups only:
-//   bits 0..7 length - 3, 9..19 distance - 1 (a match never leaves its 2 KiB sub-range), 21..25 distance symbol,
-//   26..30 length symbol index
-static_assert(dfl::kSub <= 2048, "compact match tokens hold an 11-bit distance");
-// (the match phase ORs them together from pre-shifted look-up tables)
+// other compact tokens: < 0x100 literal byte; bit 31 set: a match with its distance symbol already worked out by the match
+// phase (which needs it for the frequency counts anyway):
+//   bits 0..7 length - 3, 8..22 distance - 1, 23..27 distance symbol
+// (the encode phase looks the length code up by length - 3 in a per-block table, the distance code by symbol)
 constexpr uint32_t kNoCand = 0xFFFFu;
 
 struct PlanPar {                      // scratch of the parallel half of the plan
@@ -100,9 +108,12 @@ struct EncodeArea {
 struct __align__(16) Smem {
   union {                            // the match phase and the plan/encode phases never overlap in time
     struct {
-      uint16_t head[kWarps][(1 << kHashBits) + 32];   // per warp: hash -> most recent position (kNoCand = empty) + 32 dummy slots
+      union {
+        uint16_t head[kWarps][2][kNearSlots];         // per warp: hash -> the two most recent positions (kNoCand = empty)
+        uint16_t far_tab[kFarTabMax];                 // far pass (before the match phase): hash -> last position + 1 before the sub-range
+      };
       // pre-shifted token fields (tok_pack): length - 3 -> (length symbol index << 26) | (length - 3);
-      // distance - 1 -> distance symbol << 21 through zlib's two-level map d < 256 ? lut[d] : lut[256 + (d >> 7)]
+      // distance - 1 -> distance symbol << 23 through zlib's two-level map d < 256 ? lut[d] : lut[256 + (d >> 7)]
       uint32_t len_sym_lut[256];
       uint32_t dist_sym_lut[512];
     } m;                             // (the tables are longer than the bit stage: the look-up tables lie behind it)
@@ -113,6 +124,7 @@ struct __align__(16) Smem {
   uint32_t d_freq[32];
   uint32_t ll_enc[288];              // code | (length << 16) under the chosen block type
   uint32_t d_enc[32];
+  uint32_t len_enc[256];             // ll_enc of the length symbol of every length - 3
   uint32_t d_sorted[32];
   uint32_t warp_sums[kThreads / 32];
   uint32_t crc_tab[256];
@@ -219,6 +231,44 @@ __device__ __forceinline__ int match_len(uint32_t ds, int p, int c, int maxl) {
     }
   }
   return min(l, maxl);
+}
+
+// The same for two candidates of one position at once (the words of p are loaded once, the extension loop runs while
+// either candidate still matches).  max1 / max2 = 0 switches a candidate off.
+__device__ __forceinline__ void match_len2(uint32_t ds, int p, int c1, int c2, int max1, int max2, int& len1, int& len2) {
+  const uint32_t ap = (ds + (uint32_t)p) & ~3u, a1 = (ds + (uint32_t)c1) & ~3u, a2 = (ds + (uint32_t)c2) & ~3u;
+  const uint32_t sp = ((ds + (uint32_t)p) & 3u) * 8u, s1 = ((ds + (uint32_t)c1) & 3u) * 8u, s2 = ((ds + (uint32_t)c2) & 3u) * 8u;
+  const uint32_t p0 = lds_u32(ap), p1 = lds_u32(ap + 4u);
+  const uint32_t q0 = lds_u32(a1), q1 = lds_u32(a1 + 4u), r0 = lds_u32(a2), r1 = lds_u32(a2 + 4u);
+  uint32_t wp = lds_u32(ap + 8u), w1 = lds_u32(a1 + 8u), w2 = lds_u32(a2 + 8u);
+  const uint32_t pa = __funnelshift_r(p0, p1, sp), pb = __funnelshift_r(p1, wp, sp);
+  const uint32_t x0 = pa ^ __funnelshift_r(q0, q1, s1), x1 = pb ^ __funnelshift_r(q1, w1, s1);
+  const uint32_t y0 = pa ^ __funnelshift_r(r0, r1, s2), y1 = pb ^ __funnelshift_r(r1, w2, s2);
+  const int lx0 = __clz((int)__brev(x0)) >> 3, lx1 = __clz((int)__brev(x1)) >> 3;
+  const int ly0 = __clz((int)__brev(y0)) >> 3, ly1 = __clz((int)__brev(y1)) >> 3;
+  int l1 = lx0 + (lx0 == 4 ? lx1 : 0), l2 = ly0 + (ly0 == 4 ? ly1 : 0);
+  bool g1 = (x0 | x1) == 0 && max1 > 8, g2 = (y0 | y1) == 0 && max2 > 8;
+  int l = 8;                                          // bytes compared so far by a candidate that is still going
+  while (g1 || g2) {
+    const uint32_t np = lds_u32(ap + (uint32_t)l + 4u);
+    const uint32_t n1 = lds_u32(a1 + (uint32_t)l + 4u), n2 = lds_u32(a2 + (uint32_t)l + 4u);
+    const uint32_t xp = __funnelshift_r(wp, np, sp);
+    const uint32_t x = xp ^ __funnelshift_r(w1, n1, s1), y = xp ^ __funnelshift_r(w2, n2, s2);
+    if (g1) {
+      l1 = l + (x ? (__ffs((int)x) - 1) >> 3 : 4);
+      g1 = x == 0 && l + 4 < max1;
+    }
+    if (g2) {
+      l2 = l + (y ? (__ffs((int)y) - 1) >> 3 : 4);
+      g2 = y == 0 && l + 4 < max2;
+    }
+    wp = np;
+    w1 = n1;
+    w2 = n2;
+    l += 4;
+  }
+  len1 = min(l1, max1);
+  len2 = min(l2, max2);
 }
 
 // ---- output stream: bit stage in shared memory, flushed as aligned 16-byte vectors ------------------
@@ -341,44 +391,120 @@ __device__ void sort_rank(Smem& sm) {
   __syncthreads();
 }
 
+// ---- far pass ---------------------------------------------------------------------------------------
+// far[p] = the last position c before the 2 KiB sub-range of p whose 4 bytes equal those at p (kNoFar when the table's
+// entry for the hash of p is empty, holds other bytes, or lies farther back than max_dist).  The whole CTA takes the
+// sub-ranges in order: look up all positions of the sub-range, barrier, insert them (the largest position of a hash
+// wins, whatever the order: 16-bit compare-and-swap), barrier.  Semantics == the far pass of tools/model/deflate_model.h.
+__device__ __forceinline__ void far_insert(uint16_t* tab, uint32_t h, uint32_t v) {
+  unsigned short old = tab[h];
+  while (old < v) {
+    const unsigned short seen = atomicCAS(reinterpret_cast<unsigned short*>(tab + h), old, (unsigned short)v);
+    if (seen == old) break;
+    old = seen;
+  }
+}
+__device__ __forceinline__ void far_pass(Smem& sm, uint32_t ds, int n, int max_dist, uint16_t* __restrict__ far, int tid) {
+  constexpr int kPer = (int)dfl::kSub / kThreads;     // positions per thread and sub-range
+  static_assert(kPer * kThreads == (int)dfl::kSub, "a sub-range is a whole number of passes of the CTA");
+  const int fb = dfl::far_hash_bits((uint32_t)n);
+  uint16_t* tab = sm.u.m.far_tab;
+  for (int i = tid; i < (1 << fb) / 2; i += kThreads) reinterpret_cast<uint32_t*>(tab)[i] = 0u;
+  __syncthreads();
+  for (int s0 = 0; s0 < n; s0 += (int)dfl::kSub) {
+    uint32_t h[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      const int p = s0 + tid + k * kThreads;
+      h[k] = 0xFFFFFFFFu;                             // no position / no hash
+      if (p + 4 <= n) {
+        const uint32_t w = ld32u(ds + (uint32_t)p);
+        h[k] = dfl::hash_far(w, fb);
+        uint32_t f = kNoFar;
+        if (s0) {
+          const uint32_t c1 = tab[h[k]];              // position + 1, 0 = empty
+          if (c1 && p - (int)(c1 - 1u) <= max_dist && ld32u(ds + c1 - 1u) == w) f = c1 - 1u;
+        }
+        far[p] = (uint16_t)f;
+      }
+    }
+    if (s0 + (int)dfl::kSub >= n) break;              // the last sub-range's positions are nobody's far candidates
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kPer; ++k)
+      if (h[k] != 0xFFFFFFFFu) far_insert(tab, h[k], (uint32_t)(s0 + tid + k * kThreads + 1));
+    __syncthreads();
+  }
+  __syncthreads();                                    // far[] (global) and the table's space are handed to the match phase
+}
+
 // ---- match phase -------------------------------------------------------------------------------------
 // One warp, one 2 KiB sub-range [s0, s1) of the block: windows of 32 positions in order.
-// Semantics == tools/model Params{step = 32, cand_mode = 1, hash_bits = 10, lazy = 1, sub_log2 = 11}: candidate = nearest
-// previous position with the same 4-byte hash -- a lower lane of the window if there is one, else the most
-// recent earlier position of this sub-range from the table; greedy parse in position order.
-__device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int s0, int s1, int warp, int lane,
-                                               uint32_t* __restrict__ tokens) {
+// Semantics == the near pass / selection / parse of tools/model/deflate_model.h: candidates = the two most recent earlier
+// positions with the same 4-byte hash -- lower lanes of the window first, then the two ways of this sub-range's table;
+// the longer match wins (ties: the nearer); a near match shorter than kFarNeed yields to a strictly longer far match of
+// at least kFarMin bytes; greedy parse in position order with a one-position lazy step.
+__device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int s0, int s1, int warp, int lane, int max_dist,
+                                               const uint16_t* far, uint32_t* __restrict__ tokens) {
   constexpr unsigned kFull = 0xFFFFFFFFu;
-  volatile uint16_t* head = sm.u.m.head[warp];          // head[1024..1055]: per-lane dummy slots, always empty
+  volatile uint16_t* head0 = sm.u.m.head[warp][0];      // [512 ..]: per-lane dummy slots, always empty
+  volatile uint16_t* head1 = sm.u.m.head[warp][1];
   {
     uint32_t* h32 = reinterpret_cast<uint32_t*>(sm.u.m.head[warp]);
-    for (int i = lane; i < ((1 << kHashBits) + 32) / 2; i += 32) h32[i] = 0xFFFFFFFFu;
+    for (int i = lane; i < kNearSlots; i += 32) h32[i] = 0xFFFFFFFFu;   // both ways (2 * kNearSlots u16)
   }
   __syncwarp();
   const unsigned lt_mask = (1u << lane) - 1u;
-  const uint32_t dummy = (1u << kHashBits) + (uint32_t)lane;
+  const uint32_t dummy = (1u << kNearBits) + (uint32_t)lane;
   const int sub_end = min(n, s0 + (int)dfl::kSub);
   int carry = s0;                                     // next token start
   // this sub-range's tokens go to tokens[s0 ..], compact and in order
   uint32_t cnt = 0;
+  uint32_t far_next = s0 + lane < n ? __ldcg(far + s0 + lane) : kNoFar;   // (sub-range 0 has no far candidates: the pass wrote kNoFar)
   for (int base = s0; base < s1; base += 32) {
     const int p = base + lane;
     const bool valid = p + 4 <= n;
-    const uint32_t h = valid ? dfl::hash_word(ld32u(ds + p), kHashBits, 4) : dummy;
+    const uint32_t fc = valid ? far_next : kNoFar;
+    if (base + 32 < s1) far_next = p + 32 < n ? __ldcg(far + p + 32) : kNoFar;   // the next window's, one iteration ahead
+    const uint32_t h = valid ? dfl::hash_near(ld32u(ds + p), kNearBits) : dummy;
     const unsigned m = __match_any_sync(kFull, h);    // dummies are unique per lane
     const unsigned lower = m & lt_mask;
-    uint32_t cand = head[h];
+    const uint32_t t0 = head0[h], t1 = head1[h];
+    const int k1 = 31 - __clz((int)lower);            // nearest lower lane with this hash (-1: none)
+    const unsigned lower2 = lower & ~(lower ? 1u << k1 : 0u);
     __syncwarp();
-    if (valid && (m >> lane) == 1u) head[h] = (uint16_t)p;   // the window's highest position for this hash
+    if (valid && (m >> lane) == 1u) {                 // the window's highest position for this hash: the bucket after the window
+      head0[h] = (uint16_t)p;
+      head1[h] = (uint16_t)(lower ? (uint32_t)(base + k1) : t0);
+    }
     __syncwarp();
-    if (lower) cand = (uint32_t)(base + 31 - __clz((int)lower));
+    const uint32_t cand1 = lower ? (uint32_t)(base + k1) : t0;
+    const uint32_t cand2 = lower ? (lower2 ? (uint32_t)(base + 31 - __clz((int)lower2)) : t0) : t1;
     const int a = carry - base;                       // where the parse enters this window (>= 0)
     if (a >= 32) continue;                            // the whole window lies inside the previous match
     // every lane runs the (branch-free) first 8 bytes of the match extension; lanes without a usable candidate
     // compare their position with itself under a length limit of 0
-    const bool has_cand = cand != kNoCand && p >= carry;
-    const int c = has_cand ? (int)cand : p;
-    const int len = match_len(ds, p, c, has_cand ? min(dfl::kMaxMatch, sub_end - p) : 0);
+    const bool live = valid && p >= carry;
+    const int maxl = min(dfl::kMaxMatch, sub_end - p);
+    const bool has1 = live && cand1 != kNoCand && p - (int)cand1 <= max_dist;
+    const bool has2 = live && cand2 != kNoCand && p - (int)cand2 <= max_dist;
+    int len1, len2;
+    match_len2(ds, p, has1 ? (int)cand1 : p, has2 ? (int)cand2 : p, has1 ? maxl : 0, has2 ? maxl : 0, len1, len2);
+    int len = len1, c = (int)cand1;
+    if (len2 > len1) {
+      len = len2;
+      c = (int)cand2;
+    }
+    {   // the far candidate where the near match is short (skipped when no lane of the window wants it)
+      const bool want_far = live && fc != kNoFar && len < kFarNeed;
+      if (__any_sync(kFull, want_far)) {
+        const int lf = match_len(ds, p, want_far ? (int)fc : p, want_far ? maxl : 0);
+        if (lf >= kFarMin && lf > len) {
+          len = lf;
+          c = (int)fc;
+        }
+      }
+    }
     const bool hit = len >= dfl::kMinMatch;
     int adv = hit ? len : 1, dist = hit ? p - c : 0;
     {   // lazy step: a match yields to a strictly longer match that starts at the next position of the window
@@ -417,12 +543,12 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
       const uint32_t byte = lds_u8(ds + p);
       const uint32_t d1 = is_match ? (uint32_t)dist - 1u : 0u;
       const uint32_t len_f = sm.u.m.len_sym_lut[is_match ? adv - 3 : 0];                  // symbol << 26 | length - 3
-      const uint32_t dist_f = sm.u.m.dist_sym_lut[d1 < 256u ? d1 : 256u + (d1 >> 7)];     // symbol << 21
+      const uint32_t dist_f = sm.u.m.dist_sym_lut[d1 < 256u ? d1 : 256u + (d1 >> 7)];     // symbol << 23
       if (start) {
         atomicAdd(&sm.ll_freq[is_match ? 257u + (len_f >> 26) : byte], 1u);
-        if (is_match) atomicAdd(&sm.d_freq[dist_f >> 21], 1u);
+        if (is_match) atomicAdd(&sm.d_freq[dist_f >> 23], 1u);
         // (one 32-bit index from the scratch base: a single wide multiply-add forms the address)
-        tokens[(uint32_t)s0 + cnt + (uint32_t)__popc(starts & lt_mask)] = is_match ? (0x80000000u | len_f | dist_f | (d1 << 9)) : byte;
+        tokens[(uint32_t)s0 + cnt + (uint32_t)__popc(starts & lt_mask)] = is_match ? (0x80000000u | (len_f & 0xFFu) | dist_f | (d1 << 8)) : byte;
       }
     }
     cnt += (uint32_t)__popc(starts);
@@ -719,15 +845,15 @@ __device__ __forceinline__ int token_bits(const Smem& sm, uint32_t tok, uint32_t
     lo_n = (int)(e >> 16);
     return lo_n;
   }
-  // ll_enc / d_enc entries of length and distance symbols carry their number of extra bits in bits 24..;
-  // the extra value is the low bits of length - 3 / distance - 1 (RFC 1951's bases are aligned that way)
-  const uint32_t e = sm.ll_enc[257u + ((tok >> 26) & 31u)];
+  // len_enc / d_enc entries carry the symbol's number of extra bits in bits 24..; the extra value is the low bits of
+  // length - 3 / distance - 1 (RFC 1951's bases are aligned that way)
+  const uint32_t e = sm.len_enc[tok & 0xFFu];
   const uint32_t cl = (e >> 16) & 0xFFu, leb = e >> 24;
   lo_bits = (e & 0xFFFFu) | (((tok & 0xFFu) & ((1u << leb) - 1u)) << cl);
   lo_n = (int)(cl + leb);  // <= 20
-  const uint32_t f = sm.d_enc[(tok >> 21) & 31u];
+  const uint32_t f = sm.d_enc[(tok >> 23) & 31u];
   const uint32_t dl = (f >> 16) & 0xFFu, deb = f >> 24;
-  hi_bits = (f & 0xFFFFu) | ((((tok >> 9) & 0x7FFu) & ((1u << deb) - 1u)) << dl);
+  hi_bits = (f & 0xFFFFu) | ((((tok >> 8) & 0x7FFFu) & ((1u << deb) - 1u)) << dl);
   hi_n = (int)(dl + deb);  // <= 28
   return lo_n + hi_n;
 }
@@ -735,12 +861,13 @@ __device__ __forceinline__ int token_bits(const Smem& sm, uint32_t tok, uint32_t
 // ---- the kernel ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
     deflate_kernel(const bitar_chunk* __restrict__ ops, uint32_t n_ops, bitar_result* __restrict__ results,
-                   unsigned int* __restrict__ counter, uint32_t* __restrict__ token_scratch, int huffman,
-                   int checksum_type, unsigned long long* __restrict__ prof) {
+                   unsigned int* __restrict__ counter, uint32_t* __restrict__ token_scratch, uint16_t* far_scratch, int huffman,
+                   int checksum_type, int max_dist, int emit_index, unsigned long long* __restrict__ prof) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t* tokens = token_scratch + (size_t)blockIdx.x * kBlockMax;
+  uint16_t* far = far_scratch + (size_t)blockIdx.x * kBlockMax;
 
   if (tid == 0) {
     mbar_init(&sm.mbar, 1);
@@ -754,7 +881,7 @@ __global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
   __syncthreads();
   uint32_t tma_parity = 0;
   // optional phase timers (cycles, thread 0): 0 load, 1 match, 2 sort, 3 Huffman merge (serial), 4 tables+header, 5 encode,
-  // 6 finish, 7 depths / lengths / codes / sizes, 8 code-length RLE, 9 code-length code + block type (serial)
+  // 6 finish, 7 depths / lengths / codes / sizes, 8 code-length RLE, 9 code-length code + block type (serial), 10 far pass
   long long t_prev = prof ? clock64() : 0;
 #define BITAR_PHASE(k)                                          \
   if (prof && tid == 0) {                                       \
@@ -781,6 +908,8 @@ __global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
       const uint32_t idx_words = min(dfl::idx_entries(total), (uint32_t)(sizeof(sm.index) / 4));
       for (uint32_t i = tid; i < idx_words; i += kThreads) sm.index[i] = 0;
     }
+
+    if (total > kMaxSeg) status = BITAR_OP_DATA_ERROR;   // (the C-ABI rejects such ops before the launch: capi.cu qp_submit)
 
     if (total == 0) {  // empty input: a fixed block holding only end-of-block (03 00), as zlib emits
       __syncthreads();
@@ -822,9 +951,10 @@ __global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
       // partially filled 16-byte unit at its front
       if (tid < 4) sm.keep[tid] = sm.u.enc.stage[tid];
       static_assert(sizeof(sm.u.m.head) >= sizeof(sm.u.enc.stage), "the look-up tables must lie behind the bit stage");
+      static_assert(sizeof(sm.u.m.head) >= sizeof(sm.u.m.far_tab), "the far table borrows the near tables' space");
       for (int i = tid; i < 256; i += kThreads) sm.u.m.len_sym_lut[i] = ((uint32_t)dfl::len_sym(i + 3) << 26) | (uint32_t)i;
       for (int i = tid; i < 512; i += kThreads)
-        sm.u.m.dist_sym_lut[i] = (uint32_t)dfl::dist_sym(i < 256 ? i + 1 : ((i - 256) << 7) + 1) << 21;
+        sm.u.m.dist_sym_lut[i] = (uint32_t)dfl::dist_sym(i < 256 ? i + 1 : ((i - 256) << 7) + 1) << 23;
       for (int i = tid; i < 288; i += kThreads) sm.ll_freq[i] = 0;
       if (tid < 32) sm.d_freq[tid] = 0;
       mbar_wait(&sm.mbar, tma_parity);
@@ -835,8 +965,10 @@ __global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
 
       // ---- match + parse + count: one 2 KiB sub-range per warp at a time, no CTA-wide barrier ----
       const uint32_t ds = smem_u32(d);
+      far_pass(sm, ds, n, max_dist, far, tid);
+      BITAR_PHASE(10)
       for (int s0 = warp * (int)dfl::kSub; s0 < n; s0 += kWarps * (int)dfl::kSub)
-        match_subrange(sm, ds, n, s0, min(n, s0 + (int)dfl::kSub), warp, lane, tokens);
+        match_subrange(sm, ds, n, s0, min(n, s0 + (int)dfl::kSub), warp, lane, max_dist, far, tokens);
       __syncthreads();
       for (int i = tid; i < kStageWords; i += kThreads) sm.u.enc.stage[i] = tid < 4 && i < 4 ? sm.keep[i] : 0u;
       BITAR_PHASE(1)
@@ -1051,6 +1183,8 @@ __global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
         if (tid < dfl::kNumDist) e |= (uint32_t)dfl::dist_extra_bits(tid) << 24;
         sm.d_enc[tid] = e;
       }
+      __syncthreads();
+      for (int i = tid; i < 256; i += kThreads) sm.len_enc[i] = sm.ll_enc[257 + dfl::len_sym(i + 3)];
       // ---- header: fixed fields by thread 0, then one code-length-code length / RLE token per thread at the bit
       //      offset given by a CTA-wide prefix sum ----
       uint32_t hdr_bits = type == dfl::kDynamic ? sm.plan.header_bits : 3u;
@@ -1210,7 +1344,7 @@ __global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
         __syncthreads();
         // the parallel-inflate index goes after the byte-aligned end of the stream when it is useful and fits
         const uint32_t entries = dfl::idx_entries(total);
-        if (sm.any_coded && (uint64_t)end_byte + 4ull * (entries + 3u) <= (uint64_t)o.vcap) {
+        if (emit_index && sm.any_coded && (uint64_t)end_byte + 4ull * (entries + 3u) <= (uint64_t)o.vcap) {
           const uint32_t end_bit = (uint32_t)(o.bit - 8ull * o.vstart);
           for (uint32_t t = tid; t < entries + 3u; t += kThreads) {
             const uint32_t w = t < entries ? sm.index[t] : t == entries ? end_bit : t == entries + 1u ? total : dfl::kIndexMagic;
@@ -1236,7 +1370,7 @@ __global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
     // reset the stage for the next chunk and fetch its index
     __syncthreads();
     for (int i = tid; i < kStageWords; i += kThreads) sm.u.enc.stage[i] = 0;
-    if (tid == 0 && total == 0) sm.next_idx = gridDim.x + atomicAdd(counter, 1u);   // (an empty chunk loaded nothing)
+    if (tid == 0 && (total == 0 || total > kMaxSeg)) sm.next_idx = gridDim.x + atomicAdd(counter, 1u);   // (no block was loaded)
     __syncthreads();
     idx = sm.next_idx;
     __syncthreads();
@@ -1245,7 +1379,8 @@ __global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
 #undef BITAR_PHASE
 }
 
-inline size_t deflate_scratch_bytes(int grid) { return (size_t)grid * kBlockMax * sizeof(uint32_t); }
+inline size_t deflate_scratch_bytes(int grid) { return (size_t)grid * kBlockMax * sizeof(uint32_t); }   // tokens
+inline size_t deflate_far_bytes(int grid) { return (size_t)grid * kBlockMax * sizeof(uint16_t); }       // far candidates
 
 // resident CTAs per SM for chunks of at most max_len bytes (the shared-memory footprint follows the chunk size)
 inline cudaError_t deflate_ctas_per_sm(int device, uint32_t max_len, int* ctas_out) {
@@ -1271,15 +1406,17 @@ inline cudaError_t deflate_grid(int device, int sm_count, int* grid_out) {
 }
 
 inline cudaError_t deflate_launch(const bitar_chunk* ops, uint32_t n, bitar_result* res, unsigned int* counter,
-                                  uint32_t* scratch, int device, int sm_count, int grid_override, uint32_t max_len, int huffman,
-                                  int checksum_type, unsigned long long* prof, cudaStream_t stream) {
+                                  uint32_t* scratch, uint16_t* far, int device, int sm_count, int grid_override, uint32_t max_len,
+                                  int huffman, int checksum_type, int max_dist, int emit_index, unsigned long long* prof,
+                                  cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   int ctas = 0;
   cudaError_t e = deflate_ctas_per_sm(device, max_len, &ctas);
   if (e != cudaSuccess) return e;
   int grid = grid_override > 0 ? grid_override : sm_count * ctas;
   if ((uint32_t)grid > n) grid = (int)n;
-  deflate_kernel<<<grid, kThreads, smem_bytes(max_len), stream>>>(ops, n, res, counter, scratch, huffman, checksum_type, prof);
+  deflate_kernel<<<grid, kThreads, smem_bytes(max_len), stream>>>(ops, n, res, counter, scratch, far, huffman, checksum_type, max_dist,
+                                                                  emit_index, prof);
   return cudaGetLastError();
 }
 

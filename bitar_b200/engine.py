@@ -46,6 +46,7 @@ class Configuration:
     checksum_type: int = CHECKSUM_NONE
     slot_mem_kind: int = MEM_DEVICE
     compressed_seg_size: int = 0             # derived unless set
+    emit_index: bool = True                  # False: chunks are bare RFC 1951 streams (no parallel-inflate index)
 
     def resolved_compressed_seg_size(self):
         return self.compressed_seg_size or int(capi.lib().bitar_compressed_seg_size(self.decompressed_seg_size))
@@ -66,7 +67,7 @@ class CompressDevice:
         c = capi.Cfg(configuration.decompressed_seg_size, configuration.compressed_seg_size,
                      configuration.max_preallocate_memzones, configuration.burst_size,
                      configuration.max_sgl_segs, configuration.window_size, configuration.huffman_enc,
-                     configuration.checksum_type, configuration.slot_mem_kind)
+                     configuration.checksum_type, configuration.slot_mem_kind, 0 if configuration.emit_index else 1)
         h = C.c_void_p()
         capi.check(capi.lib().bitar_dev_open(self._device_id, self._num_qps, C.byref(c), C.byref(h)))
         self._h = h
@@ -253,7 +254,7 @@ class CompressDriver:
 
 
 # -- framing: the chunks as members of a gzip file --------------------------------------
-INDEX_MAGIC = 0xB17A0B01
+INDEX_MAGIC = 0xB17A0B02
 
 
 def stream_length(chunk):

@@ -88,12 +88,18 @@ class CudaConfiguration : public Configuration<Class_CUDA> {
   /// \brief Where the output slots live: device memory, or pinned host memory the kernels write over PCIe.
   [[nodiscard]] auto slot_memory() const noexcept { return slot_memory_; }
   void set_slot_memory(SlotMemory v) { slot_memory_ = v; }
+  /// \brief Whether a compressed chunk carries the parallel-inflate index after its final block (default).  Without it a
+  /// chunk is a bare RFC 1951 stream whose length is the buffer's size; it still inflates here, through the slower
+  /// whole-stream kernel.
+  [[nodiscard]] auto emit_index() const noexcept { return emit_index_; }
+  void set_emit_index(bool v) { emit_index_ = v; }
 
   static CudaConfiguration Defaults() { return {}; }
 
  private:
   ChecksumType checksum_type_ = ChecksumType::kNone;
   SlotMemory slot_memory_ = SlotMemory::kDevice;
+  bool emit_index_ = true;
 };
 
 }  // namespace bitar

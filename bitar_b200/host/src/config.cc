@@ -43,6 +43,7 @@ bitar_cfg CudaConfiguration::to_c() const noexcept {
   bitar_cfg c = Configuration<Class_CUDA>::to_c();
   c.checksum_type = static_cast<std::uint8_t>(checksum_type_);
   c.slot_mem_kind = static_cast<std::uint8_t>(slot_memory_);
+  c.no_index = emit_index_ ? 0 : 1;
   return c;
 }
 

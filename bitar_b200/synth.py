@@ -5,6 +5,8 @@ environment, so the benchmark and the tests generate TPC-H-lineitem-like fixed-w
 buffers instead:  sorted int64 keys, int32 dictionary indices of 7 skewed categories, and float64
 two-decimal prices, concatenated column-major in equal thirds.
 """
+import os
+
 import numpy as np
 
 SEED = 20261018
@@ -66,3 +68,69 @@ def edge_cases(seg, seed=SEED):
     ramp = (np.arange(4 * seg, dtype=np.uint32) * 2654435761 >> 13).astype(np.uint8)
     cases["lowentropy"] = (ramp & 0x0F).astype(np.uint8)
     return cases
+
+
+# ---- ratio corpus (round 2): inputs beyond the benchmark mix, for the "within 5 % of zlib level 1" gate ----
+def _files_bytes(paths, nbytes):
+    out = bytearray()
+    for p in paths:
+        try:
+            with open(p, "rb") as f:
+                out += f.read()
+        except OSError:
+            continue
+        if len(out) >= nbytes:
+            break
+    return np.frombuffer(bytes(out[:nbytes]), np.uint8).copy()
+
+
+def text_source(nbytes):
+    """Program text: the Python standard library's own sources (present in this image), concatenated by name."""
+    import glob
+    import sysconfig
+    return _files_bytes(sorted(glob.glob(os.path.join(sysconfig.get_paths()["stdlib"], "*.py"))), nbytes)
+
+
+def elf_binary(nbytes):
+    """Machine code + tables: the interpreter's ELF image."""
+    import sys
+    return _files_bytes([os.path.realpath(sys.executable)], nbytes)
+
+
+def char_strings(nbytes, width=10, seed=SEED):
+    """CHAR(width) column of 7 low-cardinality values (l_shipmode-like), space padded."""
+    rng = np.random.default_rng(seed)
+    vals = [b"AIR", b"FOB", b"MAIL", b"RAIL", b"REG AIR", b"SHIP", b"TRUCK"]
+    table = np.frombuffer(b"".join(v.ljust(width) for v in vals), np.uint8).reshape(len(vals), width)
+    idx = rng.integers(0, len(vals), size=nbytes // width + 1)
+    return np.ascontiguousarray(table[idx].reshape(-1)[:nbytes])
+
+
+def word_strings(nbytes, vocab=3000, seed=SEED):
+    """Free text over a fixed vocabulary (l_comment-like): words of 2..10 lower-case letters, Zipf-ish use."""
+    rng = np.random.default_rng(seed)
+    words = [bytes(rng.integers(97, 123, size=int(rng.integers(2, 11)), dtype=np.uint8)) + b" " for _ in range(vocab)]
+    p = 1.0 / np.arange(1, vocab + 1) ** 0.5
+    picks = rng.choice(vocab, size=nbytes // 4 + 16, p=p / p.sum())
+    out = b"".join(words[i] for i in picks)
+    return np.frombuffer(out[:nbytes], np.uint8).copy()
+
+
+def period_rows(nbytes, period=4096, seed=SEED):
+    """One random row of `period` bytes repeated: redundancy only at distance `period`."""
+    rng = np.random.default_rng(seed)
+    row = np.frombuffer(rng.bytes(period), np.uint8)
+    return np.ascontiguousarray(np.tile(row, nbytes // period + 1)[:nbytes])
+
+
+def ratio_corpus(nbytes):
+    """name -> uint8 array of (up to) nbytes: the inputs the compressed size is gated on against zlib level 1."""
+    c = {"lineitem_mix": lineitem_like(nbytes)}
+    for name in COLUMNS:
+        c[name] = column(name, nbytes)
+    c["text_source"] = text_source(nbytes)
+    c["elf_binary"] = elf_binary(nbytes)
+    c["char10_strings"] = char_strings(nbytes)
+    c["word_strings"] = word_strings(nbytes)
+    c["period4096_rows"] = period_rows(nbytes)
+    return {k: v for k, v in c.items() if v.size}

@@ -88,10 +88,14 @@ typedef struct bitar_cfg {
   uint32_t max_preallocate_slots;    /* "max_preallocate_memzones"; 0 -> 2560 (RTE_MAX_MEMZONE) */
   uint16_t burst_size;               /* kept for API parity; the GPU path enqueues whole calls */
   uint16_t max_sgl_segs;             /* must be <= 1 */
-  uint8_t window_size;               /* log2; 0 -> device max (15), src/device.cc:389-394 */
+  uint8_t window_size;               /* log2; 0 -> device max (15), src/device.cc:389-394; match distances never exceed 1 << window_size */
   uint8_t huffman_enc;               /* BITAR_HUFFMAN_*; DEFAULT -> DYNAMIC */
   uint8_t checksum_type;             /* BITAR_CHECKSUM_* */
   uint8_t slot_mem_kind;             /* BITAR_MEM_DEVICE or BITAR_MEM_PINNED */
+  uint8_t no_index;                  /* 1: chunks are bare RFC 1951 streams (`produced` = stream length); 0: the parallel-
+                                        inflate index follows the final block (deflate_common.h), which stock inflaters
+                                        leave unread and which this engine's inflate needs for its fast path */
+  uint8_t reserved[3];
 } bitar_cfg;
 
 /* One op: replaces an rte_comp_op with one src and one dst mbuf (src/memory.cc:350-430, 432-505).

@@ -75,7 +75,7 @@ def host_inflate_indexed(comp, cap, misalign=0):
                  "guard_ok": guard_ok}
 
 
-INDEX_MAGIC = 0xB17A0B01
+INDEX_MAGIC = 0xB17A0B02
 SUB = 2048
 
 

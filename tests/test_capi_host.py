@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(capi.Cfg) == 20 and C.sizeof(capi.DevInfo) == 104
+    assert C.sizeof(capi.Cfg) == 24 and C.sizeof(capi.DevInfo) == 104
     assert capi.CHUNK_DTYPE.itemsize == 24 and capi.RESULT_DTYPE.itemsize == 16
 
 

@@ -32,7 +32,7 @@ def corpus(seg=SEG):
     return chunks
 
 
-@pytest.mark.parametrize("variant", [0, 5, 12, 13, 14, 20])
+@pytest.mark.parametrize("variant", [0, 5])
 def test_reference_streams_inflate_on_gpu(cuda_device, variant):
     capi.lib().bitar_tune_inflate_variant(variant)
     dev = G.open_device(SEG)
@@ -52,10 +52,10 @@ def test_reference_streams_inflate_on_gpu(cuda_device, variant):
                 assert o.size == ref.size and np.array_equal(o, ref)
     finally:
         dev.close()
-        capi.lib().bitar_tune_inflate_variant(22)
+        capi.lib().bitar_tune_inflate_variant(0)
 
 
-@pytest.mark.parametrize("variant", [20, 22, 23, 24])
+@pytest.mark.parametrize("variant", [0])
 @pytest.mark.parametrize("huffman", [capi.HUFFMAN_DYNAMIC, capi.HUFFMAN_FIXED])
 def test_gpu_streams_inflate_through_the_index(cuda_device, variant, huffman):
     """Chunks produced by the deflate kernel carry the parallel-inflate index: the sub-range kernel must
@@ -89,7 +89,7 @@ def test_gpu_streams_inflate_through_the_index(cuda_device, variant, huffman):
         assert list(res["status"]) == [capi.OP_DATA_ERROR, capi.OP_DATA_ERROR, capi.OP_OUT_OF_SPACE]
     finally:
         dev.close()
-        capi.lib().bitar_tune_inflate_variant(22)
+        capi.lib().bitar_tune_inflate_variant(0)
 
 
 @pytest.mark.parametrize("seg", [2049, 4096, 5000, 16384])

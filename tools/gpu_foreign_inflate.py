@@ -1,5 +1,5 @@
 """Inflate speed on FOREIGN streams (zlib-produced, no parallel-inflate index): the whole-stream kernels.
-usage: python tools/gpu_foreign_inflate.py [MiB] [level] [variants...]   (variant 22 = default dispatch)"""
+usage: python tools/gpu_foreign_inflate.py [MiB] [level] [variants...]   (variant 0 = default dispatch, 5 = whole-stream kernel only)"""
 import os
 import sys
 import zlib
@@ -16,7 +16,7 @@ from bitar_b200.engine import CompressDevice, Configuration  # noqa: E402
 
 mib = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 level = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-variants = [int(v) for v in sys.argv[3:]] or [22, 5, 12, 13]
+variants = [int(v) for v in sys.argv[3:]] or [0, 5]
 seg = 59460
 data = synth.lineitem_like(mib << 20)
 n = (data.size + seg - 1) // seg

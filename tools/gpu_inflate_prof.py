@@ -11,7 +11,7 @@ from bitar_b200 import _capi as capi  # noqa: E402
 from bitar_b200 import synth  # noqa: E402
 from bitar_b200.engine import CompressDevice, Configuration  # noqa: E402
 
-variant = int(sys.argv[1]) if len(sys.argv) > 1 else 22
+variant = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 mib = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 seg = int(sys.argv[3]) if len(sys.argv) > 3 else 59460
 data = synth.lineitem_like(mib << 20)

@@ -9,6 +9,7 @@
 
 #include "../../bitar_b200/csrc/inflate_core.h"
 #include "../../bitar_b200/csrc/inflate_fast.h"
+#include "../../bitar_b200/csrc/inflate_tok.h"
 #include "deflate_model.h"
 
 #define API extern "C" __attribute__((visibility("default")))
@@ -78,17 +79,20 @@ API int host_inflate_fast(const uint8_t* in, uint32_t in_len, uint8_t* out, uint
   return 0;
 }
 
-// The indexed path of the production inflate kernel on the CPU: the index is parsed with the kernel's own
-// parse_index(), block headers are parsed by a whole-stream lane, and every 2 KiB sub-range is decoded by a
-// SUB lane that starts at its indexed bit offset (the kernel runs 32 of these per warp).
+// The two-phase path of the production inflate kernels on the CPU: the index is parsed with the kernels' own
+// parse_index(), block headers are parsed by a whole-stream lane, every 2 KiB sub-range is Huffman-decoded into token
+// units by a tk::TokLane that starts at its indexed bit offset (phase A: the kernel runs 32 of these per warp), and the
+// units of a block are resolved in order by tk::resolve_units_serial (phase B, stated serially).
 // result: [0] produced, [1] status, [2] 1 when the chunk carried an index, [3] sub-ranges decoded.
 API int host_inflate_indexed(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t cap, uint32_t* result4) {
   using namespace bitar::fl;
   using namespace bitar;
   constexpr int LB = 10, LT = 1344, DB = 8, DT = 512, RG = 128;
   using Gen = FastLane<LB, LT, DB, DT, RG, false>;
-  using Sub = FastLane<LB, LT, DB, DT, RG, true>;
+  using Tok = tk::TokLane<LB, LT, DB, DT, 16>;
   alignas(16) static thread_local uint8_t smem[LaneLayout<LB, LT, DB, DT, 256>::kStride];
+  alignas(16) static thread_local uint8_t uring[64];
+  alignas(16) static thread_local uint8_t slots[32][tk::kSlotBytes];
   static thread_local LaneScratch scratch;
   static CtaTables cta;
   for (int i = 0; i < 32; ++i) cta.dinfo[i] = dist_info(i);
@@ -107,7 +111,7 @@ API int host_inflate_indexed(const uint8_t* in, uint32_t in_len, uint8_t* out, u
     const uint32_t ns = dfl::idx_subs(blen);
     BlockBits bb;
     if (!index_block_bits(ix, b, nb, &bb)) { status = kStatusDataError; break; }
-    const uint32_t hdr = bb.hdr, block_end = bb.end;
+    const uint32_t hdr = bb.hdr;
     Gen g;
     g.bind(smem, &cta, &scratch, 0);
     g.start(in, ix.stream_bytes, out + (b << 16), blen);
@@ -123,17 +127,26 @@ API int host_inflate_indexed(const uint8_t* in, uint32_t in_len, uint8_t* out, u
       continue;
     }
     if ((uint32_t)(8ll * g.start_off + g.consumed_bits()) != index_word(ix, b * 33u + 1u)) { status = kStatusDataError; break; }
-    for (uint32_t s = 0; s < ns; ++s) {
-      Sub l;
-      l.bind_parts(g.lt, g.dt, smem + 2 * LT + 2 * DT, &cta, &scratch, 0);
+    uint32_t n_units[32] = {0};
+    for (uint32_t s = 0; s < ns; ++s) {   // phase A
+      Tok l;
+      l.bind(g.lt, g.dt, uring, cta.dinfo, &scratch);
       const uint32_t len = blen - s * dfl::kSub < dfl::kSub ? blen - s * dfl::kSub : dfl::kSub;
       uint32_t sbit, ebit;
       if (!index_sub_bits(ix, b, s, ns, bb, &sbit, &ebit)) { status = kStatusDataError; break; }
-      l.start_sub(in, ix.stream_bytes, sbit, ebit, s + 1 == ns, out + (b << 16) + s * dfl::kSub, len);
+      l.start_sub(in, ix.stream_bytes, sbit, ebit, s + 1 == ns, slots[s], len, s * dfl::kSub);
       uint64_t steps = 0;
-      while (l.state != Sub::kDone && ++steps < (1ull << 30)) l.step();
+      while (l.state != Tok::kDone && ++steps < (1ull << 30)) l.step();
       result4[3]++;
       if (l.status != kStatusOk) { status = l.status; break; }
+      n_units[s] = l.units();
+      if (n_units[s] > tk::kSlotUnits || (n_units[s] & 7u)) { status = kStatusDataError; break; }
+    }
+    uint32_t pos = 0;
+    for (uint32_t s = 0; s < ns && status == kStatusOk; ++s) {   // phase B
+      const uint32_t limit = (s + 1) * dfl::kSub < blen ? (s + 1) * dfl::kSub : blen;
+      pos = tk::resolve_units_serial(reinterpret_cast<const uint16_t*>(slots[s]), n_units[s], out + (b << 16), pos, limit);
+      if (pos != limit) status = kStatusDataError;
     }
   }
   result4[0] = status == kStatusOk ? ix.total_out : 0;

@@ -20,17 +20,24 @@ namespace bitar_model {
 using namespace bitar::dfl;
 
 struct Params {
-  int step = 32;        // positions per dictionary step: one warp window (exact nearest-previous semantics)
-  int hash_bits = 10;   // one 1024-entry table per 2 KiB sub-range (the kernel keeps one per warp)
-  int min_match = 4;    // bytes hashed (3 or 4); emitted matches are always >= 3
-  int cand_mode = 1;    // 0 table only, 1 warp-near else table, 2 best of both
-  int far3 = 4096;      // reject length-3 matches farther than this (0 = keep all)
+  // The match finder of the sm_100a kernel (deflate_kernel.cuh), stated sequentially.  Per 64 KiB block:
+  //   far pass   : a table of 2^far_bits(n) entries holds, for every hash of 4 bytes, the last position BEFORE the current
+  //                2 KiB sub-range; every position gets the entry of its hash as its FAR candidate when the 4 bytes
+  //                really are equal (the kernel runs this pass sub-range by sub-range with the whole CTA).
+  //   near pass  : per sub-range a 2-way table of 2^near_bits buckets (the two most recent positions of a hash before
+  //                the current window of 32 positions) and the positions of the window itself; the two most recent
+  //                positions with the hash of p are candidates, the longer match wins (ties: the nearer).
+  //   selection  : when the near match is shorter than far_need bytes, a far match of at least far_min bytes that is
+  //                strictly longer replaces it.  A token never straddles a sub-range boundary (that is what lets the
+  //                inflate kernel Huffman-decode 32 sub-ranges of a block in parallel, deflate_common.h).
+  int near_bits = 9;
+  int far_need = 8;
+  int far_min = 4;
+  int lazy = 1;         // 1: a match yields to a strictly longer match starting at the next position of its window
+  int max_dist = kMaxDist;   // the configured window (1 << window_size)
   int huffman = 2;      // 1 fixed only, 2 dynamic (min of stored/fixed/dynamic)
   int block = 65536;    // sub-block size inside a chunk (window restarts at sub-block start)
-  int near_mode = 0;    // 0: nearest lower lane of the window with the same HASH; 1..: same 4-byte WORD at a distance of set #near_mode
-  int lazy = 1;         // 1: a match yields to a strictly longer match starting at the next position of its window
-  int sub_log2 = kSubLog2;  // matches stay inside the 2^sub_log2-byte sub-range of their position and the
-                        // parallel-inflate index is appended (deflate_common.h); 0 = off
+  int sub_log2 = kSubLog2;
 };
 
 struct BitWriter {
@@ -59,9 +66,8 @@ inline uint32_t load32(const uint8_t* d, size_t n, size_t p) {  // zero padded p
   return w;
 }
 
-inline int match_len(const uint8_t* d, int n, int p, int c, int sub_log2 = 0) {
-  int maxl = std::min(kMaxMatch, n - p), l = 0;
-  if (sub_log2) maxl = std::min(maxl, (((p >> sub_log2) + 1) << sub_log2) - p);
+inline int match_len(const uint8_t* d, int p, int c, int maxl) {
+  int l = 0;
   while (l < maxl && d[p + l] == d[c + l]) ++l;
   return l;
 }
@@ -69,74 +75,94 @@ inline int match_len(const uint8_t* d, int n, int p, int c, int sub_log2 = 0) {
 // Tokenise one sub-block d[0..n): tok[p] as in deflate_common.h.
 inline void find_tokens(const uint8_t* d, int n, const Params& P, std::vector<uint32_t>& tok) {
   tok.assign((size_t)n, 0);
-  std::vector<uint32_t> head((size_t)1 << P.hash_bits, 0);
-  std::vector<uint32_t> h(P.step), old(P.step);
-  std::vector<int> near(P.step), adv(P.step), mdist(P.step);
-  std::vector<uint8_t> valid(P.step);
-  int carry = 0;
-  for (int base = 0; base < n; base += P.step) {
-    if (P.sub_log2 && (base & ((1 << P.sub_log2) - 1)) == 0) std::fill(head.begin(), head.end(), 0u);   // per sub-range table
-    for (int t = 0; t < P.step; ++t) {
-      int p = base + t;
-      valid[t] = p + 4 <= n;
-      h[t] = valid[t] ? hash_word(load32(d, (size_t)n, (size_t)p), P.hash_bits, P.min_match) : 0;
-      old[t] = valid[t] ? head[h[t]] : 0;
-      near[t] = -1;
-    }
-    static const int kSets[4][16] = {{0}, {1, 2, 3, 4, 6, 8, 12, 16, 24, 0}, {1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16, 20, 24, 28, 0}, {1, 2, 4, 8, 16, 0}};
-    for (int w0 = 0; w0 < P.step; w0 += 32)
-      for (int l = 1; l < 32 && w0 + l < P.step; ++l) {
-        if (!valid[w0 + l]) continue;
-        if (P.near_mode == 0) {
-          for (int k = l - 1; k >= 0; --k)
-            if (valid[w0 + k] && h[w0 + k] == h[w0 + l]) {
-              near[w0 + l] = base + w0 + k;
-              break;
-            }
-        } else {
-          for (const int* dd = kSets[P.near_mode]; *dd; ++dd)
-            if (*dd <= l && load32(d, (size_t)n, (size_t)(base + w0 + l)) == load32(d, (size_t)n, (size_t)(base + w0 + l - *dd))) {
-              near[w0 + l] = base + w0 + l - *dd;
-              break;
-            }
+  const int SUB = 1 << P.sub_log2;
+  constexpr int kNone = -1;
+  // ---- far pass ----
+  std::vector<int> far((size_t)n, kNone);
+  {
+    const int fb = far_hash_bits((uint32_t)n);
+    std::vector<int> C((size_t)1 << fb, kNone);
+    for (int s0 = 0; s0 < n; s0 += SUB) {
+      const int s1 = std::min(n, s0 + SUB);
+      if (s0)
+        for (int p = s0; p < s1 && p + 4 <= n; ++p) {
+          const uint32_t w = load32(d, (size_t)n, (size_t)p);
+          const int c = C[hash_far(w, fb)];
+          if (c != kNone && p - c <= P.max_dist && load32(d, (size_t)n, (size_t)c) == w) far[(size_t)p] = c;
         }
+      for (int p = s0; p < s1 && p + 4 <= n; ++p) C[hash_far(load32(d, (size_t)n, (size_t)p), fb)] = p;
+    }
+  }
+  // ---- near pass, selection and parse, windows of 32 positions ----
+  std::vector<int> head0((size_t)1 << P.near_bits), head1((size_t)1 << P.near_bits);
+  int carry = 0;
+  for (int base = 0; base < n; base += 32) {
+    if ((base & (SUB - 1)) == 0) {
+      std::fill(head0.begin(), head0.end(), kNone);
+      std::fill(head1.begin(), head1.end(), kNone);
+      carry = base;
+    }
+    const int sub_end = std::min(n, (base & ~(SUB - 1)) + SUB);
+    uint32_t h[32];
+    int adv[32], mdist[32];
+    bool valid[32];
+    int c1[32], c2[32];
+    for (int t = 0; t < 32; ++t) {
+      const int p = base + t;
+      valid[t] = p + 4 <= n;
+      h[t] = valid[t] ? hash_near(load32(d, (size_t)n, (size_t)p), P.near_bits) : 0;
+      c1[t] = c2[t] = kNone;
+      if (!valid[t]) continue;
+      int k1 = -1, k2 = -1;   // the two nearest lower positions of the window with this hash
+      for (int k = t - 1; k >= 0; --k)
+        if (valid[k] && h[k] == h[t]) {
+          if (k1 < 0) k1 = k;
+          else {
+            k2 = k;
+            break;
+          }
+        }
+      if (k1 >= 0) {
+        c1[t] = base + k1;
+        c2[t] = k2 >= 0 ? base + k2 : head0[h[t]];
+      } else {
+        c1[t] = head0[h[t]];
+        c2[t] = head1[h[t]];
       }
-    for (int t = 0; t < P.step; ++t)
-      if (valid[t]) head[h[t]] = std::max(head[h[t]], (uint32_t)(base + t + 1));
-    for (int t = 0; t < P.step; ++t) {
-      int p = base + t;
+    }
+    for (int t = 0; t < 32; ++t)   // the table after this window: the two most recent positions of every hash
+      if (valid[t]) {
+        head1[h[t]] = head0[h[t]];
+        head0[h[t]] = base + t;
+      }
+    for (int t = 0; t < 32; ++t) {
+      const int p = base + t;
       adv[t] = 1;
       mdist[t] = 0;
       if (!valid[t]) continue;
-      int best = 0, bdist = 0;
-      auto consider = [&](int c) {
-        if (c < 0 || p - c > kMaxDist) return;
-        if (P.sub_log2 && (c >> P.sub_log2) != (p >> P.sub_log2)) return;   // other sub-range
-        int l = match_len(d, n, p, c, P.sub_log2);
-        if (l > best) {  // first considered wins ties
-          best = l;
-          bdist = p - c;
-        }
-      };
-      int c_old = old[t] ? (int)old[t] - 1 : -1;
-      if (P.cand_mode == 0) consider(c_old);
-      else if (P.cand_mode == 1) consider(near[t] >= 0 ? near[t] : c_old);
-      else {
-        consider(near[t]);
-        if (c_old != near[t]) consider(c_old);
+      const int maxl = std::min(kMaxMatch, sub_end - p);
+      int best = 0, bc = kNone;
+      if (c1[t] != kNone && p - c1[t] <= P.max_dist) best = match_len(d, p, c1[t], maxl), bc = c1[t];
+      if (c2[t] != kNone && p - c2[t] <= P.max_dist) {
+        const int l = match_len(d, p, c2[t], maxl);
+        if (l > best) best = l, bc = c2[t];
       }
-      if (best >= kMinMatch && !(best == 3 && P.far3 && bdist > P.far3)) {
+      if (best < P.far_need && far[(size_t)p] != kNone) {
+        const int l = match_len(d, p, far[(size_t)p], maxl);
+        if (l >= P.far_min && l > best) best = l, bc = far[(size_t)p];
+      }
+      if (best >= kMinMatch) {
         adv[t] = best;
-        mdist[t] = bdist;
+        mdist[t] = p - bc;
       }
     }
     if (P.lazy)   // decided on the matches as found (not on already reduced neighbours): one pass, in place is fine going up
-      for (int t = 0; t + 1 < P.step; ++t)
-        if (adv[t] > 1 && adv[t + 1] > adv[t] + (P.lazy - 1)) adv[t] = 1, mdist[t] = 0;
-    int lim = std::min(n, base + P.step);
+      for (int t = 0; t + 1 < 32; ++t)
+        if (adv[t] > 1 && adv[t + 1] > adv[t]) adv[t] = 1, mdist[t] = 0;
+    const int lim = std::min(n, base + 32);
     int pos = carry;
     while (pos < lim) {
-      int t = pos - base;
+      const int t = pos - base;
       tok[(size_t)pos] = adv[t] > 1 ? tok_match(adv[t], mdist[t]) : 1u;
       pos += adv[t];
     }

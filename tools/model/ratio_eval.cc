@@ -52,15 +52,13 @@ int main(int argc, char** argv) {
     auto eq = kv.find('=');
     std::string k = kv.substr(0, eq);
     int v = atoi(kv.substr(eq + 1).c_str());
-    if (k == "step") P.step = v;
-    else if (k == "hash_bits") P.hash_bits = v;
-    else if (k == "min_match") P.min_match = v;
-    else if (k == "cand_mode") P.cand_mode = v;
-    else if (k == "far3") P.far3 = v;
+    if (k == "near_bits") P.near_bits = v;
+    else if (k == "far_need") P.far_need = v;
+    else if (k == "far_min") P.far_min = v;
+    else if (k == "max_dist") P.max_dist = v;
     else if (k == "huffman") P.huffman = v;
     else if (k == "block") P.block = v;
     else if (k == "lazy") P.lazy = v;
-    else if (k == "near_mode") P.near_mode = v;
     else if (k == "sub_log2") P.sub_log2 = v;
     else return fprintf(stderr, "unknown key %s\n", k.c_str()), 2;
   }
