@@ -73,12 +73,9 @@ struct QueuePair {
   uint32_t* d_tokens = nullptr;    // deflate token scratch (grid * 64 Ki u32), allocated on first use
   uint16_t* d_far = nullptr;       // deflate far-candidate scratch (grid * 64 Ki u16)
   bitar::xk::Task* d_tasks = nullptr;   // indexed inflate: one task per 64 KiB block
-  uint32_t* d_block_state = nullptr;    //   what phase A left of the block (coded / done / bad)
   size_t tasks_cap = 0;
-  uint8_t* d_units = nullptr;           //   token units between the two phases: `subs` slots per task
+  uint8_t* d_units = nullptr;           //   token units between the two phases: `subs` slots per resident group of lanes
   size_t units_cap = 0;
-  uint16_t* d_unit_cnt = nullptr;       //   units per slot
-  size_t unit_cnt_cap = 0;
   uint32_t* d_generic = nullptr;        // ops left to the whole-stream kernel
   uint32_t* d_indexed = nullptr;        // ops on the two-phase path
   size_t generic_cap = 0;
@@ -700,9 +697,7 @@ int bitar_dev_close(bitar_dev* dev) {
     if (q->d_tokens) cudaFree(q->d_tokens);
     if (q->d_far) cudaFree(q->d_far);
     if (q->d_tasks) cudaFree(q->d_tasks);
-    if (q->d_block_state) cudaFree(q->d_block_state);
     if (q->d_units) cudaFree(q->d_units);
-    if (q->d_unit_cnt) cudaFree(q->d_unit_cnt);
     if (q->d_generic) cudaFree(q->d_generic);
     if (q->d_indexed) cudaFree(q->d_indexed);
     if (q->h_orig) cudaFreeHost(q->h_orig);
@@ -771,6 +766,9 @@ inline uint32_t op_blocks(const bitar_chunk& c) {   // 64 KiB blocks an op's out
 }
 }  // namespace
 
+using TokWide = bitar::xk::TokConfig<9, 864, 7, 256, 16, 32, 2>;    // a warp per 64 KiB block
+using TokSmall = bitar::xk::TokConfig<9, 864, 7, 256, 8, 8, 4>;     // four blocks of at most 8 sub-ranges per warp
+
 int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, bitar_result* results) {
   const int variant = inflate_variant();
   const int ck = dev ? dev->cfg.checksum_type : 0, id = dev ? dev->id : 0, sms = dev ? dev->sm_count : 0;
@@ -791,12 +789,12 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
         // segments of at most 8 sub-ranges (16 KiB) are decoded four to a warp, with as many unit slots as they need
         small_mode = max_cap <= kSmallSubs * bitar::dfl::kSub;
         if (small_mode) subs = max_cap ? (max_cap + bitar::dfl::kSub - 1u) >> bitar::dfl::kSubLog2 : 1u;
-        size_t cap2 = q->tasks_cap;
+        // (staged calls run up to kStageLanes batches side by side: one scratch each)
+        const size_t one = small_mode ? TokSmall::scratch_bytes(id, sms, subs) : TokWide::scratch_bytes(id, sms, subs);
+        if (one == 0) return cudaErrorLaunchOutOfResources;
         cudaError_t e = grow(&q->d_tasks, &q->tasks_cap, total_blocks);
-        if (e == cudaSuccess) e = grow(&q->d_block_state, &cap2, total_blocks);
-        if (e == cudaSuccess) e = grow(&q->d_units, &q->units_cap, total_blocks * subs * (size_t)bitar::tk::kSlotBytes);
-        if (e == cudaSuccess) e = grow(&q->d_unit_cnt, &q->unit_cnt_cap, total_blocks * subs);
-        cap2 = q->generic_cap;
+        if (e == cudaSuccess) e = grow(&q->d_units, &q->units_cap, one * (q->nb > 1 ? kStageLanes : 1u));
+        size_t cap2 = q->generic_cap;
         if (e == cudaSuccess) e = grow(&q->d_generic, &q->generic_cap, (size_t)n_all);
         if (e == cudaSuccess) e = grow(&q->d_indexed, &cap2, (size_t)n_all);
         return e;
@@ -816,21 +814,21 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
         for (uint32_t i = 0; i < first; ++i) before += op_blocks(q->h_ops[i]);
         for (uint32_t i = 0; i < n; ++i) blocks += op_blocks(h_ops[i]);
         Task* const tasks = q->d_tasks + before;
-        uint32_t* const state = q->d_block_state + before;
-        uint8_t* const units = q->d_units + before * subs * (size_t)bitar::tk::kSlotBytes;
-        uint16_t* const unit_cnt = q->d_unit_cnt + before * subs;
+        // the batch's stream decides the scratch: batches on one stream run one after the other
+        uint32_t lane_idx = 0;
+        for (uint32_t k = 0; k < kStageLanes; ++k)
+          if (st == q->lane[k]) lane_idx = k;
+        uint8_t* const units = q->d_units + (q->nb > 1 ? lane_idx : 0u) * (q->units_cap / (q->nb > 1 ? kStageLanes : 1u) / 16u * 16u);
         uint32_t* const generic = q->d_generic + first;
         uint32_t* const indexed = q->d_indexed + first;
         Counters* pc = reinterpret_cast<Counters*>(counters);
         inflate_plan_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_ops, n, d_res, tasks, indexed, generic, pc, 1);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
-        if (small_mode) e = TokConfig<9, 864, 7, 256, 8, 8, 4>::launch(d_ops, d_res, tasks, pc, units, unit_cnt, state, subs, (uint32_t)blocks, id, sms, st);
-        else e = TokConfig<9, 864, 7, 256, 16, 32>::launch(d_ops, d_res, tasks, pc, units, unit_cnt, state, subs, (uint32_t)blocks, id, sms, st);
+        if (small_mode) e = TokSmall::launch(d_ops, d_res, tasks, pc, units, subs, (uint32_t)blocks, id, sms, st);
+        else e = TokWide::launch(d_ops, d_res, tasks, pc, units, subs, (uint32_t)blocks, id, sms, st);
         if (e != cudaSuccess) return e;
-        e = ResolveConfig<8, 1024, 8>::launch(d_ops, d_res, tasks, pc, units, unit_cnt, state, subs, (uint32_t)blocks, id, sms, st);
-        if (e != cudaSuccess) return e;
-        g_launches.fetch_add(3);
+        g_launches.fetch_add(2);
         if (ck != BITAR_CHECKSUM_NONE) {
           inflate_checksum_kernel<<<(n + 3) / 4 < (uint32_t)(8 * sms) ? (n + 3) / 4 : (uint32_t)(8 * sms), 128, 0, st>>>(d_ops, d_res, indexed, pc, ck);
           e = cudaGetLastError();

@@ -110,7 +110,7 @@ struct __align__(16) Smem {
     struct {
       union {
         uint16_t head[kWarps][2][kNearSlots];         // per warp: hash -> the two most recent positions (kNoCand = empty)
-        uint16_t far_tab[kFarTabMax];                 // far pass (before the match phase): hash -> last position + 1 before the sub-range
+        uint32_t far_tab[kFarTabMax];                 // far pass (before the match phase): hash -> last position + 1 before the sub-range
       };
       // pre-shifted token fields (tok_pack): length - 3 -> (length symbol index << 26) | (length - 3);
       // distance - 1 -> distance symbol << 23 through zlib's two-level map d < 256 ? lut[d] : lut[256 + (d >> 7)]
@@ -395,21 +395,13 @@ __device__ void sort_rank(Smem& sm) {
 // far[p] = the last position c before the 2 KiB sub-range of p whose 4 bytes equal those at p (kNoFar when the table's
 // entry for the hash of p is empty, holds other bytes, or lies farther back than max_dist).  The whole CTA takes the
 // sub-ranges in order: look up all positions of the sub-range, barrier, insert them (the largest position of a hash
-// wins, whatever the order: 16-bit compare-and-swap), barrier.  Semantics == the far pass of tools/model/deflate_model.h.
-__device__ __forceinline__ void far_insert(uint16_t* tab, uint32_t h, uint32_t v) {
-  unsigned short old = tab[h];
-  while (old < v) {
-    const unsigned short seen = atomicCAS(reinterpret_cast<unsigned short*>(tab + h), old, (unsigned short)v);
-    if (seen == old) break;
-    old = seen;
-  }
-}
+// wins, whatever the order: atomicMax), barrier.  Semantics == the far pass of tools/model/deflate_model.h.
 __device__ __forceinline__ void far_pass(Smem& sm, uint32_t ds, int n, int max_dist, uint16_t* __restrict__ far, int tid) {
   constexpr int kPer = (int)dfl::kSub / kThreads;     // positions per thread and sub-range
   static_assert(kPer * kThreads == (int)dfl::kSub, "a sub-range is a whole number of passes of the CTA");
   const int fb = dfl::far_hash_bits((uint32_t)n);
-  uint16_t* tab = sm.u.m.far_tab;
-  for (int i = tid; i < (1 << fb) / 2; i += kThreads) reinterpret_cast<uint32_t*>(tab)[i] = 0u;
+  uint32_t* tab = sm.u.m.far_tab;
+  for (int i = tid; i < (1 << fb); i += kThreads) tab[i] = 0u;
   __syncthreads();
   for (int s0 = 0; s0 < n; s0 += (int)dfl::kSub) {
     uint32_t h[kPer];
@@ -432,7 +424,7 @@ __device__ __forceinline__ void far_pass(Smem& sm, uint32_t ds, int n, int max_d
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < kPer; ++k)
-      if (h[k] != 0xFFFFFFFFu) far_insert(tab, h[k], (uint32_t)(s0 + tid + k * kThreads + 1));
+      if (h[k] != 0xFFFFFFFFu) atomicMax(&tab[h[k]], (uint32_t)(s0 + tid + k * kThreads + 1));
     __syncthreads();
   }
   __syncthreads();                                    // far[] (global) and the table's space are handed to the match phase

@@ -298,6 +298,172 @@ struct TokLane {
   }
 };
 
+// ---- phase B: one LANE resolves one block ------------------------------------------------------------------------
+// The units of the block's sub-ranges in stream order: literal bytes and LZ77 copies through a short ring in shared
+// memory that leaves as aligned 16-byte vector stores; matches farther back than the ring read the lane's own earlier
+// output (L1/L2).  The copy chain of a block is serial, so the parallelism of this phase is across blocks: 32 per
+// warp, every lane a state machine of its own (step() = one token).
+template <int RING>
+struct ResolveLane {
+  static_assert(RING >= 128 && (RING & (RING - 1)) == 0, "ring: power of two >= 128");
+  static constexpr uint32_t RM = RING - 1;
+  static constexpr uint32_t kPiece = RING / 2;   // bytes copied between two flushes (<= RING - 16 - 19)
+  enum : uint32_t { kIdle = 0, kRun = 1, kBad = 2 };
+
+  sptr ring_s;
+  const uint16_t* up;        // next unit of the current sub-range
+  uint32_t urem;             // units left in it
+  const uint8_t* slots;      // the block's unit slots (kSlotBytes each)
+  const uint16_t* cnts;      // units per slot
+  uint32_t s, ns;            // next sub-range, sub-ranges of the block
+  // output: "virtual" positions v = offset + (dst & 15), so that v % 16 == address % 16
+  uint8_t* vbase;
+  uint32_t vstart, vpos, vflushed, vcap;
+  uint32_t state;
+
+  BITAR_HD void bind(uint8_t* ring_) {
+    ring_s = fl::sp_of(ring_);
+    up = nullptr;
+    slots = nullptr;
+    cnts = nullptr;
+    vbase = nullptr;
+    urem = s = ns = vstart = vpos = vflushed = vcap = 0;
+    state = kIdle;
+  }
+  BITAR_HD void start_block(uint8_t* dst, uint32_t len, const uint8_t* slots_, const uint16_t* cnts_, uint32_t n_subs) {
+    const uint32_t mis = (uint32_t)((uintptr_t)dst & 15u);
+    vbase = dst - mis;
+    vstart = vpos = vflushed = mis;
+    vcap = mis + len;
+    slots = slots_;
+    cnts = cnts_;
+    s = 0;
+    ns = n_subs;
+    urem = 0;
+    state = kRun;
+  }
+  BITAR_HD static uint32_t ld_unit(const uint16_t* p) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__ldg(p);
+#else
+    return *p;
+#endif
+  }
+  BITAR_HD void emit(uint32_t byte) {
+    fl::s_st8(ring_s + (vpos & RM), byte);
+    vpos++;
+  }
+  // Store every complete 16-byte vector below vpos (and the unaligned head of the block).
+  BITAR_HD void flush() {
+    while (vpos - vflushed >= 16u || ((vflushed & 15u) && vpos >= ((vflushed + 15u) & ~15u))) {
+      if (vflushed & 15u) {
+        const uint32_t a = (vflushed + 15u) & ~15u;
+        for (uint32_t v = vflushed; v < a; ++v) vbase[v] = (uint8_t)fl::s_ld8(ring_s + (v & RM));
+        vflushed = a;
+        continue;
+      }
+      uint32_t w0, w1, w2, w3;
+      fl::s_ld128(ring_s + (vflushed & RM), w0, w1, w2, w3);
+#if defined(__CUDA_ARCH__)
+      *reinterpret_cast<uint4*>(vbase + vflushed) = make_uint4(w0, w1, w2, w3);
+#else
+      uint32_t* o32 = reinterpret_cast<uint32_t*>(vbase + vflushed);
+      o32[0] = w0; o32[1] = w1; o32[2] = w2; o32[3] = w3;
+#endif
+      vflushed += 16u;
+    }
+  }
+  BITAR_HD void finish() {
+    flush();
+    for (uint32_t v = vflushed; v < vpos; ++v) vbase[v] = (uint8_t)fl::s_ld8(ring_s + (v & RM));
+    vflushed = vpos;
+  }
+  // LZ77 copy (1 <= dist <= vpos - vstart, vpos + len <= vcap), in pieces that fit the ring
+  BITAR_HD void copy(uint32_t len, uint32_t dist) {
+    for (;;) {
+      const uint32_t piece = len < kPiece ? len : kPiece;
+      const uint32_t src = vpos - dist;
+      uint32_t j = 0;
+      if (dist < (uint32_t)RING) {           // the source is still in the ring
+        if (dist >= 4u) {
+          for (; j + 4u <= piece; j += 4u) {
+            const uint32_t b0 = fl::s_ld8(ring_s + ((src + j) & RM)), b1 = fl::s_ld8(ring_s + ((src + j + 1u) & RM));
+            const uint32_t b2 = fl::s_ld8(ring_s + ((src + j + 2u) & RM)), b3 = fl::s_ld8(ring_s + ((src + j + 3u) & RM));
+            fl::s_st8(ring_s + ((vpos + j) & RM), b0);
+            fl::s_st8(ring_s + ((vpos + j + 1u) & RM), b1);
+            fl::s_st8(ring_s + ((vpos + j + 2u) & RM), b2);
+            fl::s_st8(ring_s + ((vpos + j + 3u) & RM), b3);
+          }
+        }
+        for (; j < piece; ++j) fl::s_st8(ring_s + ((vpos + j) & RM), fl::s_ld8(ring_s + ((src + j) & RM)));
+      } else {                               // flushed long ago: dist >= RING, so src + piece <= vflushed
+        const uint8_t* g = vbase + src;
+        for (; j + 4u <= piece; j += 4u) {
+          const uint32_t b0 = g[j], b1 = g[j + 1u], b2 = g[j + 2u], b3 = g[j + 3u];
+          fl::s_st8(ring_s + ((vpos + j) & RM), b0);
+          fl::s_st8(ring_s + ((vpos + j + 1u) & RM), b1);
+          fl::s_st8(ring_s + ((vpos + j + 2u) & RM), b2);
+          fl::s_st8(ring_s + ((vpos + j + 3u) & RM), b3);
+        }
+        for (; j < piece; ++j) fl::s_st8(ring_s + ((vpos + j) & RM), g[j]);
+      }
+      vpos += piece;
+      len -= piece;
+      if (len == 0) return;
+      flush();
+    }
+  }
+  // the next sub-range's units, or the end of the block
+  BITAR_HD void next_slot() {
+    if (s < ns) {
+      up = reinterpret_cast<const uint16_t*>(slots + (size_t)s * kSlotBytes);
+      urem = cnts[s];
+      if (urem > kSlotUnits) state = kBad;
+      ++s;
+      return;
+    }
+    if (vpos != vcap) {
+      state = kBad;
+      return;
+    }
+    finish();
+    state = kIdle;
+  }
+  // one token
+  BITAR_HD void step() {
+    if (state != kRun) return;
+    if (urem == 0) {
+      next_slot();
+      return;
+    }
+    const uint32_t u = ld_unit(up);
+    ++up;
+    --urem;
+    if (u < 0x100u) {
+      if (vpos >= vcap) {
+        state = kBad;
+        return;
+      }
+      emit(u);
+    } else if (u & kUnitHead) {
+      const uint32_t len = (u & 0xFFu) + 3u;
+      if (urem == 0) {
+        state = kBad;
+        return;
+      }
+      const uint32_t dist = ld_unit(up) + 1u;
+      ++up;
+      --urem;
+      if (dist > vpos - vstart || vpos + len > vcap) {   // (phase A checked both against the block)
+        state = kBad;
+        return;
+      }
+      copy(len, dist);
+    }
+    if (vpos - vflushed >= 16u) flush();
+  }
+};
+
 // Phase B stated serially (host tests, and the definition the kernel is checked against): resolve the units of one
 // sub-range into out[pos ..]; `base` = first byte of the block.  Returns the new position, or 0xFFFFFFFF on a unit
 // sequence that phase A cannot have produced.

@@ -4,17 +4,19 @@
 //   plan kernel     one thread per op: finds the index at the end of the buffer (fl::parse_index), turns every
 //                   64 KiB block of an indexed chunk into a TASK and sends everything else (zlib streams, stored-only
 //                   chunks, tiny chunks) to the whole-stream kernel (inflate_kernel.cuh).
-//   phase A (tok)   persistent CTAs, one task per WARP at a time, fetched from a global counter:
-//                     1. all lanes parse the block header together (same bits, same registers),
+//   inflate kernel  persistent CTAs, one task per WARP at a time, fetched from a global counter; two phases per block:
+//   phase A (tok)     1. all lanes parse the block header together (same bits, same registers),
 //                     2. the warp builds the two decode tables cooperatively in its shared memory,
 //                     3. lane s Huffman-decodes sub-range s (2 KiB of output) from its indexed bit offset into token
-//                        units (tk::TokLane, inflate_tok.h) and checks that it ends exactly at the next offset.
+//                        units (tk::TokLane, inflate_tok.h) in the warp's own scratch (L2 resident, reused per block)
+//                        and checks that it ends exactly at the next offset.
 //                   A block offers 32 independent symbol chains instead of one.  Stored blocks are copied here.
-//   phase B (res)   persistent CTAs, one task per GROUP of 8 lanes: the block's units in stream order -- literal bytes
-//                   and LZ77 copies through a 1 KiB ring in shared memory (sources farther back come from the block's
-//                   own flushed output), leaving as aligned 16-byte vector stores.  The copy chain of a block is
-//                   serial, so this phase lives on many blocks in flight (four per warp) and few instructions per
-//                   token.
+//   phase B (res)   the same warp takes the block's units in stream order, 32 at a time (one per lane: prefix sum of the
+//                   token lengths, literal bytes stored at once, LZ77 copies one match after the other with the lanes
+//                   as bytes) through a 4 KiB ring in shared memory -- the space of the tables, which are done with;
+//                   sources farther back come from the block's own flushed output; the ring leaves as aligned
+//                   16-byte vector stores, 512 bytes per flush.  The copy chain of a block is serial: this phase lives
+//                   on few instructions per token and on the other warps of the SM being in phase A meanwhile.
 //   checksum        (only when configured) one warp per indexed op over the finished output.
 //
 // Replaces: rte_compressdev decompress ops assembled at /root/reference/src/memory.cc:432-505 and executed
@@ -41,8 +43,6 @@ struct Counters {
   unsigned int n_indexed, res_next, ck_next, pad;
 };
 constexpr uint32_t kSmallSubs = 8;
-// block state left by phase A for phase B
-constexpr uint32_t kBlockCoded = 0, kBlockDone = 1, kBlockBad = 2;
 
 __global__ void __launch_bounds__(128)
     inflate_plan_kernel(const bitar_chunk* __restrict__ ops, uint32_t n_ops, bitar_result* __restrict__ results,
@@ -182,22 +182,182 @@ __device__ __forceinline__ uint32_t warp_build_table(const uint8_t* lens, int n,
   return fl::kStatusOk;
 }
 
+// ---- phase B ------------------------------------------------------------------------------------------
+// One group of G lanes resolves one block right after decoding it: the units of its sub-ranges in stream order, G at a
+// time (one per lane): prefix sum of the token lengths, literal bytes stored at once, LZ77 copies one match after the
+// other with the lanes as bytes.  Positions are "virtual" (offset in the block + (address of the block & 15)), so that
+// multiples of 16 are 16-byte aligned addresses.
+// CTA-shared constants: lane % d and the largest multiple of d that fits the group, for copies whose source overlaps them.
+struct ResolveLut {
+  uint8_t mod[32][32];   // [d][lane]
+  uint8_t per32[32];     // [d] for a group of 32 lanes
+  uint8_t per8[32];      //     ... of 8 lanes
+};
+__device__ __forceinline__ void resolve_lut_init(ResolveLut* lut) {
+  for (unsigned i = threadIdx.x; i < 1024u; i += blockDim.x) lut->mod[i >> 5][i & 31u] = (uint8_t)((i >> 5) ? (i & 31u) % (i >> 5) : 0u);
+  if (threadIdx.x < 32u) {
+    const unsigned d = threadIdx.x ? threadIdx.x : 1u;
+    lut->per32[threadIdx.x] = (uint8_t)(32u - 32u % d);
+    lut->per8[threadIdx.x] = (uint8_t)(d <= 8u ? 8u - 8u % d : 8u);
+  }
+}
+// shared-memory accesses by 32-bit shared address (device only)
+__device__ __forceinline__ uint32_t r_ld8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void r_st8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ uint4 r_ld128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+
+template <int G, int RING>
+struct ResolveGroup {
+  static_assert(RING >= 2048 && (RING & (RING - 1)) == 0, "ring: power of two");
+  static constexpr uint32_t RM = RING - 1;
+  static constexpr uint32_t kPartMax = 4u * 258u + 8u;          // bytes 8 units can produce: the most written ahead of a match
+  static constexpr uint32_t kFlush = 16u * G;                   // one vector per lane
+  static constexpr uint32_t kNear = RING - kPartMax - 258u - 32u;   // matches at most this far back find their source in the ring
+  uint32_t ring_s;          // shared address of the group's ring (followed by 16 match records of 8 bytes when G == 32)
+  uint32_t lut_s;           // shared address of the CTA's ResolveLut
+  uint8_t* vbase;           // block address - mis
+  uint32_t flushed;         // virtual position below which everything is in global memory
+  unsigned gmask;
+  int gl;
+
+  // store the complete 16-byte vectors below `upto` (all bytes below are final), and the unaligned head of the block
+  __device__ __forceinline__ void flush(uint32_t upto) {
+    if (flushed & 15u) {
+      const uint32_t a = (flushed + 15u) & ~15u;
+      if (upto < a) return;
+      for (uint32_t v = flushed + (uint32_t)gl; v < a; v += G) vbase[v] = (uint8_t)r_ld8(ring_s + (v & RM));
+      flushed = a;
+    }
+    const uint32_t end = upto & ~15u;
+    for (uint32_t v = flushed + 16u * (uint32_t)gl; v < end; v += kFlush) *reinterpret_cast<uint4*>(vbase + v) = r_ld128(ring_s + (v & RM));
+    if (end > flushed) flushed = end;
+    __syncwarp(gmask);      // the stores are ordered before later reads of the group (far sources)
+  }
+  __device__ __forceinline__ void finish(uint32_t upto) {
+    flush(upto);
+    for (uint32_t v = flushed + (uint32_t)gl; v < upto; v += G) vbase[v] = (uint8_t)r_ld8(ring_s + (v & RM));
+    flushed = upto;
+    __syncwarp(gmask);
+  }
+
+  // out[dst .. dst + len) = out[dst - dist ..]; everything below dst is final.  All arguments are uniform in the group,
+  // so the branches do not diverge.
+  __device__ __forceinline__ void copy(uint32_t dst, uint32_t len, uint32_t dist) {
+    const uint32_t lane_u = (uint32_t)gl;
+    const uint32_t dp = dst + lane_u, sp = dp - dist;
+    if (dist >= len || dist >= (uint32_t)G) {
+      if (dist <= kNear) {
+        if (lane_u < len) r_st8(ring_s + (dp & RM), r_ld8(ring_s + (sp & RM)));
+        for (uint32_t k = G; k < len; k += G) {             // a match longer than a pass of the group
+          __syncwarp(gmask);                                  // (this pass may read what the last one wrote: dist < 2 G)
+          if (k + lane_u < len) r_st8(ring_s + ((dp + k) & RM), r_ld8(ring_s + ((sp + k) & RM)));
+        }
+      } else {
+        // flushed long ago: dist > kNear, so the source ends below `flushed`
+        for (uint32_t k = lane_u; k < len; k += G) r_st8(ring_s + ((dst + k) & RM), (uint32_t)__ldcg(vbase + (dst - dist) + k));
+      }
+    } else {
+      // the source overlaps the copy and repeats inside one pass: every lane keeps its byte, a pass writes a whole
+      // number of periods
+      const uint32_t r = r_ld8(lut_s + dist * 32u + lane_u);
+      const uint32_t per = r_ld8(lut_s + 1024u + (G == 32 ? 0u : 32u) + dist);
+      const uint32_t byte = r_ld8(ring_s + ((dst - dist + r) & RM));
+      if (lane_u < per)
+        for (uint32_t k = lane_u; k < len; k += per) r_st8(ring_s + ((dst + k) & RM), byte);
+    }
+    __syncwarp(gmask);
+  }
+
+  // The units of one sub-range (n_units of them, a multiple of 8, at `units`) from virtual position `pos`; returns the
+  // new position, or 0xFFFFFFFF when the units do not add up to `sub_limit` (they always do when phase A succeeded).
+  __device__ __forceinline__ uint32_t resolve(const uint16_t* units, uint32_t n_units, uint32_t pos, uint32_t sub_limit) {
+    const int wlane = (int)(threadIdx.x & 31u);
+    const int gbase = wlane - gl;
+    // two groups of units in flight ahead of the one being resolved (ld.cg: the scratch is rewritten for every block)
+    uint32_t u0 = (uint32_t)gl < n_units ? __ldcg(units + gl) : tk::kUnitNop;
+    uint32_t u1 = (uint32_t)(G + gl) < n_units ? __ldcg(units + G + gl) : tk::kUnitNop;
+    for (uint32_t i = 0; i < n_units; i += G) {
+      const uint32_t u = u0;
+      u0 = u1;
+      u1 = i + 2u * G + (uint32_t)gl < n_units ? __ldcg(units + i + 2u * G + (uint32_t)gl) : tk::kUnitNop;
+      const bool is_head = (u & tk::kUnitHead) != 0u;
+      const unsigned hm = __ballot_sync(gmask, is_head);
+      const bool is_cont = gl > 0 && ((hm >> (wlane - 1)) & 1u);
+      const bool is_lit = !is_head && !is_cont && u < 0x100u;
+      const uint32_t olen = is_lit ? 1u : is_head ? (u & 0xFFu) + 3u : 0u;
+      uint32_t incl = olen;
+#pragma unroll
+      for (int d = 1; d < G; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(gmask, incl, d, G);
+        if (gl >= d) incl += v;
+      }
+      const uint32_t total = __shfl_sync(gmask, incl, G - 1, G);
+      if (pos + total > sub_limit) return 0xFFFFFFFFu;
+      const uint32_t my = pos + incl - olen;            // where this lane's token starts
+      // groups of 8 units are resolved together when the G units produce more than fits ahead of a match in the ring
+      const int parts = G > 8 && total > kPartMax ? G / 8 : 1;
+      for (int part = 0; part < parts; ++part) {
+        const bool mine = parts == 1 || (gl >> 3) == part;
+        if (is_lit && mine) r_st8(ring_s + (my & RM), u);
+        unsigned heads = (hm >> gbase) & (G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u));
+        if (parts > 1) heads &= 0xFFu << (8 * part);
+        if (G == 32) {
+          // the heads leave their (start, length, distance) in shared memory in stream order: a match is then one
+          // broadcast read away for the whole warp
+          const uint32_t rec_s = ring_s + (uint32_t)RING;
+          const int nh = __popc(heads);
+          const uint32_t next_u = __shfl_down_sync(gmask, u, 1, G);          // a head's distance sits in the next lane
+          if (is_head && mine) {
+            const uint32_t rank = (uint32_t)__popc(heads & ((1u << gl) - 1u));
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(rec_s + 8u * rank), "r"(my | (olen << 20)), "r"(next_u + 1u) : "memory");
+          }
+          __syncwarp(gmask);
+          for (int t = 0; t < nh; ++t) {
+            uint32_t w0, dist;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(dist) : "r"(rec_s + 8u * (uint32_t)t) : "memory");
+            copy(w0 & 0xFFFFFu, w0 >> 20, dist);
+          }
+        } else {
+          __syncwarp(gmask);
+          while (heads) {
+            const int h = __ffs((int)heads) - 1;
+            heads &= heads - 1u;
+            const uint32_t len = __shfl_sync(gmask, olen, h, G);
+            const uint32_t dist = __shfl_sync(gmask, u, h + 1, G) + 1u;
+            const uint32_t dst = __shfl_sync(gmask, my, h, G);
+            copy(dst, len, dist);
+            if (dst + len - flushed >= 2u * kFlush) flush(dst + len);
+          }
+        }
+        if (parts > 1) flush(pos + __shfl_sync(gmask, incl, 8 * part + 7, G));   // everything up to the end of this part is final
+      }
+      pos += total;
+      if (pos - flushed >= kFlush) flush(pos);
+    }
+    return pos == sub_limit ? pos : 0xFFFFFFFFu;
+  }
+};
+
 // ---- phase A ------------------------------------------------------------------------------------------
 // GROUP = 32: a warp per block (up to 32 sub-ranges).  GROUP = 8: four blocks of at most 8 sub-ranges per warp
 // (small segments), each with its own tables; the groups of a warp run the same code on their own tasks and only
-// ever synchronise among their own lanes.  Task t owns `subs` slots of the unit scratch (tk::kSlotBytes each), `subs`
-// entries of the unit-count array and one block-state word.
+// ever synchronise among their own lanes.  Every group owns `subs` slots of the unit scratch (tk::kSlotBytes each).
 template <int LBITS, int LT, int DBITS, int DT, int WARPS, int GROUP, int MIN_CTAS>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
     inflate_tok_kernel(const bitar_chunk* __restrict__ ops, bitar_result* __restrict__ results, const Task* __restrict__ tasks,
-                       Counters* __restrict__ pc, uint8_t* __restrict__ scratch, uint16_t* __restrict__ unit_cnt,
-                       uint32_t* __restrict__ block_state, uint32_t subs) {
+                       Counters* __restrict__ pc, uint8_t* scratch, uint32_t subs) {
   using Lane = tk::TokLane<LBITS, LT, DBITS, DT, 16>;
   using WS = WarpSmem<LT, DT, 16, GROUP>;
   constexpr int kGroupsPerWarp = 32 / GROUP;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint32_t* dinfo = reinterpret_cast<uint32_t*>(smem_raw + (size_t)WARPS * kGroupsPerWarp * sizeof(WS));
+  ResolveLut* lut = reinterpret_cast<ResolveLut*>(dinfo + 32);
   if (threadIdx.x < 32) dinfo[threadIdx.x] = fl::dist_info((int)threadIdx.x);
+  resolve_lut_init(lut);
   __syncthreads();
 
   const int wlane = (int)(threadIdx.x & 31u);
@@ -207,6 +367,16 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
   WS& ws = *reinterpret_cast<WS*>(smem_raw + (size_t)((threadIdx.x >> 5) * kGroupsPerWarp + gbase / GROUP) * sizeof(WS));
   Lane L;
   L.bind(ws.lt, ws.dt, ws.ring + lane * WS::kRingStride, dinfo, &ws.sc);
+  // phase B: the group's ring takes the space of the tables and unit rings once phase A is done with them
+  constexpr int kRing = GROUP == 32 ? 4096 : 2048;
+  static_assert(sizeof(WS) >= (size_t)kRing + (GROUP == 32 ? 128u : 0u), "the resolve ring (+ match records) borrows the group's phase-A space");
+  ResolveGroup<GROUP, kRing> R;
+  R.gl = lane;
+  R.gmask = kFull;
+  R.ring_s = (uint32_t)__cvta_generic_to_shared(&ws);
+  R.lut_s = (uint32_t)__cvta_generic_to_shared(lut);
+  // the group's unit scratch: `subs` slots, rewritten for every block
+  uint8_t* const slots = scratch + ((size_t)(blockIdx.x * WARPS + (threadIdx.x >> 5)) * kGroupsPerWarp + gbase / GROUP) * subs * tk::kSlotBytes;
   const uint32_t n_tasks = pc->n_tasks;
 
   for (;;) {
@@ -328,193 +498,31 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
             const uint32_t len = min(dfl::kSub, blen - s * dfl::kSub);
             if (!fl::index_sub_bits(ix, b, s, ns, bb, &sbit, &ebit)) L.status = fl::kStatusDataError;
             else
-              L.start_sub(src, ix.stream_bytes, sbit, ebit, s + 1u == ns, scratch + ((size_t)t * subs + s) * tk::kSlotBytes, len,
-                          s * dfl::kSub);
+              L.start_sub(src, ix.stream_bytes, sbit, ebit, s + 1u == ns, slots + (size_t)s * tk::kSlotBytes, len, s * dfl::kSub);
           }
           while (L.state != Lane::kDone) L.step();
           status = L.status;
-          if ((uint32_t)lane < subs) unit_cnt[(size_t)t * subs + (uint32_t)lane] = (uint16_t)((uint32_t)lane < ns ? L.units() : 0u);
+          // ---- phase B: the block's units in stream order ----
+          const uint32_t my_units = (uint32_t)lane < ns ? L.units() : 0u;
+          if (!__any_sync(kFull, status != fl::kStatusOk)) {   // (also orders the unit stores before the loads below)
+            const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);
+            R.vbase = out - mis;
+            R.flushed = mis;
+            uint32_t pos = mis;
+            for (uint32_t s = 0; s < ns; ++s) {
+              const uint32_t nu = __shfl_sync(kFull, my_units, (int)s, GROUP);
+              pos = R.resolve(reinterpret_cast<const uint16_t*>(slots + (size_t)s * tk::kSlotBytes), nu, pos, mis + min(blen, (s + 1u) * dfl::kSub));
+              if (pos == 0xFFFFFFFFu) break;
+            }
+            if (pos == 0xFFFFFFFFu) status = fl::kStatusDataError;
+            else R.finish(pos);
+          }
+          __syncwarp(kFull);   // the ring's space goes back to phase A
         }
       }
     }
-    // the block's state for phase B: any lane's failure fails the block (and the op)
-    const bool bad = __any_sync(kFull, status != fl::kStatusOk);
-    if (status != fl::kStatusOk) atomicMax(&results[tk_.op].status, status);
-    if (lane == 0) block_state[t] = bad ? kBlockBad : type == 0u ? kBlockDone : kBlockCoded;
+    if (status != fl::kStatusOk) atomicMax(&results[tk_.op].status, status);   // any lane's failure fails the op
     __syncwarp(kFull);
-  }
-}
-
-// ---- phase B ------------------------------------------------------------------------------------------
-// One group of G lanes resolves one block: the units of its sub-ranges in order.  Positions are "virtual"
-// (offset in the block + (address of the block & 15)), so that multiples of 16 are 16-byte aligned addresses.
-// shared-memory accesses by 32-bit shared address (device only)
-__device__ __forceinline__ uint32_t r_ld8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ void r_st8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v)); }
-__device__ __forceinline__ uint4 r_ld128(uint32_t a) {
-  uint4 v;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-  return v;
-}
-
-template <int G, int RING>
-struct ResolveGroup {
-  static_assert(RING >= 1024 && (RING & (RING - 1)) == 0, "ring: power of two, a longest match + a flush unit + slack");
-  static constexpr uint32_t RM = RING - 1;
-  static constexpr uint32_t kNear = RING - 258 - 160;   // matches at most this far back find their source in the ring
-  uint32_t ring_s;          // shared address of the group's ring
-  uint8_t* vbase;           // block address - mis
-  uint32_t flushed;         // virtual position below which everything is in global memory
-  unsigned gmask;
-  int gl, gbase;
-
-  // store every complete 16-byte vector below `upto` (all bytes below are final), and the unaligned head of the block
-  __device__ __forceinline__ void flush(uint32_t upto) {
-    if (flushed & 15u) {
-      const uint32_t a = (flushed + 15u) & ~15u;
-      if (upto < a) return;
-      for (uint32_t v = flushed + (uint32_t)gl; v < a; v += G) vbase[v] = (uint8_t)r_ld8(ring_s + (v & RM));
-      flushed = a;
-    }
-    const uint32_t end = upto & ~15u;
-    for (uint32_t v = flushed + 16u * (uint32_t)gl; v < end; v += 16u * G) {
-      *reinterpret_cast<uint4*>(vbase + v) = r_ld128(ring_s + (v & RM));
-    }
-    if (end > flushed) flushed = end;
-    __syncwarp(gmask);      // the stores are ordered before later reads of the group (far sources)
-  }
-  __device__ __forceinline__ void finish(uint32_t upto) {
-    flush(upto);
-    for (uint32_t v = flushed + (uint32_t)gl; v < upto; v += G) vbase[v] = (uint8_t)r_ld8(ring_s + (v & RM));
-    flushed = upto;
-    __syncwarp(gmask);
-  }
-
-  // out[dst .. dst + len) = out[dst - dist ..]; everything below dst is final
-  __device__ __forceinline__ void copy(uint32_t dst, uint32_t len, uint32_t dist) {
-    if (dist < (uint32_t)G) {
-      // the pattern repeats inside one pass of the group: every lane keeps its byte, a pass writes a whole number of periods
-      uint32_t r = (uint32_t)gl;
-      while (r >= dist) r -= dist;
-      const uint32_t byte = r_ld8(ring_s + ((dst - dist + r) & RM));
-      uint32_t per = (uint32_t)G;
-      {
-        uint32_t g = (uint32_t)G;
-        while (g >= dist) g -= dist;
-        per -= g;                                      // the largest multiple of dist that fits G
-      }
-      __syncwarp(gmask);
-      for (uint32_t k = (uint32_t)gl; k < len; k += per)
-        if ((uint32_t)gl < per) r_st8(ring_s + ((dst + k) & RM), byte);
-    } else if (dist <= kNear) {
-      for (uint32_t k = (uint32_t)gl; k < len + (uint32_t)gl; k += G) {   // (same trip count for every lane of the group)
-        uint32_t byte = 0;
-        if (k < len) byte = r_ld8(ring_s + ((dst - dist + k) & RM));
-        __syncwarp(gmask);
-        if (k < len) r_st8(ring_s + ((dst + k) & RM), byte);
-        __syncwarp(gmask);                             // a pass may read what the previous pass wrote (dist < 2 G)
-      }
-    } else {
-      // flushed long ago: dist > kNear, so the source ends below `flushed` (at most 143 bytes are pending)
-      const uint8_t* g = vbase + (dst - dist);
-      for (uint32_t k = (uint32_t)gl; k < len; k += G) r_st8(ring_s + ((dst + k) & RM), __ldcg(g + k));
-    }
-    __syncwarp(gmask);
-  }
-};
-
-template <int G, int RING, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
-    inflate_resolve_kernel(const bitar_chunk* __restrict__ ops, bitar_result* __restrict__ results, const Task* __restrict__ tasks,
-                           Counters* __restrict__ pc, const uint8_t* __restrict__ scratch, const uint16_t* __restrict__ unit_cnt,
-                           const uint32_t* __restrict__ block_state, uint32_t subs) {
-  constexpr int kGroupsPerWarp = 32 / G;
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int wlane = (int)(threadIdx.x & 31u);
-  ResolveGroup<G, RING> R;
-  R.gl = wlane % G;
-  R.gbase = wlane - R.gl;
-  R.gmask = G == 32 ? 0xFFFFFFFFu : (((1u << G) - 1u) << R.gbase);
-  R.ring_s = (uint32_t)__cvta_generic_to_shared(smem_raw + (size_t)((threadIdx.x >> 5) * kGroupsPerWarp + R.gbase / G) * RING);
-  const uint32_t n_tasks = pc->n_tasks;
-  const unsigned below = (1u << wlane) - 1u;
-  (void)below;
-
-  for (;;) {
-    uint32_t t = 0;
-    if (R.gl == 0) t = atomicAdd(&pc->res_next, 1u);
-    t = __shfl_sync(R.gmask, t, R.gbase);
-    if (t >= n_tasks) break;
-    if (block_state[t] != kBlockCoded) continue;
-    const Task tk_ = tasks[t];
-    const bitar_chunk op = ops[tk_.op];
-    const uint32_t total_out = results[tk_.op].produced;
-    const uint32_t blen = min(65536u, total_out - (tk_.block << 16)), ns = dfl::idx_subs(blen);
-    uint8_t* out = static_cast<uint8_t*>(op.dst) + ((size_t)tk_.block << 16);
-    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);
-    R.vbase = out - mis;
-    R.flushed = mis;
-    uint32_t pos = mis;                               // next byte to produce (virtual)
-    bool ok = true;
-    for (uint32_t s = 0; s < ns && ok; ++s) {
-      const uint32_t n_units = unit_cnt[(size_t)t * subs + s];
-      const uint16_t* units = reinterpret_cast<const uint16_t*>(scratch + ((size_t)t * subs + s) * tk::kSlotBytes);
-      const uint32_t sub_limit = mis + min(blen, (s + 1u) * dfl::kSub);
-      // two groups of units in flight ahead of the one being resolved
-      uint32_t u0 = (uint32_t)R.gl < n_units ? units[R.gl] : tk::kUnitNop;
-      uint32_t u1 = (uint32_t)(G + R.gl) < n_units ? units[G + R.gl] : tk::kUnitNop;
-      for (uint32_t i = 0; i < n_units; i += G) {
-        const uint32_t u = u0;
-        u0 = u1;
-        u1 = i + 2u * G + (uint32_t)R.gl < n_units ? units[i + 2u * G + (uint32_t)R.gl] : tk::kUnitNop;
-        const bool is_head = (u & tk::kUnitHead) != 0u;
-        const unsigned hm = __ballot_sync(R.gmask, is_head);
-        const bool is_cont = R.gl > 0 && ((hm >> (wlane - 1)) & 1u);
-        const bool is_lit = !is_head && !is_cont && u < 0x100u;
-        const uint32_t olen = is_lit ? 1u : is_head ? (u & 0xFFu) + 3u : 0u;
-        uint32_t incl = olen;
-#pragma unroll
-        for (int d = 1; d < G; d <<= 1) {
-          const uint32_t v = __shfl_up_sync(R.gmask, incl, d, G);
-          if (R.gl >= d) incl += v;
-        }
-        const uint32_t total = __shfl_sync(R.gmask, incl, G - 1, G);
-        const uint32_t my = pos + incl - olen;        // where this lane's token starts
-        if (pos + total > sub_limit) {                // cannot happen with units phase A wrote for this sub-range
-          ok = false;
-          break;
-        }
-        unsigned heads = (hm >> R.gbase) & ((G == 32) ? 0xFFFFFFFFu : ((1u << G) - 1u));
-        bool lit_pending = is_lit;
-        while (heads) {
-          const int h = __ffs((int)heads) - 1;
-          heads &= heads - 1u;
-          if (lit_pending && R.gl < h) {              // the literals before this match
-            r_st8(R.ring_s + (my & R.RM), u);
-            lit_pending = false;
-          }
-          const uint32_t len = __shfl_sync(R.gmask, olen, h, G);
-          const uint32_t dist = __shfl_sync(R.gmask, u, h + 1, G) + 1u;
-          const uint32_t dst = __shfl_sync(R.gmask, my, h, G);
-          __syncwarp(R.gmask);
-          if (dist > dst - mis) {                     // (phase A checked this against the block start)
-            ok = false;
-            break;
-          }
-          R.copy(dst, len, dist);
-          if (dst + len - R.flushed >= 128u) R.flush(dst + len);
-        }
-        if (!ok) break;
-        if (lit_pending) r_st8(R.ring_s + (my & R.RM), u);
-        __syncwarp(R.gmask);
-        pos += total;
-        if (pos - R.flushed >= 128u) R.flush(pos);
-      }
-      if (ok && pos != sub_limit) ok = false;
-    }
-    if (ok) R.finish(pos);
-    else if (R.gl == 0) atomicMax(&results[tk_.op].status, (uint32_t)BITAR_OP_DATA_ERROR);
-    __syncwarp(R.gmask);
   }
 }
 
@@ -545,7 +553,7 @@ __global__ void __launch_bounds__(128)
 template <int LBITS, int LT, int DBITS, int DT, int WARPS, int GROUP = 32, int MIN_CTAS = 2>
 struct TokConfig {
   static constexpr int kThreads = WARPS * 32;
-  static constexpr size_t kSmem = (size_t)WARPS * (32 / GROUP) * sizeof(WarpSmem<LT, DT, 16, GROUP>) + 32 * sizeof(uint32_t);
+  static constexpr size_t kSmem = (size_t)WARPS * (32 / GROUP) * sizeof(WarpSmem<LT, DT, 16, GROUP>) + 32 * sizeof(uint32_t) + sizeof(ResolveLut);
   static int ctas_per_sm(int device) {
     static int per_device[64] = {0};
     int& c = per_device[device & 63];
@@ -557,10 +565,13 @@ struct TokConfig {
     }
     return c;
   }
+  // bytes of unit scratch the largest grid needs: `subs` slots per group
+  static size_t scratch_bytes(int device, int sm_count, uint32_t subs) {
+    return (size_t)sm_count * (size_t)ctas_per_sm(device) * WARPS * (32 / GROUP) * subs * tk::kSlotBytes;
+  }
   // n_tasks_max: upper bound of the task count (the real count lives on the device)
-  static cudaError_t launch(const bitar_chunk* ops, bitar_result* res, const Task* tasks, Counters* pc, uint8_t* scratch,
-                            uint16_t* unit_cnt, uint32_t* block_state, uint32_t subs, uint32_t n_tasks_max, int device, int sm_count,
-                            cudaStream_t stream) {
+  static cudaError_t launch(const bitar_chunk* ops, bitar_result* res, const Task* tasks, Counters* pc, uint8_t* scratch, uint32_t subs,
+                            uint32_t n_tasks_max, int device, int sm_count, cudaStream_t stream) {
     const int c = ctas_per_sm(device);
     if (c < 1) return cudaErrorLaunchOutOfResources;
     uint32_t grid = (uint32_t)(sm_count * c);
@@ -568,38 +579,7 @@ struct TokConfig {
     const uint32_t want = (n_tasks_max + per_cta - 1) / per_cta;
     if (want < grid) grid = want;
     if (grid == 0) return cudaSuccess;
-    inflate_tok_kernel<LBITS, LT, DBITS, DT, WARPS, GROUP, MIN_CTAS><<<grid, kThreads, kSmem, stream>>>(ops, res, tasks, pc, scratch, unit_cnt,
-                                                                                               block_state, subs);
-    return cudaGetLastError();
-  }
-};
-
-template <int G, int RING, int WARPS>
-struct ResolveConfig {
-  static constexpr int kThreads = WARPS * 32;
-  static constexpr size_t kSmem = (size_t)WARPS * (32 / G) * RING;
-  static int ctas_per_sm(int device) {
-    static int per_device[64] = {0};
-    int& c = per_device[device & 63];
-    if (c == 0) {
-      auto kern = inflate_resolve_kernel<G, RING, WARPS>;
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem) != cudaSuccess) return 0;
-      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, kern, kThreads, kSmem) != cudaSuccess) return 0;
-    }
-    return c;
-  }
-  static cudaError_t launch(const bitar_chunk* ops, bitar_result* res, const Task* tasks, Counters* pc, const uint8_t* scratch,
-                            const uint16_t* unit_cnt, const uint32_t* block_state, uint32_t subs, uint32_t n_tasks_max, int device,
-                            int sm_count, cudaStream_t stream) {
-    const int c = ctas_per_sm(device);
-    if (c < 1) return cudaErrorLaunchOutOfResources;
-    uint32_t grid = (uint32_t)(sm_count * c);
-    const uint32_t per_cta = WARPS * (32 / G);
-    const uint32_t want = (n_tasks_max + per_cta - 1) / per_cta;
-    if (want < grid) grid = want;
-    if (grid == 0) return cudaSuccess;
-    inflate_resolve_kernel<G, RING, WARPS><<<grid, kThreads, kSmem, stream>>>(ops, res, tasks, pc, scratch, unit_cnt, block_state, subs);
+    inflate_tok_kernel<LBITS, LT, DBITS, DT, WARPS, GROUP, MIN_CTAS><<<grid, kThreads, kSmem, stream>>>(ops, res, tasks, pc, scratch, subs);
     return cudaGetLastError();
   }
 };

@@ -12,7 +12,7 @@ from bitar_b200 import _capi as capi  # noqa: E402
 from bitar_b200 import synth  # noqa: E402
 from bitar_b200.engine import CompressDevice, Configuration  # noqa: E402
 
-NAMES = ["load", "match", "sort", "merge", "tables+hdr", "encode", "finish", "lengths+codes", "cl_rle", "cl_tree+type", "-", "-", "-", "-", "-", "-"]
+NAMES = ["load", "match", "sort", "merge", "tables+hdr", "encode", "finish", "lengths+codes", "cl_rle", "cl_tree+type", "far", "-", "-", "-", "-", "-"]
 
 
 def main():
@@ -36,7 +36,7 @@ def main():
         k, _ = dev.last_ms(0)
         out = np.zeros(16, np.uint64)
         L.bitar_debug_deflate_profile(0, out.ctypes.data)
-        tot = float(out[:10].sum())
+        tot = float(out[:11].sum())
         print(f"[{wname}] kernel {k:.3f} ms ({data.size / k / 1e6:.1f} GB/s); cycles/chunk:",
               " ".join(f"{nm}={int(v) // n}({100 * v / tot:.0f}%)" for nm, v in zip(NAMES, out) if v), flush=True)
         dev.close()

@@ -142,11 +142,16 @@ API int host_inflate_indexed(const uint8_t* in, uint32_t in_len, uint8_t* out, u
       n_units[s] = l.units();
       if (n_units[s] > tk::kSlotUnits || (n_units[s] & 7u)) { status = kStatusDataError; break; }
     }
-    uint32_t pos = 0;
-    for (uint32_t s = 0; s < ns && status == kStatusOk; ++s) {   // phase B
-      const uint32_t limit = (s + 1) * dfl::kSub < blen ? (s + 1) * dfl::kSub : blen;
-      pos = tk::resolve_units_serial(reinterpret_cast<const uint16_t*>(slots[s]), n_units[s], out + (b << 16), pos, limit);
-      if (pos != limit) status = kStatusDataError;
+    if (status == kStatusOk) {   // phase B: the kernel's lane (one block per lane)
+      alignas(16) static thread_local uint8_t ring[256];
+      uint16_t cnts[32];
+      for (uint32_t s = 0; s < 32; ++s) cnts[s] = (uint16_t)n_units[s];
+      tk::ResolveLane<256> r;
+      r.bind(ring);
+      r.start_block(out + (b << 16), blen, &slots[0][0], cnts, ns);
+      uint64_t steps = 0;
+      while (r.state == tk::ResolveLane<256>::kRun && ++steps < (1ull << 30)) r.step();
+      if (r.state != tk::ResolveLane<256>::kIdle) status = kStatusDataError;
     }
   }
   result4[0] = status == kStatusOk ? ix.total_out : 0;

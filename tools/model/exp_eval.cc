@@ -25,6 +25,7 @@ struct XP {
   int far8 = 0;         // far table keyed by 8 bytes
   int ways = 1;         // near table ways (2: also the second most recent position)
   int nice = 8;         // stop trying older candidates once a match this long is found
+  int zone = 0;         // far_mode 3: far sources only from the first `zone` bytes of a sub-range, far matches only after them
   int cbits = 12;        // far_mode 3: cumulative table bits
   int both = 0;         // far_mode 3: also look into T_{s-1} exact table     // 1: near table is block-wide sequential (no cage, no reset) -- ablation
 };
@@ -69,7 +70,7 @@ static void find_tokens_x(const uint8_t* d, int n, const Params& P, std::vector<
     if (!X.nearblock && (base & (SUB - 1)) == 0) std::fill(head.begin(), head.end(), 0u), std::fill(head2.begin(), head2.end(), 0u);
     if (X.far_mode == 3 && (base & (SUB - 1)) == 0)
       for (; c_upto < base; ++c_upto)
-        if (c_upto + 4 <= n) C[hash32(load32(d, n, c_upto), X.cbits)] = c_upto;
+        if (c_upto + 4 <= n && (!X.zone || (c_upto & (SUB - 1)) + 4 <= X.zone)) C[hash32(load32(d, n, c_upto), X.cbits)] = c_upto;
     for (int t = 0; t < P.step; ++t) {
       int p = base + t;
       valid[t] = p + 4 <= n;
@@ -133,8 +134,9 @@ static void find_tokens_x(const uint8_t* d, int n, const Params& P, std::vector<
       } else if (X.far_mode == 3 && (!X.need || best < X.need)) {
         uint32_t w = load32(d, n, p);
         int c = C[hash32(w, X.cbits)];
-        if (c >= 0 && p - c <= kMaxDist && load32(d, n, c) == w) {
+        if (c >= 0 && p - c <= kMaxDist && load32(d, n, c) == w && (!X.zone || r >= X.zone)) {
           int l = match_len(d, n, p, c, P.sub_log2);
+          if (X.zone) l = std::min(l, X.zone - (c & (SUB - 1)));
           if (l >= X.far_min && l > best + (best >= 3 ? X.bonus : 0)) best = l, bdist = p - c;
         }
       } else if (X.far_mode == 2 && (!X.need || best < X.need)) {
@@ -243,6 +245,7 @@ int main(int argc, char** argv) {
     else if (k == "nearblock") X.nearblock = v;
     else if (k == "cbits") X.cbits = v;
     else if (k == "both") X.both = v;
+    else if (k == "zone") X.zone = v;
     else if (k == "ways") X.ways = v;
     else if (k == "nice") X.nice = v;
     else if (k == "ins") X.ins = v;

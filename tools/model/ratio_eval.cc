@@ -62,6 +62,7 @@ int main(int argc, char** argv) {
     else if (k == "sub_log2") P.sub_log2 = v;
     else return fprintf(stderr, "unknown key %s\n", k.c_str()), 2;
   }
+  uint64_t g_far = 0, g_deferred = 0, g_all = 0, g_dirty_bytes = 0, g_sub_dirty = 0, g_subs = 0;
   uint64_t zsum = 0, msum = 0, lits = 0, matches = 0, mbytes = 0, fr[6] = {0, 0, 0, 0, 0, 0};
   int types[3] = {0, 0, 0};
   for (size_t off = 0; off < data.size(); off += seg) {
@@ -69,6 +70,27 @@ int main(int argc, char** argv) {
     auto z = zdeflate(data.data() + off, n, 1, P.huffman == 1 ? Z_FIXED : Z_DEFAULT_STRATEGY);
     std::vector<bitar_model::BlockStats> st;
     auto m = bitar_model::deflate_chunk(data.data() + off, n, P, &st);
+    {   // how much a decoder that resolves sub-range-local matches itself would have to defer (experiment)
+      std::vector<uint32_t> tok;
+      for (size_t o2 = 0; o2 < n; o2 += 65536) {
+        int bl = (int)std::min((size_t)65536, n - o2);
+        bitar_model::find_tokens(data.data() + off + o2, bl, P, tok);
+        std::vector<uint8_t> dirty((size_t)bl, 0);
+        for (int s0 = 0; s0 < bl; s0 += 2048) {
+          bool any = false;
+          for (int p = s0; p < std::min(bl, s0 + 2048); ++p) {
+            uint32_t t = tok[(size_t)p];
+            if (t <= 1) continue;
+            int len = bitar_model::tok_len(t), dist = bitar_model::tok_dist(t);
+            bool far = p - dist < s0, d = far;
+            for (int k = 0; k < len && !d; ++k) d = dirty[(size_t)(p - dist + k)];
+            g_all++; g_far += far; g_deferred += d;
+            if (d) { for (int k = 0; k < len; ++k) dirty[(size_t)(p + k)] = 1; g_dirty_bytes += len; any = true; }
+          }
+          g_subs++; g_sub_dirty += any;
+        }
+      }
+    }
     if (!zcheck(m, data.data() + off, n)) {
       if (getenv("DUMP_BAD")) { FILE* g = fopen(getenv("DUMP_BAD"), "wb"); fwrite(m.data(), 1, m.size(), g); fclose(g); }
       return fprintf(stderr, "MODEL STREAM INVALID at chunk %zu\n", off / seg), 1;
@@ -88,6 +110,8 @@ int main(int argc, char** argv) {
          (double)data.size() / msum, (double)msum / zsum, (unsigned long long)lits,
          (unsigned long long)matches, matches ? (double)mbytes / matches : 0.0,
          (double)data.size() / (double)(lits + matches), types[0], types[1], types[2]);
+  printf("far matches %.1f%%, deferred (far or reading deferred bytes) %.1f%% of matches, %.1f%% of bytes; sub-ranges with any: %.1f%%\n", 100.0 * g_far / g_all,
+         100.0 * g_deferred / g_all, 100.0 * g_dirty_bytes / data.size(), 100.0 * g_sub_dirty / g_subs);
   printf("matches farther than 128 / 256 / 512 B: %.1f%% / %.1f%% / %.1f%% of matches, %.1f%% / %.1f%% / %.1f%% of all bytes\n", 100.0 * fr[0] / matches, 100.0 * fr[2] / matches,
          100.0 * fr[4] / matches, 100.0 * fr[1] / data.size(), 100.0 * fr[3] / data.size(), 100.0 * fr[5] / data.size());
   return 0;
