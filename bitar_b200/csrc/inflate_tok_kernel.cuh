@@ -194,7 +194,7 @@ struct ResolveLut {
   uint8_t per8[32];      //     ... of 8 lanes
 };
 __device__ __forceinline__ void resolve_lut_init(ResolveLut* lut) {
-  for (unsigned i = threadIdx.x; i < 1024u; i += blockDim.x) lut->mod[i >> 5][i & 31u] = (uint8_t)((i >> 5) ? (i & 31u) % (i >> 5) : 0u);
+  for (unsigned i = threadIdx.x; i < 1024u; i += blockDim.x) lut->mod[i >> 5][i & 31u] = (uint8_t)((i >> 5) ? (i & 31u) % (i >> 5) : (i & 31u));   // row 0: the identity
   if (threadIdx.x < 32u) {
     const unsigned d = threadIdx.x ? threadIdx.x : 1u;
     lut->per32[threadIdx.x] = (uint8_t)(32u - 32u % d);
@@ -342,6 +342,178 @@ struct ResolveGroup {
   }
 };
 
+// The same for a whole warp per block (the 64 KiB blocks of ordinary segments), laid out for few instructions per match:
+// the block goes through a LINEAR window in shared memory -- the previous sub-range and the current one side by side,
+// indexed by position, no wrap-around -- so that a copy is `buf[d + lane] = buf[s + f(lane)]` with everything worked out
+// by the match's head lane beforehand (all heads of a batch in parallel) and left in a record the warp reads by
+// broadcast.  Matches whose source lies below the window (flushed output) are independent of the batch: they are copied
+// first, their loads in flight together; the others follow one after the other.  A sub-range leaves the window as
+// aligned 16-byte vectors when it is complete; then the window slides by one sub-range.
+struct ResolveWarp {
+  static constexpr uint32_t kWin = dfl::kSub;                 // bytes of a sub-range
+  static constexpr uint32_t kBuf = 2u * kWin + 16u;           // previous + current sub-range + the block's misalignment
+  static constexpr uint32_t kBytes = kBuf + 16u * 16u + 16u * 8u;   // + a record per possible match of a batch (near, far)
+  uint32_t buf_s;           // shared address of the window (16-byte aligned)
+  uint32_t lut_s;           // shared address of the CTA's ResolveLut
+  uint8_t* vbase;           // block address - mis
+  uint32_t flushed;         // virtual position below which everything is in global memory
+  uint32_t cur0;            // virtual position of window index kWin (a multiple of 16)
+  int gl;
+
+  __device__ __forceinline__ void begin(uint8_t* out) {
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);
+    vbase = out - mis;
+    flushed = mis;
+    cur0 = 0;
+  }
+  // shared address of virtual position v
+  __device__ __forceinline__ uint32_t at(uint32_t v) const { return buf_s + kWin + (v - cur0); }
+
+  // store what is final: the unaligned head of the block, then the complete 16-byte vectors below `upto`
+  __device__ __forceinline__ void flush(uint32_t upto) {
+    if (flushed & 15u) {
+      const uint32_t a = (flushed + 15u) & ~15u;
+      if (upto < a) return;
+      for (uint32_t v = flushed + (uint32_t)gl; v < a; v += 32u) vbase[v] = (uint8_t)r_ld8(at(v));
+      flushed = a;
+    }
+    const uint32_t end = upto & ~15u;
+    for (uint32_t v = flushed + 16u * (uint32_t)gl; v < end; v += 512u) *reinterpret_cast<uint4*>(vbase + v) = r_ld128(at(v));
+    if (end > flushed) flushed = end;
+  }
+  __device__ __forceinline__ void finish(uint32_t upto) {
+    flush(upto);
+    for (uint32_t v = flushed + (uint32_t)gl; v < upto; v += 32u) vbase[v] = (uint8_t)r_ld8(at(v));
+    flushed = upto;
+    __syncwarp();
+  }
+  // the current sub-range becomes the previous one (no pass reads what another pass writes, except lane 0's first and
+  // last vector, which program order takes care of)
+  __device__ __forceinline__ void slide() {
+    for (uint32_t i = 16u * (uint32_t)gl; i < kWin + 16u; i += 512u) {
+      const uint4 v = r_ld128(buf_s + kWin + i);
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(buf_s + i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+    cur0 += kWin;
+    __syncwarp();
+  }
+
+  // the rare shapes, out of line: what is left of far matches longer than a pass of the warp ...
+  __device__ __noinline__ void far_rest(uint32_t a0, uint32_t s0, uint32_t a1, uint32_t s1) {
+    const uint32_t lane_u = (uint32_t)gl, l0 = a0 >> 20, l1 = a1 >> 20;
+#pragma unroll 1
+    for (uint32_t k = 32u + lane_u; k < l0; k += 32u) r_st8((a0 & 0xFFFFFu) + k, (uint32_t)__ldcg(vbase + s0 + k));
+#pragma unroll 1
+    for (uint32_t k = 32u + lane_u; k < l1; k += 32u) r_st8((a1 & 0xFFFFFu) + k, (uint32_t)__ldcg(vbase + s1 + k));
+  }
+  // ... and near matches longer than a pass: a pattern (every lane keeps the byte of its place in the period, a pass
+  // writes a whole number of periods), or a plain copy pass by pass
+  __device__ __noinline__ void near_long(uint32_t a, uint32_t len, uint32_t sa, uint32_t row, uint32_t per) {
+    const uint32_t lane_u = (uint32_t)gl;
+    if (row != lut_s) {
+      const uint32_t byte = r_ld8(sa + r_ld8(row + lane_u));
+      if (lane_u < per) {
+#pragma unroll 1
+        for (uint32_t k = lane_u; k < len; k += per) r_st8(a + k, byte);
+      }
+    } else {
+#pragma unroll 1
+      for (uint32_t k = lane_u; k < len + lane_u; k += 32u) {
+        if (k < len) r_st8(a + k, r_ld8(sa + k));
+        __syncwarp();            // (the next pass may read what this one wrote: dist < 64)
+      }
+    }
+  }
+
+  // The units of one sub-range (n_units of them, a multiple of 8, at `units`) from virtual position `pos`; returns the
+  // new position, or 0xFFFFFFFF when the units do not add up to `sub_limit` (they always do when phase A succeeded).
+  __device__ __forceinline__ uint32_t resolve(const uint16_t* units, uint32_t n_units, uint32_t pos, uint32_t sub_limit) {
+    const uint32_t lane_u = (uint32_t)gl;
+    const uint32_t near_s = buf_s + kBuf, far_s = near_s + 16u * 16u;
+    const uint32_t bias = buf_s + kWin - cur0;                // shared address of virtual position 0 (mod 2^32)
+    // two batches of units in flight ahead of the one being resolved (ld.cg: the scratch is rewritten for every block)
+    uint32_t u0 = lane_u < n_units ? __ldcg(units + lane_u) : tk::kUnitNop;
+    uint32_t u1 = 32u + lane_u < n_units ? __ldcg(units + 32u + lane_u) : tk::kUnitNop;
+    for (uint32_t i = 0; i < n_units; i += 32u) {
+      const uint32_t u = u0;
+      u0 = u1;
+      u1 = i + 64u + lane_u < n_units ? __ldcg(units + i + 64u + lane_u) : tk::kUnitNop;
+      const bool is_head = (u & tk::kUnitHead) != 0u;
+      const unsigned heads = __ballot_sync(0xFFFFFFFFu, is_head);
+      const bool is_cont = ((heads << 1) >> lane_u) & 1u;     // the unit after a head: its distance (a head is never in lane 31)
+      const bool is_lit = !is_head && !is_cont && u < 0x100u;
+      const uint32_t olen = is_lit ? 1u : is_head ? (u & 0xFFu) + 3u : 0u;
+      uint32_t incl = olen;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (gl >= d) incl += v;
+      }
+      const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+      if (pos + total > sub_limit) return 0xFFFFFFFFu;
+      const uint32_t my = pos + incl - olen;                  // where this lane's token starts
+      const uint32_t da = bias + my;
+      if (is_lit) r_st8(da, u);
+      const uint32_t dist = __shfl_down_sync(0xFFFFFFFFu, u, 1) + 1u;   // a head's distance sits in the next lane
+      const bool is_far = is_head && dist > my - cur0 + kWin;           // the source starts below the window
+      const unsigned fars = __ballot_sync(0xFFFFFFFFu, is_far);
+      const unsigned nears = heads & ~fars;
+      if (is_head) {
+        const unsigned below = (1u << lane_u) - 1u;
+        if (is_far) {
+          // destination address | length, virtual position of the source
+          asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(far_s + 8u * (uint32_t)__popc(fars & below)), "r"(da | (olen << 20)), "r"(my - dist) : "memory");
+        } else {
+          // destination address | length, source address, row of lane -> source byte (lane % dist for a source that
+          // overlaps the copy: a repeating pattern; the identity else), bytes a pass may write (whole periods)
+          const bool pattern = dist < olen && dist < 32u;
+          const uint32_t row = lut_s + (pattern ? dist * 32u : 0u);
+          const uint32_t per = pattern ? r_ld8(lut_s + 1024u + dist) : 32u;
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(near_s + 16u * (uint32_t)__popc(nears & below)), "r"(da | (olen << 20)),
+                       "r"(da - dist), "r"(row), "r"(per) : "memory");
+        }
+      }
+      __syncwarp();
+      {   // the far matches: nothing in this batch depends on their sources, so their loads go out together
+        const int nf = __popc(fars);
+#pragma unroll 1
+        for (int t = 0; t < nf; t += 2) {
+          uint32_t a0, s0, a1 = 0, s1 = 0;
+          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a0), "=r"(s0) : "r"(far_s + 8u * (uint32_t)t) : "memory");
+          if (t + 1 < nf) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a1), "=r"(s1) : "r"(far_s + 8u * (uint32_t)(t + 1)) : "memory");
+          const uint32_t l0 = a0 >> 20, l1 = a1 >> 20;
+          uint32_t b0 = 0, b1 = 0;
+          if (lane_u < l0) b0 = (uint32_t)__ldcg(vbase + s0 + lane_u);
+          if (lane_u < l1) b1 = (uint32_t)__ldcg(vbase + s1 + lane_u);
+          if (lane_u < l0) r_st8((a0 & 0xFFFFFu) + lane_u, b0);
+          if (lane_u < l1) r_st8((a1 & 0xFFFFFu) + lane_u, b1);
+          if (l0 > 32u || l1 > 32u) far_rest(a0, s0, a1, s1);
+        }
+        __syncwarp();
+      }
+      const int nn = __popc(nears);
+#pragma unroll 1
+      for (int t = 0; t < nn; ++t) {
+        uint32_t w0, sa, row, per;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(sa), "=r"(row), "=r"(per) : "r"(near_s + 16u * (uint32_t)t) : "memory");
+        const uint32_t len = w0 >> 20, a = w0 & 0xFFFFFu;
+        if (len <= 32u) {
+          // one pass: lane k takes byte k of the match from byte (k mod dist) of its source (k itself when they do not overlap)
+          const uint32_t byte = r_ld8(sa + r_ld8(row + lane_u));
+          if (lane_u < len) r_st8(a + lane_u, byte);
+        } else {
+          near_long(a, len, sa, row, per);
+        }
+        __syncwarp();
+      }
+      pos += total;
+    }
+    if (pos != sub_limit) return 0xFFFFFFFFu;
+    flush(pos);
+    return pos;
+  }
+};
+
 // ---- phase A ------------------------------------------------------------------------------------------
 // GROUP = 32: a warp per block (up to 32 sub-ranges).  GROUP = 8: four blocks of at most 8 sub-ranges per warp
 // (small segments), each with its own tables; the groups of a warp run the same code on their own tasks and only
@@ -367,14 +539,18 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
   WS& ws = *reinterpret_cast<WS*>(smem_raw + (size_t)((threadIdx.x >> 5) * kGroupsPerWarp + gbase / GROUP) * sizeof(WS));
   Lane L;
   L.bind(ws.lt, ws.dt, ws.ring + lane * WS::kRingStride, dinfo, &ws.sc);
-  // phase B: the group's ring takes the space of the tables and unit rings once phase A is done with them
-  constexpr int kRing = GROUP == 32 ? 4096 : 2048;
-  static_assert(sizeof(WS) >= (size_t)kRing + (GROUP == 32 ? 128u : 0u), "the resolve ring (+ match records) borrows the group's phase-A space");
-  ResolveGroup<GROUP, kRing> R;
+  // phase B: the resolver's window / ring takes the space of the tables and unit rings once phase A is done with them
+  constexpr int kRing = 2048;
+  static_assert(sizeof(WS) >= (GROUP == 32 ? (size_t)ResolveWarp::kBytes : (size_t)kRing), "the resolver borrows the group's phase-A space");
+  ResolveGroup<GROUP == 32 ? 8 : GROUP, kRing> R;    // (groups of 8 lanes; unused by the warp-per-block instance)
   R.gl = lane;
   R.gmask = kFull;
   R.ring_s = (uint32_t)__cvta_generic_to_shared(&ws);
   R.lut_s = (uint32_t)__cvta_generic_to_shared(lut);
+  ResolveWarp W;
+  W.gl = lane;
+  W.buf_s = (uint32_t)__cvta_generic_to_shared(&ws);
+  W.lut_s = (uint32_t)__cvta_generic_to_shared(lut);
   // the group's unit scratch: `subs` slots, rewritten for every block
   uint8_t* const slots = scratch + ((size_t)(blockIdx.x * WARPS + (threadIdx.x >> 5)) * kGroupsPerWarp + gbase / GROUP) * subs * tk::kSlotBytes;
   const uint32_t n_tasks = pc->n_tasks;
@@ -506,16 +682,28 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
           const uint32_t my_units = (uint32_t)lane < ns ? L.units() : 0u;
           if (!__any_sync(kFull, status != fl::kStatusOk)) {   // (also orders the unit stores before the loads below)
             const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);
-            R.vbase = out - mis;
-            R.flushed = mis;
             uint32_t pos = mis;
-            for (uint32_t s = 0; s < ns; ++s) {
-              const uint32_t nu = __shfl_sync(kFull, my_units, (int)s, GROUP);
-              pos = R.resolve(reinterpret_cast<const uint16_t*>(slots + (size_t)s * tk::kSlotBytes), nu, pos, mis + min(blen, (s + 1u) * dfl::kSub));
-              if (pos == 0xFFFFFFFFu) break;
+            if (GROUP == 32) {
+              W.begin(out);
+              for (uint32_t s = 0; s < ns; ++s) {
+                const uint32_t nu = __shfl_sync(kFull, my_units, (int)s, GROUP);
+                if (s) W.slide();
+                pos = W.resolve(reinterpret_cast<const uint16_t*>(slots + (size_t)s * tk::kSlotBytes), nu, pos, mis + min(blen, (s + 1u) * dfl::kSub));
+                if (pos == 0xFFFFFFFFu) break;
+              }
+              if (pos == 0xFFFFFFFFu) status = fl::kStatusDataError;
+              else W.finish(pos);
+            } else {
+              R.vbase = out - mis;
+              R.flushed = mis;
+              for (uint32_t s = 0; s < ns; ++s) {
+                const uint32_t nu = __shfl_sync(kFull, my_units, (int)s, GROUP);
+                pos = R.resolve(reinterpret_cast<const uint16_t*>(slots + (size_t)s * tk::kSlotBytes), nu, pos, mis + min(blen, (s + 1u) * dfl::kSub));
+                if (pos == 0xFFFFFFFFu) break;
+              }
+              if (pos == 0xFFFFFFFFu) status = fl::kStatusDataError;
+              else R.finish(pos);
             }
-            if (pos == 0xFFFFFFFFu) status = fl::kStatusDataError;
-            else R.finish(pos);
           }
           __syncwarp(kFull);   // the ring's space goes back to phase A
         }
