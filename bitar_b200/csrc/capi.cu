@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(256) stage_copy_kernel(const bitar_chunk* __re
     dst = static_cast<uint8_t*>(to[i].dst);
     n = min(results[i].produced, to[i].dst_cap);
   }
+  if (src == dst) return;   // this op's buffer is device memory, used in place
   const uint32_t head = min(n, (16u - (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u)) & 15u);
   if (threadIdx.x < head) dst[threadIdx.x] = src[threadIdx.x];
   const uint32_t vecs = (n - head) >> 4;
@@ -285,13 +286,46 @@ bool is_host_memory(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
+// The same per op of a call, one driver query per 2 MiB of address space (host and device allocations never share
+// such a region under unified addressing; a 1 GiB call costs ~500 queries instead of one per op).
+struct HostProbe {
+  uintptr_t region = ~(uintptr_t)0;
+  bool host = false;
+  bool operator()(const void* p) {
+    const uintptr_t r = reinterpret_cast<uintptr_t>(p) >> 21;
+    if (r != region) {
+      region = r;
+      host = is_host_memory(p);
+    }
+    return host;
+  }
+};
+
 // Rewrites q->h_ops to staged device addresses when the call's buffers are host memory (caller's ops are
 // kept in q->h_orig).  Called with the queue pair idle, before the descriptors are uploaded.
 int inflate_prepare_staging(QueuePair* q, uint32_t n, bool allow_batches) {
   q->nb = 1;
   q->per = n;
-  q->stage_src = q->h_ops[0].src != nullptr && q->h_ops[0].src_len > 0 && is_host_memory(q->h_ops[0].src);
-  q->stage_dst = q->h_ops[0].dst != nullptr && is_host_memory(q->h_ops[0].dst);
+  // Every op is classified: host-resident sources / destinations are staged, device-resident ones are used in place
+  // (a call may mix them: the C++ facade stages pageable buffers itself and passes pool slots as they are).
+  uint32_t host_src = 0, host_dst = 0, with_src = 0, with_dst = 0;
+  {
+    HostProbe ps, pd;
+    for (uint32_t i = 0; i < n; ++i) {
+      const bitar_chunk& c = q->h_ops[i];
+      if (c.src != nullptr && c.src_len > 0) {
+        ++with_src;
+        host_src += ps(c.src) ? 1u : 0u;
+      }
+      if (c.dst != nullptr && c.dst_cap > 0) {
+        ++with_dst;
+        host_dst += pd(c.dst) ? 1u : 0u;
+      }
+    }
+  }
+  q->stage_src = host_src != 0;
+  q->stage_dst = host_dst != 0;
+  const bool all_src_host = host_src == with_src && with_src == n, all_dst_host = host_dst == with_dst && with_dst == n;
   if (!q->stage_src && !q->stage_dst) return BITAR_OK;
   if (q->orig_cap < n) {
     if (q->h_orig) cudaFreeHost(q->h_orig);
@@ -312,7 +346,7 @@ int inflate_prepare_staging(QueuePair* q, uint32_t n, bool allow_batches) {
   q->stage_out_bytes = need_out;
   // Staged calls with a host-resident destination run in batches (qp_submit): at most kMaxStageBatches, each of at
   // least kStageBatchBytes of output.
-  if (q->stage_dst && n > 1 && allow_batches) {
+  if (q->stage_dst && all_dst_host && n > 1 && allow_batches) {
     static const size_t env_bytes = getenv("BITAR_STAGE_BATCH_MIB") ? (size_t)atoi(getenv("BITAR_STAGE_BATCH_MIB")) << 20 : kStageBatchBytes;
     const size_t tuned = g_stage_batch_bytes.load();
     const size_t batch_bytes = tuned ? tuned : env_bytes;
@@ -325,7 +359,7 @@ int inflate_prepare_staging(QueuePair* q, uint32_t n, bool allow_batches) {
   // sources at a constant stride with room for the widest row?
   const size_t mis0 = reinterpret_cast<uintptr_t>(q->h_orig[0].src) & 15u;
   q->stage_src_strided = false;
-  if (q->stage_src && n > 1 && g_stage_strided.load()) {
+  if (q->stage_src && all_src_host && n > 1 && g_stage_strided.load()) {
     const uint8_t* s0 = static_cast<const uint8_t*>(q->h_orig[0].src);
     const uint8_t* s1 = static_cast<const uint8_t*>(q->h_orig[1].src);
     const size_t stride = s1 > s0 ? (size_t)(s1 - s0) : 0;
@@ -368,7 +402,7 @@ int inflate_prepare_staging(QueuePair* q, uint32_t n, bool allow_batches) {
   // layout and a batch goes back with ONE copy-engine transfer (which, unlike a kernel, runs beside the inflate
   // kernels of the other batches and queue pairs); only the call's last segment, the one that may be short, is
   // copied by produced size.
-  q->stage_dst_contig = q->stage_dst && n > 1;
+  q->stage_dst_contig = q->stage_dst && all_dst_host && n > 1;
   for (uint32_t i = 1; i < n && q->stage_dst_contig; ++i)
     q->stage_dst_contig = q->h_orig[i].dst_cap == q->h_orig[0].dst_cap &&
                           static_cast<uint8_t*>(q->h_orig[i].dst) == static_cast<uint8_t*>(q->h_orig[0].dst) + (size_t)i * q->h_orig[0].dst_cap;
@@ -378,14 +412,14 @@ int inflate_prepare_staging(QueuePair* q, uint32_t n, bool allow_batches) {
     if (q->stage_src_strided) {
       const uint32_t b = i / q->per;
       c.src = q->d_stage_in + q->batch_in_off[b] + (size_t)(i - b * q->per) * q->batch_pitch[b] + mis0;
-    } else if (q->stage_src) {
+    } else if (q->stage_src && (all_src_host || (c.src != nullptr && c.src_len > 0 && is_host_memory(c.src)))) {
       const size_t mis = reinterpret_cast<uintptr_t>(c.src) & 15u;
       c.src = q->d_stage_in + at_in + mis;
       at_in += (((size_t)c.src_len + 15u) & ~(size_t)15u) + 32u;
     }
     if (q->stage_dst_contig) {
       c.dst = q->d_stage_out + (reinterpret_cast<uintptr_t>(q->h_orig[0].dst) & 15u) + (size_t)i * c.dst_cap;
-    } else if (q->stage_dst) {
+    } else if (q->stage_dst && (all_dst_host || (c.dst != nullptr && c.dst_cap > 0 && is_host_memory(c.dst)))) {
       const size_t mis = reinterpret_cast<uintptr_t>(c.dst) & 15u;
       c.dst = q->d_stage_out + at_out + mis;
       at_out += (((size_t)c.dst_cap + 15u) & ~(size_t)15u) + 32u;
@@ -460,10 +494,10 @@ int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, b
       uint8_t* const stage = q->d_stage_in + q->batch_in_off[b];
       if (rows)
         e = cudaMemcpy2DAsync(stage, q->batch_pitch[b], static_cast<const uint8_t*>(q->h_orig[first].src) - mis0, q->src_stride,
-                              q->batch_pitch[b], rows, cudaMemcpyHostToDevice, st);
+                              q->batch_pitch[b], rows, cudaMemcpyDefault, st);
       if (e == cudaSuccess && last)
         e = cudaMemcpyAsync(stage + (size_t)(count - 1) * q->batch_pitch[b] + mis0, q->h_orig[n - 1].src, q->h_orig[n - 1].src_len,
-                            cudaMemcpyHostToDevice, st);
+                            cudaMemcpyDefault, st);
     } else if (q->stage_src) {
       stage_copy_kernel<<<count, 256, 0, st>>>(q->d_orig + first, q->d_ops + first, nullptr, 0);
       e = cudaGetLastError();
@@ -484,7 +518,7 @@ int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, b
       // short, goes by its produced size
       const uint32_t full = last ? count - 1 : count;
       if (full)
-        e = cudaMemcpyAsync(q->h_orig[first].dst, q->h_ops[first].dst, (size_t)full * q->h_orig[0].dst_cap, cudaMemcpyDeviceToHost, st);
+        e = cudaMemcpyAsync(q->h_orig[first].dst, q->h_ops[first].dst, (size_t)full * q->h_orig[0].dst_cap, cudaMemcpyDefault, st);
       if (e == cudaSuccess && last) {
         stage_copy_kernel<<<1, 256, 0, st>>>(q->d_ops + (n - 1), q->d_orig + (n - 1), q->d_res + (n - 1), 1);
         e = cudaGetLastError();

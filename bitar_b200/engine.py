@@ -270,6 +270,12 @@ def stream_length(chunk):
     return c.size
 
 
+def strip_index(chunk):
+    """The raw DEFLATE stream of a compressed chunk (numpy uint8 array), without the parallel-inflate index."""
+    c = np.ascontiguousarray(chunk, dtype=np.uint8)
+    return c[:stream_length(c)]
+
+
 def gzip_members(chunks, results, sizes):
     """RFC 1952 framing: every compressed chunk becomes one gzip member (header, raw DEFLATE stream, CRC-32,
     ISIZE); the concatenation is a valid multi-member gzip file that gzip / zlib tools decompress to the original

@@ -302,3 +302,25 @@ def test_random_structured_inputs_round_trip_on_the_cpu_builds():
             assert info["indexed"] == (index is not None)
             if index is not None:
                 assert info["status"] == 0 and info["guard_ok"] and np.array_equal(out, d), (i, n, info)
+
+
+@pytest.mark.parametrize("name", ["lineitem_mix", "sorted_int64", "dict_int32", "price_f64", "text_source", "elf_binary",
+                                  "char10_strings", "word_strings", "period4096_rows"])
+def test_model_ratio_corpus_within_tolerance_of_zlib_level_1(name):
+    """The sequential model of the deflate kernel (the GPU tests pin the kernel to it bit for bit) on every input of the
+    ratio corpus: at most 5 % more bytes than zlib level 1 on identical 59 460-byte chunks, every stream valid under
+    zlib and under the two-phase decoder of the inflate kernels (host build)."""
+    from bitar_b200 import synth
+    data = synth.ratio_corpus(768 << 10)[name]
+    seg = 59460
+    model_bytes = zlib_bytes = 0
+    for off in range(0, data.size, seg):
+        ch = data[off:off + seg]
+        z = M.model_deflate(ch, 2)
+        model_bytes += z.size
+        zlib_bytes += O.deflate_chunk(ch, 1, 15, O.HUFFMAN_DYNAMIC).size
+        assert np.array_equal(O.inflate_chunk(z, ch.size), ch)
+        if off == 0:
+            out, info = M.host_inflate_indexed(z, ch.size)
+            assert info["status"] == 0 and info["indexed"] and np.array_equal(out, ch)
+    assert model_bytes <= 1.05 * zlib_bytes, (name, model_bytes, zlib_bytes, model_bytes / zlib_bytes)
