@@ -26,9 +26,28 @@ sys.path.insert(0, ROOT)
 
 METRIC = "deflate+inflate round-trip throughput, uncompressed bytes (bitar Compress->Decompress)"
 SEG_DEFAULT = 59460          # apps/app_common.h:39 kDecompressedSegSize
-# DRAM bytes moved per uncompressed byte, from ncu (dram__bytes_read.sum + dram__bytes_write.sum, 256 MiB launch)
-DEFLATE_DRAM_BYTES_PER_BYTE = (289.780736e6 + 109.076992e6) / 268435456
-INFLATE_DRAM_BYTES_PER_BYTE = (161.789440e6 + 255.810048e6) / 268435456
+REF_SAMPLE_MIB = 96          # --impl reference: MiB of the workload one step processes (equal parts of the three columns)
+
+
+def dram_traffic():
+    """DRAM bytes per uncompressed byte of the two codec kernels, as tools/profile_round.sh wrote them from an
+    `ncu --set full` capture (dram__bytes_read.sum + dram__bytes_write.sum); None when no capture is committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_dram_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+def config_of(args):
+    """The workload both arms run (identical in both lines, so that the driver's same_config holds)."""
+    n = ((args.mib << 20) + args.seg - 1) // args.seg
+    return {"workload": f"{args.mib} MiB/GPU lineitem-like Arrow columns (sorted int64, dict int32, f64 prices), seg {args.seg} B "
+                        f"({n} chunks), dynamic Huffman, level-1-equivalent, Compress() then Decompress()",
+            "seg": args.seg, "chunks_per_gpu": n, "mib_per_gpu": args.mib,
+            "l2": "inputs (>= 1 GiB) exceed the 126 MB L2; no flush needed",
+            "reference_sample": f"a step of --impl reference runs the first {REF_SAMPLE_MIB // 3} MiB of each column third of this buffer "
+                                f"({REF_SAMPLE_MIB} MiB) on all host threads; its throughput is per byte of that sample"}
 
 
 def peaks():
@@ -74,20 +93,12 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def cpu_baseline(data, seg, threads, want_seconds=10.0):
-    """Times the CPU path (oracle: bitar chunking over zlib level 1, one z_stream per worker) on a
-    bounded sample of the workload.  Returns (dict, sample bytes)."""
+def cpu_baseline(data, seg, threads):
+    """Times the CPU path (oracle: bitar chunking over zlib level 1, one z_stream per worker) on a bounded sample of
+    the workload (the same sample --impl reference uses).  Returns the cpu_baseline record."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
-    sample = data
-    # ~0.1 GB/s/core deflate: bound the sample so one pass takes roughly want_seconds / 3
-    budget = int(0.08e9 * threads * want_seconds / 3)
-    budget = max(seg * threads * 4, budget // seg * seg)
-    if sample.size > budget:
-        # equal parts of each third so the column mix is preserved
-        third = data.size // 3
-        part = budget // 3 // seg * seg
-        sample = np.concatenate([data[i * third:i * third + part] for i in range(3)])
+    sample = column_sample(data, seg, REF_SAMPLE_MIB)
     t0 = time.perf_counter()
     slots, produced = O.compress_buffer(sample, seg, threads=threads)
     t1 = time.perf_counter()
@@ -101,33 +112,53 @@ def cpu_baseline(data, seg, threads, want_seconds=10.0):
                   f"raw deflate level 1 / inflate, one reused z_stream per worker",
         "deflate_gbps": u / (t1 - t0) / 1e9, "inflate_gbps": u / (t2 - t1) / 1e9,
         "ratio": u / float(produced.sum()),
-    }, u
+    }
+
+
+def column_sample(data, seg, mib):
+    """Equal parts of the three column thirds, `mib` MiB in all (whole segments)."""
+    third = data.size // 3
+    part = min(third, (mib << 20) // 3) // seg * seg
+    return np.concatenate([data[i * third:i * third + part] for i in range(3)])
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU path (bitar chunking + zlib, restated in oracle/ because
-    the reference cannot be built here) on all host threads, bounded sample per step."""
+    the reference cannot be built here) on all host threads; every step is the same bounded sample of the workload."""
     if rank != 0:
         return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
     from bitar_b200 import synth
     threads = max(1, (os.cpu_count() or 2) - 1)     # one core stays the main lcore, src/driver.cc:198-220
-    data = synth.lineitem_like(min(args.mib, 256) << 20)
-    times = []
-    base = None
+    data = synth.lineitem_like(args.mib << 20)
+    sample = column_sample(data, args.seg, REF_SAMPLE_MIB)
+    del data
+    times, td, ti, produced = [], [], [], None
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        base, u = cpu_baseline(data, args.seg, threads, want_seconds=4.0)
+        slots, produced = O.compress_buffer(sample, args.seg, threads=threads)
+        t1 = time.perf_counter()
+        out, got = O.decompress_buffer(slots, produced, args.seg, threads=threads)
+        t2 = time.perf_counter()
+        if i == 0:
+            assert out.size == sample.size and np.array_equal(out, sample)
         if i >= args.warmup:
-            times.append(time.perf_counter() - t0)
-    value = base["value"]
+            times.append(t2 - t0)
+            td.append(t1 - t0)
+            ti.append(t2 - t1)
+    u = sample.size
+    value = u / float(np.mean(times)) / 1e9          # mean over the timed steps, the timer ms_per_step comes from
+    base = {"value": value, "unit": "GB/s", "cores": threads, "kind": "port",
+            "sample": f"{u >> 20} MiB of the workload (equal column mix), seg {args.seg}, zlib {O.lib().oracle_zlib_version().decode()} "
+                      f"raw deflate level 1 / inflate, one reused z_stream per worker",
+            "deflate_gbps": u / float(np.mean(td)) / 1e9, "inflate_gbps": u / float(np.mean(ti)) / 1e9,
+            "ratio": u / float(produced.sum())}
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{args.mib} MiB/GPU lineitem-like Arrow columns (sorted int64, dict int32, f64 prices), "
-                               f"seg {args.seg} B ({((args.mib << 20) + args.seg - 1) // args.seg} chunks), dynamic Huffman, level-1-equivalent",
-                   "seg": args.seg, "chunks_per_gpu": ((args.mib << 20) + args.seg - 1) // args.seg,
-                   "timing": f"host wall clock; every step is a bounded sample of that workload ({base['sample']})"},
+        "config": config_of(args), "timing": "host wall clock around Compress() + Decompress() of the sample, mean over the timed steps",
         "cpu_baseline": base,
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -144,6 +175,9 @@ def main():
     ap.add_argument("--qps", type=int, default=8, help="queue pairs used by the end-to-end leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-config4", action="store_true", help="skip the BASELINE config 4 leg (8 GiB per GPU, generated on the device)")
+    ap.add_argument("--config4-gib", type=int, default=8)
+    ap.add_argument("--no-extras", action="store_true", help="skip the ratio corpus and the foreign-stream inflate leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -175,7 +209,7 @@ def main():
 
     # ---------------- device-resident leg ----------------
     dev = CompressDevice(local_rank, max(1, args.qps)).Initialize(
-        Configuration(decompressed_seg_size=seg, max_preallocate_memzones=n + 64))
+        Configuration(decompressed_seg_size=seg, max_preallocate_memzones=n + 256))
     src = torch.from_numpy(data).cuda()
     out = torch.empty(n * seg + 64, dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
@@ -225,11 +259,22 @@ def main():
     if not args.no_e2e:
         e2e = run_e2e(args, L, capi, C, torch, dist, world, local_rank, data, seg, n, U)
 
+    # ---------------- ratio corpus and reference-compressed streams (rank 0) ----------------
+    ratio_corpus = foreign = None
+    if not args.no_extras and rank == 0:
+        ratio_corpus = run_ratio_corpus(dev, capi, torch, seg)
+        foreign = run_foreign(dev, torch, data, seg)
+
+    # ---------------- BASELINE config 4: 8 GiB per GPU, generated on the device ----------------
+    config4 = None
+    if not args.no_config4:
+        config4 = run_config4(args, capi, torch, dist, world, local_rank, rank, seg)
+
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     base = None
     if not args.no_cpu and world == 1 and rank == 0:
         threads = max(1, (os.cpu_count() or 2) - 1)
-        base, _ = cpu_baseline(data, seg, threads)
+        base = cpu_baseline(data, seg, threads)
 
     # zlib level-1 ratio on identical chunks (sample)
     zratio = None
@@ -245,29 +290,35 @@ def main():
     if rank == 0:
         peak, which = peaks()
         achieved = (U + Cbytes) / (kd_ms * 1e-3) / 1e9
+        traffic = dram_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"{args.mib} MiB/GPU lineitem-like Arrow columns (sorted int64, dict int32, f64 prices), "
-                                   f"seg {seg} B ({n} chunks), dynamic Huffman, level-1-equivalent, device-resident",
-                       "seg": seg, "chunks_per_gpu": n, "l2": "inputs (>= 1 GiB) exceed the 126 MB L2; no flush needed",
-                       "timing": "CUDA events on the queue pair's stream, max over ranks"},
+            "config": config_of(args), "timing": "device-resident: CUDA events on the queue pair's stream, max over ranks",
             "deflate_gbps": world * U / (td_ms * 1e-3) / 1e9, "inflate_gbps": world * U / (ti_ms * 1e-3) / 1e9,
             "deflate_kernel_ms": kd_ms, "inflate_kernel_ms": ki_ms, "wall_ms_per_step": wall_ms,
             "ratio": U / Cbytes, "zlib_level1_ratio": zratio,
-            # dominant kernel = deflate_kernel (74 % of the device-resident step's GPU time, profiles/r01_launches_bench_1GiB_q.csv).
-            # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture at 256 MiB
-            # (profiles/r01_ncu_full_deflate_and_indexed_inflate_256MiB_q.txt), scaled linearly to this launch's bytes.
+            # dominant kernel = deflate_kernel (the larger share of the device-resident step's GPU time, see the ncu launch
+            # list under profiles/).  achieved = algorithmic bytes (U + C) / the kernel's time from CUDA events in this run;
+            # traffic = DRAM bytes of one `ncu --set full` capture, scaled to this launch's bytes (profiles/r02_dram_traffic.json).
             "roofline": {"bound": "hbm", "kernel": "deflate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": DEFLATE_DRAM_BYTES_PER_BYTE * U, "peak_source": which,
+                         "frac": achieved / peak,
+                         "traffic": traffic["deflate_bytes_per_byte"] * U if traffic else None, "peak_source": which,
+                         "traffic_source": traffic["source"] if traffic else None,
                          "algorithmic_bytes": "U + C per launch (read input once, write the stream once)",
-                         "note": "issue- and latency-bound integer kernel: 66 % issue-slot utilisation, 1.5 % DRAM throughput (ncu)",
-                         "inflate": {"kernel": "inflate_indexed_kernel", "achieved": (U + Cbytes) / (ki_ms * 1e-3) / 1e9,
+                         "note": "issue-bound integer kernel (ncu: issue-slot utilisation, not DRAM, is what saturates)",
+                         "inflate": {"kernel": "inflate_tok_kernel", "achieved": (U + Cbytes) / (ki_ms * 1e-3) / 1e9,
                                      "frac": (U + Cbytes) / (ki_ms * 1e-3) / 1e9 / peak,
-                                     "traffic": INFLATE_DRAM_BYTES_PER_BYTE * U}},
+                                     "traffic": traffic["inflate_bytes_per_byte"] * U if traffic else None}},
             "clocks": clocks, "gpu_launches": launches,
         }
+        if ratio_corpus:
+            line["ratio_corpus"] = ratio_corpus
+        if foreign:
+            line.update(foreign)
+        if config4:
+            line["config4"] = config4
         if e2e:
             line["e2e"] = e2e
         if base:
@@ -277,6 +328,116 @@ def main():
         dist.destroy_process_group()
 
 
+def run_ratio_corpus(dev, capi, torch, seg, nbytes=4 << 20):
+    """Compressed size next to zlib level 1 on every input of synth.ratio_corpus() (identical chunks)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    from bitar_b200 import synth
+    out = {}
+    threads = max(1, (os.cpu_count() or 2) - 1)
+    for name, d in synth.ratio_corpus(nbytes).items():
+        src = torch.from_numpy(d).cuda()
+        torch.cuda.synchronize()
+        ops, slots = dev.compress_ops(src.data_ptr(), d.size)
+        res = dev.enqueue("deflate", 0, ops)
+        dev.wait(0)
+        dev.put_slots(slots)
+        _, zp = O.compress_buffer(d, seg, threads=threads)
+        g, z = int(res["produced"].sum()), int(zp.sum())
+        out[name] = {"ratio": round(d.size / g, 4), "zlib_level1_ratio": round(d.size / z, 4), "bytes_vs_zlib": round(g / z, 4)}
+    return out
+
+
+def run_foreign(dev, torch, data, seg, mib=256):
+    """Inflate of reference-compressed streams (zlib level 1, no index: the reference's own output,
+    /root/reference/src/memory.cc:432-505) of the same workload, device-resident."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    sample = column_sample(data, seg, mib)
+    slots, produced = O.compress_buffer(sample, seg, threads=max(1, (os.cpu_count() or 2) - 1))
+    d_slots = torch.from_numpy(slots.reshape(-1)).cuda()
+    out = torch.empty(slots.shape[0] * seg + 64, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ptrs = np.uint64(d_slots.data_ptr()) + np.arange(slots.shape[0], dtype=np.uint64) * np.uint64(slots.shape[1])
+    iops = dev.decompress_ops(ptrs, produced, out.data_ptr())
+    best = 1e9
+    for _ in range(3):
+        r = dev.enqueue("inflate", 0, iops)
+        dev.wait(0)
+        best = min(best, dev.last_ms(0)[1])
+    ok = int(r["produced"].sum()) == sample.size and bool(torch.equal(out[:sample.size], torch.from_numpy(sample).cuda()))
+    return {"inflate_foreign_gbps": sample.size / (best * 1e-3) / 1e9, "inflate_foreign_ok": ok,
+            "inflate_foreign_sample": f"{sample.size >> 20} MiB of the workload compressed by zlib level 1 (no index): whole-stream kernel"}
+
+
+def gen_lineitem_on_device(torch, nbytes, seed):
+    """synth.lineitem_like() generated on the device (BASELINE config 4: the 64 GiB corpus does not fit the host)."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    third = (nbytes // 3) // 8 * 8
+    a = torch.cumsum(torch.randint(0, 4, (third // 8,), generator=g, device="cuda", dtype=torch.int64), 0)
+    p = torch.tensor([.30, .20, .15, .12, .10, .08, .05], device="cuda").cumsum(0)
+    b = torch.bucketize(torch.rand(third // 4, generator=g, device="cuda"), p).clamp_(max=6).to(torch.int32)
+    rest = (nbytes - 2 * third) // 8
+    c = torch.randint(90_000, 10_500_000, (rest,), generator=g, device="cuda", dtype=torch.int64).to(torch.float64) / 100.0
+    buf = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    buf[:third] = a.view(torch.uint8)
+    buf[third:2 * third] = b.view(torch.uint8)
+    buf[2 * third:2 * third + rest * 8] = c.view(torch.uint8)
+    return buf
+
+
+def run_config4(args, capi, torch, dist, world, local_rank, rank, seg):
+    """BASELINE config 4: a 64 GiB columnar corpus sharded 8 GiB per GPU, compress + inflate, device-resident: eight
+    1 GiB buffers per GPU, one per queue pair, all queue pairs at once; the pool holds ceil(bytes / S) + n_qp slots as
+    the reference sizes it (/root/reference/apps/app_common.cc:94-100)."""
+    from bitar_b200.engine import CompressDevice, Configuration
+    gib = args.config4_gib
+    per = 1 << 30
+    n_per = (per + seg - 1) // seg
+    dev = CompressDevice(local_rank, gib).Initialize(Configuration(decompressed_seg_size=seg, max_preallocate_memzones=gib * n_per + gib))
+    bufs = [gen_lineitem_on_device(torch, per, 20261018 + 1000 * rank + k) for k in range(gib)]
+    outs = [torch.empty(n_per * seg + 64, dtype=torch.uint8, device="cuda") for _ in range(gib)]
+    torch.cuda.synchronize()
+    slots_free0 = dev.slots_free()
+
+    def one_pass():
+        t0 = time.perf_counter()
+        plan = [dev.compress_ops(b.data_ptr(), per) for b in bufs]          # Take() of every chunk's slot
+        res = [dev.enqueue("deflate", q, plan[q][0]) for q in range(gib)]
+        for q in range(gib):
+            dev.wait(q)
+        t1 = time.perf_counter()
+        pend = [dev.enqueue("inflate", q, dev.decompress_ops(plan[q][1], res[q]["produced"], outs[q].data_ptr())) for q in range(gib)]
+        for q in range(gib):
+            dev.wait(q)
+        t2 = time.perf_counter()
+        comp = sum(int(r["produced"].sum()) for r in res)
+        total = sum(int(r["produced"].sum()) for r in pend)
+        for q in range(gib):
+            dev.put_slots(plan[q][1])
+        return t1 - t0, t2 - t1, comp, total
+
+    one_pass()                                                               # warm-up (scratch allocation, clocks)
+    td, ti, comp, total = one_pass()
+    ok = total == gib * per and all(bool(torch.equal(o[:per], b)) for o, b in zip(outs, bufs))
+    t = torch.tensor([td, ti], dtype=torch.float64, device="cuda")
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    td, ti = [float(x) for x in t.cpu()]
+    rec = {"gib_per_gpu": gib, "chunks_per_gpu": gib * n_per, "pool_slots": gib * n_per + gib, "queue_pairs": gib,
+           "deflate_gbps": world * gib * per / td / 1e9, "inflate_gbps": world * gib * per / ti / 1e9,
+           "round_trip_gbps": world * gib * per / (td + ti) / 1e9, "ratio": gib * per / comp, "round_trip_ok": bool(int(flag.cpu()[0])),
+           "slots_back": dev.slots_free() == slots_free0,
+           "timing": "host wall clock around all queue pairs of a device (Take + enqueue + wait), max over ranks; data generated on the device"}
+    dev.close()
+    del bufs, outs
+    torch.cuda.empty_cache()
+    return rec
+
+
 def run_e2e(args, L, capi, C, torch, dist, world, local_rank, data, seg, n, U):
     """Compress() + Decompress() with every user-visible buffer in pinned host memory, as a bitar
     application holds them (the Rtememzone pool of apps/demo_app.cc:119-122,517-522):
@@ -284,7 +445,15 @@ def run_e2e(args, L, capi, C, torch, dist, world, local_rank, data, seg, n, U):
                   writes the streams straight into pinned output slots (D2H = C bytes) -- zero-copy;
       decompress: called with the pinned slots and the pinned destination; the library gathers the slots into
                   device memory (H2D = C bytes), inflates, and scatters the result back (D2H = U bytes).
-    The input is split evenly over --qps queue pairs that run concurrently (apps/demo_app.cc:577-596)."""
+    The input is split evenly over --qps queue pairs that run concurrently (apps/demo_app.cc:577-596).  Every step
+    Take()s its output slots, builds its op lists and Recycle()s the slots inside the timed region, as the reference's
+    Compress() / Recycle() do per chunk (src/memory.cc:405-425, src/device.cc:320-327).
+    Two schedules are timed: `pipelined` (the headline e2e value) chains CompressAsync -> callback -> DecompressAsync per
+    queue pair (src/include/util.h:216-236), the odd queue pairs half a phase behind the even ones, so that one half
+    decompresses (device-to-host traffic) while the other compresses (host-to-device traffic); `phase_separated` waits
+    for every queue pair's compress before any decompress starts, as demo_app's evaluation does."""
+    from collections import deque
+
     from bitar_b200.engine import CompressDevice, Configuration
     qps = max(1, args.qps)
     dev = CompressDevice(local_rank, qps).Initialize(
@@ -294,46 +463,111 @@ def run_e2e(args, L, capi, C, torch, dist, world, local_rank, data, seg, n, U):
     capi.check(L.bitar_mem_alloc(capi.MEM_PINNED, local_rank, n * seg, 64, C.byref(h_out)))
     C.memmove(h_in.value, data.ctypes.data, U)
     torch.cuda.synchronize()
-    ops, slots = dev.compress_ops(h_in.value, U)
     per = (n + qps - 1) // qps
     parts = [(q * per, min(n, (q + 1) * per)) for q in range(qps) if q * per < n]
 
-    def step():
-        # Compress(): every queue pair deflates its part, reading the pinned input and writing the pinned slots
-        results = [dev.enqueue("deflate", q, ops[a:b]) for q, (a, b) in enumerate(parts)]
+    def part_ops(a, b):
+        nbytes = min(U, b * seg) - a * seg
+        return dev.compress_ops(h_in.value + a * seg, nbytes)             # Take()s b - a slots
+
+    phase_ms = [0.0, 0.0]
+
+    def step_separated():
+        t_a = time.perf_counter()
+        plan = [part_ops(a, b) for a, b in parts]
+        results = [dev.enqueue("deflate", q, plan[q][0]) for q in range(len(parts))]
         for q in range(len(parts)):
             dev.wait(q)
-        produced = np.concatenate([r["produced"] for r in results])
-        # Decompress(): pinned slots -> pinned destination; the library stages both through device memory
+        phase_ms[0] = (time.perf_counter() - t_a) * 1e3
         pending = []
         for q, (a, b) in enumerate(parts):
-            iops = dev.decompress_ops(slots[a:b], produced[a:b], h_out.value + a * seg)
+            iops = dev.decompress_ops(plan[q][1], results[q]["produced"], h_out.value + a * seg)
             pending.append(dev.enqueue("inflate", q, iops))
         for q in range(len(parts)):
             dev.wait(q)
+        comp = sum(int(r["produced"].sum()) for r in results)
         total = sum(int(r["produced"].sum()) for r in pending)
-        return int(produced.sum()), int(produced.sum()), total
+        for q in range(len(parts)):
+            dev.put_slots(plan[q][1])
+        phase_ms[1] = (time.perf_counter() - t_a) * 1e3 - phase_ms[0]
+        return comp, total
 
-    for _ in range(max(1, args.warmup)):
-        cbytes, h2d, total = step()
-    back = np.ctypeslib.as_array(C.cast(h_out.value, C.POINTER(C.c_uint8)), shape=(U,))
-    assert total == U and np.array_equal(back, data), "end-to-end round trip differs"
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    step_ms = []
-    for _ in range(args.steps):
-        t_step = time.perf_counter()
-        cbytes, h2d, total = step()
-        step_ms.append(round((time.perf_counter() - t_step) * 1e3, 3))
-    torch.cuda.synchronize()
-    dt = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    dt = float(dt.cpu()[0])
-    # PCIe roofline of this leg, measured in the same run: plain pinned <-> device copies of U bytes
+    K = 2                                                                   # sub-parts per queue pair
+
+    def step_pipelined():
+        todo = []
+        for a, b in parts:
+            m = (b - a + K - 1) // K
+            todo.append(deque((a + k * m, min(b, a + (k + 1) * m)) for k in range(K) if a + k * m < b))
+        state = ["idle"] * len(parts)                                        # idle -> c -> d -> idle
+        cur = [None] * len(parts)
+        comp = total = 0
+        odd_released = len(parts) < 2
+
+        def start_compress(q):
+            a, b = todo[q].popleft()
+            ops_, slots_ = part_ops(a, b)
+            cur[q] = (a, b, slots_, dev.enqueue("deflate", q, ops_))
+            state[q] = "c"
+
+        for q in range(0, len(parts), 2):
+            start_compress(q)
+        done = 0
+        while done < len(parts):
+            progressed = False
+            for q in range(len(parts)):
+                if state[q] in ("c", "d") and not dev.busy(q):
+                    capi.check(L.bitar_qp_result(dev._h, q))
+                    a, b, slots_, res_ = cur[q]
+                    if state[q] == "c":
+                        comp += int(res_["produced"].sum())
+                        iops = dev.decompress_ops(slots_, res_["produced"], h_out.value + a * seg)
+                        cur[q] = (a, b, slots_, dev.enqueue("inflate", q, iops))
+                        state[q] = "d"
+                        if not odd_released:                                 # the odd queue pairs start half a phase late
+                            odd_released = True
+                            for o in range(1, len(parts), 2):
+                                start_compress(o)
+                    else:
+                        total += int(res_["produced"].sum())
+                        dev.put_slots(slots_)
+                        if todo[q]:
+                            start_compress(q)
+                        else:
+                            state[q] = "idle"
+                            done += 1
+                    progressed = True
+            if not progressed:
+                time.sleep(0.00005)
+        return comp, total
+
+    def timed(step):
+        for _ in range(max(1, args.warmup)):
+            comp, total = step()
+        back = np.ctypeslib.as_array(C.cast(h_out.value, C.POINTER(C.c_uint8)), shape=(U,))
+        assert total == U and np.array_equal(back, data), "end-to-end round trip differs"
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step_ms = []
+        for _ in range(args.steps):
+            t_step = time.perf_counter()
+            comp, total = step()
+            step_ms.append(round((time.perf_counter() - t_step) * 1e3, 3))
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - t0) / args.steps], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt.cpu()[0]), step_ms, comp
+
+    dt_sep, ms_sep, cbytes = timed(step_separated)
+    sep_phases = {"compress_ms": round(phase_ms[0], 3), "decompress_ms": round(phase_ms[1], 3)}
+    dt, step_ms, cbytes = timed(step_pipelined)
+    # PCIe roofline of this leg, measured in the same run: plain pinned <-> device copies of U bytes, one direction at
+    # a time and both at once (two queue pairs' streams)
     d_tmp = torch.empty(U, dtype=torch.uint8, device="cuda")
+    d_tmp2 = torch.empty(U, dtype=torch.uint8, device="cuda")
     pcie = {}
     for name, dst, src in (("h2d_gbps", d_tmp.data_ptr(), h_in.value), ("d2h_gbps", h_out.value, d_tmp.data_ptr())):
         best = 1e9
@@ -344,19 +578,33 @@ def run_e2e(args, L, capi, C, torch, dist, world, local_rank, data, seg, n, U):
             dev.wait(0)
             best = min(best, time.perf_counter() - t1)
         pcie[name] = U / best / 1e9
-    del d_tmp
-    # each step moves U + C bytes in each direction; with both directions overlapped the floor is max(dir) / bw
-    floor = max((U + h2d) / (pcie["h2d_gbps"] * 1e9), (cbytes + U) / (pcie["d2h_gbps"] * 1e9))
-    pcie["frac_of_pcie_floor"] = floor / dt
+    if len(parts) > 1:
+        best = 1e9
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            capi.check(L.bitar_qp_memcpy(dev._h, 0, d_tmp2.data_ptr(), h_in.value, U))
+            capi.check(L.bitar_qp_memcpy(dev._h, 1, h_out.value, d_tmp.data_ptr(), U))
+            dev.wait(0)
+            dev.wait(1)
+            best = min(best, time.perf_counter() - t1)
+        pcie["both_directions_gbps_each"] = U / best / 1e9
+    del d_tmp, d_tmp2
+    # each step moves U + C bytes in each direction; with both directions busy at once the floor is (U + C) / bandwidth
+    both = pcie.get("both_directions_gbps_each", min(pcie["h2d_gbps"], pcie["d2h_gbps"]))
+    floor_pipe = (U + cbytes) / (both * 1e9)
+    floor_sep = U / (pcie["h2d_gbps"] * 1e9) + U / (pcie["d2h_gbps"] * 1e9)
+    pcie["frac_of_pcie_floor"] = floor_pipe / dt
+    pcie["phase_separated_frac_of_pcie_floor"] = floor_sep / dt_sep
     for b in (h_in, h_out):
         capi.check(L.bitar_mem_free(capi.MEM_PINNED, local_rank, b))
-    for s in slots[::-1]:
-        dev.put_slot(s)
     dev.close()
-    return {"value": world * U / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(U + h2d),
-            "d2h_bytes_per_step": int(cbytes + U), "ms_per_step": dt * 1e3, "step_ms": step_ms, "queue_pairs": len(parts), "pcie": pcie,
+    return {"value": world * U / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(U + cbytes),
+            "d2h_bytes_per_step": int(cbytes + U), "ms_per_step": dt * 1e3, "step_ms": step_ms, "queue_pairs": len(parts),
+            "schedule": f"pipelined: per queue pair Compress -> Decompress of {K} sub-parts back to back, odd queue pairs half a phase behind",
+            "phase_separated": {"value": world * U / dt_sep / 1e9, "ms_per_step": dt_sep * 1e3, "step_ms": ms_sep, "last_step": sep_phases}, "pcie": pcie,
             "path": "pinned host in/out through the C-ABI: compress reads and writes host memory in place (zero-copy over "
-                    "PCIe), decompress is staged through device memory by the library in batches on three extra streams per queue pair (strided copy-engine gather -- rows go at the pitch of the batch's widest stream, so somewhat more than C bytes cross PCIe --, inflate, copy-engine copy-back)"}
+                    "PCIe), decompress is staged through device memory by the library in batches on three extra streams per queue pair (strided copy-engine gather -- rows go at the pitch of the batch's widest stream, so somewhat more than C bytes cross PCIe --, inflate, copy-engine copy-back); Take / op lists / Recycle inside the timed step"}
 
 
 if __name__ == "__main__":

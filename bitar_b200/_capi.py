@@ -50,7 +50,7 @@ EXPORTS = [
     "bitar_reference_compressed_seg_size", "bitar_dev_open", "bitar_dev_close", "bitar_dev_config",
     "bitar_dev_num_qps", "bitar_qp_deflate", "bitar_qp_inflate", "bitar_qp_wait", "bitar_qp_result", "bitar_qp_busy",
     "bitar_qp_on_complete", "bitar_qp_last_ms", "bitar_qp_stream", "bitar_kernel_launches",
-    "bitar_slot_take", "bitar_slot_take_n", "bitar_slot_put", "bitar_slot_size", "bitar_slots_free",
+    "bitar_slot_take", "bitar_slot_take_n", "bitar_slot_put", "bitar_slot_put_n", "bitar_slot_size", "bitar_slots_free",
     "bitar_mem_alloc", "bitar_mem_free", "bitar_host_register", "bitar_host_unregister", "bitar_ptr_kind", "bitar_mem_copy", "bitar_current_device",
     "bitar_qp_memcpy", "bitar_last_error", "bitar_version",
 ]
@@ -89,6 +89,7 @@ def lib():
         f.argtypes = [vp, u16, vp, u32, vp]
     L.bitar_qp_wait.argtypes = [vp, u16]
     L.bitar_qp_busy.argtypes = [vp, u16]
+    L.bitar_qp_result.argtypes = [vp, u16]
     L.bitar_qp_on_complete.argtypes = [vp, u16, vp, vp]
     L.bitar_qp_last_ms.argtypes = [vp, u16, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.bitar_qp_stream.restype = vp
@@ -98,6 +99,8 @@ def lib():
     L.bitar_slot_take.argtypes = [vp]
     L.bitar_slot_take_n.argtypes = [vp, u32, vp]
     L.bitar_slot_put.argtypes = [vp, vp]
+    L.bitar_slot_put_n.restype = u32
+    L.bitar_slot_put_n.argtypes = [vp, vp, u32]
     L.bitar_slot_size.restype = u32
     L.bitar_slot_size.argtypes = [vp]
     L.bitar_slots_free.restype = u32

@@ -88,6 +88,13 @@ struct QueuePair {
   uint8_t* d_stage_out = nullptr;
   size_t stage_out_cap = 0;
   bool stage_src = false, stage_dst = false;
+  // deflate of a host-resident buffer: the input goes to the device stage in pieces by the copy engine (its own stream),
+  // the kernel of piece b starts when piece b has arrived
+  bool dstage = false;
+  const uint8_t* dstage_base = nullptr;
+  size_t dstage_total = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy[kMaxStageBatches] = {};
   bool stage_dst_contig = false;        // destinations form one range of equal-capacity segments (Decompress())
   size_t stage_out_bytes = 0;           // sum of the call's destination capacities
   uint32_t nb = 1, per = 0;             // batches of the call, ops per batch
@@ -393,7 +400,11 @@ int inflate_prepare_staging(QueuePair* q, uint32_t n, bool allow_batches) {
   }
   if (q->stage_dst && !q->ev_fork) {
     for (uint32_t k = 0; k < kStageLanes; ++k) {
-      CU_TRY(cudaStreamCreateWithFlags(&q->lane[k], cudaStreamNonBlocking), BITAR_E_OUT_OF_MEMORY);
+      // (highest priority: a batch's inflate kernel goes ahead of other queue pairs' compress launches, its copy-back
+      // then runs beside them)
+      int prio_lo = 0, prio_hi = 0;
+      cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+      CU_TRY(cudaStreamCreateWithPriority(&q->lane[k], cudaStreamNonBlocking, prio_hi), BITAR_E_OUT_OF_MEMORY);
       CU_TRY(cudaEventCreateWithFlags(&q->ev_lane[k], cudaEventDisableTiming), BITAR_E_OUT_OF_MEMORY);
     }
     CU_TRY(cudaEventCreateWithFlags(&q->ev_fork, cudaEventDisableTiming), BITAR_E_OUT_OF_MEMORY);
@@ -428,6 +439,47 @@ int inflate_prepare_staging(QueuePair* q, uint32_t n, bool allow_batches) {
   return BITAR_OK;
 }
 
+// Compress() of a buffer in pinned / registered HOST memory: the kernel's own bulk loads over PCIe reach ~43 GB/s and
+// slow to a crawl next to device-to-host traffic (read requests queue behind posted writes: measured 25 + 19 ms side by
+// side -> 37 ms, tools/pcie_overlap_probe.py).  The segments of a Compress() call are consecutive pieces of one buffer
+// (src/device.cc:168-170), so the call copies that range to a device stage with the copy engine, in pieces, and the
+// kernel of a piece starts when the piece has arrived.  Rewrites q->h_ops to staged addresses.
+constexpr size_t kDeflateStageMin = (size_t)4 << 20;
+int deflate_prepare_staging(QueuePair* q, uint32_t n) {
+  q->dstage = false;
+  static const int off = getenv("BITAR_DEFLATE_STAGE") ? !atoi(getenv("BITAR_DEFLATE_STAGE")) : 0;
+  if (off || n < 8 || q->h_ops[0].src == nullptr || !is_host_memory(q->h_ops[0].src)) return BITAR_OK;
+  const uint8_t* base = static_cast<const uint8_t*>(q->h_ops[0].src);
+  size_t total = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    if (static_cast<const uint8_t*>(q->h_ops[i].src) != base + total) return BITAR_OK;   // not one range: read in place
+    total += q->h_ops[i].src_len;
+  }
+  if (total < kDeflateStageMin) return BITAR_OK;
+  const size_t mis = reinterpret_cast<uintptr_t>(base) & 15u;
+  if (q->stage_in_cap < total + 64) {
+    if (q->d_stage_in) cudaFree(q->d_stage_in);
+    q->d_stage_in = nullptr; q->stage_in_cap = 0;
+    CU_TRY(cudaMalloc((void**)&q->d_stage_in, total + 64), BITAR_E_OUT_OF_MEMORY);
+    q->stage_in_cap = total + 64;
+  }
+  if (!q->copy_stream) {
+    CU_TRY(cudaStreamCreateWithFlags(&q->copy_stream, cudaStreamNonBlocking), BITAR_E_OUT_OF_MEMORY);
+    for (uint32_t k = 0; k < kMaxStageBatches; ++k) {
+      CU_TRY(cudaEventCreateWithFlags(&q->ev_copy[k], cudaEventDisableTiming), BITAR_E_OUT_OF_MEMORY);
+    }
+  }
+  size_t at = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    q->h_ops[i].src = q->d_stage_in + mis + at;   // (same misalignment as the original: the bulk loads see the same layout)
+    at += q->h_ops[i].src_len;
+  }
+  q->dstage = true;
+  q->dstage_base = base;
+  q->dstage_total = total;
+  return BITAR_OK;
+}
+
 enum { kSubmitDeflate = 0, kSubmitInflate = 1, kSubmitInflateOneBatch = 2 };
 
 // prepare(q, n): allocations for the whole call, before anything is enqueued;
@@ -459,6 +511,9 @@ int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, b
   q->per = n;
   if (inflate) {
     rc = inflate_prepare_staging(q, n, mode == kSubmitInflate);
+    if (rc) return rc;
+  } else {
+    rc = deflate_prepare_staging(q, n);
     if (rc) return rc;
   }
   q->user_out = results;
@@ -747,6 +802,9 @@ int bitar_dev_close(bitar_dev* dev) {
       if (q->lane[k]) cudaStreamDestroy(q->lane[k]);
     }
     if (q->ev_fork) cudaEventDestroy(q->ev_fork);
+    for (uint32_t k = 0; k < kMaxStageBatches; ++k)
+      if (q->ev_copy[k]) cudaEventDestroy(q->ev_copy[k]);
+    if (q->copy_stream) cudaStreamDestroy(q->copy_stream);
 
     if (q->stream) cudaStreamDestroy(q->stream);
     delete q;
@@ -781,14 +839,47 @@ int bitar_qp_deflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
         uint32_t max_len = 0;
         for (uint32_t i = 0; i < count; ++i) max_len = q->h_ops[first + i].src_len > max_len ? q->h_ops[first + i].src_len : max_len;
         const int max_dist = 1 << dev->cfg.window_size, emit_index = dev->cfg.no_index ? 0 : 1;
+        // host-resident input (read over PCIe by the kernel's bulk loads): the call yields the SMs a few times so that
+        // other queue pairs' inflate batches -- whose copy-back uses the other PCIe direction -- run beside it
+        static const int env_splits = getenv("BITAR_DEFLATE_SPLITS") ? atoi(getenv("BITAR_DEFLATE_SPLITS")) : 0;
+        const uint32_t splits = env_splits > 0 ? (uint32_t)env_splits : 1u;
         static const int small_mode = getenv("BITAR_DEFLATE_SMALL") ? atoi(getenv("BITAR_DEFLATE_SMALL")) : 1;   // 0: off (A/B runs)
-        if (small_mode && max_len <= (uint32_t)bitar::dks::kBlockMax)
-          return bitar::dks::deflate_launch(q->d_ops + first, count, q->d_res + first, counters, q->d_tokens, q->d_far, dev->id, dev->sm_count, 0,
-                                            max_len, dev->cfg.huffman_enc, dev->cfg.checksum_type, max_dist, emit_index,
-                                            g_deflate_prof.load(), st);
-        return bitar::dk::deflate_launch(q->d_ops + first, count, q->d_res + first, counters, q->d_tokens, q->d_far, dev->id, dev->sm_count,
-                                         dev->deflate_grid_override, (uint32_t)bitar::dk::kBlockMax, dev->cfg.huffman_enc,
-                                         dev->cfg.checksum_type, max_dist, emit_index, g_deflate_prof.load(), st);
+        const bool small = small_mode && max_len <= (uint32_t)bitar::dks::kBlockMax;
+        auto launch_part = [&](uint32_t a, uint32_t cnt, unsigned int* ctr, uint32_t parts) -> cudaError_t {
+          // calls whose chunks all fit 16 KiB (8 sub-ranges: half of a 16-warp CTA would idle) go to the instance with
+          // 4 warps per CTA and three to four times the CTAs per SM; same output
+          if (small)
+            return bitar::dks::deflate_launch(q->d_ops + a, cnt, q->d_res + a, ctr, q->d_tokens, q->d_far, dev->id, dev->sm_count, 0, max_len,
+                                              dev->cfg.huffman_enc, dev->cfg.checksum_type, max_dist, emit_index, g_deflate_prof.load(), st, parts);
+          return bitar::dk::deflate_launch(q->d_ops + a, cnt, q->d_res + a, ctr, q->d_tokens, q->d_far, dev->id, dev->sm_count,
+                                           dev->deflate_grid_override, (uint32_t)bitar::dk::kBlockMax, dev->cfg.huffman_enc,
+                                           dev->cfg.checksum_type, max_dist, emit_index, g_deflate_prof.load(), st, parts);
+        };
+        if (!q->dstage) {
+          g_launches.fetch_add(bitar::dk::deflate_splits(count, splits) - 1u);
+          return launch_part(first, count, counters, splits);
+        }
+        // host-resident input: pieces of at least 8 MiB, at most 8; copy b runs beside kernel b - 1
+        uint32_t pieces = (uint32_t)(q->dstage_total / ((size_t)8 << 20));
+        pieces = pieces < 1 ? 1 : pieces > kMaxStageBatches ? kMaxStageBatches : pieces;
+        const uint32_t per = (count + pieces - 1) / pieces;
+        const size_t mis = reinterpret_cast<uintptr_t>(q->dstage_base) & 15u;
+        size_t off = 0;
+        uint32_t b = 0;
+        for (uint32_t a = 0; a < count; a += per, ++b) {
+          const uint32_t cnt = count - a < per ? count - a : per;
+          size_t bytes = 0;
+          for (uint32_t i = 0; i < cnt; ++i) bytes += q->h_ops[first + a + i].src_len;
+          // (throttling the copies to two pieces ahead of the kernels measured slower: 43 against 41 ms per GiB end to end)
+          cudaError_t e = cudaMemcpyAsync(q->d_stage_in + mis + off, q->dstage_base + off, bytes, cudaMemcpyDefault, q->copy_stream);
+          if (e == cudaSuccess) e = cudaEventRecord(q->ev_copy[b], q->copy_stream);
+          if (e == cudaSuccess) e = cudaStreamWaitEvent(st, q->ev_copy[b], 0);
+          if (e == cudaSuccess) e = launch_part(first + a, cnt, counters + b, 1);
+          if (e != cudaSuccess) return e;
+          off += bytes;
+        }
+        g_launches.fetch_add(b - 1u);
+        return cudaSuccess;
       },
       kSubmitDeflate);
 }
@@ -977,6 +1068,18 @@ int bitar_slot_put(bitar_dev* dev, const void* addr) {
   if (dev->occupied.erase(addr) == 0) return 0;  // not a slot we handed out: ignore (src/memory.cc:201-205)
   dev->free_slots.push_back(const_cast<void*>(addr));
   return 1;
+}
+
+uint32_t bitar_slot_put_n(bitar_dev* dev, const void* const* addrs, uint32_t n) {
+  if (!dev || (!addrs && n)) return 0;
+  std::lock_guard<std::mutex> lock(dev->mu);
+  uint32_t back = 0;
+  for (uint32_t i = n; i-- > 0;) {   // in reverse, as CompressDevice::Recycle walks its BufferVector (src/device.cc:320-327)
+    if (!addrs[i] || dev->occupied.erase(addrs[i]) == 0) continue;
+    dev->free_slots.push_back(const_cast<void*>(addrs[i]));
+    ++back;
+  }
+  return back;
 }
 
 uint32_t bitar_slot_size(const bitar_dev* dev) { return dev ? dev->cfg.compressed_seg_size : 0; }

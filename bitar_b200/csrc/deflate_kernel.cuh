@@ -1397,19 +1397,35 @@ inline cudaError_t deflate_grid(int device, int sm_count, int* grid_out) {
   return cudaSuccess;
 }
 
+// launches a call of n ops is split into when `want` are asked for
+inline uint32_t deflate_splits(uint32_t n, uint32_t want) {
+  if (want > 8u) want = 8u;
+  return (want < 1u || n < 4u * want) ? 1u : want;
+}
+
 inline cudaError_t deflate_launch(const bitar_chunk* ops, uint32_t n, bitar_result* res, unsigned int* counter,
                                   uint32_t* scratch, uint16_t* far, int device, int sm_count, int grid_override, uint32_t max_len,
                                   int huffman, int checksum_type, int max_dist, int emit_index, unsigned long long* prof,
-                                  cudaStream_t stream) {
+                                  cudaStream_t stream, uint32_t splits = 1) {
   if (n == 0) return cudaSuccess;
   int ctas = 0;
   cudaError_t e = deflate_ctas_per_sm(device, max_len, &ctas);
   if (e != cudaSuccess) return e;
-  int grid = grid_override > 0 ? grid_override : sm_count * ctas;
-  if ((uint32_t)grid > n) grid = (int)n;
-  deflate_kernel<<<grid, kThreads, smem_bytes(max_len), stream>>>(ops, n, res, counter, scratch, far, huffman, checksum_type, max_dist,
-                                                                  emit_index, prof);
-  return cudaGetLastError();
+  // `splits` > 1: the call goes out as that many launches over consecutive parts of the op list (each with its own work
+  // counter, at most 8).  A persistent grid holds every SM until its list is drained; between launches the kernels other
+  // queue pairs have waiting -- an inflate whose copy-back should run beside this compress -- get their turn.
+  splits = deflate_splits(n, splits);
+  const uint32_t per = (n + splits - 1u) / splits;
+  for (uint32_t k = 0, first = 0; first < n; ++k, first += per) {
+    const uint32_t count = n - first < per ? n - first : per;
+    int grid = grid_override > 0 ? grid_override : sm_count * ctas;
+    if ((uint32_t)grid > count) grid = (int)count;
+    deflate_kernel<<<grid, kThreads, smem_bytes(max_len), stream>>>(ops + first, count, res + first, counter + k, scratch, far, huffman,
+                                                                    checksum_type, max_dist, emit_index, prof);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 }  // namespace BITAR_DK_NS

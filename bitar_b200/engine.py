@@ -143,6 +143,11 @@ class CompressDevice:
     def put_slot(self, ptr):
         return int(capi.lib().bitar_slot_put(self._h, C.c_void_p(int(ptr))))
 
+    def put_slots(self, ptrs):
+        """Recycle an array of slot addresses in one call; returns the number recycled."""
+        arr = np.ascontiguousarray(ptrs, dtype=np.uint64)
+        return int(capi.lib().bitar_slot_put_n(self._h, arr.ctypes.data if arr.size else None, arr.size))
+
     def slots_free(self):
         return int(capi.lib().bitar_slots_free(self._h))
 
@@ -210,7 +215,7 @@ class CompressDevice:
 
     def Recycle(self, buffers):
         """Returns the number of buffers recycled, walking in reverse (src/device.cc:320-327)."""
-        return sum(self.put_slot(b.ptr) for b in reversed(buffers))
+        return self.put_slots(np.array([b.ptr for b in buffers], np.uint64))
 
     def _entry_guard(self, qp):  # src/device.cc:443-462
         if qp >= self._num_qps:

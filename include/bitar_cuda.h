@@ -173,6 +173,9 @@ BITAR_API uint64_t bitar_kernel_launches(void);
 BITAR_API void* bitar_slot_take(bitar_dev* dev);
 BITAR_API int bitar_slot_take_n(bitar_dev* dev, uint32_t n, void** slots);
 BITAR_API int bitar_slot_put(bitar_dev* dev, const void* addr);
+/* CompressDevice::Recycle(BufferVector) in one call (src/device.cc:320-327): puts the n addresses back in reverse order and
+ * returns how many of them were occupied slots of this device. */
+BITAR_API uint32_t bitar_slot_put_n(bitar_dev* dev, const void* const* addrs, uint32_t n);
 BITAR_API uint32_t bitar_slot_size(const bitar_dev* dev);
 BITAR_API uint32_t bitar_slots_free(bitar_dev* dev);
 
