@@ -51,7 +51,7 @@ EXPORTS = [
     "bitar_dev_num_qps", "bitar_qp_deflate", "bitar_qp_inflate", "bitar_qp_wait", "bitar_qp_result", "bitar_qp_busy",
     "bitar_qp_on_complete", "bitar_qp_last_ms", "bitar_qp_stream", "bitar_kernel_launches",
     "bitar_slot_take", "bitar_slot_take_n", "bitar_slot_put", "bitar_slot_put_n", "bitar_slot_size", "bitar_slots_free",
-    "bitar_mem_alloc", "bitar_mem_free", "bitar_host_register", "bitar_host_unregister", "bitar_ptr_kind", "bitar_mem_copy", "bitar_current_device",
+    "bitar_mem_alloc", "bitar_mem_free", "bitar_host_register", "bitar_host_unregister", "bitar_ptr_kind", "bitar_mem_copy", "bitar_current_device", "bitar_set_device",
     "bitar_qp_memcpy", "bitar_last_error", "bitar_version",
 ]
 

@@ -1138,6 +1138,11 @@ int bitar_current_device(int* device_id) {
   return BITAR_OK;
 }
 
+int bitar_set_device(int device_id) {
+  CU_TRY(cudaSetDevice(device_id), BITAR_E_INVALID);
+  return BITAR_OK;
+}
+
 int bitar_qp_memcpy(bitar_dev* dev, uint16_t qp, void* dst, const void* src, size_t n) {
   if (!dev || qp >= dev->qps.size()) return fail(BITAR_E_INVALID, "bad device/queue pair");
   CU_TRY(cudaSetDevice(dev->id), BITAR_E_INVALID);

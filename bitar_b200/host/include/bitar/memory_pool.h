@@ -39,16 +39,20 @@ class CudaAllocatorTracker {
   mutable std::mutex mutex_{};
 };
 
-enum class MemoryPoolBackend : std::uint8_t { System, CudaPinnedHost };
+enum class MemoryPoolBackend : std::uint8_t { System, CudaPinnedHost, CudaDevice };
 
-/// \brief Get the memory pool for the selected backend.  CudaPinnedHost is the Rtememzone analogue: memory the
-/// device reads and writes in place (zero-copy over PCIe) and the CPU can touch, which Arrow's allocation
-/// helpers do (they zero the padding of every buffer on the CPU) -- the reason there is no device-memory POOL.
+/// \brief Get the memory pool for the selected backend (/root/reference/src/include/memory_pool.h:65-74).
+/// CudaPinnedHost is the Rtememzone analogue for buffers the CPU also touches: memory the device reads and writes in
+/// place (zero-copy over PCIe).  CudaDevice hands out memory of the calling thread's current CUDA device
+/// (cudaMallocAsync): Allocate / Reallocate (device-side copy) / Free and the pool statistics work like any pool's, but
+/// the bytes are not addressable by the CPU -- Arrow's own allocation helpers (arrow::AllocateBuffer, builders) zero the
+/// padding of what they allocate on the CPU and must not be given this pool; use AllocateDeviceBuffer() below.
 arrow::MemoryPool* GetMemoryPool(MemoryPoolBackend backend);
 
-/// \brief A resizable buffer in the memory of CUDA device \p device_id (cudaMallocAsync), for callers that keep
-/// their data resident in HBM.  Typed as a CPU arrow::Buffer whose data() is a device address (Arrow C++ in this
-/// image ships without arrow::cuda); never dereference it on the host.
+/// \brief A resizable buffer in the memory of CUDA device \p device_id, allocated from the CudaDevice pool (so that
+/// it shows in the pool's statistics and the tracker), for callers that keep their data resident in HBM.  Typed as a
+/// CPU arrow::Buffer whose data() is a device address (Arrow C++ in this image ships without arrow::cuda); never
+/// dereference it on the host.  Resize() / Reserve() never touch the bytes from the CPU.
 arrow::Result<std::unique_ptr<arrow::ResizableBuffer>> AllocateDeviceBuffer(std::int64_t size, int device_id);
 
 }  // namespace bitar

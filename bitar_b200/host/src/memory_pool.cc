@@ -32,7 +32,9 @@ class CudaMemoryPool : public arrow::MemoryPool {
       return arrow::Status::OK();
     }
     void* p = nullptr;
-    const int device = -1;
+    int device = -1;
+    if (kind_ == BITAR_MEM_DEVICE && bitar_current_device(&device) != BITAR_OK)
+      return arrow::Status::Invalid("no current CUDA device: ", bitar_last_error());
     const int rc = bitar_mem_alloc(kind_, device, static_cast<std::size_t>(size), static_cast<std::size_t>(alignment), &p);
     if (rc != BITAR_OK) return arrow::Status::OutOfMemory("malloc of size ", size, " failed: ", bitar_last_error());
     *out = static_cast<std::uint8_t*>(p);
@@ -49,7 +51,14 @@ class CudaMemoryPool : public arrow::MemoryPool {
     ARROW_RETURN_NOT_OK(Allocate(new_size, alignment, &fresh));
     const std::int64_t n = old_size < new_size ? old_size : new_size;
     if (n > 0) {
-      std::memcpy(fresh, old, static_cast<std::size_t>(n));
+      if (kind_ == BITAR_MEM_DEVICE) {
+        if (bitar_mem_copy(fresh, old, static_cast<std::size_t>(n)) != BITAR_OK) {
+          Free(fresh, new_size, alignment);
+          return arrow::Status::IOError("device copy failed: ", bitar_last_error());
+        }
+      } else {
+        std::memcpy(fresh, old, static_cast<std::size_t>(n));
+      }
     }
     Free(old, old_size, alignment);
     *ptr = fresh;
@@ -85,17 +94,15 @@ class CudaMemoryPool : public arrow::MemoryPool {
   std::atomic<std::int64_t> bytes_{0}, max_{0}, total_{0}, count_{0};
 };
 
-// device-resident ResizableBuffer: Resize() never touches the bytes from the CPU
+// device-resident ResizableBuffer over the CudaDevice pool: Resize() never touches the bytes from the CPU
 class DeviceBuffer : public arrow::ResizableBuffer {
  public:
-  DeviceBuffer(std::uint8_t* data, std::int64_t size, int device) : arrow::ResizableBuffer(data, size), device_{device} {
+  DeviceBuffer(std::uint8_t* data, std::int64_t size, int device, arrow::MemoryPool* pool)
+      : arrow::ResizableBuffer(data, size), device_{device}, pool_{pool} {
     capacity_ = size;
   }
   ~DeviceBuffer() override {
-    if (data_ != nullptr) {
-      bitar_mem_free(BITAR_MEM_DEVICE, device_, const_cast<std::uint8_t*>(data_));
-      CudaAllocatorTracker::Instance()->Release(data_);
-    }
+    if (data_ != nullptr) pool_->Free(const_cast<std::uint8_t*>(data_), capacity_, 256);
   }
   arrow::Status Resize(const std::int64_t new_size, bool /*shrink_to_fit*/) override {
     if (new_size < 0) return arrow::Status::Invalid("Negative buffer resize: ", new_size);
@@ -105,36 +112,32 @@ class DeviceBuffer : public arrow::ResizableBuffer {
   }
   arrow::Status Reserve(const std::int64_t new_capacity) override {
     if (new_capacity <= capacity_) return arrow::Status::OK();
-    void* p = nullptr;
-    if (bitar_mem_alloc(BITAR_MEM_DEVICE, device_, static_cast<std::size_t>(new_capacity), 256, &p) != BITAR_OK)
-      return arrow::Status::OutOfMemory("device allocation of ", new_capacity, " bytes failed: ", bitar_last_error());
-    if (size_ > 0 && bitar_mem_copy(p, data_, static_cast<std::size_t>(size_)) != BITAR_OK) {
-      bitar_mem_free(BITAR_MEM_DEVICE, device_, p);
-      return arrow::Status::IOError("device copy failed: ", bitar_last_error());
-    }
-    if (data_ != nullptr) {
-      bitar_mem_free(BITAR_MEM_DEVICE, device_, const_cast<std::uint8_t*>(data_));
-      CudaAllocatorTracker::Instance()->Release(data_);
-    }
-    data_ = static_cast<std::uint8_t*>(p);
+    std::uint8_t* p = const_cast<std::uint8_t*>(data_);
+    ARROW_RETURN_NOT_OK(pool_->Reallocate(capacity_, new_capacity, 256, &p));   // alloc + device-side copy + free
+    data_ = p;
     capacity_ = new_capacity;
-    CudaAllocatorTracker::Instance()->Emplace(data_, {static_cast<std::size_t>(new_capacity), BITAR_MEM_DEVICE, device_});
     return arrow::Status::OK();
   }
 
  private:
   const int device_;
+  arrow::MemoryPool* const pool_;
 };
 
 }  // namespace
 
 arrow::Result<std::unique_ptr<arrow::ResizableBuffer>> AllocateDeviceBuffer(std::int64_t size, int device_id) {
   if (size < 0) return arrow::Status::Invalid("negative size");
-  void* p = nullptr;
-  if (bitar_mem_alloc(BITAR_MEM_DEVICE, device_id, static_cast<std::size_t>(size), 256, &p) != BITAR_OK)
-    return arrow::Status::OutOfMemory("device allocation of ", size, " bytes failed: ", bitar_last_error());
-  CudaAllocatorTracker::Instance()->Emplace(static_cast<std::uint8_t*>(p), {static_cast<std::size_t>(size), BITAR_MEM_DEVICE, device_id});
-  return std::unique_ptr<arrow::ResizableBuffer>(new DeviceBuffer(static_cast<std::uint8_t*>(p), size, device_id));
+  int current = -1;
+  if (bitar_current_device(&current) != BITAR_OK) return arrow::Status::Invalid("no current CUDA device: ", bitar_last_error());
+  if (current != device_id && bitar_set_device(device_id) != BITAR_OK)
+    return arrow::Status::Invalid("cannot select CUDA device ", device_id, ": ", bitar_last_error());
+  auto* pool = GetMemoryPool(MemoryPoolBackend::CudaDevice);
+  std::uint8_t* p = nullptr;
+  auto st = pool->Allocate(size > 0 ? size : 1, 256, &p);
+  if (current != device_id) bitar_set_device(current);
+  ARROW_RETURN_NOT_OK(st);
+  return std::unique_ptr<arrow::ResizableBuffer>(new DeviceBuffer(p, size, device_id, pool));
 }
 
 CudaAllocatorTracker* CudaAllocatorTracker::Instance() {
@@ -163,6 +166,10 @@ arrow::MemoryPool* GetMemoryPool(MemoryPoolBackend backend) {   // memory_pool.c
   switch (backend) {
     case MemoryPoolBackend::CudaPinnedHost: {
       static CudaMemoryPool pool(BITAR_MEM_PINNED, "cuda_pinned_host");
+      return &pool;
+    }
+    case MemoryPoolBackend::CudaDevice: {
+      static CudaMemoryPool pool(BITAR_MEM_DEVICE, "cuda_device");
       return &pool;
     }
     case MemoryPoolBackend::System:

@@ -194,6 +194,8 @@ BITAR_API int bitar_ptr_kind(const void* ptr, int* device_id);
 BITAR_API int bitar_mem_copy(void* dst, const void* src, size_t n);
 /* The calling thread's current CUDA device (device pools allocate there). */
 BITAR_API int bitar_current_device(int* device_id);
+/* Select the calling thread's current CUDA device (what the device pool allocates from next). */
+BITAR_API int bitar_set_device(int device_id);
 /* Plain copies on the queue pair's stream (host<->device staging for pageable buffers). */
 BITAR_API int bitar_qp_memcpy(bitar_dev* dev, uint16_t qp, void* dst, const void* src, size_t n);
 

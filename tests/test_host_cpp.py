@@ -74,3 +74,38 @@ def test_demo_app_content_mode(tmp_path, fmt):
     assert r.returncode == 0 and "PASSED" in r.stdout and "MISMATCH" not in r.stdout
     if fmt != "raw":
         assert "deserialised table: OK" in r.stdout and f"{n} rows x 4 columns" in r.stdout
+
+
+def test_framing_helpers_against_zlib():
+    """bitar/framing.h (zlib / gzip wrappers around a chunk's raw stream, and unframing) against zlib itself."""
+    subprocess.check_call(["make", "-C", HOST, "-s", "tests/framing_test"])
+    r = subprocess.run([os.path.join(HOST, "tests", "framing_test")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "framing: OK" in r.stdout, r.stderr
+
+
+@pytest.mark.gpu
+def test_device_memory_pool():
+    """GetMemoryPool(CudaDevice): Allocate / Reallocate (device-side copy) / Free, statistics, tracker, and
+    AllocateDeviceBuffer() on top of it (/root/reference/src/memory_pool.cc:125-188,321-350)."""
+    _build()
+    r = subprocess.run([os.path.join(HOST, "tests", "pool_test")], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "device pool: OK" in r.stdout
+
+
+@pytest.mark.gpu
+def test_demo_app_async_over_all_devices_in_one_process():
+    """bitar's own multi-device model: ONE process, every visible device, CompressAsync / DecompressAsync over every
+    (device, queue pair) (/root/reference/apps/demo_app.cc:556-607, src/driver.cc:100-158).  Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU visible: the single-process multi-device flow needs two")
+    _build()
+    r = subprocess.run([DEMO, "--bytes", str(512 << 20), "--mode", "async", "--qps", "2"], capture_output=True, text=True, timeout=900)
+    print(r.stdout[-4000:], r.stderr[-2000:])
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, "demo_async_all_devices.txt"), "w") as f:
+        f.write(r.stdout)
+    assert r.returncode == 0 and "PASSED" in r.stdout and "MISMATCH" not in r.stdout
+    assert f"{torch.cuda.device_count()} device(s)" in r.stdout
