@@ -15,6 +15,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <unordered_map>
 #include <unordered_set>
 #include <vector>
 
@@ -132,6 +133,11 @@ struct bitar_dev {
   std::vector<void*> slabs;
   std::vector<void*> free_slots;                 // LIFO
   std::unordered_set<const void*> occupied;
+  // chained segments (max_sgl_segs = k > 1): the pool hands out GROUPS of k slots that lie back to back (a stream's
+  // destination is one range); free_slots then holds group bases, and a group returns when all its slots came back
+  uint32_t group = 1;
+  std::vector<std::pair<uint8_t*, size_t>> slab_ranges;
+  std::unordered_map<const void*, uint32_t> group_out;   // group base -> slots of it that are out
   uint32_t slot_stride = 0;
   uint32_t grow_warned = 0;
 };
@@ -191,12 +197,64 @@ int free_kind(int kind, int device, void* p) {
 // grow the slot pool by `count` slots carved from one slab (caller holds dev->mu)
 int pool_grow(bitar_dev* dev, uint32_t count) {
   void* slab = nullptr;
+  count = (count + dev->group - 1) / dev->group * dev->group;
   int rc = alloc_kind(dev->cfg.slot_mem_kind, dev->id, (size_t)count * dev->slot_stride, &slab);
   if (rc) return rc;
   dev->slabs.push_back(slab);
+  dev->slab_ranges.emplace_back(static_cast<uint8_t*>(slab), (size_t)count * dev->slot_stride);
+  if (dev->group > 1) {   // group bases, ascending addresses out first
+    for (uint32_t i = count / dev->group; i-- > 0;)
+      dev->free_slots.push_back(static_cast<uint8_t*>(slab) + (size_t)i * dev->group * dev->slot_stride);
+    return BITAR_OK;
+  }
   // push in reverse so that Take() hands out ascending addresses (contiguous runs for take_n)
   for (uint32_t i = count; i-- > 0;) dev->free_slots.push_back(static_cast<uint8_t*>(slab) + (size_t)i * dev->slot_stride);
   return BITAR_OK;
+}
+
+// chained segments: take n slots as ceil(n / group) groups (caller holds dev->mu); the last group may hand out fewer
+int pool_take_groups(bitar_dev* dev, uint32_t n, void** slots) {
+  const uint32_t k = dev->group, need = (n + k - 1) / k;
+  if (dev->free_slots.size() < need) {
+    if (dev->grow_warned++ % 32 == 0)
+      fprintf(stderr, "[bitar] WARNING: allocating output slots in the critical path (performance will be impacted)\n");
+    std::vector<void*> old;
+    old.swap(dev->free_slots);
+    int rc = pool_grow(dev, (need - (uint32_t)old.size()) * k);
+    if (rc) {
+      dev->free_slots.swap(old);
+      return rc;
+    }
+    dev->free_slots.insert(dev->free_slots.begin(), old.begin(), old.end());
+  }
+  for (uint32_t g = 0, i = 0; g < need; ++g) {
+    uint8_t* base = static_cast<uint8_t*>(dev->free_slots.back());
+    dev->free_slots.pop_back();
+    const uint32_t cnt = n - i < k ? n - i : k;
+    dev->group_out[base] = cnt;
+    for (uint32_t j = 0; j < cnt; ++j, ++i) {
+      slots[i] = base + (size_t)j * dev->slot_stride;
+      dev->occupied.insert(slots[i]);
+    }
+  }
+  return BITAR_OK;
+}
+// chained segments: a slot comes back; its group is free again when all of its slots are (caller holds dev->mu)
+int pool_put_grouped(bitar_dev* dev, const void* addr) {
+  if (dev->occupied.erase(addr) == 0) return 0;
+  const uint8_t* a = static_cast<const uint8_t*>(addr);
+  for (const auto& r : dev->slab_ranges)
+    if (a >= r.first && a < r.first + r.second) {
+      const size_t gbytes = (size_t)dev->group * dev->slot_stride;
+      const uint8_t* base = r.first + (size_t)(a - r.first) / gbytes * gbytes;
+      auto it = dev->group_out.find(base);
+      if (it != dev->group_out.end() && --it->second == 0) {
+        dev->group_out.erase(it);
+        dev->free_slots.push_back(const_cast<uint8_t*>(base));
+      }
+      break;
+    }
+  return 1;
 }
 
 int qp_reserve(bitar_dev* dev, QueuePair* q, uint32_t n) {
@@ -657,7 +715,7 @@ int bitar_cuda_device_info(int device_id, bitar_dev_info* info) {
   info->supports_dynamic = 1;
   info->supports_crc32 = 1;
   info->supports_adler32 = 1;
-  info->supports_sgl = 0;
+  info->supports_sgl = 1;
   snprintf(info->name, sizeof info->name, "%s", p.name);
   return BITAR_OK;
 }
@@ -692,10 +750,14 @@ int bitar_dev_open(int device_id, uint16_t n_qps, const bitar_cfg* cfg_in, bitar
   // ValidateConfiguration, src/device.cc:352-415 (+ BlueField specifics 558-577)
   if (cfg.burst_size == 0) cfg.burst_size = 32;
   if (cfg.max_sgl_segs < 1) cfg.max_sgl_segs = 1;
-  if (cfg.max_sgl_segs > 1) return fail(BITAR_E_INVALID, "Compress device does not support chained mbufs.");
+  if (cfg.max_sgl_segs > BITAR_MAX_SGL_SEGS)
+    return fail(BITAR_E_INVALID, "max_sgl_segs (%u) is not in the range of [1, %u]", (unsigned)cfg.max_sgl_segs, BITAR_MAX_SGL_SEGS);
   if (cfg.decompressed_seg_size == 0) cfg.decompressed_seg_size = 2048;
   if (cfg.decompressed_seg_size < BITAR_MIN_SEG_SIZE || cfg.decompressed_seg_size > BITAR_MAX_SEG_SIZE)
     return fail(BITAR_E_INVALID, "decompressed_seg_size is not in the range of [%u, %u]", BITAR_MIN_SEG_SIZE, BITAR_MAX_SEG_SIZE);
+  if ((uint64_t)cfg.max_sgl_segs * cfg.decompressed_seg_size > BITAR_MAX_SEG_SIZE)
+    return fail(BITAR_E_INVALID, "max_sgl_segs * decompressed_seg_size (%u * %u) is above the largest stream (%u bytes)",
+                (unsigned)cfg.max_sgl_segs, cfg.decompressed_seg_size, BITAR_MAX_SEG_SIZE);
   if (cfg.window_size == 0) cfg.window_size = info.window_max;
   if (cfg.window_size < info.window_min || cfg.window_size > info.window_max)
     return fail(BITAR_E_INVALID, "window_size is not in the range of [%u, %u]", info.window_min, info.window_max);
@@ -718,7 +780,9 @@ int bitar_dev_open(int device_id, uint16_t n_qps, const bitar_cfg* cfg_in, bitar
   dev->id = device_id;
   dev->sm_count = info.sm_count;
   dev->cfg = cfg;
-  dev->slot_stride = (cfg.compressed_seg_size + 255u) & ~255u;
+  // chained segments (max_sgl_segs > 1): the slots of a stream are one contiguous range, so they lie back to back
+  dev->slot_stride = cfg.max_sgl_segs > 1 ? cfg.compressed_seg_size : (cfg.compressed_seg_size + 255u) & ~255u;
+  dev->group = cfg.max_sgl_segs > 1 ? cfg.max_sgl_segs : 1;
   {
     // keep freed device memory cached in the pool (allocation is off the timed path, as in
     // apps/demo_app.cc:517-522,587-590, but re-use must stay cheap)
@@ -1020,6 +1084,10 @@ uint64_t bitar_kernel_launches(void) { return g_launches.load(); }
 void* bitar_slot_take(bitar_dev* dev) {
   if (!dev) return nullptr;
   std::lock_guard<std::mutex> lock(dev->mu);
+  if (dev->group > 1) {
+    void* one = nullptr;
+    return pool_take_groups(dev, 1, &one) == BITAR_OK ? one : nullptr;
+  }
   if (dev->free_slots.empty()) {
     // growing on the critical path, as DeviceMemory::Take does with a warning (src/memory.cc:167-175)
     if (dev->grow_warned++ % 32 == 0)
@@ -1036,6 +1104,10 @@ void* bitar_slot_take(bitar_dev* dev) {
 int bitar_slot_take_n(bitar_dev* dev, uint32_t n, void** slots) {
   if (!dev || (!slots && n)) return fail(BITAR_E_INVALID, "bad argument");
   std::lock_guard<std::mutex> lock(dev->mu);
+  if (dev->group > 1) {
+    int rc = pool_take_groups(dev, n, slots);
+    return rc ? fail(BITAR_E_IO_ERROR, "output slot pool exhausted") : BITAR_OK;
+  }
   if (dev->free_slots.size() < n) {
     uint32_t add = n - (uint32_t)dev->free_slots.size();
     if (dev->grow_warned++ % 32 == 0)
@@ -1065,6 +1137,7 @@ int bitar_slot_take_n(bitar_dev* dev, uint32_t n, void** slots) {
 int bitar_slot_put(bitar_dev* dev, const void* addr) {
   if (!dev || !addr) return 0;
   std::lock_guard<std::mutex> lock(dev->mu);
+  if (dev->group > 1) return pool_put_grouped(dev, addr);
   if (dev->occupied.erase(addr) == 0) return 0;  // not a slot we handed out: ignore (src/memory.cc:201-205)
   dev->free_slots.push_back(const_cast<void*>(addr));
   return 1;
@@ -1075,7 +1148,12 @@ uint32_t bitar_slot_put_n(bitar_dev* dev, const void* const* addrs, uint32_t n) 
   std::lock_guard<std::mutex> lock(dev->mu);
   uint32_t back = 0;
   for (uint32_t i = n; i-- > 0;) {   // in reverse, as CompressDevice::Recycle walks its BufferVector (src/device.cc:320-327)
-    if (!addrs[i] || dev->occupied.erase(addrs[i]) == 0) continue;
+    if (!addrs[i]) continue;
+    if (dev->group > 1) {
+      back += (uint32_t)pool_put_grouped(dev, addrs[i]);
+      continue;
+    }
+    if (dev->occupied.erase(addrs[i]) == 0) continue;
     dev->free_slots.push_back(const_cast<void*>(addrs[i]));
     ++back;
   }
@@ -1087,7 +1165,7 @@ uint32_t bitar_slot_size(const bitar_dev* dev) { return dev ? dev->cfg.compresse
 uint32_t bitar_slots_free(bitar_dev* dev) {
   if (!dev) return 0;
   std::lock_guard<std::mutex> lock(dev->mu);
-  return (uint32_t)dev->free_slots.size();
+  return (uint32_t)dev->free_slots.size() * dev->group;
 }
 
 int bitar_mem_alloc(int kind, int device_id, size_t size, size_t alignment, void** out) {

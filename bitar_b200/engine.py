@@ -101,6 +101,11 @@ class CompressDevice:
     def slot(self):
         return int(self.cfg.compressed_seg_size)
 
+    @property
+    def sgl(self):
+        """Segments chained into one stream (max_sgl_segs, src/include/config.h:90-96)."""
+        return max(1, int(self.cfg.max_sgl_segs))
+
     def _guard(self):
         if self._h is None:
             raise BitarError(capi.E_INVALID, f"Compress device {self._device_id} has not started")
@@ -154,10 +159,27 @@ class CompressDevice:
     # -- array-level Compress/Decompress (what bench.py times) -------------------------------------------
     def compress_ops(self, src_ptr, nbytes, slots=None):
         """Op list of Compress(): segment i = [i*S, min((i+1)*S, size)) -> slot i (src/memory.cc:350-430)."""
-        S = self.seg
+        S, k = self.seg, self.sgl
         n = (nbytes + S - 1) // S
         if slots is None:
             slots = self.take_slots(n)
+        if k > 1:
+            # chained segments (src/memory.cc:350-430 with max_sgl_segs > 1): one op = one stream over k segments, its
+            # destination the k slots taken for them, which must be one contiguous range
+            g = (n + k - 1) // k
+            cnt = np.minimum(k, n - np.arange(g) * k)
+            first = slots[::k]
+            expect = np.repeat(first, k)[:n] + (np.arange(n, dtype=np.uint64) % np.uint64(k)) * np.uint64(self.slot)
+            if not np.array_equal(expect, slots):
+                self.put_slots(slots)
+                raise BitarError(capi.E_IO_ERROR, "the output slots of a chained operation are not contiguous")
+            ops = np.zeros(g, capi.CHUNK_DTYPE)
+            off = np.arange(g, dtype=np.uint64) * np.uint64(k * S)
+            ops["src"] = np.uint64(src_ptr) + off
+            ops["src_len"] = np.minimum(np.uint64(k * S), np.uint64(nbytes) - off).astype(np.uint32)
+            ops["dst"] = first
+            ops["dst_cap"] = (cnt * self.slot).astype(np.uint32)
+            return ops, slots
         ops = np.zeros(n, capi.CHUNK_DTYPE)
         off = np.arange(n, dtype=np.uint64) * np.uint64(S)
         ops["src"] = np.uint64(src_ptr) + off
@@ -193,6 +215,10 @@ class CompressDevice:
                 self.put_slot(s)
             raise
         self.last_results = res
+        if self.sgl > 1:
+            bufs, unused = sgl_split(slots, res["produced"], self.sgl, self.slot)
+            self.put_slots(unused)       # the slots a stream did not reach (the reference leaves them occupied)
+            return bufs
         return [Buf(int(p), int(n)) for p, n in zip(slots, res["produced"])]
 
     def Decompress(self, queue_pair_id, compressed_buffers, decompressed_buffer):
@@ -200,14 +226,25 @@ class CompressDevice:
         Resize()s the ResizableBuffer, src/device.cc:315).  decompressed_buffer.size is its capacity."""
         if not compressed_buffers:
             return 0
-        need = len(compressed_buffers) * self.seg
+        if self.sgl > 1:
+            streams = sgl_join(compressed_buffers, self.slot)
+            need = len(streams) * self.sgl * self.seg
+        else:
+            need = len(compressed_buffers) * self.seg
         if decompressed_buffer is None or decompressed_buffer.size < need:
             raise BitarError(capi.E_CAPACITY, f"The decompressed_buffer is required to be >= {need} bytes")
         self._guard()
         self._entry_guard(queue_pair_id)
-        ops = self.decompress_ops(np.array([b.ptr for b in compressed_buffers], np.uint64),
-                                  np.array([b.size for b in compressed_buffers], np.uint32),
-                                  decompressed_buffer.ptr)
+        if self.sgl > 1:
+            ops = np.zeros(len(streams), capi.CHUNK_DTYPE)
+            ops["src"] = [p for p, _ in streams]
+            ops["src_len"] = [n for _, n in streams]
+            ops["dst"] = np.uint64(decompressed_buffer.ptr) + np.arange(len(streams), dtype=np.uint64) * np.uint64(self.sgl * self.seg)
+            ops["dst_cap"] = self.sgl * self.seg
+        else:
+            ops = self.decompress_ops(np.array([b.ptr for b in compressed_buffers], np.uint64),
+                                      np.array([b.size for b in compressed_buffers], np.uint32),
+                                      decompressed_buffer.ptr)
         res = self.enqueue("inflate", queue_pair_id, ops)
         self.wait(queue_pair_id)
         self.last_results = res
@@ -222,6 +259,48 @@ class CompressDevice:
             raise BitarError(capi.E_INVALID, f"queue_pair_id must be in the range of [0, {self._num_qps})")
         if self.busy(qp):
             raise BitarError(capi.E_CANCELLED, f"Queue pair {qp} of compress device {self._device_id} is busy")
+
+
+def sgl_split(slots, produced, k, slot):
+    """Chained segments, compress side: the buffers of every stream as the reference's dequeue callback lists them
+    (src/device.cc:183-195) -- one per destination slot that holds data, all of them full but the last.  A stream that
+    ends exactly at a slot boundary gets an empty buffer after it, so that the end of a stream is always a buffer shorter
+    than a slot (what sgl_join() goes by).  Returns (buffers, slots the streams did not reach)."""
+    bufs, unused = [], []
+    n = len(slots)
+    for g, p in enumerate(produced):
+        p = int(p)
+        cnt = min(k, n - g * k)
+        used = (p + slot - 1) // slot
+        for j in range(used):
+            bufs.append(Buf(int(slots[g * k + j]), min(slot, p - j * slot)))
+        if p % slot == 0:
+            bufs.append(Buf(int(slots[g * k]) + p, 0))
+            if used < cnt:
+                used += 1     # the empty buffer sits on (and keeps) the next slot
+        unused.extend(int(x) for x in slots[g * k + used:g * k + cnt])
+    return bufs, np.array(unused, np.uint64)
+
+
+def sgl_join(buffers, slot):
+    """Chained segments, decompress side (src/memory.cc:432-505 with max_sgl_segs > 1): the buffers of one stream are
+    consecutive full slots and end with a shorter one; they must be one contiguous range.  Returns [(address, bytes)]
+    per stream."""
+    streams, i = [], 0
+    while i < len(buffers):
+        first, total = buffers[i].ptr, 0
+        while True:
+            b = buffers[i]
+            if b.ptr != first + total:
+                raise BitarError(capi.E_INVALID, "the compressed buffers of a chained operation are not contiguous")
+            total += b.size
+            i += 1
+            if b.size < slot:
+                break
+            if i == len(buffers):
+                raise BitarError(capi.E_INVALID, "the last chained operation has no end (a buffer shorter than a slot)")
+        streams.append((first, total))
+    return streams
 
 
 class CompressDriver:

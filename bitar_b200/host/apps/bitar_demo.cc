@@ -118,7 +118,7 @@ bool SameBytes(const std::uint8_t* a, const std::uint8_t* b, std::size_t n, bool
 
 int main(int argc, char** argv) {
   std::size_t bytes = 64u << 20;
-  std::uint32_t seg = 59460, qps_per_device = 2;
+  std::uint32_t seg = 59460, qps_per_device = 2, sgl = 1;
   std::string file, mode = "both";
   bool on_device = false, bytes_given = false;
   for (int i = 1; i < argc; ++i) {
@@ -130,7 +130,8 @@ int main(int argc, char** argv) {
     else if (a == "--file") file = next();
     else if (a == "--mode") mode = next();
     else if (a == "--device") on_device = true;
-    else { std::fprintf(stderr, "usage: %s [--file F | --bytes N] [--seg S] [--qps Q] [--mode sync|async|both] [--device]\n", argv[0]); return 2; }
+    else if (a == "--sgl") sgl = (std::uint32_t)std::stoul(next());
+    else { std::fprintf(stderr, "usage: %s [--file F | --bytes N] [--seg S] [--qps Q] [--mode sync|async|both] [--device] [--sgl K]\n", argv[0]); return 2; }
   }
 
   auto* driver = bitar::CompressDriver<bitar::Class_CUDA>::Instance();
@@ -176,6 +177,7 @@ int main(int argc, char** argv) {
   for (auto& d : devices) {   // app_common.cc:87-100: memzones = ceil((chunks + nQP) / nDev)
     auto cfg = std::make_unique<bitar::CudaConfiguration>();
     cfg->set_decompressed_seg_size(seg);
+    cfg->set_max_sgl_segs((std::uint16_t)sgl);   // K segments chained into one stream (src/include/config.h:90-96)
     cfg->set_max_preallocate_memzones((std::uint32_t)std::max<std::size_t>(20, (n_chunks + total_qps) / devices.size() + total_qps));
     cfg->set_slot_memory(on_device ? bitar::SlotMemory::kDevice : bitar::SlotMemory::kPinnedHost);
     CHECK_OK(d->Initialize(std::move(cfg)));
@@ -195,7 +197,7 @@ int main(int argc, char** argv) {
       auto compressed = std::move(*comp_r);
       std::int64_t csize = 0;
       for (auto& b : compressed) csize += b->size();
-      auto out_r = allocate((std::int64_t)(compressed.size() * (std::size_t)seg), dev->device_id());
+      auto out_r = allocate((std::int64_t)((n_chunks + sgl - 1) / sgl * sgl * (std::size_t)seg), dev->device_id());
       CHECK_OK(out_r.status());
       auto output = std::move(*out_r);
       auto t2 = Clock::now();
@@ -212,7 +214,7 @@ int main(int argc, char** argv) {
         failures += !table_r.ok();
         if (table_r.ok()) std::printf("  %lld rows x %d columns\n", (long long)(*table_r)->num_rows(), (*table_r)->num_columns());
       }
-      if (t == 0 && !on_device) {
+      if (t == 0 && !on_device && sgl == 1) {
         // the same compressed segments from ordinary heap memory (as if read back from storage): Decompress()
         // stages them itself
         bitar::BufferVector heap;
@@ -244,7 +246,7 @@ int main(int argc, char** argv) {
     std::printf("async (%zu queue pairs):\n", total_qps);
     struct Part { Device* dev; const std::unique_ptr<Device>* owner; std::uint16_t qp; std::size_t off, len; };
     std::vector<Part> parts;
-    const std::size_t per = (n_chunks + total_qps - 1) / total_qps * seg;   // even split on segment boundaries
+    const std::size_t per = ((n_chunks + total_qps - 1) / total_qps + sgl - 1) / sgl * sgl * seg;   // even split on segment (chain) boundaries
     std::size_t off = 0;
     for (auto& d : devices)
       for (std::uint16_t q = 0; q < d->num_qps() && off < bytes; ++q) {
@@ -274,7 +276,7 @@ int main(int argc, char** argv) {
 
       std::vector<std::unique_ptr<arrow::ResizableBuffer>> outs;
       for (std::size_t i = 0; i < parts.size(); ++i) {
-        auto r = allocate((std::int64_t)(results[i].size() * (std::size_t)seg), parts[i].dev->device_id());
+        auto r = allocate((std::int64_t)(((parts[i].len + seg - 1) / seg + sgl - 1) / sgl * sgl * (std::size_t)seg), parts[i].dev->device_id());
         CHECK_OK(r.status());
         outs.push_back(std::move(*r));
       }

@@ -74,6 +74,8 @@ class CompressDevice {
   arrow::Result<BufferVector> FinishCompress(std::uint16_t queue_pair_id, bool in_callback = false);
   arrow::Status EnqueueDecompress(std::uint16_t queue_pair_id, const BufferVector& compressed_buffers,
                                   const std::unique_ptr<arrow::ResizableBuffer>& decompressed_buffer);
+  arrow::Status EnqueueDecompressChained(std::uint16_t queue_pair_id, const BufferVector& compressed_buffers,
+                                  const std::unique_ptr<arrow::ResizableBuffer>& decompressed_buffer);
   arrow::Status FinishDecompress(std::uint16_t queue_pair_id, const std::unique_ptr<arrow::ResizableBuffer>& decompressed_buffer,
                                  bool in_callback = false);
   arrow::Status OnComplete(std::uint16_t queue_pair_id, void (*fn)(void*), void* arg);

@@ -154,16 +154,26 @@ arrow::Status CompressDevice<Class>::EnqueueCompress(std::uint16_t queue_pair_id
     q.slots.clear();
     return arrow::Status::IOError("Unable to get enough output slots: ", bitar_last_error());   // src/memory.cc:407-410
   }
-  q.ops.resize(n);
-  q.results.assign(n, bitar_result{0, BITAR_OP_NOT_RUN, 0});
   const std::uint32_t slot = bitar_slot_size(handle_);
-  for (std::size_t i = 0; i < n; ++i) {   // AssembleFrom(span, offset), src/memory.cc:350-430
-    q.ops[i].src = decompressed_buffer->data() + i * seg;
-    q.ops[i].src_len = static_cast<std::uint32_t>(std::min(seg, size - i * seg));
-    q.ops[i].dst = q.slots[i];
-    q.ops[i].dst_cap = slot;
+  // AssembleFrom(span, offset), src/memory.cc:350-430: max_sgl_segs segments chained into one operation = one stream
+  // over k * S bytes whose destination is the k slots taken for them (they must be one contiguous range)
+  const std::size_t k = std::max<std::size_t>(1, configuration_->max_sgl_segs());
+  const std::size_t n_ops = (n + k - 1) / k;
+  q.ops.resize(n_ops);
+  q.results.assign(n_ops, bitar_result{0, BITAR_OP_NOT_RUN, 0});
+  for (std::size_t g = 0; g < n_ops; ++g) {
+    const std::size_t cnt = std::min(k, n - g * k);
+    for (std::size_t j = 1; j < cnt; ++j)
+      if (static_cast<std::uint8_t*>(q.slots[g * k + j]) != static_cast<std::uint8_t*>(q.slots[g * k]) + j * slot) {
+        ReleaseSlots(queue_pair_id);
+        return arrow::Status::IOError("The output slots of a chained operation are not contiguous");
+      }
+    q.ops[g].src = decompressed_buffer->data() + g * k * seg;
+    q.ops[g].src_len = static_cast<std::uint32_t>(std::min(k * seg, size - g * k * seg));
+    q.ops[g].dst = q.slots[g * k];
+    q.ops[g].dst_cap = static_cast<std::uint32_t>(cnt * slot);
   }
-  const int rc = bitar_qp_deflate(handle_, queue_pair_id, q.ops.data(), static_cast<std::uint32_t>(n), q.results.data());
+  const int rc = bitar_qp_deflate(handle_, queue_pair_id, q.ops.data(), static_cast<std::uint32_t>(n_ops), q.results.data());
   if (rc != BITAR_OK) {
     ReleaseSlots(queue_pair_id);
     return internal::StatusFromC(rc);
@@ -183,10 +193,31 @@ arrow::Result<BufferVector> CompressDevice<Class>::FinishCompress(std::uint16_t 
     ReleaseSlots(queue_pair_id);
     return internal::StatusFromC(rc);
   }
-  out.reserve(q.ops.size());
-  for (std::size_t i = 0; i < q.ops.size(); ++i)   // non-owning views into the slots, src/device.cc:183-195
-    out.emplace_back(std::make_unique<arrow::Buffer>(static_cast<const std::uint8_t*>(q.slots[i]),
-                                                     static_cast<std::int64_t>(q.results[i].produced)));
+  out.reserve(q.slots.size());
+  const std::size_t k = std::max<std::size_t>(1, configuration_->max_sgl_segs());
+  if (k == 1) {
+    for (std::size_t i = 0; i < q.ops.size(); ++i)   // non-owning views into the slots, src/device.cc:183-195
+      out.emplace_back(std::make_unique<arrow::Buffer>(static_cast<const std::uint8_t*>(q.slots[i]),
+                                                       static_cast<std::int64_t>(q.results[i].produced)));
+  } else {
+    // chained segments: one buffer per destination slot that holds data, all of them full but the last, as the
+    // reference's dequeue callback lists them (src/device.cc:183-195).  A stream that ends exactly at a slot boundary
+    // gets an empty buffer after it, so that the end of a stream is always a buffer shorter than a slot (what
+    // Decompress() goes by).  Slots a stream did not reach go back to the pool (the reference leaves them occupied).
+    const std::size_t slot = bitar_slot_size(handle_), n = q.slots.size();
+    for (std::size_t g = 0; g < q.ops.size(); ++g) {
+      const std::size_t p = q.results[g].produced, cnt = std::min(k, n - g * k);
+      std::size_t used = (p + slot - 1) / slot;
+      const auto* base = static_cast<const std::uint8_t*>(q.slots[g * k]);
+      for (std::size_t j = 0; j < used; ++j)
+        out.emplace_back(std::make_unique<arrow::Buffer>(base + j * slot, static_cast<std::int64_t>(std::min(slot, p - j * slot))));
+      if (p % slot == 0) {
+        out.emplace_back(std::make_unique<arrow::Buffer>(base + p, 0));
+        if (used < cnt) ++used;   // the empty buffer sits on (and keeps) the next slot
+      }
+      for (std::size_t j = cnt; j-- > used;) bitar_slot_put(handle_, q.slots[g * k + j]);
+    }
+  }
   q.slots.clear();
   return out;
 }
@@ -210,6 +241,8 @@ arrow::Status CompressDevice<Class>::EnqueueDecompress(std::uint16_t queue_pair_
     return arrow::Status::OK();
   }
   const auto seg = static_cast<std::size_t>(configuration_ ? configuration_->decompressed_seg_size() : 0);
+  const std::size_t k = configuration_ ? std::max<std::size_t>(1, configuration_->max_sgl_segs()) : 1;
+  if (k > 1) return EnqueueDecompressChained(queue_pair_id, compressed_buffers, decompressed_buffer);
   const std::size_t n = compressed_buffers.size();
   if (decompressed_buffer == nullptr || static_cast<std::size_t>(decompressed_buffer->capacity()) < n * seg)
     return arrow::Status::CapacityError("The decompressed_buffer is required to be >= ", n * seg, " bytes");   // src/device.cc:248-254
@@ -250,6 +283,46 @@ arrow::Status CompressDevice<Class>::EnqueueDecompress(std::uint16_t queue_pair_
   }
   return internal::StatusFromC(
       bitar_qp_inflate(handle_, queue_pair_id, q.ops.data(), static_cast<std::uint32_t>(n), q.results.data()));
+}
+
+// Chained segments (AssembleFrom(buffers, ...) with max_sgl_segs > 1, src/memory.cc:432-505): the buffers of one stream are
+// consecutive full slots and end with a shorter one; they must be one contiguous, device-accessible range.  Stream g
+// inflates to decompressed_buffer + g * k * S.
+template <typename Class>
+arrow::Status CompressDevice<Class>::EnqueueDecompressChained(std::uint16_t queue_pair_id, const BufferVector& compressed_buffers,
+                                                              const std::unique_ptr<arrow::ResizableBuffer>& decompressed_buffer) {
+  auto& q = qp_state_[queue_pair_id < num_qps_ ? queue_pair_id : 0];
+  const auto seg = static_cast<std::size_t>(configuration_->decompressed_seg_size());
+  const std::size_t k = configuration_->max_sgl_segs(), slot = bitar_slot_size(handle_);
+  std::vector<bitar_chunk> ops;
+  for (std::size_t i = 0; i < compressed_buffers.size();) {
+    if (compressed_buffers[i] == nullptr) return arrow::Status::Invalid("null compressed buffer");
+    const std::uint8_t* first = compressed_buffers[i]->data();
+    std::size_t total = 0;
+    for (;;) {
+      const auto& b = compressed_buffers[i];
+      if (b == nullptr || b->data() != first + total)
+        return arrow::Status::Invalid("The compressed buffers of a chained operation are not contiguous");
+      total += static_cast<std::size_t>(b->size());
+      ++i;
+      if (static_cast<std::size_t>(b->size()) < slot) break;
+      if (i == compressed_buffers.size())
+        return arrow::Status::Invalid("The last chained operation has no end (a buffer shorter than a slot)");
+    }
+    if (bitar_ptr_kind(first, nullptr) == 0) return arrow::Status::Invalid("Chained compressed buffers must be device-accessible memory");
+    ops.push_back(bitar_chunk{first, nullptr, static_cast<std::uint32_t>(total), static_cast<std::uint32_t>(k * seg)});
+  }
+  const std::size_t need = std::max(ops.size() * k * seg, compressed_buffers.size() * seg);   // (the second: src/device.cc:248-254)
+  if (decompressed_buffer == nullptr || static_cast<std::size_t>(decompressed_buffer->capacity()) < ops.size() * k * seg)
+    return arrow::Status::CapacityError("The decompressed_buffer is required to be >= ", need, " bytes");
+  ARROW_RETURN_NOT_OK(EntryGuard(queue_pair_id));
+  Unregister(queue_pair_id);
+  ARROW_RETURN_NOT_OK(MakeAccessible(decompressed_buffer->mutable_data(), ops.size() * k * seg, &q.registered));
+  for (std::size_t g = 0; g < ops.size(); ++g) ops[g].dst = decompressed_buffer->mutable_data() + g * k * seg;
+  q.ops = std::move(ops);
+  q.results.assign(q.ops.size(), bitar_result{0, BITAR_OP_NOT_RUN, 0});
+  return internal::StatusFromC(
+      bitar_qp_inflate(handle_, queue_pair_id, q.ops.data(), static_cast<std::uint32_t>(q.ops.size()), q.results.data()));
 }
 
 template <typename Class>

@@ -61,6 +61,7 @@ extern "C" {
 #define BITAR_MIN_SEG_SIZE 8u
 #define BITAR_REF_MAX_SEG_SIZE 59460u
 #define BITAR_MAX_SEG_SIZE (1u << 20)
+#define BITAR_MAX_SGL_SEGS 16u         /* segments chained into one stream; max_sgl_segs * S <= BITAR_MAX_SEG_SIZE */
 #define BITAR_MIN_PREALLOCATE_SLOTS 20u /* kMinPreallocateMemzones, src/include/memory.h:51 */
 #define BITAR_MAX_INFLIGHT_OPS 512u     /* kMaxInflightOps, src/include/memory.h:50 (informational) */
 
@@ -76,7 +77,7 @@ typedef struct bitar_dev_info {
   uint8_t window_min, window_max; /* log2, 8..15 */
   uint8_t supports_fixed, supports_dynamic;
   uint8_t supports_crc32, supports_adler32;
-  uint8_t supports_sgl; /* 0: max_sgl_segs must be 1 */
+  uint8_t supports_sgl; /* 1: max_sgl_segs up to BITAR_MAX_SGL_SEGS */
   uint8_t reserved;
   char name[64];
 } bitar_dev_info;
@@ -87,7 +88,9 @@ typedef struct bitar_cfg {
   uint32_t compressed_seg_size;      /* slot bytes; 0 -> bitar_compressed_seg_size(S) */
   uint32_t max_preallocate_slots;    /* "max_preallocate_memzones"; 0 -> 2560 (RTE_MAX_MEMZONE) */
   uint16_t burst_size;               /* kept for API parity; the GPU path enqueues whole calls */
-  uint16_t max_sgl_segs;             /* must be <= 1 */
+  uint16_t max_sgl_segs;             /* segments chained into one stream (src/include/config.h:90-96, src/memory.cc:394-398):
+                                        1 .. 16, max_sgl_segs * S <= 1 MiB; the slots then lie back to back (a stream's
+                                        output is one op whose dst spans its slots) */
   uint8_t window_size;               /* log2; 0 -> device max (15), src/device.cc:389-394; match distances never exceed 1 << window_size */
   uint8_t huffman_enc;               /* BITAR_HUFFMAN_*; DEFAULT -> DYNAMIC */
   uint8_t checksum_type;             /* BITAR_CHECKSUM_* */

@@ -56,3 +56,23 @@ def test_worker_distribution_rule():
     assert E.distribute_workers(8, 8) == [1] * 8
     assert E.distribute_workers(19, 8) == [3, 3, 3, 2, 2, 2, 2, 2]
     assert sum(E.distribute_workers(31, 8)) == 31
+
+
+def test_chained_segment_buffer_lists():
+    """The host logic of max_sgl_segs > 1 (src/memory.cc:394-398,471-475): a stream's buffers are full slots and a
+    shorter last one, an empty buffer marks a stream that ends at a slot boundary, unused slots are reported back."""
+    import numpy as np
+    from bitar_b200.engine import BitarError, Buf, sgl_join, sgl_split
+    slot, k = 1000, 4
+    slots = np.array([10000 + i * slot for i in range(10)], np.uint64)
+    bufs, unused = sgl_split(slots, [2500, 1000, 37], k, slot)
+    assert [(b.ptr, b.size) for b in bufs] == [(10000, 1000), (11000, 1000), (12000, 500), (14000, 1000), (15000, 0), (18000, 37)]
+    assert list(unused) == [13000, 16000, 17000, 19000]
+    assert sgl_join(bufs, slot) == [(10000, 2500), (14000, 1000), (18000, 37)]
+    bufs, unused = sgl_split(slots[:4], [4000], k, slot)          # every slot full: the end marker has no slot of its own
+    assert [(b.ptr, b.size) for b in bufs][-1] == (14000, 0) and len(unused) == 0 and sgl_join(bufs, slot) == [(10000, 4000)]
+    import pytest
+    with pytest.raises(BitarError):
+        sgl_join([Buf(10000, 1000), Buf(12000, 10)], slot)          # a gap
+    with pytest.raises(BitarError):
+        sgl_join([Buf(10000, 1000)], slot)                          # no end

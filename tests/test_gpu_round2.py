@@ -167,3 +167,41 @@ def test_one_call_mixes_host_and_device_buffers(cuda_device):
         capi.check(L.bitar_mem_free(capi.MEM_PINNED, 0, hp))
     finally:
         dev.close()
+
+
+@pytest.mark.parametrize("k,seg", [(4, 59460), (16, 59460), (3, 4096)])
+def test_chained_segments(cuda_device, k, seg):
+    """max_sgl_segs = k (/root/reference/src/include/config.h:90-96, src/memory.cc:394-398,420-424): k segments are ONE
+    operation, i.e. one DEFLATE stream over k * S bytes whose output spans the k slots taken for them; Compress() lists a
+    buffer per slot that holds data, Decompress() puts the streams together again; zlib inflates every stream; every slot
+    comes back."""
+    from bitar_b200.engine import Buf, sgl_join
+    data = synth.lineitem_like(37 * seg + 1234)
+    dev = G.open_device(seg, max_sgl_segs=k, max_preallocate_memzones=64)
+    try:
+        assert dev.sgl == k
+        free0 = dev.slots_free()
+        src = G.to_dev(data)
+        bufs = dev.Compress(0, Buf(src.data_ptr(), data.size))
+        streams = sgl_join(bufs, dev.slot)
+        assert len(streams) == (data.size + k * seg - 1) // (k * seg)
+        assert all(b.size <= dev.slot for b in bufs)
+        for g, (ptr, n) in enumerate(streams):
+            t = torch.empty(n, dtype=torch.uint8, device="cuda")
+            capi.check(capi.lib().bitar_qp_memcpy(dev._h, 0, t.data_ptr(), ptr, n))
+            dev.wait(0)
+            part = data[g * k * seg:(g + 1) * k * seg]
+            assert np.array_equal(O.inflate_chunk(t.cpu().numpy(), part.size), part), g
+        out = torch.full((len(streams) * k * seg + 64,), 0xA5, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        total = dev.Decompress(0, bufs, Buf(out.data_ptr(), len(streams) * k * seg))
+        assert total == data.size and np.array_equal(out[:total].cpu().numpy(), data)
+        dev.Recycle(bufs)
+        assert dev.slots_free() == free0
+        # a second round finds contiguous groups again
+        bufs = dev.Compress(0, Buf(src.data_ptr(), data.size))
+        assert len(sgl_join(bufs, dev.slot)) == len(streams)
+        dev.Recycle(bufs)
+        assert dev.slots_free() == free0
+    finally:
+        dev.close()

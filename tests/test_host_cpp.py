@@ -33,13 +33,14 @@ def test_host_facade_builds_and_fails_loudly_without_a_device():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("args", [["--bytes", str(48 << 20)], ["--bytes", str(20 << 20), "--device", "--seg", "65536"],
-                                  ["--bytes", str(3 << 20), "--seg", "4096", "--qps", "3"]])
+                                  ["--bytes", str(3 << 20), "--seg", "4096", "--qps", "3"],
+                                  ["--bytes", str(40 << 20), "--sgl", "4"], ["--bytes", str(24 << 20), "--device", "--sgl", "8", "--seg", "32768"]])
 def test_demo_app_flow(args):
     _build()
     r = subprocess.run([DEMO] + args, capture_output=True, text=True, timeout=600)
     print(r.stdout[-3000:], r.stderr[-2000:])
     assert r.returncode == 0 and "PASSED" in r.stdout and "MISMATCH" not in r.stdout
-    if "--device" not in args:   # Decompress() stages heap-resident compressed buffers itself
+    if "--device" not in args and "--sgl" not in args:   # Decompress() stages heap-resident compressed buffers itself
         assert "pageable compressed input: OK" in r.stdout
 
 
