@@ -7,16 +7,19 @@
 //   inflate kernel  persistent CTAs, one task per WARP at a time, fetched from a global counter; two phases per block:
 //   phase A (tok)     1. all lanes parse the block header together (same bits, same registers),
 //                     2. the warp builds the two decode tables cooperatively in its shared memory,
-//                     3. lane s Huffman-decodes sub-range s (2 KiB of output) from its indexed bit offset into token
-//                        units (tk::TokLane, inflate_tok.h) in the warp's own scratch (L2 resident, reused per block)
-//                        and checks that it ends exactly at the next offset.
+//                     3. lane s Huffman-decodes sub-range s (2 KiB of output) from its indexed bit offset into a token
+//                        map (tk::TokLane, inflate_tok.h: compact literals, compact distances, one start bit per output
+//                        byte) in the warp's own scratch (L2 resident, reused per block) and checks that it ends exactly
+//                        at the next offset.
 //                   A block offers 32 independent symbol chains instead of one.  Stored blocks are copied here.
-//   phase B (res)   the same warp takes the block's units in stream order, 32 at a time (one per lane: prefix sum of the
-//                   token lengths, literal bytes stored at once, LZ77 copies one match after the other with the lanes
-//                   as bytes) through a 4 KiB ring in shared memory -- the space of the tables, which are done with;
-//                   sources farther back come from the block's own flushed output; the ring leaves as aligned
-//                   16-byte vector stores, 512 bytes per flush.  The copy chain of a block is serial: this phase lives
-//                   on few instructions per token and on the other warps of the SM being in phase A meanwhile.
+//   phase B (res)   the same warp resolves the block in stream order, BYTE-parallel: 32 output bytes per step, one per
+//                   lane.  Two population counts on the start bits tell a lane whether its byte is the k-th literal of
+//                   the sub-range or a byte of the m-th match; both streams are read one step ahead.  A match byte
+//                   copies from a 4 KiB ring of the latest output in shared memory -- the space of the tables, which are
+//                   done with -- or, for sources farther back, from the block's own flushed output (L2); sources inside
+//                   the step's own 32 bytes are followed by pointer jumping over shuffles (five rounds cover any
+//                   chain).  The ring leaves as aligned 16-byte vector stores once per sub-range.  The cost of a step
+//                   does not depend on how many tokens it holds.
 //   checksum        (only when configured) one warp per indexed op over the finished output.
 //
 // Replaces: rte_compressdev decompress ops assembled at /root/reference/src/memory.cc:432-505 and executed
@@ -74,9 +77,9 @@ __global__ void __launch_bounds__(128)
 }
 
 // shared memory of one GROUP of lanes (a whole warp, or 8 lanes for small blocks): the block's tables + the lanes' rings
-template <int LT, int DT, int URING, int GROUP>
+template <int LT, int DT, int GROUP>
 struct __align__(16) WarpSmem {
-  static constexpr int kRingStride = 2 * URING + 16;   // 16-byte aligned, lanes spread over the banks
+  static constexpr int kRingStride = (int)tk::kLaneRingBytes + 16;   // 16-byte aligned, lanes spread over the banks
   uint16_t lt[LT];
   uint16_t dt[DT];
   fl::LaneScratch sc;        // code lengths + canonical side arrays of the block (shared by the group)
@@ -183,48 +186,48 @@ __device__ __forceinline__ uint32_t warp_build_table(const uint8_t* lens, int n,
 }
 
 // ---- phase B ------------------------------------------------------------------------------------------
-// One group of G lanes resolves one block right after decoding it: the units of its sub-ranges in stream order, G at a
-// time (one per lane): prefix sum of the token lengths, literal bytes stored at once, LZ77 copies one match after the
-// other with the lanes as bytes.  Positions are "virtual" (offset in the block + (address of the block & 15)), so that
-// multiples of 16 are 16-byte aligned addresses.
-// CTA-shared constants: lane % d and the largest multiple of d that fits the group, for copies whose source overlaps them.
-struct ResolveLut {
-  uint8_t mod[32][32];   // [d][lane]
-  uint8_t per32[32];     // [d] for a group of 32 lanes
-  uint8_t per8[32];      //     ... of 8 lanes
-};
-__device__ __forceinline__ void resolve_lut_init(ResolveLut* lut) {
-  for (unsigned i = threadIdx.x; i < 1024u; i += blockDim.x) lut->mod[i >> 5][i & 31u] = (uint8_t)((i >> 5) ? (i & 31u) % (i >> 5) : (i & 31u));   // row 0: the identity
-  if (threadIdx.x < 32u) {
-    const unsigned d = threadIdx.x ? threadIdx.x : 1u;
-    lut->per32[threadIdx.x] = (uint8_t)(32u - 32u % d);
-    lut->per8[threadIdx.x] = (uint8_t)(d <= 8u ? 8u - 8u % d : 8u);
-  }
-}
+// One group of G lanes resolves one block right after decoding it, sub-range by sub-range, G output bytes per step.
+// Positions are "virtual" (offset in the block + (address of the block & 15)), so that multiples of 16 are 16-byte
+// aligned addresses, in the ring as in global memory.
 // shared-memory accesses by 32-bit shared address (device only)
-__device__ __forceinline__ uint32_t r_ld8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ void r_st8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ uint32_t r_ld8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t r_ld32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void r_st8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void r_st32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ uint4 r_ld128(uint32_t a) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
   return v;
 }
+__device__ __forceinline__ void r_st128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
-template <int G, int RING>
-struct ResolveGroup {
-  static_assert(RING >= 2048 && (RING & (RING - 1)) == 0, "ring: power of two");
+// RING : bytes of the latest output kept in shared memory.  FLUSH: the ring is stored every FLUSH bytes of a sub-range.
+// A match byte whose source lies at most kNear back reads the ring; a source farther back lies below the last flush.
+template <int G, int RING, int FLUSH>
+struct ResolveBytes {
+  static_assert(G == 32 || G == 8, "a warp, or a quarter of one");
+  static_assert((RING & (RING - 1)) == 0 && dfl::kSub % FLUSH == 0 && FLUSH % G == 0, "ring: power of two; whole steps between flushes");
   static constexpr uint32_t RM = RING - 1;
-  static constexpr uint32_t kPartMax = 4u * 258u + 8u;          // bytes 8 units can produce: the most written ahead of a match
-  static constexpr uint32_t kFlush = 16u * G;                   // one vector per lane
-  static constexpr uint32_t kNear = RING - kPartMax - 258u - 32u;   // matches at most this far back find their source in the ring
-  uint32_t ring_s;          // shared address of the group's ring (followed by 16 match records of 8 bytes when G == 32)
-  uint32_t lut_s;           // shared address of the CTA's ResolveLut
+  static constexpr uint32_t kNear = RING - G;                   // (the step's own stores may already have replaced anything older)
+  static_assert(kNear >= (uint32_t)FLUSH + G + 16u, "a source that is not in the ring must have been flushed");
+  static_assert(RING >= FLUSH + 16 + G, "a flush reads what the ring still holds");
+  static constexpr uint32_t kBitsBytes = 272u;                  // staged start bits: 64 words, the sentinel's word, padding
+  static constexpr uint32_t kBytes = RING + kBitsBytes;
+  static constexpr uint32_t kAll = G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u);
+  uint32_t ring_s;          // shared address of the group's ring (16-byte aligned), followed by the staged start bits
   uint8_t* vbase;           // block address - mis
   uint32_t flushed;         // virtual position below which everything is in global memory
-  unsigned gmask;
-  int gl;
+  unsigned gmask;           // the group's lanes in the warp
+  int gl;                   // lane inside the group
 
-  // store the complete 16-byte vectors below `upto` (all bytes below are final), and the unaligned head of the block
+  __device__ __forceinline__ void begin(uint8_t* out) {
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);
+    vbase = out - mis;
+    flushed = mis;
+  }
+  // store what is final: the unaligned head of the block, then the complete 16-byte vectors below `upto`
   __device__ __forceinline__ void flush(uint32_t upto) {
     if (flushed & 15u) {
       const uint32_t a = (flushed + 15u) & ~15u;
@@ -233,7 +236,7 @@ struct ResolveGroup {
       flushed = a;
     }
     const uint32_t end = upto & ~15u;
-    for (uint32_t v = flushed + 16u * (uint32_t)gl; v < end; v += kFlush) *reinterpret_cast<uint4*>(vbase + v) = r_ld128(ring_s + (v & RM));
+    for (uint32_t v = flushed + 16u * (uint32_t)gl; v < end; v += 16u * G) *reinterpret_cast<uint4*>(vbase + v) = r_ld128(ring_s + (v & RM));
     if (end > flushed) flushed = end;
     __syncwarp(gmask);      // the stores are ordered before later reads of the group (far sources)
   }
@@ -244,273 +247,87 @@ struct ResolveGroup {
     __syncwarp(gmask);
   }
 
-  // out[dst .. dst + len) = out[dst - dist ..]; everything below dst is final.  All arguments are uniform in the group,
-  // so the branches do not diverge.
-  __device__ __forceinline__ void copy(uint32_t dst, uint32_t len, uint32_t dist) {
-    const uint32_t lane_u = (uint32_t)gl;
-    const uint32_t dp = dst + lane_u, sp = dp - dist;
-    if (dist >= len || dist >= (uint32_t)G) {
-      if (dist <= kNear) {
-        if (lane_u < len) r_st8(ring_s + (dp & RM), r_ld8(ring_s + (sp & RM)));
-        for (uint32_t k = G; k < len; k += G) {             // a match longer than a pass of the group
-          __syncwarp(gmask);                                  // (this pass may read what the last one wrote: dist < 2 G)
-          if (k + lane_u < len) r_st8(ring_s + ((dp + k) & RM), r_ld8(ring_s + ((sp + k) & RM)));
-        }
-      } else {
-        // flushed long ago: dist > kNear, so the source ends below `flushed`
-        for (uint32_t k = lane_u; k < len; k += G) r_st8(ring_s + ((dst + k) & RM), (uint32_t)__ldcg(vbase + (dst - dist) + k));
-      }
+  // start bits of step k: literals and match heads among its G bytes
+  __device__ __forceinline__ void masks(uint32_t k, uint32_t& lit, uint32_t& head) const {
+    const uint32_t bm_s = ring_s + (uint32_t)RING;
+    uint32_t s, nx;
+    if (G == 32) {
+      s = r_ld32(bm_s + 4u * k);
+      nx = r_ld32(bm_s + 4u * k + 4u);
     } else {
-      // the source overlaps the copy and repeats inside one pass: every lane keeps its byte, a pass writes a whole
-      // number of periods
-      const uint32_t r = r_ld8(lut_s + dist * 32u + lane_u);
-      const uint32_t per = r_ld8(lut_s + 1024u + (G == 32 ? 0u : 32u) + dist);
-      const uint32_t byte = r_ld8(ring_s + ((dst - dist + r) & RM));
-      if (lane_u < per)
-        for (uint32_t k = lane_u; k < len; k += per) r_st8(ring_s + ((dst + k) & RM), byte);
+      s = r_ld8(bm_s + k);
+      nx = r_ld8(bm_s + k + 1u);
+    }
+    const uint32_t n = (s >> 1) | ((nx & 1u) << (G - 1));       // the NEXT byte starts a token
+    lit = s & n;
+    head = s & ~n;
+  }
+  // this lane's literal, or the distance - 1 of the match its byte belongs to (a step ahead of its use)
+  __device__ __forceinline__ uint32_t fetch(const uint8_t* slot, uint32_t lit, uint32_t head, bool valid, uint32_t lbase, uint32_t hbase) const {
+    const uint32_t le = kAll >> (G - 1 - gl), lt = le >> 1;   // the lanes up to and including / below this one
+    uint32_t x = 0;
+    if (valid) {
+      if ((lit >> gl) & 1u) x = (uint32_t)__ldcg(slot + tk::kSlotLits + lbase + (uint32_t)__popc(lit & lt));
+      else x = (uint32_t)__ldcg(reinterpret_cast<const uint16_t*>(slot + tk::kSlotDists) + (hbase + (uint32_t)__popc(head & le) - 1u));
+    }
+    return x;
+  }
+
+  // The `len` bytes of one sub-range, from its slot, to virtual position v0 on.
+  __device__ __forceinline__ void resolve_sub(const uint8_t* slot, uint32_t v0, uint32_t len) {
+    const uint32_t lane_u = (uint32_t)gl;
+    const uint32_t bm_s = ring_s + (uint32_t)RING;
+    // stage the start bits; the byte after the sub-range counts as a start (tokens never straddle sub-ranges)
+    for (uint32_t i = lane_u; i < 16u; i += G) r_st128(bm_s + 16u * i, __ldcg(reinterpret_cast<const uint4*>(slot + tk::kSlotBits) + i));
+    __syncwarp(gmask);
+    if (lane_u == 0) {
+      const uint32_t w = len >> 5, sh = len & 31u;
+      const uint32_t old = sh ? r_ld32(bm_s + 4u * w) & ((1u << sh) - 1u) : 0u;
+      r_st32(bm_s + 4u * w, old | (1u << sh));
+      r_st32(bm_s + 4u * w + 4u, 0u);
     }
     __syncwarp(gmask);
-  }
-
-  // The units of one sub-range (n_units of them, a multiple of 8, at `units`) from virtual position `pos`; returns the
-  // new position, or 0xFFFFFFFF when the units do not add up to `sub_limit` (they always do when phase A succeeded).
-  __device__ __forceinline__ uint32_t resolve(const uint16_t* units, uint32_t n_units, uint32_t pos, uint32_t sub_limit) {
-    const int wlane = (int)(threadIdx.x & 31u);
-    const int gbase = wlane - gl;
-    // two groups of units in flight ahead of the one being resolved (ld.cg: the scratch is rewritten for every block)
-    uint32_t u0 = (uint32_t)gl < n_units ? __ldcg(units + gl) : tk::kUnitNop;
-    uint32_t u1 = (uint32_t)(G + gl) < n_units ? __ldcg(units + G + gl) : tk::kUnitNop;
-    for (uint32_t i = 0; i < n_units; i += G) {
-      const uint32_t u = u0;
-      u0 = u1;
-      u1 = i + 2u * G + (uint32_t)gl < n_units ? __ldcg(units + i + 2u * G + (uint32_t)gl) : tk::kUnitNop;
-      const bool is_head = (u & tk::kUnitHead) != 0u;
-      const unsigned hm = __ballot_sync(gmask, is_head);
-      const bool is_cont = gl > 0 && ((hm >> (wlane - 1)) & 1u);
-      const bool is_lit = !is_head && !is_cont && u < 0x100u;
-      const uint32_t olen = is_lit ? 1u : is_head ? (u & 0xFFu) + 3u : 0u;
-      uint32_t incl = olen;
+    const uint32_t nsteps = (len + G - 1u) / G;
+    uint32_t lbase = 0, hbase = 0;                  // literals / match heads of the sub-range before the step being fetched
+    uint32_t lit_n, head_n;
+    masks(0, lit_n, head_n);
+    uint32_t x_n = fetch(slot, lit_n, head_n, lane_u < len, 0u, 0u);
+#pragma unroll 1
+    for (uint32_t k = 0; k < nsteps; ++k) {
+      const uint32_t lit = lit_n, head = head_n, x = x_n;
+      const uint32_t off = k * G + lane_u;
+      const bool valid = off < len;
+      if (k + 1u < nsteps) {                        // the next step's literal / distance: their places follow from the start bits alone
+        lbase += (uint32_t)__popc(lit);
+        hbase += (uint32_t)__popc(head);
+        masks(k + 1u, lit_n, head_n);
+        x_n = fetch(slot, lit_n, head_n, off + G < len, lbase, hbase);
+      }
+      const uint32_t pv = v0 + off;
+      const uint32_t left = len - k * G;
+      const uint32_t want = left >= (uint32_t)G ? kAll : ((1u << left) - 1u);
+      uint32_t b = x;
+      if ((lit & want) != want) {                   // the step holds match bytes
+        const uint32_t dist = x + 1u;
+        const bool mb = valid && !((lit >> lane_u) & 1u);
+        const bool inside = mb && dist <= lane_u;   // the source is a byte of this very step
+        const bool far = mb && dist > kNear;
+        if (mb && !inside && !far) b = r_ld8(ring_s + ((pv - dist) & RM));
+        if (__any_sync(gmask, far)) {
+          if (far) b = (uint32_t)__ldcg(vbase + (pv - dist));
+        }
+        if (__any_sync(gmask, inside)) {            // follow the chain of sources to a byte that is known: G - 1 hops at most
+          uint32_t ptr = inside ? lane_u - dist : lane_u;
 #pragma unroll
-      for (int d = 1; d < G; d <<= 1) {
-        const uint32_t v = __shfl_up_sync(gmask, incl, d, G);
-        if (gl >= d) incl += v;
-      }
-      const uint32_t total = __shfl_sync(gmask, incl, G - 1, G);
-      if (pos + total > sub_limit) return 0xFFFFFFFFu;
-      const uint32_t my = pos + incl - olen;            // where this lane's token starts
-      // groups of 8 units are resolved together when the G units produce more than fits ahead of a match in the ring
-      const int parts = G > 8 && total > kPartMax ? G / 8 : 1;
-      for (int part = 0; part < parts; ++part) {
-        const bool mine = parts == 1 || (gl >> 3) == part;
-        if (is_lit && mine) r_st8(ring_s + (my & RM), u);
-        unsigned heads = (hm >> gbase) & (G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u));
-        if (parts > 1) heads &= 0xFFu << (8 * part);
-        if (G == 32) {
-          // the heads leave their (start, length, distance) in shared memory in stream order: a match is then one
-          // broadcast read away for the whole warp
-          const uint32_t rec_s = ring_s + (uint32_t)RING;
-          const int nh = __popc(heads);
-          const uint32_t next_u = __shfl_down_sync(gmask, u, 1, G);          // a head's distance sits in the next lane
-          if (is_head && mine) {
-            const uint32_t rank = (uint32_t)__popc(heads & ((1u << gl) - 1u));
-            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(rec_s + 8u * rank), "r"(my | (olen << 20)), "r"(next_u + 1u) : "memory");
-          }
-          __syncwarp(gmask);
-          for (int t = 0; t < nh; ++t) {
-            uint32_t w0, dist;
-            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w0), "=r"(dist) : "r"(rec_s + 8u * (uint32_t)t) : "memory");
-            copy(w0 & 0xFFFFFu, w0 >> 20, dist);
-          }
-        } else {
-          __syncwarp(gmask);
-          while (heads) {
-            const int h = __ffs((int)heads) - 1;
-            heads &= heads - 1u;
-            const uint32_t len = __shfl_sync(gmask, olen, h, G);
-            const uint32_t dist = __shfl_sync(gmask, u, h + 1, G) + 1u;
-            const uint32_t dst = __shfl_sync(gmask, my, h, G);
-            copy(dst, len, dist);
-            if (dst + len - flushed >= 2u * kFlush) flush(dst + len);
-          }
-        }
-        if (parts > 1) flush(pos + __shfl_sync(gmask, incl, 8 * part + 7, G));   // everything up to the end of this part is final
-      }
-      pos += total;
-      if (pos - flushed >= kFlush) flush(pos);
-    }
-    return pos == sub_limit ? pos : 0xFFFFFFFFu;
-  }
-};
-
-// The same for a whole warp per block (the 64 KiB blocks of ordinary segments), laid out for few instructions per match:
-// the block goes through a LINEAR window in shared memory -- the previous sub-range and the current one side by side,
-// indexed by position, no wrap-around -- so that a copy is `buf[d + lane] = buf[s + f(lane)]` with everything worked out
-// by the match's head lane beforehand (all heads of a batch in parallel) and left in a record the warp reads by
-// broadcast.  Matches whose source lies below the window (flushed output) are independent of the batch: they are copied
-// first, their loads in flight together; the others follow one after the other.  A sub-range leaves the window as
-// aligned 16-byte vectors when it is complete; then the window slides by one sub-range.
-struct ResolveWarp {
-  static constexpr uint32_t kWin = dfl::kSub;                 // bytes of a sub-range
-  static constexpr uint32_t kBuf = 2u * kWin + 16u;           // previous + current sub-range + the block's misalignment
-  static constexpr uint32_t kBytes = kBuf + 16u * 16u + 16u * 8u;   // + a record per possible match of a batch (near, far)
-  uint32_t buf_s;           // shared address of the window (16-byte aligned)
-  uint32_t lut_s;           // shared address of the CTA's ResolveLut
-  uint8_t* vbase;           // block address - mis
-  uint32_t flushed;         // virtual position below which everything is in global memory
-  uint32_t cur0;            // virtual position of window index kWin (a multiple of 16)
-  int gl;
-
-  __device__ __forceinline__ void begin(uint8_t* out) {
-    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);
-    vbase = out - mis;
-    flushed = mis;
-    cur0 = 0;
-  }
-  // shared address of virtual position v
-  __device__ __forceinline__ uint32_t at(uint32_t v) const { return buf_s + kWin + (v - cur0); }
-
-  // store what is final: the unaligned head of the block, then the complete 16-byte vectors below `upto`
-  __device__ __forceinline__ void flush(uint32_t upto) {
-    if (flushed & 15u) {
-      const uint32_t a = (flushed + 15u) & ~15u;
-      if (upto < a) return;
-      for (uint32_t v = flushed + (uint32_t)gl; v < a; v += 32u) vbase[v] = (uint8_t)r_ld8(at(v));
-      flushed = a;
-    }
-    const uint32_t end = upto & ~15u;
-    for (uint32_t v = flushed + 16u * (uint32_t)gl; v < end; v += 512u) *reinterpret_cast<uint4*>(vbase + v) = r_ld128(at(v));
-    if (end > flushed) flushed = end;
-  }
-  __device__ __forceinline__ void finish(uint32_t upto) {
-    flush(upto);
-    for (uint32_t v = flushed + (uint32_t)gl; v < upto; v += 32u) vbase[v] = (uint8_t)r_ld8(at(v));
-    flushed = upto;
-    __syncwarp();
-  }
-  // the current sub-range becomes the previous one (no pass reads what another pass writes, except lane 0's first and
-  // last vector, which program order takes care of)
-  __device__ __forceinline__ void slide() {
-    for (uint32_t i = 16u * (uint32_t)gl; i < kWin + 16u; i += 512u) {
-      const uint4 v = r_ld128(buf_s + kWin + i);
-      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(buf_s + i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-    }
-    cur0 += kWin;
-    __syncwarp();
-  }
-
-  // the rare shapes, out of line: what is left of far matches longer than a pass of the warp ...
-  __device__ __noinline__ void far_rest(uint32_t a0, uint32_t s0, uint32_t a1, uint32_t s1) {
-    const uint32_t lane_u = (uint32_t)gl, l0 = a0 >> 20, l1 = a1 >> 20;
-#pragma unroll 1
-    for (uint32_t k = 32u + lane_u; k < l0; k += 32u) r_st8((a0 & 0xFFFFFu) + k, (uint32_t)__ldcg(vbase + s0 + k));
-#pragma unroll 1
-    for (uint32_t k = 32u + lane_u; k < l1; k += 32u) r_st8((a1 & 0xFFFFFu) + k, (uint32_t)__ldcg(vbase + s1 + k));
-  }
-  // ... and near matches longer than a pass: a pattern (every lane keeps the byte of its place in the period, a pass
-  // writes a whole number of periods), or a plain copy pass by pass
-  __device__ __noinline__ void near_long(uint32_t a, uint32_t len, uint32_t sa, uint32_t row, uint32_t per) {
-    const uint32_t lane_u = (uint32_t)gl;
-    if (row != lut_s) {
-      const uint32_t byte = r_ld8(sa + r_ld8(row + lane_u));
-      if (lane_u < per) {
-#pragma unroll 1
-        for (uint32_t k = lane_u; k < len; k += per) r_st8(a + k, byte);
-      }
-    } else {
-#pragma unroll 1
-      for (uint32_t k = lane_u; k < len + lane_u; k += 32u) {
-        if (k < len) r_st8(a + k, r_ld8(sa + k));
-        __syncwarp();            // (the next pass may read what this one wrote: dist < 64)
-      }
-    }
-  }
-
-  // The units of one sub-range (n_units of them, a multiple of 8, at `units`) from virtual position `pos`; returns the
-  // new position, or 0xFFFFFFFF when the units do not add up to `sub_limit` (they always do when phase A succeeded).
-  __device__ __forceinline__ uint32_t resolve(const uint16_t* units, uint32_t n_units, uint32_t pos, uint32_t sub_limit) {
-    const uint32_t lane_u = (uint32_t)gl;
-    const uint32_t near_s = buf_s + kBuf, far_s = near_s + 16u * 16u;
-    const uint32_t bias = buf_s + kWin - cur0;                // shared address of virtual position 0 (mod 2^32)
-    // two batches of units in flight ahead of the one being resolved (ld.cg: the scratch is rewritten for every block)
-    uint32_t u0 = lane_u < n_units ? __ldcg(units + lane_u) : tk::kUnitNop;
-    uint32_t u1 = 32u + lane_u < n_units ? __ldcg(units + 32u + lane_u) : tk::kUnitNop;
-    for (uint32_t i = 0; i < n_units; i += 32u) {
-      const uint32_t u = u0;
-      u0 = u1;
-      u1 = i + 64u + lane_u < n_units ? __ldcg(units + i + 64u + lane_u) : tk::kUnitNop;
-      const bool is_head = (u & tk::kUnitHead) != 0u;
-      const unsigned heads = __ballot_sync(0xFFFFFFFFu, is_head);
-      const bool is_cont = ((heads << 1) >> lane_u) & 1u;     // the unit after a head: its distance (a head is never in lane 31)
-      const bool is_lit = !is_head && !is_cont && u < 0x100u;
-      const uint32_t olen = is_lit ? 1u : is_head ? (u & 0xFFu) + 3u : 0u;
-      uint32_t incl = olen;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (gl >= d) incl += v;
-      }
-      const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-      if (pos + total > sub_limit) return 0xFFFFFFFFu;
-      const uint32_t my = pos + incl - olen;                  // where this lane's token starts
-      const uint32_t da = bias + my;
-      if (is_lit) r_st8(da, u);
-      const uint32_t dist = __shfl_down_sync(0xFFFFFFFFu, u, 1) + 1u;   // a head's distance sits in the next lane
-      const bool is_far = is_head && dist > my - cur0 + kWin;           // the source starts below the window
-      const unsigned fars = __ballot_sync(0xFFFFFFFFu, is_far);
-      const unsigned nears = heads & ~fars;
-      if (is_head) {
-        const unsigned below = (1u << lane_u) - 1u;
-        if (is_far) {
-          // destination address | length, virtual position of the source
-          asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(far_s + 8u * (uint32_t)__popc(fars & below)), "r"(da | (olen << 20)), "r"(my - dist) : "memory");
-        } else {
-          // destination address | length, source address, row of lane -> source byte (lane % dist for a source that
-          // overlaps the copy: a repeating pattern; the identity else), bytes a pass may write (whole periods)
-          const bool pattern = dist < olen && dist < 32u;
-          const uint32_t row = lut_s + (pattern ? dist * 32u : 0u);
-          const uint32_t per = pattern ? r_ld8(lut_s + 1024u + dist) : 32u;
-          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(near_s + 16u * (uint32_t)__popc(nears & below)), "r"(da | (olen << 20)),
-                       "r"(da - dist), "r"(row), "r"(per) : "memory");
+          for (int r = 1; r < G; r <<= 1) ptr = __shfl_sync(gmask, ptr, (int)ptr, G);
+          b = __shfl_sync(gmask, b, (int)ptr, G);
         }
       }
-      __syncwarp();
-      {   // the far matches: nothing in this batch depends on their sources, so their loads go out together
-        const int nf = __popc(fars);
-#pragma unroll 1
-        for (int t = 0; t < nf; t += 2) {
-          uint32_t a0, s0, a1 = 0, s1 = 0;
-          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a0), "=r"(s0) : "r"(far_s + 8u * (uint32_t)t) : "memory");
-          if (t + 1 < nf) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a1), "=r"(s1) : "r"(far_s + 8u * (uint32_t)(t + 1)) : "memory");
-          const uint32_t l0 = a0 >> 20, l1 = a1 >> 20;
-          uint32_t b0 = 0, b1 = 0;
-          if (lane_u < l0) b0 = (uint32_t)__ldcg(vbase + s0 + lane_u);
-          if (lane_u < l1) b1 = (uint32_t)__ldcg(vbase + s1 + lane_u);
-          if (lane_u < l0) r_st8((a0 & 0xFFFFFu) + lane_u, b0);
-          if (lane_u < l1) r_st8((a1 & 0xFFFFFu) + lane_u, b1);
-          if (l0 > 32u || l1 > 32u) far_rest(a0, s0, a1, s1);
-        }
-        __syncwarp();
-      }
-      const int nn = __popc(nears);
-#pragma unroll 1
-      for (int t = 0; t < nn; ++t) {
-        uint32_t w0, sa, row, per;
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(sa), "=r"(row), "=r"(per) : "r"(near_s + 16u * (uint32_t)t) : "memory");
-        const uint32_t len = w0 >> 20, a = w0 & 0xFFFFFu;
-        if (len <= 32u) {
-          // one pass: lane k takes byte k of the match from byte (k mod dist) of its source (k itself when they do not overlap)
-          const uint32_t byte = r_ld8(sa + r_ld8(row + lane_u));
-          if (lane_u < len) r_st8(a + lane_u, byte);
-        } else {
-          near_long(a, len, sa, row, per);
-        }
-        __syncwarp();
-      }
-      pos += total;
+      if (valid) r_st8(ring_s + (pv & RM), b);
+      __syncwarp(gmask);
+      if (FLUSH < (int)dfl::kSub && ((k + 1u) * G) % FLUSH == 0u && (k + 1u) * G < len) flush(v0 + (k + 1u) * G);
     }
-    if (pos != sub_limit) return 0xFFFFFFFFu;
-    flush(pos);
-    return pos;
+    flush(v0 + len);
   }
 };
 
@@ -522,14 +339,13 @@ template <int LBITS, int LT, int DBITS, int DT, int WARPS, int GROUP, int MIN_CT
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
     inflate_tok_kernel(const bitar_chunk* __restrict__ ops, bitar_result* __restrict__ results, const Task* __restrict__ tasks,
                        Counters* __restrict__ pc, uint8_t* scratch, uint32_t subs) {
-  using Lane = tk::TokLane<LBITS, LT, DBITS, DT, 16>;
-  using WS = WarpSmem<LT, DT, 16, GROUP>;
+  using Lane = tk::TokLane<LBITS, LT, DBITS, DT>;
+  using WS = WarpSmem<LT, DT, GROUP>;
+  using Res = ResolveBytes<GROUP, GROUP == 32 ? 4096 : 2048, GROUP == 32 ? 2048 : 1024>;
   constexpr int kGroupsPerWarp = 32 / GROUP;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint32_t* dinfo = reinterpret_cast<uint32_t*>(smem_raw + (size_t)WARPS * kGroupsPerWarp * sizeof(WS));
-  ResolveLut* lut = reinterpret_cast<ResolveLut*>(dinfo + 32);
   if (threadIdx.x < 32) dinfo[threadIdx.x] = fl::dist_info((int)threadIdx.x);
-  resolve_lut_init(lut);
   __syncthreads();
 
   const int wlane = (int)(threadIdx.x & 31u);
@@ -539,19 +355,13 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
   WS& ws = *reinterpret_cast<WS*>(smem_raw + (size_t)((threadIdx.x >> 5) * kGroupsPerWarp + gbase / GROUP) * sizeof(WS));
   Lane L;
   L.bind(ws.lt, ws.dt, ws.ring + lane * WS::kRingStride, dinfo, &ws.sc);
-  // phase B: the resolver's window / ring takes the space of the tables and unit rings once phase A is done with them
-  constexpr int kRing = 2048;
-  static_assert(sizeof(WS) >= (GROUP == 32 ? (size_t)ResolveWarp::kBytes : (size_t)kRing), "the resolver borrows the group's phase-A space");
-  ResolveGroup<GROUP == 32 ? 8 : GROUP, kRing> R;    // (groups of 8 lanes; unused by the warp-per-block instance)
+  // phase B: the resolver's ring takes the space of the tables and lane rings once phase A is done with them
+  static_assert(sizeof(WS) >= (size_t)Res::kBytes, "the resolver borrows the group's phase-A space");
+  Res R;
   R.gl = lane;
   R.gmask = kFull;
   R.ring_s = (uint32_t)__cvta_generic_to_shared(&ws);
-  R.lut_s = (uint32_t)__cvta_generic_to_shared(lut);
-  ResolveWarp W;
-  W.gl = lane;
-  W.buf_s = (uint32_t)__cvta_generic_to_shared(&ws);
-  W.lut_s = (uint32_t)__cvta_generic_to_shared(lut);
-  // the group's unit scratch: `subs` slots, rewritten for every block
+  // the group's token-map scratch: `subs` slots, rewritten for every block
   uint8_t* const slots = scratch + ((size_t)(blockIdx.x * WARPS + (threadIdx.x >> 5)) * kGroupsPerWarp + gbase / GROUP) * subs * tk::kSlotBytes;
   const uint32_t n_tasks = pc->n_tasks;
 
@@ -664,10 +474,9 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
         if (status == fl::kStatusOk)
           status = warp_build_table<GROUP>(ws.sc.lens, nlen, fl::kLitLen, ws.lt, LBITS, LT, ws.sc.ll_count, ws.sc.ll_first,
                                            ws.sc.ll_offs, ws.sc.ll_sorted, ws.cnt, ws.at, lane, kFull);
-        // ---- lane s decodes sub-range s into units ----
+        // ---- lane s decodes sub-range s into its token map ----
         if (status == fl::kStatusOk) {
           L.state = Lane::kDone;
-          L.upos = 0;
           if ((uint32_t)lane < ns) {
             const uint32_t s = (uint32_t)lane;
             uint32_t sbit, ebit;
@@ -678,32 +487,13 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
           }
           while (L.state != Lane::kDone) L.step();
           status = L.status;
-          // ---- phase B: the block's units in stream order ----
-          const uint32_t my_units = (uint32_t)lane < ns ? L.units() : 0u;
-          if (!__any_sync(kFull, status != fl::kStatusOk)) {   // (also orders the unit stores before the loads below)
+          // ---- phase B: the block's bytes in stream order ----
+          if (!__any_sync(kFull, status != fl::kStatusOk)) {   // (also orders the lanes' map stores before the loads below)
             const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);
-            uint32_t pos = mis;
-            if (GROUP == 32) {
-              W.begin(out);
-              for (uint32_t s = 0; s < ns; ++s) {
-                const uint32_t nu = __shfl_sync(kFull, my_units, (int)s, GROUP);
-                if (s) W.slide();
-                pos = W.resolve(reinterpret_cast<const uint16_t*>(slots + (size_t)s * tk::kSlotBytes), nu, pos, mis + min(blen, (s + 1u) * dfl::kSub));
-                if (pos == 0xFFFFFFFFu) break;
-              }
-              if (pos == 0xFFFFFFFFu) status = fl::kStatusDataError;
-              else W.finish(pos);
-            } else {
-              R.vbase = out - mis;
-              R.flushed = mis;
-              for (uint32_t s = 0; s < ns; ++s) {
-                const uint32_t nu = __shfl_sync(kFull, my_units, (int)s, GROUP);
-                pos = R.resolve(reinterpret_cast<const uint16_t*>(slots + (size_t)s * tk::kSlotBytes), nu, pos, mis + min(blen, (s + 1u) * dfl::kSub));
-                if (pos == 0xFFFFFFFFu) break;
-              }
-              if (pos == 0xFFFFFFFFu) status = fl::kStatusDataError;
-              else R.finish(pos);
-            }
+            R.begin(out);
+            for (uint32_t s = 0; s < ns; ++s)
+              R.resolve_sub(slots + (size_t)s * tk::kSlotBytes, mis + s * dfl::kSub, min(dfl::kSub, blen - s * dfl::kSub));
+            R.finish(mis + blen);
           }
           __syncwarp(kFull);   // the ring's space goes back to phase A
         }
@@ -741,7 +531,7 @@ __global__ void __launch_bounds__(128)
 template <int LBITS, int LT, int DBITS, int DT, int WARPS, int GROUP = 32, int MIN_CTAS = 2>
 struct TokConfig {
   static constexpr int kThreads = WARPS * 32;
-  static constexpr size_t kSmem = (size_t)WARPS * (32 / GROUP) * sizeof(WarpSmem<LT, DT, 16, GROUP>) + 32 * sizeof(uint32_t) + sizeof(ResolveLut);
+  static constexpr size_t kSmem = (size_t)WARPS * (32 / GROUP) * sizeof(WarpSmem<LT, DT, GROUP>) + 32 * sizeof(uint32_t);
   static int ctas_per_sm(int device) {
     static int per_device[64] = {0};
     int& c = per_device[device & 63];

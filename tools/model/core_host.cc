@@ -80,18 +80,18 @@ API int host_inflate_fast(const uint8_t* in, uint32_t in_len, uint8_t* out, uint
 }
 
 // The two-phase path of the production inflate kernels on the CPU: the index is parsed with the kernels' own
-// parse_index(), block headers are parsed by a whole-stream lane, every 2 KiB sub-range is Huffman-decoded into token
-// units by a tk::TokLane that starts at its indexed bit offset (phase A: the kernel runs 32 of these per warp), and the
-// units of a block are resolved in order by tk::resolve_units_serial (phase B, stated serially).
+// parse_index(), block headers are parsed by a whole-stream lane, every 2 KiB sub-range is Huffman-decoded into its token
+// map by a tk::TokLane that starts at its indexed bit offset (phase A: the kernel runs 32 of these per warp), and the
+// maps of a block are resolved in order by tk::resolve_sub_serial (phase B, stated serially).
 // result: [0] produced, [1] status, [2] 1 when the chunk carried an index, [3] sub-ranges decoded.
 API int host_inflate_indexed(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t cap, uint32_t* result4) {
   using namespace bitar::fl;
   using namespace bitar;
   constexpr int LB = 10, LT = 1344, DB = 8, DT = 512, RG = 128;
   using Gen = FastLane<LB, LT, DB, DT, RG, false>;
-  using Tok = tk::TokLane<LB, LT, DB, DT, 16>;
+  using Tok = tk::TokLane<LB, LT, DB, DT>;
   alignas(16) static thread_local uint8_t smem[LaneLayout<LB, LT, DB, DT, 256>::kStride];
-  alignas(16) static thread_local uint8_t uring[64];
+  alignas(16) static thread_local uint8_t uring[tk::kLaneRingBytes];
   alignas(16) static thread_local uint8_t slots[32][tk::kSlotBytes];
   static thread_local LaneScratch scratch;
   static CtaTables cta;
@@ -127,7 +127,6 @@ API int host_inflate_indexed(const uint8_t* in, uint32_t in_len, uint8_t* out, u
       continue;
     }
     if ((uint32_t)(8ll * g.start_off + g.consumed_bits()) != index_word(ix, b * 33u + 1u)) { status = kStatusDataError; break; }
-    uint32_t n_units[32] = {0};
     for (uint32_t s = 0; s < ns; ++s) {   // phase A
       Tok l;
       l.bind(g.lt, g.dt, uring, cta.dinfo, &scratch);
@@ -139,20 +138,13 @@ API int host_inflate_indexed(const uint8_t* in, uint32_t in_len, uint8_t* out, u
       while (l.state != Tok::kDone && ++steps < (1ull << 30)) l.step();
       result4[3]++;
       if (l.status != kStatusOk) { status = l.status; break; }
-      n_units[s] = l.units();
-      if (n_units[s] > tk::kSlotUnits || (n_units[s] & 7u)) { status = kStatusDataError; break; }
+      if (l.literals() > dfl::kSub || l.matches() > 682u) { status = kStatusDataError; break; }
     }
-    if (status == kStatusOk) {   // phase B: the kernel's lane (one block per lane)
-      alignas(16) static thread_local uint8_t ring[256];
-      uint16_t cnts[32];
-      for (uint32_t s = 0; s < 32; ++s) cnts[s] = (uint16_t)n_units[s];
-      tk::ResolveLane<256> r;
-      r.bind(ring);
-      r.start_block(out + (b << 16), blen, &slots[0][0], cnts, ns);
-      uint64_t steps = 0;
-      while (r.state == tk::ResolveLane<256>::kRun && ++steps < (1ull << 30)) r.step();
-      if (r.state != tk::ResolveLane<256>::kIdle) status = kStatusDataError;
-    }
+    if (status == kStatusOk)   // phase B
+      for (uint32_t s = 0; s < ns; ++s) {
+        const uint32_t len = blen - s * dfl::kSub < dfl::kSub ? blen - s * dfl::kSub : dfl::kSub;
+        if (!tk::resolve_sub_serial(slots[s], out + (b << 16), s * dfl::kSub, len)) { status = kStatusDataError; break; }
+      }
   }
   result4[0] = status == kStatusOk ? ix.total_out : 0;
   result4[1] = status;
