@@ -4,16 +4,14 @@
 // Why two phases (DESIGN.md "Inflate"): a match of a sub-range may copy from anywhere in the preceding 32 KiB of its
 // block, i.e. from bytes that the lane of ANOTHER sub-range is still producing.  Phase A therefore only does what is
 // independent per sub-range -- the serial bit-level work, 32 chains per block -- and leaves behind, per sub-range,
-// three things in its SLOT of a scratch area:
-//     literals   the literal bytes, compact, in stream order                                   (<= 2048 bytes)
-//     distances  D - 1 of every match, compact, in stream order, 16 bits each                  (<= 682 entries)
-//     starts     one bit per OUTPUT byte of the sub-range: set where a token (literal or match) starts
+// two things in its SLOT of a scratch area:
+//     tokens   16 bits per token, compact, in stream order: the byte of a literal, or D - 1 of a match   (<= 2048)
+//     starts   one bit per OUTPUT byte of the sub-range: set where a token (literal or match) starts
 // A set bit followed by a set bit is a literal; a set bit followed by a clear bit is the head of a match whose length
 // is the distance to the next set bit (matches are at least 3 bytes; a token never straddles a sub-range, so the byte
 // after a sub-range always counts as a start).  Phase B is then BYTE-parallel: lane i of a group takes output byte i of
-// a 32-byte piece, finds its token with two population counts on the start bits, and knows at once whether it is a
-// literal (the k-th of the sub-range) or byte j of a match (the m-th distance): no prefix sums over token lengths, no
-// loop over matches.
+// a 32-byte piece; the number of start bits up to its own says which token of the sub-range its byte belongs to, the
+// bit after its own whether that token is a literal: no prefix sums over token lengths, no loop over matches.
 //
 // BITAR_HD: the same source is compiled for the CPU (tools/model/core_host.cc, tests/test_core_host.py).
 //
@@ -33,15 +31,15 @@ using fl::kStatusOk;
 using fl::kStatusTruncated;
 using fl::sptr;
 
-// slot of one sub-range (16-byte aligned parts; vectors are stored whole, hence the slack)
-constexpr uint32_t kSlotLits = 0u;                                 // 2048 literal bytes + one spare vector
-constexpr uint32_t kSlotDists = 2064u;                             // 688 x u16 (682 matches of 3 bytes at most)
-constexpr uint32_t kSlotBits = kSlotDists + 688u * 2u;             // 64 words of start bits
-constexpr uint32_t kSlotBytes = kSlotBits + 256u;                  // 3696: a multiple of 16
+// slot of one sub-range (16-byte aligned parts; vectors are stored whole and phase B reads up to a step past the last
+// token without looking at it, hence the slack)
+constexpr uint32_t kSlotToks = 0u;                                 // 2048 x u16 + 32 spare
+constexpr uint32_t kSlotBits = 4096u + 64u;                        // 64 words of start bits
+constexpr uint32_t kSlotBytes = kSlotBits + 256u;                  // 4416: a multiple of 16
 constexpr uint32_t kSubsPerTask = 32u;                             // a task = one 64 KiB block
 constexpr size_t kTaskBytes = (size_t)kSubsPerTask * kSlotBytes;
-static_assert(kSlotBytes % 16u == 0 && kSlotDists % 16u == 0 && kSlotBits % 16u == 0, "slot parts are vector aligned");
-constexpr uint32_t kLaneRingBytes = 64u;                           // per lane in shared memory: 32 literal bytes + 16 distances
+static_assert(kSlotBytes % 16u == 0 && kSlotBits % 16u == 0, "slot parts are vector aligned");
+constexpr uint32_t kLaneRingBytes = 32u;                           // per lane in shared memory: 16 tokens
 
 BITAR_HD void s_st16(sptr a, uint32_t v) {
 #if defined(__CUDA_ARCH__)
@@ -54,8 +52,8 @@ BITAR_HD void s_st16(sptr a, uint32_t v) {
 // One sub-range of a Huffman-coded block: symbols in, token map out.  The decode tables belong to the group (built once
 // per block by the kernel); the lane starts at an indexed bit offset, must produce exactly `olen` bytes worth of
 // tokens and must end exactly where the index says the next sub-range starts.
-// The lane stages literals (32 bytes) and distances (16 entries) in shared memory; both leave as aligned 16-byte
-// vectors.  A step appends at most 4 literals and one match.
+// The lane stages 16 tokens in shared memory; they leave as aligned 16-byte vectors.  A step appends at most 4
+// literals and one match.
 template <int LBITS, int LT, int DBITS, int DT>
 struct TokLane {
   static constexpr uint32_t LMASK = (1u << LBITS) - 1u, DMASK = (1u << DBITS) - 1u;
@@ -70,8 +68,7 @@ struct TokLane {
   uint32_t lo, hi, cnt;
   // output
   uint8_t* slot;                 // 16-byte aligned
-  uint32_t lpos, lflushed;       // literals appended / stored
-  uint32_t dpos, dflushed;       // distances appended / stored
+  uint32_t tpos, tflushed;       // tokens appended / stored
   uint32_t sbits;                // start bits of the 32 output bytes around opos
   uint32_t opos, olen, before;   // bytes produced, bytes to produce, bytes of the block before this sub-range
   uint32_t state, status;
@@ -89,7 +86,7 @@ struct TokLane {
     words = nullptr;
     slot = nullptr;
     in_len = nwords = wpos = next = skip = start_off = lo = hi = cnt = 0;
-    lpos = lflushed = dpos = dflushed = sbits = opos = olen = before = sub_end_bit = sub_eob = 0;
+    tpos = tflushed = sbits = opos = olen = before = sub_end_bit = sub_eob = 0;
   }
 
   // Decode `len` bytes worth of tokens from the symbol at stream bit `start_bit`; the sub-range must end at `end_bit`,
@@ -102,7 +99,7 @@ struct TokLane {
     bits_init(start_bit >> 3);
     drop(start_bit & 7u);
     slot = slot_;
-    lpos = lflushed = dpos = dflushed = sbits = opos = 0;
+    tpos = tflushed = sbits = opos = 0;
     olen = len;
     before = block_before;
     state = len ? (uint32_t)kDecode : (uint32_t)kSubEnd;
@@ -110,8 +107,7 @@ struct TokLane {
     sub_end_bit = end_bit;
     sub_eob = eob ? 1u : 0u;
   }
-  BITAR_HD uint32_t literals() const { return lpos; }
-  BITAR_HD uint32_t matches() const { return dpos; }
+  BITAR_HD uint32_t tokens() const { return tpos; }
 
   // ---- bit reader (as fl::FastLane) ----
   BITAR_HD void bits_init(uint32_t off) {
@@ -158,23 +154,24 @@ struct TokLane {
 
   // ---- output ----
   BITAR_HD void st_bits(uint32_t w, uint32_t v) { reinterpret_cast<uint32_t*>(slot + kSlotBits)[w] = v; }
-  // a token of n bytes starts at opos
-  BITAR_HD void token(uint32_t n) {
+  // a token of n bytes starts at opos: v = the byte of a literal, the distance - 1 of a match
+  BITAR_HD void token(uint32_t v, uint32_t n) {
+    s_st16(ring_s + ((tpos & 15u) << 1), v);
+    tpos++;
     sbits |= 1u << (opos & 31u);
     const uint32_t np = opos + n;
     if ((np ^ opos) >> 5) {                     // the word of start bits is complete (a long match skips whole words)
       uint32_t w = opos >> 5;
       st_bits(w, sbits);
       sbits = 0;
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
       for (++w; w < (np >> 5); ++w) st_bits(w, 0u);
     }
     opos = np;
   }
-  BITAR_HD void literal(uint32_t byte) {
-    fl::s_st8(ring_s + (lpos & 31u), byte);
-    lpos++;
-    token(1u);
-  }
+  BITAR_HD void literal(uint32_t byte) { token(byte, 1u); }
   BITAR_HD void flush_vec(sptr from, uint8_t* to) {
     uint32_t w0, w1, w2, w3;
     fl::s_ld128(from, w0, w1, w2, w3);
@@ -185,20 +182,15 @@ struct TokLane {
     o32[0] = w0; o32[1] = w1; o32[2] = w2; o32[3] = w3;
 #endif
   }
-  BITAR_HD void flush() {   // every complete vector (a step adds at most 4 literals and one distance)
-    if (lpos - lflushed >= 16u) {
-      flush_vec(ring_s + (lflushed & 31u), slot + kSlotLits + lflushed);
-      lflushed += 16u;
-    }
-    if (dpos - dflushed >= 8u) {
-      flush_vec(ring_s + 32u + ((dflushed & 15u) << 1), slot + kSlotDists + 2u * dflushed);
-      dflushed += 8u;
+  BITAR_HD void flush() {   // a complete vector of 8 tokens (a step adds at most 5)
+    if (tpos - tflushed >= 8u) {
+      flush_vec(ring_s + ((tflushed & 15u) << 1), slot + kSlotToks + 2u * tflushed);
+      tflushed += 8u;
     }
   }
   BITAR_HD void finish() {
     flush();
-    if (lpos > lflushed) flush_vec(ring_s + (lflushed & 31u), slot + kSlotLits + lflushed);          // (whole vectors: the slot has the room)
-    if (dpos > dflushed) flush_vec(ring_s + 32u + ((dflushed & 15u) << 1), slot + kSlotDists + 2u * dflushed);
+    if (tpos > tflushed) flush_vec(ring_s + ((tflushed & 15u) << 1), slot + kSlotToks + 2u * tflushed);   // (a whole vector: the slot has the room)
     if (opos & 31u) st_bits(opos >> 5, sbits);
     state = kDone;
   }
@@ -253,9 +245,7 @@ struct TokLane {
     const uint32_t dist = (di & 0xFFFFu) + take(di >> 16);
     if (overrun()) return fail(kStatusTruncated);
     if (dist > before + opos || opos + len > olen) return fail(kStatusDataError);   // outside the block / the sub-range
-    s_st16(ring_s + 32u + ((dpos & 15u) << 1), dist - 1u);
-    dpos++;
-    token(len);
+    token(dist - 1u, len);
   }
 
   // fewer than 5 bytes left -- one symbol at a time, so that the lane stops exactly at the end
@@ -324,22 +314,23 @@ struct TokLane {
 // the `len` output bytes of one sub-range from its slot; base[pos ..] receives them, everything below pos is final.
 // Returns false on a map that phase A cannot have produced.
 inline bool resolve_sub_serial(const uint8_t* slot, uint8_t* base, uint32_t pos, uint32_t len) {
-  const uint8_t* lits = slot + kSlotLits;
   const uint32_t* bits = reinterpret_cast<const uint32_t*>(slot + kSlotBits);
-  uint32_t li = 0, di = 0, dist = 0;
+  uint32_t ti = 0, dist = 0;
   for (uint32_t i = 0; i < len; ++i) {
     const bool start = (bits[i >> 5] >> (i & 31u)) & 1u;
     const bool next_start = i + 1u == len || ((bits[(i + 1u) >> 5] >> ((i + 1u) & 31u)) & 1u);
+    uint16_t t16 = 0;
+    if (start) {
+      if (ti >= 2048u) return false;
+      memcpy(&t16, slot + kSlotToks + 2u * ti++, 2);
+    }
     if (start && next_start) {
-      base[pos + i] = lits[li++];
+      if (t16 > 0xFFu) return false;
+      base[pos + i] = (uint8_t)t16;
       continue;
     }
-    if (start) {
-      uint16_t d16;
-      memcpy(&d16, slot + kSlotDists + 2u * di++, 2);
-      dist = (uint32_t)d16 + 1u;
-    }
-    if (dist == 0 || dist > pos + i || li > 2048u || di > 688u) return false;
+    if (start) dist = (uint32_t)t16 + 1u;
+    if (dist == 0 || dist > pos + i) return false;
     base[pos + i] = base[pos + i - dist];
   }
   return true;

@@ -8,13 +8,13 @@
 //   phase A (tok)     1. all lanes parse the block header together (same bits, same registers),
 //                     2. the warp builds the two decode tables cooperatively in its shared memory,
 //                     3. lane s Huffman-decodes sub-range s (2 KiB of output) from its indexed bit offset into a token
-//                        map (tk::TokLane, inflate_tok.h: compact literals, compact distances, one start bit per output
-//                        byte) in the warp's own scratch (L2 resident, reused per block) and checks that it ends exactly
+//                        map (tk::TokLane, inflate_tok.h: 16 bits per token and one start bit per output byte)
+//                        in the warp's own scratch (L2 resident, reused per block) and checks that it ends exactly
 //                        at the next offset.
 //                   A block offers 32 independent symbol chains instead of one.  Stored blocks are copied here.
 //   phase B (res)   the same warp resolves the block in stream order, BYTE-parallel: 32 output bytes per step, one per
-//                   lane.  Two population counts on the start bits tell a lane whether its byte is the k-th literal of
-//                   the sub-range or a byte of the m-th match; both streams are read one step ahead.  A match byte
+//                   lane.  A population count on the start bits tells a lane which token of the sub-range its byte
+//                   belongs to, the bit after its own whether that is a literal; tokens are read one step ahead.  A match byte
 //                   copies from a 4 KiB ring of the latest output in shared memory -- the space of the tables, which are
 //                   done with -- or, for sources farther back, from the block's own flushed output (L2); sources inside
 //                   the step's own 32 bytes are followed by pointer jumping over shuffles (five rounds cover any
@@ -247,10 +247,10 @@ struct ResolveBytes {
     __syncwarp(gmask);
   }
 
-  // start bits of step k: literals and match heads among its G bytes
-  __device__ __forceinline__ void masks(uint32_t k, uint32_t& lit, uint32_t& head) const {
+  // start bits of step k (s) and which of them are literals (a start whose NEXT byte is a start too)
+  __device__ __forceinline__ void masks(uint32_t k, uint32_t& s, uint32_t& lit) const {
     const uint32_t bm_s = ring_s + (uint32_t)RING;
-    uint32_t s, nx;
+    uint32_t nx;
     if (G == 32) {
       s = r_ld32(bm_s + 4u * k);
       nx = r_ld32(bm_s + 4u * k + 4u);
@@ -258,58 +258,47 @@ struct ResolveBytes {
       s = r_ld8(bm_s + k);
       nx = r_ld8(bm_s + k + 1u);
     }
-    const uint32_t n = (s >> 1) | ((nx & 1u) << (G - 1));       // the NEXT byte starts a token
-    lit = s & n;
-    head = s & ~n;
-  }
-  // this lane's literal, or the distance - 1 of the match its byte belongs to (a step ahead of its use)
-  __device__ __forceinline__ uint32_t fetch(const uint8_t* slot, uint32_t lit, uint32_t head, bool valid, uint32_t lbase, uint32_t hbase) const {
-    const uint32_t le = kAll >> (G - 1 - gl), lt = le >> 1;   // the lanes up to and including / below this one
-    uint32_t x = 0;
-    if (valid) {
-      if ((lit >> gl) & 1u) x = (uint32_t)__ldcg(slot + tk::kSlotLits + lbase + (uint32_t)__popc(lit & lt));
-      else x = (uint32_t)__ldcg(reinterpret_cast<const uint16_t*>(slot + tk::kSlotDists) + (hbase + (uint32_t)__popc(head & le) - 1u));
-    }
-    return x;
+    lit = s & ((s >> 1) | (nx << (G - 1)));
+    if (G != 32) lit &= kAll;
   }
 
   // The `len` bytes of one sub-range, from its slot, to virtual position v0 on.
   __device__ __forceinline__ void resolve_sub(const uint8_t* slot, uint32_t v0, uint32_t len) {
     const uint32_t lane_u = (uint32_t)gl;
     const uint32_t bm_s = ring_s + (uint32_t)RING;
-    // stage the start bits; the byte after the sub-range counts as a start (tokens never straddle sub-ranges)
+    // stage the start bits.  Everything from bit `len` on reads as a start: the byte after the sub-range is one (tokens
+    // never straddle sub-ranges), and the lanes of the last step that lie past the end then look like literals -- they
+    // fetch a token of the slot's slack and store it to ring positions nobody reads before they are written again.
     for (uint32_t i = lane_u; i < 16u; i += G) r_st128(bm_s + 16u * i, __ldcg(reinterpret_cast<const uint4*>(slot + tk::kSlotBits) + i));
     __syncwarp(gmask);
     if (lane_u == 0) {
       const uint32_t w = len >> 5, sh = len & 31u;
       const uint32_t old = sh ? r_ld32(bm_s + 4u * w) & ((1u << sh) - 1u) : 0u;
-      r_st32(bm_s + 4u * w, old | (1u << sh));
-      r_st32(bm_s + 4u * w + 4u, 0u);
+      r_st32(bm_s + 4u * w, old | (0xFFFFFFFFu << sh));
+      r_st32(bm_s + 4u * w + 4u, 0xFFFFFFFFu);
+      r_st32(bm_s + 4u * w + 8u, 0xFFFFFFFFu);
     }
     __syncwarp(gmask);
+    const uint16_t* toks = reinterpret_cast<const uint16_t*>(slot + tk::kSlotToks);
+    const uint32_t le = kAll >> (G - 1 - gl);       // the lanes up to and including this one
     const uint32_t nsteps = (len + G - 1u) / G;
-    uint32_t lbase = 0, hbase = 0;                  // literals / match heads of the sub-range before the step being fetched
-    uint32_t lit_n, head_n;
-    masks(0, lit_n, head_n);
-    uint32_t x_n = fetch(slot, lit_n, head_n, lane_u < len, 0u, 0u);
+    uint32_t tbase = 0;                             // tokens of the sub-range that start before the step being fetched
+    uint32_t s_n, lit_n;
+    masks(0, s_n, lit_n);
+    // this lane's token -- the byte of a literal, or the distance - 1 of the match its byte belongs to -- is the one of
+    // the nearest start at or below its byte; fetched a step ahead of its use (its place follows from the start bits alone)
+    uint32_t x_n = (uint32_t)__ldcg(toks + ((uint32_t)__popc(s_n & le) - 1u));
+    uint32_t pv = v0 + lane_u;
 #pragma unroll 1
     for (uint32_t k = 0; k < nsteps; ++k) {
-      const uint32_t lit = lit_n, head = head_n, x = x_n;
-      const uint32_t off = k * G + lane_u;
-      const bool valid = off < len;
-      if (k + 1u < nsteps) {                        // the next step's literal / distance: their places follow from the start bits alone
-        lbase += (uint32_t)__popc(lit);
-        hbase += (uint32_t)__popc(head);
-        masks(k + 1u, lit_n, head_n);
-        x_n = fetch(slot, lit_n, head_n, off + G < len, lbase, hbase);
-      }
-      const uint32_t pv = v0 + off;
-      const uint32_t left = len - k * G;
-      const uint32_t want = left >= (uint32_t)G ? kAll : ((1u << left) - 1u);
+      const uint32_t lit = lit_n, x = x_n;
+      tbase += (uint32_t)__popc(s_n);
+      masks(k + 1u, s_n, lit_n);
+      x_n = (uint32_t)__ldcg(toks + (tbase + (uint32_t)__popc(s_n & le) - 1u));
       uint32_t b = x;
-      if ((lit & want) != want) {                   // the step holds match bytes
+      if (lit != kAll) {                            // the step holds match bytes
         const uint32_t dist = x + 1u;
-        const bool mb = valid && !((lit >> lane_u) & 1u);
+        const bool mb = !((lit >> lane_u) & 1u);
         const bool inside = mb && dist <= lane_u;   // the source is a byte of this very step
         const bool far = mb && dist > kNear;
         if (mb && !inside && !far) b = r_ld8(ring_s + ((pv - dist) & RM));
@@ -323,7 +312,8 @@ struct ResolveBytes {
           b = __shfl_sync(gmask, b, (int)ptr, G);
         }
       }
-      if (valid) r_st8(ring_s + (pv & RM), b);
+      r_st8(ring_s + (pv & RM), b);
+      pv += G;
       __syncwarp(gmask);
       if (FLUSH < (int)dfl::kSub && ((k + 1u) * G) % FLUSH == 0u && (k + 1u) * G < len) flush(v0 + (k + 1u) * G);
     }

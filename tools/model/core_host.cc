@@ -138,7 +138,7 @@ API int host_inflate_indexed(const uint8_t* in, uint32_t in_len, uint8_t* out, u
       while (l.state != Tok::kDone && ++steps < (1ull << 30)) l.step();
       result4[3]++;
       if (l.status != kStatusOk) { status = l.status; break; }
-      if (l.literals() > dfl::kSub || l.matches() > 682u) { status = kStatusDataError; break; }
+      if (l.tokens() > dfl::kSub) { status = kStatusDataError; break; }
     }
     if (status == kStatusOk)   // phase B
       for (uint32_t s = 0; s < ns; ++s) {
