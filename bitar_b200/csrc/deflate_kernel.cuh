@@ -204,56 +204,41 @@ __device__ __forceinline__ uint32_t ld32u(uint32_t saddr) {
   return __funnelshift_r(lds_u32(a), lds_u32(a + 4), (saddr & 3u) * 8u);
 }
 
-// Length of the common prefix of the bytes at p and c (both in the block held in shared memory), at most maxl.
-// Both streams are read as aligned words, one new word per stream and step; the previous word is carried.
-__device__ __forceinline__ int match_len(uint32_t ds, int p, int c, int maxl) {
-  const uint32_t ap = (ds + (uint32_t)p) & ~3u, ac = (ds + (uint32_t)c) & ~3u;
-  const uint32_t sp = ((ds + (uint32_t)p) & 3u) * 8u, sc = ((ds + (uint32_t)c) & 3u) * 8u;
-  // the first 8 bytes without a branch (six independent loads, one latency): most matches of columnar data end here
-  const uint32_t p0 = lds_u32(ap), p1 = lds_u32(ap + 4u), c0 = lds_u32(ac), c1 = lds_u32(ac + 4u);
-  uint32_t wp = lds_u32(ap + 8u), wc = lds_u32(ac + 8u);
-  const uint32_t x0 = __funnelshift_r(p0, p1, sp) ^ __funnelshift_r(c0, c1, sc);
-  const uint32_t x1 = __funnelshift_r(p1, wp, sp) ^ __funnelshift_r(c1, wc, sc);
-  // equal leading bytes of each word: clz(brev(x)) >> 3 is 0..3, or 4 when the words are equal -- no branch
-  const int l0 = __clz((int)__brev(x0)) >> 3, l1 = __clz((int)__brev(x1)) >> 3;
-  int l = l0 + (l0 == 4 ? l1 : 0);
-  if ((x0 | x1) == 0 && maxl > 8) {
-    while (l < maxl) {
-      const uint32_t np = lds_u32(ap + (uint32_t)l + 4u), nc = lds_u32(ac + (uint32_t)l + 4u);
-      const uint32_t x = __funnelshift_r(wp, np, sp) ^ __funnelshift_r(wc, nc, sc);
-      if (x) {
-        l += (__ffs((int)x) - 1) >> 3;
-        break;
-      }
-      wp = np;
-      wc = nc;
-      l += 4;
-    }
-  }
-  return min(l, maxl);
+// Lengths of the common prefixes of the bytes at p with the bytes at three candidates (all in the block held in shared
+// memory): the two near candidates c1 / c2, at most max1 / max2 bytes, and the far candidate c3, at most max3 bytes, which
+// only counts where both near matches stay below kFarNeed bytes (len3 = 0 otherwise).  max = 0 switches a candidate off
+// (the caller then passes p itself as the candidate).  All streams are read as aligned words, one new word per stream
+// and step; the words of p are loaded once for the three.  The first 8 bytes go without a branch (most matches of
+// columnar data end there); the loop then runs while any candidate still matches.
+__device__ __forceinline__ int prefix8(uint32_t x0, uint32_t x1) {
+  // equal leading bytes of the first differing word: clz(brev(z)) >> 3 is 0..3, or 4 when z == 0 (both words equal)
+  const uint32_t z = x0 ? x0 : x1;
+  return (x0 ? 0 : 4) + (__clz((int)__brev(z)) >> 3);
 }
-
-// The same for two candidates of one position at once (the words of p are loaded once, the extension loop runs while
-// either candidate still matches).  max1 / max2 = 0 switches a candidate off.
-__device__ __forceinline__ void match_len2(uint32_t ds, int p, int c1, int c2, int max1, int max2, int& len1, int& len2) {
-  const uint32_t ap = (ds + (uint32_t)p) & ~3u, a1 = (ds + (uint32_t)c1) & ~3u, a2 = (ds + (uint32_t)c2) & ~3u;
-  const uint32_t sp = ((ds + (uint32_t)p) & 3u) * 8u, s1 = ((ds + (uint32_t)c1) & 3u) * 8u, s2 = ((ds + (uint32_t)c2) & 3u) * 8u;
+__device__ __forceinline__ void match_len3(uint32_t ds, int p, int c1, int c2, int c3, int max1, int max2, int max3, int& len1, int& len2,
+                                           int& len3) {
+  const uint32_t ap = (ds + (uint32_t)p) & ~3u, a1 = (ds + (uint32_t)c1) & ~3u, a2 = (ds + (uint32_t)c2) & ~3u, a3 = (ds + (uint32_t)c3) & ~3u;
+  const uint32_t sp = ((ds + (uint32_t)p) & 3u) * 8u, s1 = ((ds + (uint32_t)c1) & 3u) * 8u, s2 = ((ds + (uint32_t)c2) & 3u) * 8u,
+                 s3 = ((ds + (uint32_t)c3) & 3u) * 8u;
   const uint32_t p0 = lds_u32(ap), p1 = lds_u32(ap + 4u);
-  const uint32_t q0 = lds_u32(a1), q1 = lds_u32(a1 + 4u), r0 = lds_u32(a2), r1 = lds_u32(a2 + 4u);
-  uint32_t wp = lds_u32(ap + 8u), w1 = lds_u32(a1 + 8u), w2 = lds_u32(a2 + 8u);
+  const uint32_t q0 = lds_u32(a1), q1 = lds_u32(a1 + 4u), r0 = lds_u32(a2), r1 = lds_u32(a2 + 4u), t0 = lds_u32(a3), t1 = lds_u32(a3 + 4u);
+  uint32_t wp = lds_u32(ap + 8u), w1 = lds_u32(a1 + 8u), w2 = lds_u32(a2 + 8u), w3 = lds_u32(a3 + 8u);
   const uint32_t pa = __funnelshift_r(p0, p1, sp), pb = __funnelshift_r(p1, wp, sp);
   const uint32_t x0 = pa ^ __funnelshift_r(q0, q1, s1), x1 = pb ^ __funnelshift_r(q1, w1, s1);
   const uint32_t y0 = pa ^ __funnelshift_r(r0, r1, s2), y1 = pb ^ __funnelshift_r(r1, w2, s2);
-  const int lx0 = __clz((int)__brev(x0)) >> 3, lx1 = __clz((int)__brev(x1)) >> 3;
-  const int ly0 = __clz((int)__brev(y0)) >> 3, ly1 = __clz((int)__brev(y1)) >> 3;
-  int l1 = lx0 + (lx0 == 4 ? lx1 : 0), l2 = ly0 + (ly0 == 4 ? ly1 : 0);
-  bool g1 = (x0 | x1) == 0 && max1 > 8, g2 = (y0 | y1) == 0 && max2 > 8;
+  const uint32_t z0 = pa ^ __funnelshift_r(t0, t1, s3), z1 = pb ^ __funnelshift_r(t1, w3, s3);
+  int l1 = prefix8(x0, x1), l2 = prefix8(y0, y1), l3 = prefix8(z0, z1);
+  // the far candidate counts where the near matches are short: min(l, max) < kFarNeed for both (kFarNeed == 8: a near
+  // match that reaches 8 bytes here either stops there or grows in the loop)
+  static_assert(kFarNeed == 8, "the far rule is decided on the first 8 bytes");
+  const bool far_on = min(l1, max1) < kFarNeed && min(l2, max2) < kFarNeed;
+  bool g1 = l1 == 8 && max1 > 8, g2 = l2 == 8 && max2 > 8, g3 = far_on && l3 == 8 && max3 > 8;
   int l = 8;                                          // bytes compared so far by a candidate that is still going
-  while (g1 || g2) {
+  while (g1 || g2 || g3) {
     const uint32_t np = lds_u32(ap + (uint32_t)l + 4u);
-    const uint32_t n1 = lds_u32(a1 + (uint32_t)l + 4u), n2 = lds_u32(a2 + (uint32_t)l + 4u);
+    const uint32_t n1 = lds_u32(a1 + (uint32_t)l + 4u), n2 = lds_u32(a2 + (uint32_t)l + 4u), n3 = lds_u32(a3 + (uint32_t)l + 4u);
     const uint32_t xp = __funnelshift_r(wp, np, sp);
-    const uint32_t x = xp ^ __funnelshift_r(w1, n1, s1), y = xp ^ __funnelshift_r(w2, n2, s2);
+    const uint32_t x = xp ^ __funnelshift_r(w1, n1, s1), y = xp ^ __funnelshift_r(w2, n2, s2), z = xp ^ __funnelshift_r(w3, n3, s3);
     if (g1) {
       l1 = l + (x ? (__ffs((int)x) - 1) >> 3 : 4);
       g1 = x == 0 && l + 4 < max1;
@@ -262,13 +247,19 @@ __device__ __forceinline__ void match_len2(uint32_t ds, int p, int c1, int c2, i
       l2 = l + (y ? (__ffs((int)y) - 1) >> 3 : 4);
       g2 = y == 0 && l + 4 < max2;
     }
+    if (g3) {
+      l3 = l + (z ? (__ffs((int)z) - 1) >> 3 : 4);
+      g3 = z == 0 && l + 4 < max3;
+    }
     wp = np;
     w1 = n1;
     w2 = n2;
+    w3 = n3;
     l += 4;
   }
   len1 = min(l1, max1);
   len2 = min(l2, max2);
+  len3 = far_on ? min(l3, max3) : 0;
 }
 
 // ---- output stream: bit stage in shared memory, flushed as aligned 16-byte vectors ------------------
@@ -451,13 +442,18 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
   const int sub_end = min(n, s0 + (int)dfl::kSub);
   int carry = s0;                                     // next token start
   // this sub-range's tokens go to tokens[s0 ..], compact and in order
+  uint32_t* __restrict__ tokp = tokens + s0;
   uint32_t cnt = 0;
-  uint32_t far_next = s0 + lane < n ? __ldcg(far + s0 + lane) : kNoFar;   // (sub-range 0 has no far candidates: the pass wrote kNoFar)
+  // far candidates of a window, read one window ahead (sub-range 0 has none: the pass wrote kNoFar; entries of positions
+  // without four bytes are never used: `valid` below; the scratch has a window of slack past the block)
+  const uint16_t* farp = far + s0 + lane;
+  uint32_t far_next = __ldcg(farp);
   for (int base = s0; base < s1; base += 32) {
     const int p = base + lane;
     const bool valid = p + 4 <= n;
     const uint32_t fc = valid ? far_next : kNoFar;
-    if (base + 32 < s1) far_next = p + 32 < n ? __ldcg(far + p + 32) : kNoFar;   // the next window's, one iteration ahead
+    farp += 32;
+    far_next = __ldcg(farp);                          // the next window's, one iteration ahead
     const uint32_t h = valid ? dfl::hash_near(ld32u(ds + p), kNearBits) : dummy;
     const unsigned m = __match_any_sync(kFull, h);    // dummies are unique per lane
     const unsigned lower = m & lt_mask;
@@ -480,22 +476,18 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
     const int maxl = min(dfl::kMaxMatch, sub_end - p);
     const bool has1 = live && cand1 != kNoCand && p - (int)cand1 <= max_dist;
     const bool has2 = live && cand2 != kNoCand && p - (int)cand2 <= max_dist;
-    int len1, len2;
-    match_len2(ds, p, has1 ? (int)cand1 : p, has2 ? (int)cand2 : p, has1 ? maxl : 0, has2 ? maxl : 0, len1, len2);
+    const bool has3 = live && fc != kNoFar;           // the far candidate: tried where the near matches are short
+    int len1, len2, len3;
+    match_len3(ds, p, has1 ? (int)cand1 : p, has2 ? (int)cand2 : p, has3 ? (int)fc : p, has1 ? maxl : 0, has2 ? maxl : 0, has3 ? maxl : 0, len1,
+               len2, len3);
     int len = len1, c = (int)cand1;
     if (len2 > len1) {
       len = len2;
       c = (int)cand2;
     }
-    {   // the far candidate where the near match is short (skipped when no lane of the window wants it)
-      const bool want_far = live && fc != kNoFar && len < kFarNeed;
-      if (__any_sync(kFull, want_far)) {
-        const int lf = match_len(ds, p, want_far ? (int)fc : p, want_far ? maxl : 0);
-        if (lf >= kFarMin && lf > len) {
-          len = lf;
-          c = (int)fc;
-        }
-      }
+    if (len3 >= kFarMin && len3 > len) {
+      len = len3;
+      c = (int)fc;
     }
     const bool hit = len >= dfl::kMinMatch;
     int adv = hit ? len : 1, dist = hit ? p - c : 0;
@@ -506,27 +498,18 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
         dist = 0;
       }
     }
-    // Greedy parse of the window from a: literal lanes hand the parse to their neighbour, so only the match lanes
-    // on the way cost a step (one shuffle each); every lane walks redundantly.
-    unsigned reach = 0;
+    // Greedy parse of the window from a: the token starts are the positions reached from a by t -> t + adv[t].  Every
+    // lane collects the positions reached from ITS position, doubling the number of hops per round (five rounds cover
+    // the 32 hops of a window of literals); lane a's set is the parse.
+    unsigned reach;
     {
-      const unsigned matches = __ballot_sync(kFull, adv > 1);
-      int pos = a;
-      for (;;) {
-        const unsigned ahead = matches & (0xFFFFFFFFu << pos);
-        if (!ahead) {                                 // literals to the end of the window
-          reach |= 0xFFFFFFFFu << pos;
-          carry = base + 32;
-          break;
-        }
-        const int q = __ffs((int)ahead) - 1;          // next match start: pos..q all start tokens
-        reach |= (0xFFFFFFFFu << pos) & (0xFFFFFFFFu >> (31 - q));
-        pos = q + __shfl_sync(kFull, adv, q);
-        if (pos >= 32) {
-          carry = base + pos;
-          break;
-        }
-      }
+      const int nxt = lane + adv;
+      unsigned r = (lt_mask + 1u) | (nxt < 32 ? 1u << nxt : 0u);
+#pragma unroll
+      for (int round = 0; round < 5; ++round) r |= __shfl_sync(kFull, r, 31 - __clz((int)r));
+      reach = __shfl_sync(kFull, r, a);
+      const int last = 31 - __clz((int)reach);      // the last token start of the window
+      carry = base + last + __shfl_sync(kFull, adv, last);
     }
     const bool start = (reach & (lt_mask + 1u)) != 0u && p < n;   // lt_mask + 1 == this lane's bit
     const unsigned starts = __ballot_sync(kFull, start);
@@ -540,7 +523,7 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
         atomicAdd(&sm.ll_freq[is_match ? 257u + (len_f >> 26) : byte], 1u);
         if (is_match) atomicAdd(&sm.d_freq[dist_f >> 23], 1u);
         // (one 32-bit index from the scratch base: a single wide multiply-add forms the address)
-        tokens[(uint32_t)s0 + cnt + (uint32_t)__popc(starts & lt_mask)] = is_match ? (0x80000000u | (len_f & 0xFFu) | dist_f | (d1 << 8)) : byte;
+        tokp[cnt + (uint32_t)__popc(starts & lt_mask)] = is_match ? (0x80000000u | (len_f & 0xFFu) | dist_f | (d1 << 8)) : byte;
       }
     }
     cnt += (uint32_t)__popc(starts);
@@ -1372,7 +1355,7 @@ __global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
 }
 
 inline size_t deflate_scratch_bytes(int grid) { return (size_t)grid * kBlockMax * sizeof(uint32_t); }   // tokens
-inline size_t deflate_far_bytes(int grid) { return (size_t)grid * kBlockMax * sizeof(uint16_t); }       // far candidates
+inline size_t deflate_far_bytes(int grid) { return ((size_t)grid * kBlockMax + 64u) * sizeof(uint16_t); }   // far candidates (+ a window of slack)
 
 // resident CTAs per SM for chunks of at most max_len bytes (the shared-memory footprint follows the chunk size)
 inline cudaError_t deflate_ctas_per_sm(int device, uint32_t max_len, int* ctas_out) {

@@ -33,6 +33,7 @@ struct Params {
   int near_bits = 9;
   int far_need = 8;
   int far_min = 4;
+  int select = 0;       // EXPERIMENT: candidate selection variants (0 = the kernel's)
   int lazy = 1;         // 1: a match yields to a strictly longer match starting at the next position of its window
   int max_dist = kMaxDist;   // the configured window (1 << window_size)
   int huffman = 2;      // 1 fixed only, 2 dynamic (min of stored/fixed/dynamic)
@@ -142,6 +143,7 @@ inline void find_tokens(const uint8_t* d, int n, const Params& P, std::vector<ui
       if (!valid[t]) continue;
       const int maxl = std::min(kMaxMatch, sub_end - p);
       int best = 0, bc = kNone;
+      if (P.select == 0) {
       if (c1[t] != kNone && p - c1[t] <= P.max_dist) best = match_len(d, p, c1[t], maxl), bc = c1[t];
       if (c2[t] != kNone && p - c2[t] <= P.max_dist) {
         const int l = match_len(d, p, c2[t], maxl);
@@ -150,6 +152,35 @@ inline void find_tokens(const uint8_t* d, int n, const Params& P, std::vector<ui
       if (best < P.far_need && far[(size_t)p] != kNone) {
         const int l = match_len(d, p, far[(size_t)p], maxl);
         if (l >= P.far_min && l > best) best = l, bc = far[(size_t)p];
+      }
+      } else {
+        const uint32_t wp = load32(d, (size_t)n, (size_t)p);
+        auto ok4 = [&](int c) { return c != kNone && p - c <= P.max_dist && load32(d, (size_t)n, (size_t)c) == wp; };
+        int cands[3] = {c1[t], c2[t], far[(size_t)p]};
+        if (P.select == 1) {          // first candidate whose 4 bytes are equal
+          for (int k = 0; k < 3; ++k) if (ok4(cands[k])) { best = match_len(d, p, cands[k], maxl); bc = cands[k]; break; }
+        } else if (P.select == 2) {   // c1 else c2 (first verified), then far when short
+          for (int k = 0; k < 2; ++k) if (ok4(cands[k])) { best = match_len(d, p, cands[k], maxl); bc = cands[k]; break; }
+          if (best < P.far_need && far[(size_t)p] != kNone) {
+            const int l = match_len(d, p, far[(size_t)p], maxl);
+            if (l >= P.far_min && l > best) best = l, bc = far[(size_t)p];
+          }
+        } else if (P.select == 3) {   // longer of c1 / c2 judged on 8 bytes, winner extended; far when short
+          int l1 = ok4(cands[0]) ? std::min(8, match_len(d, p, cands[0], maxl)) : 0;
+          int l2 = ok4(cands[1]) ? std::min(8, match_len(d, p, cands[1], maxl)) : 0;
+          int w = l2 > l1 ? 1 : 0;
+          if (std::max(l1, l2) >= 4) { best = match_len(d, p, cands[w], maxl); bc = cands[w]; }
+          if (best < P.far_need && far[(size_t)p] != kNone) {
+            const int l = match_len(d, p, far[(size_t)p], maxl);
+            if (l >= P.far_min && l > best) best = l, bc = far[(size_t)p];
+          }
+        } else if (P.select == 4) {   // c1 only, then far when short
+          if (ok4(cands[0])) { best = match_len(d, p, cands[0], maxl); bc = cands[0]; }
+          if (best < P.far_need && far[(size_t)p] != kNone) {
+            const int l = match_len(d, p, far[(size_t)p], maxl);
+            if (l >= P.far_min && l > best) best = l, bc = far[(size_t)p];
+          }
+        }
       }
       if (best >= kMinMatch) {
         adv[t] = best;
