@@ -33,9 +33,9 @@ using fl::sptr;
 
 // slot of one sub-range (16-byte aligned parts; vectors are stored whole and phase B reads up to a step past the last
 // token without looking at it, hence the slack)
-constexpr uint32_t kSlotToks = 0u;                                 // 2048 x u16 + 32 spare
-constexpr uint32_t kSlotBits = 4096u + 64u;                        // 64 words of start bits
-constexpr uint32_t kSlotBytes = kSlotBits + 256u;                  // 4416: a multiple of 16
+constexpr uint32_t kSlotToks = 0u;                                 // 2048 x u16 + 64 spare
+constexpr uint32_t kSlotBits = 4096u + 128u;                       // 64 words of start bits
+constexpr uint32_t kSlotBytes = kSlotBits + 256u;                  // 4480: a multiple of 16
 constexpr uint32_t kSubsPerTask = 32u;                             // a task = one 64 KiB block
 constexpr size_t kTaskBytes = (size_t)kSubsPerTask * kSlotBytes;
 static_assert(kSlotBytes % 16u == 0 && kSlotBits % 16u == 0, "slot parts are vector aligned");

@@ -213,7 +213,7 @@ struct ResolveBytes {
   static constexpr uint32_t kNear = RING - G;                   // (the step's own stores may already have replaced anything older)
   static_assert(kNear >= (uint32_t)FLUSH + G + 16u, "a source that is not in the ring must have been flushed");
   static_assert(RING >= FLUSH + 16 + G, "a flush reads what the ring still holds");
-  static constexpr uint32_t kBitsBytes = 272u;                  // staged start bits: 64 words, the sentinel's word, padding
+  static constexpr uint32_t kBitsBytes = 288u;                  // staged start bits: 64 words, then words that read as "all starts"
   static constexpr uint32_t kBytes = RING + kBitsBytes;
   static constexpr uint32_t kAll = G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u);
   uint32_t ring_s;          // shared address of the group's ring (16-byte aligned), followed by the staged start bits
@@ -277,24 +277,36 @@ struct ResolveBytes {
       r_st32(bm_s + 4u * w, old | (0xFFFFFFFFu << sh));
       r_st32(bm_s + 4u * w + 4u, 0xFFFFFFFFu);
       r_st32(bm_s + 4u * w + 8u, 0xFFFFFFFFu);
+      r_st32(bm_s + 4u * w + 12u, 0xFFFFFFFFu);
     }
     __syncwarp(gmask);
     const uint16_t* toks = reinterpret_cast<const uint16_t*>(slot + tk::kSlotToks);
     const uint32_t le = kAll >> (G - 1 - gl);       // the lanes up to and including this one
     const uint32_t nsteps = (len + G - 1u) / G;
+    // Software pipeline, two steps deep.  This lane's token for a step -- the byte of a literal, or the distance - 1 of
+    // the match its byte belongs to -- is the one of the nearest start at or below its byte; its place follows from
+    // the start bits alone, so it is fetched two steps ahead (x2), and a source that lies below the ring (a FAR match
+    // byte: its address needs the token) one step ahead (fb1).
     uint32_t tbase = 0;                             // tokens of the sub-range that start before the step being fetched
-    uint32_t s_n, lit_n;
-    masks(0, s_n, lit_n);
-    // this lane's token -- the byte of a literal, or the distance - 1 of the match its byte belongs to -- is the one of
-    // the nearest start at or below its byte; fetched a step ahead of its use (its place follows from the start bits alone)
-    uint32_t x_n = (uint32_t)__ldcg(toks + ((uint32_t)__popc(s_n & le) - 1u));
+    uint32_t s2, lit1, lit2;
+    masks(0, s2, lit1);
+    uint32_t x1 = (uint32_t)__ldcg(toks + ((uint32_t)__popc(s2 & le) - 1u));
+    tbase += (uint32_t)__popc(s2);
+    masks(1, s2, lit2);
+    uint32_t x2 = (uint32_t)__ldcg(toks + (tbase + (uint32_t)__popc(s2 & le) - 1u));
     uint32_t pv = v0 + lane_u;
+    uint32_t fb1 = 0;
+    if (!((lit1 >> lane_u) & 1u) && x1 + 1u > kNear) fb1 = (uint32_t)__ldcg(vbase + (pv - (x1 + 1u)));
 #pragma unroll 1
     for (uint32_t k = 0; k < nsteps; ++k) {
-      const uint32_t lit = lit_n, x = x_n;
-      tbase += (uint32_t)__popc(s_n);
-      masks(k + 1u, s_n, lit_n);
-      x_n = (uint32_t)__ldcg(toks + (tbase + (uint32_t)__popc(s_n & le) - 1u));
+      const uint32_t lit = lit1, x = x1, fb = fb1;
+      lit1 = lit2;
+      x1 = x2;
+      tbase += (uint32_t)__popc(s2);
+      masks(k + 2u, s2, lit2);
+      x2 = (uint32_t)__ldcg(toks + (tbase + (uint32_t)__popc(s2 & le) - 1u));
+      fb1 = 0;
+      if (!((lit1 >> lane_u) & 1u) && x1 + 1u > kNear) fb1 = (uint32_t)__ldcg(vbase + (pv + G - (x1 + 1u)));
       uint32_t b = x;
       if (lit != kAll) {                            // the step holds match bytes
         const uint32_t dist = x + 1u;
@@ -302,9 +314,7 @@ struct ResolveBytes {
         const bool inside = mb && dist <= lane_u;   // the source is a byte of this very step
         const bool far = mb && dist > kNear;
         if (mb && !inside && !far) b = r_ld8(ring_s + ((pv - dist) & RM));
-        if (__any_sync(gmask, far)) {
-          if (far) b = (uint32_t)__ldcg(vbase + (pv - dist));
-        }
+        if (far) b = fb;
         if (__any_sync(gmask, inside)) {            // follow the chain of sources to a byte that is known: G - 1 hops at most
           uint32_t ptr = inside ? lane_u - dist : lane_u;
 #pragma unroll
