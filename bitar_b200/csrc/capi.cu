@@ -514,6 +514,9 @@ int deflate_prepare_staging(QueuePair* q, uint32_t n) {
     total += q->h_ops[i].src_len;
   }
   if (total < kDeflateStageMin) return BITAR_OK;
+  // few, long chunks (a CTA spends milliseconds on one): the pieces of a staged call run one after the other, each
+  // with fewer chunks than the grid has CTAs -- reading in place, all chunks at once, is faster (1 MiB chunks: 8 -> 40 GB/s)
+  if (total / n >= ((size_t)256 << 10) && n < 1184) return BITAR_OK;
   const size_t mis = reinterpret_cast<uintptr_t>(base) & 15u;
   if (q->stage_in_cap < total + 64) {
     if (q->d_stage_in) cudaFree(q->d_stage_in);
