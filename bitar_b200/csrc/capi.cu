@@ -959,7 +959,7 @@ inline uint32_t op_blocks(const bitar_chunk& c) {   // 64 KiB blocks an op's out
 }  // namespace
 
 using TokWide = bitar::xk::TokConfig<9, 864, 7, 256, 16, 32, 2>;    // a warp per 64 KiB block
-using TokSmall = bitar::xk::TokConfig<9, 864, 7, 256, 8, 8, 4>;     // four blocks of at most 8 sub-ranges per warp
+using TokSmall = bitar::xk::TokConfig<9, 864, 7, 256, 2, 8, 7>;     // four blocks of at most 8 sub-ranges per warp; small CTAs: shared memory (3.9 KB per block) decides how many warps an SM holds (14)
 
 int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, bitar_result* results) {
   const int variant = inflate_variant();

@@ -41,6 +41,7 @@ struct Params {
   int sub_log2 = kSubLog2;
 };
 
+static long g_win_total = 0, g_win_nocand = 0, g_win_skipped = 0, g_win_1cand = 0;
 struct BitWriter {
   std::vector<uint8_t> out;
   uint64_t acc = 0;
@@ -136,6 +137,25 @@ inline void find_tokens(const uint8_t* d, int n, const Params& P, std::vector<ui
         head1[h[t]] = head0[h[t]];
         head0[h[t]] = base + t;
       }
+    {   // EXPERIMENT: windows in which no live lane has a candidate with 3 equal bytes
+      g_win_total++;
+      if (carry - base >= 32) g_win_skipped++;
+      else {
+        bool any = false, two = false;
+        for (int t = 0; t < 32; ++t) {
+          const int p = base + t;
+          if (!valid[t] || p < carry) continue;
+          const uint32_t wp = load32(d, (size_t)n, (size_t)p) & 0xFFFFFFu;
+          int cnt = 0;
+          for (int c : {c1[t], c2[t], far[(size_t)p]})
+            if (c != kNone && p - c <= P.max_dist && (load32(d, (size_t)n, (size_t)c) & 0xFFFFFFu) == wp) cnt++;
+          any |= cnt > 0;
+          two |= cnt > 1;
+        }
+        if (!any) g_win_nocand++;
+        else if (!two) g_win_1cand++;
+      }
+    }
     for (int t = 0; t < 32; ++t) {
       const int p = base + t;
       adv[t] = 1;

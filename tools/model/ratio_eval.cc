@@ -111,6 +111,7 @@ int main(int argc, char** argv) {
          (double)data.size() / msum, (double)msum / zsum, (unsigned long long)lits,
          (unsigned long long)matches, matches ? (double)mbytes / matches : 0.0,
          (double)data.size() / (double)(lits + matches), types[0], types[1], types[2]);
+  printf("windows: %ld total, %.1f%% skipped (covered), %.1f%% without any 3-byte candidate, %.1f%% with at most one per lane\n", bitar_model::g_win_total, 100.0 * bitar_model::g_win_skipped / bitar_model::g_win_total, 100.0 * bitar_model::g_win_nocand / bitar_model::g_win_total, 100.0 * bitar_model::g_win_1cand / bitar_model::g_win_total);
   printf("far matches %.1f%%, deferred (far or reading deferred bytes) %.1f%% of matches, %.1f%% of bytes; sub-ranges with any: %.1f%%\n", 100.0 * g_far / g_all,
          100.0 * g_deferred / g_all, 100.0 * g_dirty_bytes / data.size(), 100.0 * g_sub_dirty / g_subs);
   printf("matches farther than 128 / 256 / 512 B: %.1f%% / %.1f%% / %.1f%% of matches, %.1f%% / %.1f%% / %.1f%% of all bytes\n", 100.0 * fr[0] / matches, 100.0 * fr[2] / matches,
