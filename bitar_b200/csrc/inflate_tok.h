@@ -238,12 +238,13 @@ struct TokLane {
     const uint32_t len = (e >> 8) + 3u + take((e >> 4) & 7u);
     uint32_t d = fl::s_ld16(dt_s + ((lo & DMASK) << 1));
     if ((d & fl::kBadDist) == fl::kBadDist) d = d_resolve(d);
-    if ((d & fl::kBadDist) == fl::kBadDist) return fail(overrun() ? kStatusTruncated : kStatusDataError);
+    if ((d & fl::kBadDist) == fl::kBadDist) return fail(kStatusDataError);
     drop(d & 15u);
     refill();
     const uint32_t di = fl::s_ld32(dinfo_s + ((d >> 4) << 2));
     const uint32_t dist = (di & 0xFFFFu) + take(di >> 16);
-    if (overrun()) return fail(kStatusTruncated);
+    // (no test for running past the input here: the reader yields zeros there, and a lane that used them cannot end on
+    // the bit offset the index demands -- sub_end() reports it; an indexed chunk is never truncated, its trailer says so)
     if (dist > before + opos || opos + len > olen) return fail(kStatusDataError);   // outside the block / the sub-range
     token(dist - 1u, len);
   }
