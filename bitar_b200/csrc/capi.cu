@@ -625,6 +625,10 @@ int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, b
       zero_counters_kernel<<<1, 8, 0, st>>>(counters);
       e = cudaGetLastError();
     }
+    // the contiguous copy-back below takes whole segments whatever their ops produced: a failed or short op must not hand
+    // the caller bytes that an earlier call left in the stage
+    if (e == cudaSuccess && q->stage_dst_contig)
+      e = cudaMemsetAsync(q->h_ops[first].dst, 0, (size_t)count * q->h_orig[0].dst_cap, st);
     if (e == cudaSuccess) e = launch(q, first, count, counters, st);
     g_launches.fetch_add(2);   // the counter reset + the batch's last codec kernel (the others are counted where they launch)
     if (e == cudaSuccess && !lanes) e = cudaEventRecord(q->ev_k1, st);

@@ -205,3 +205,44 @@ def test_chained_segments(cuda_device, k, seg):
         assert dev.slots_free() == free0
     finally:
         dev.close()
+
+
+def test_failed_op_of_a_staged_call_never_exposes_stale_stage_bytes(cuda_device):
+    """Decompress() with everything in pinned host memory is staged through device memory and copied back in whole
+    segments (one copy-engine transfer per batch).  When an op in the middle fails, the caller's segment may be left as
+    it was or zeroed -- it must never receive bytes that an EARLIER call left in the stage."""
+    import ctypes as C
+    L = capi.lib()
+    seg = 59460
+    data = synth.lineitem_like(12 * seg)
+    n = data.size // seg
+    dev = G.open_device(seg, slot_mem_kind=capi.MEM_PINNED, max_preallocate_memzones=n + 8)
+    h_in, h_out = C.c_void_p(), C.c_void_p()
+    try:
+        capi.check(L.bitar_mem_alloc(capi.MEM_PINNED, 0, data.size, 64, C.byref(h_in)))
+        capi.check(L.bitar_mem_alloc(capi.MEM_PINNED, 0, n * seg + 64, 64, C.byref(h_out)))
+        C.memmove(h_in.value, data.ctypes.data, data.size)
+        ops, slots = dev.compress_ops(h_in.value, data.size)
+        res = dev.enqueue("deflate", 0, ops)
+        dev.wait(0)
+        back = np.ctypeslib.as_array(C.cast(h_out.value, C.POINTER(C.c_uint8)), shape=(n * seg + 64,))
+        dev.enqueue("inflate", 0, dev.decompress_ops(slots, res["produced"], h_out.value))   # fills the stage with plaintext
+        dev.wait(0)
+        assert np.array_equal(back[:data.size], data)
+        C.memset(h_out.value, 0xA5, n * seg + 64)
+        slot5 = np.ctypeslib.as_array(C.cast(int(slots[5]), C.POINTER(C.c_uint8)), shape=(int(res["produced"][5]),))
+        slot5[0] |= 0x06                                       # block type 3: no such block
+        ires = dev.enqueue("inflate", 0, dev.decompress_ops(slots, res["produced"], h_out.value))
+        with pytest.raises(capi.BitarError):
+            dev.wait(0)
+        assert int(ires["status"][5]) != 0 and (np.delete(ires["status"], 5) == 0).all()
+        seg5 = back[5 * seg:6 * seg]
+        assert ((seg5 == 0) | (seg5 == 0xA5)).all(), "the failed op's segment received stale bytes"
+        for i in (4, 6):
+            assert np.array_equal(back[i * seg:(i + 1) * seg], data[i * seg:(i + 1) * seg])
+        assert sum(dev.put_slot(s) for s in slots[::-1]) == n
+    finally:
+        for b in (h_in, h_out):
+            if b.value:
+                L.bitar_mem_free(capi.MEM_PINNED, 0, b)
+        dev.close()
