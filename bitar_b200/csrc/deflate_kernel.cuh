@@ -388,8 +388,8 @@ __device__ void sort_rank(Smem& sm) {
 // sub-ranges in order: look up all positions of the sub-range, barrier, insert them (the largest position of a hash
 // wins, whatever the order: atomicMax), barrier.  Semantics == the far pass of tools/model/deflate_model.h.
 __device__ __forceinline__ void far_pass(Smem& sm, uint32_t ds, int n, int max_dist, uint16_t* __restrict__ far, int tid) {
-  constexpr int kPer = (int)dfl::kSub / kThreads;     // positions per thread and sub-range
-  static_assert(kPer * kThreads == (int)dfl::kSub, "a sub-range is a whole number of passes of the CTA");
+  constexpr int kPer = ((int)dfl::kSub + kThreads - 1) / kThreads;   // positions per thread and sub-range
+  constexpr bool kExact = kPer * kThreads == (int)dfl::kSub;           // (else the last pass of the CTA is partly idle)
   const int fb = dfl::far_hash_bits((uint32_t)n);
   uint32_t* tab = sm.u.m.far_tab;
   for (int i = tid; i < (1 << fb); i += kThreads) tab[i] = 0u;
@@ -400,7 +400,7 @@ __device__ __forceinline__ void far_pass(Smem& sm, uint32_t ds, int n, int max_d
     for (int k = 0; k < kPer; ++k) {
       const int p = s0 + tid + k * kThreads;
       h[k] = 0xFFFFFFFFu;                             // no position / no hash
-      if (p + 4 <= n) {
+      if (p + 4 <= n && (kExact || tid + k * kThreads < (int)dfl::kSub)) {
         const uint32_t w = ld32u(ds + (uint32_t)p);
         h[k] = dfl::hash_far(w, fb);
         uint32_t f = kNoFar;
@@ -925,8 +925,8 @@ __global__ void __launch_bounds__(kThreads, BITAR_DK_MIN_CTAS)
       // the hash tables take the space of the bit stage for the duration of the match phase: park the
       // partially filled 16-byte unit at its front
       if (tid < 4) sm.keep[tid] = sm.u.enc.stage[tid];
-      static_assert(sizeof(sm.u.m.head) >= sizeof(sm.u.enc.stage), "the look-up tables must lie behind the bit stage");
-      static_assert(sizeof(sm.u.m.head) >= sizeof(sm.u.m.far_tab), "the far table borrows the near tables' space");
+      static_assert(sizeof(sm.u.m.head) >= sizeof(sm.u.enc.stage) || sizeof(sm.u.m.far_tab) >= sizeof(sm.u.enc.stage),
+                    "the look-up tables must lie behind the bit stage");
       for (int i = tid; i < 256; i += kThreads) sm.u.m.len_sym_lut[i] = ((uint32_t)dfl::len_sym(i + 3) << 26) | (uint32_t)i;
       for (int i = tid; i < 512; i += kThreads)
         sm.u.m.dist_sym_lut[i] = (uint32_t)dfl::dist_sym(i < 256 ? i + 1 : ((i - 256) << 7) + 1) << 23;
