@@ -33,6 +33,7 @@ struct Params {
   int near_bits = 9;
   int far_need = 8;
   int far_min = 4;
+  int pair = 0;         // EXPERIMENT: the near tables survive from an even sub-range into the odd one after it
   int select = 0;       // EXPERIMENT: candidate selection variants (0 = the kernel's)
   int lazy = 1;         // 1: a match yields to a strictly longer match starting at the next position of its window
   int max_dist = kMaxDist;   // the configured window (1 << window_size)
@@ -100,8 +101,10 @@ inline void find_tokens(const uint8_t* d, int n, const Params& P, std::vector<ui
   int carry = 0;
   for (int base = 0; base < n; base += 32) {
     if ((base & (SUB - 1)) == 0) {
-      std::fill(head0.begin(), head0.end(), kNone);
-      std::fill(head1.begin(), head1.end(), kNone);
+      if (!(P.pair && ((base / SUB) % P.pair) != 0)) {
+        std::fill(head0.begin(), head0.end(), kNone);
+        std::fill(head1.begin(), head1.end(), kNone);
+      }
       carry = base;
     }
     const int sub_end = std::min(n, (base & ~(SUB - 1)) + SUB);

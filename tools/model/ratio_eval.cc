@@ -60,6 +60,7 @@ int main(int argc, char** argv) {
     else if (k == "block") P.block = v;
     else if (k == "lazy") P.lazy = v;
     else if (k == "select") P.select = v;
+    else if (k == "pair") P.pair = v;
     else if (k == "sub_log2") P.sub_log2 = v;
     else return fprintf(stderr, "unknown key %s\n", k.c_str()), 2;
   }
