@@ -297,7 +297,7 @@ struct ResolveBytes {
     uint32_t pv = v0 + lane_u;
     uint32_t fb1 = 0;
     if (!((lit1 >> lane_u) & 1u) && x1 + 1u > kNear) fb1 = (uint32_t)__ldcg(vbase + (pv - (x1 + 1u)));
-#pragma unroll 1
+#pragma unroll 2
     for (uint32_t k = 0; k < nsteps; ++k) {
       const uint32_t lit = lit1, x = x1, fb = fb1;
       lit1 = lit2;
