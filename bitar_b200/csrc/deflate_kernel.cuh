@@ -234,28 +234,32 @@ __device__ __forceinline__ void match_len3(uint32_t ds, int p, int c1, int c2, i
   const bool far_on = min(l1, max1) < kFarNeed && min(l2, max2) < kFarNeed;
   bool g1 = l1 == 8 && max1 > 8, g2 = l2 == 8 && max2 > 8, g3 = far_on && l3 == 8 && max3 > 8;
   int l = 8;                                          // bytes compared so far by a candidate that is still going
-  while (g1 || g2 || g3) {
-    const uint32_t np = lds_u32(ap + (uint32_t)l + 4u);
-    const uint32_t n1 = lds_u32(a1 + (uint32_t)l + 4u), n2 = lds_u32(a2 + (uint32_t)l + 4u), n3 = lds_u32(a3 + (uint32_t)l + 4u);
-    const uint32_t xp = __funnelshift_r(wp, np, sp);
-    const uint32_t x = xp ^ __funnelshift_r(w1, n1, s1), y = xp ^ __funnelshift_r(w2, n2, s2), z = xp ^ __funnelshift_r(w3, n3, s3);
+  while (g1 || g2 || g3) {                            // 8 bytes per round
+    const uint32_t np0 = lds_u32(ap + (uint32_t)l + 4u), np1 = lds_u32(ap + (uint32_t)l + 8u);
+    const uint32_t m10 = lds_u32(a1 + (uint32_t)l + 4u), m11 = lds_u32(a1 + (uint32_t)l + 8u);
+    const uint32_t m20 = lds_u32(a2 + (uint32_t)l + 4u), m21 = lds_u32(a2 + (uint32_t)l + 8u);
+    const uint32_t m30 = lds_u32(a3 + (uint32_t)l + 4u), m31 = lds_u32(a3 + (uint32_t)l + 8u);
+    const uint32_t xp0 = __funnelshift_r(wp, np0, sp), xp1 = __funnelshift_r(np0, np1, sp);
     if (g1) {
-      l1 = l + (x ? (__ffs((int)x) - 1) >> 3 : 4);
-      g1 = x == 0 && l + 4 < max1;
+      const uint32_t x0 = xp0 ^ __funnelshift_r(w1, m10, s1), x1 = xp1 ^ __funnelshift_r(m10, m11, s1);
+      l1 = l + prefix8(x0, x1);
+      g1 = (x0 | x1) == 0 && l + 8 < max1;
     }
     if (g2) {
-      l2 = l + (y ? (__ffs((int)y) - 1) >> 3 : 4);
-      g2 = y == 0 && l + 4 < max2;
+      const uint32_t y0 = xp0 ^ __funnelshift_r(w2, m20, s2), y1 = xp1 ^ __funnelshift_r(m20, m21, s2);
+      l2 = l + prefix8(y0, y1);
+      g2 = (y0 | y1) == 0 && l + 8 < max2;
     }
     if (g3) {
-      l3 = l + (z ? (__ffs((int)z) - 1) >> 3 : 4);
-      g3 = z == 0 && l + 4 < max3;
+      const uint32_t z0 = xp0 ^ __funnelshift_r(w3, m30, s3), z1 = xp1 ^ __funnelshift_r(m30, m31, s3);
+      l3 = l + prefix8(z0, z1);
+      g3 = (z0 | z1) == 0 && l + 8 < max3;
     }
-    wp = np;
-    w1 = n1;
-    w2 = n2;
-    w3 = n3;
-    l += 4;
+    wp = np1;
+    w1 = m11;
+    w2 = m21;
+    w3 = m31;
+    l += 8;
   }
   len1 = min(l1, max1);
   len2 = min(l2, max2);
