@@ -387,8 +387,9 @@ __device__ void sort_rank(Smem& sm) {
 }
 
 // ---- far pass ---------------------------------------------------------------------------------------
-// far[p] = the last position c before the 2 KiB sub-range of p whose 4 bytes equal those at p (kNoFar when the table's
-// entry for the hash of p is empty, holds other bytes, or lies farther back than max_dist).  The whole CTA takes the
+// far[p] = the last position c before the 2 KiB sub-range of p whose 4 bytes hash like those at p (kNoFar when the table's
+// entry for the hash of p is empty or lies farther back than max_dist; a candidate that holds other bytes is weeded out
+// by the match phase).  The whole CTA takes the
 // sub-ranges in order: look up all positions of the sub-range, barrier, insert them (the largest position of a hash
 // wins, whatever the order: atomicMax), barrier.  Semantics == the far pass of tools/model/deflate_model.h.
 __device__ __forceinline__ void far_pass(Smem& sm, uint32_t ds, int n, int max_dist, uint16_t* __restrict__ far, int tid) {
@@ -410,7 +411,10 @@ __device__ __forceinline__ void far_pass(Smem& sm, uint32_t ds, int n, int max_d
         uint32_t f = kNoFar;
         if (s0) {
           const uint32_t c1 = tab[h[k]];              // position + 1, 0 = empty
-          if (c1 && p - (int)(c1 - 1u) <= max_dist && ld32u(ds + c1 - 1u) == w) f = c1 - 1u;
+          // (whether the candidate's 4 bytes really equal those at p is left to the match phase: its extension of the
+          // far candidate yields fewer than kFarMin bytes otherwise, which the selection rejects -- same tokens, one
+          // unaligned read less per position here)
+          if (c1 && p - (int)(c1 - 1u) <= max_dist) f = c1 - 1u;
         }
         far[p] = (uint16_t)f;
       }
