@@ -109,7 +109,7 @@ struct __align__(16) Smem {
   union {                            // the match phase and the plan/encode phases never overlap in time
     struct {
       union {
-        uint16_t head[kWarps][2][kNearSlots];         // per warp: hash -> the two most recent positions (kNoCand = empty)
+        uint32_t head[kWarps][kNearSlots];            // per warp: hash -> the two most recent positions, 16 bits each (kNoCand = empty)
         uint32_t far_tab[kFarTabMax];                 // far pass (before the match phase): hash -> last position + 1 before the sub-range
       };
       // pre-shifted token fields (tok_pack): length - 3 -> (length symbol index << 26) | (length - 3);
@@ -401,6 +401,31 @@ __device__ __forceinline__ void far_pass(Smem& sm, uint32_t ds, int n, int max_d
   __syncthreads();
   for (int s0 = 0; s0 < n; s0 += (int)dfl::kSub) {
     uint32_t h[kPer];
+    if (kPer == 4 && kExact && s0 + (int)dfl::kSub + 4 <= n) {
+      // a full sub-range with a thread per 4 CONSECUTIVE positions: their four 4-byte windows come out of three aligned
+      // words, their far candidates leave as one 8-byte store
+      const int p0 = s0 + 4 * tid;
+      const uint32_t a = (ds + (uint32_t)p0) & ~3u, sh = (ds + (uint32_t)p0) & 3u;
+      const uint32_t w0 = lds_u32(a), w1 = lds_u32(a + 4u), w2 = lds_u32(a + 8u);
+      uint32_t f[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t o = sh + (uint32_t)k;            // byte offset of the window in (w0, w1, w2): 0 .. 6
+        const uint32_t w = __funnelshift_r(o < 4u ? w0 : w1, o < 4u ? w1 : w2, (o & 3u) * 8u);
+        h[k] = dfl::hash_far(w, fb);
+        f[k] = kNoFar;
+        if (s0) {
+          const uint32_t c1 = tab[h[k]];
+          if (c1 && p0 + k - (int)(c1 - 1u) <= max_dist) f[k] = c1 - 1u;
+        }
+      }
+      *reinterpret_cast<uint2*>(far + p0) = make_uint2(f[0] | (f[1] << 16), f[2] | (f[3] << 16));
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) atomicMax(&tab[h[k]], (uint32_t)(p0 + k + 1));
+      __syncthreads();
+      continue;
+    }
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
       const int p = s0 + tid + k * kThreads;
@@ -438,12 +463,8 @@ __device__ __forceinline__ void far_pass(Smem& sm, uint32_t ds, int n, int max_d
 __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int s0, int s1, int warp, int lane, int max_dist,
                                                const uint16_t* far, uint32_t* __restrict__ tokens) {
   constexpr unsigned kFull = 0xFFFFFFFFu;
-  volatile uint16_t* head0 = sm.u.m.head[warp][0];      // [512 ..]: per-lane dummy slots, always empty
-  volatile uint16_t* head1 = sm.u.m.head[warp][1];
-  {
-    uint32_t* h32 = reinterpret_cast<uint32_t*>(sm.u.m.head[warp]);
-    for (int i = lane; i < kNearSlots; i += 32) h32[i] = 0xFFFFFFFFu;   // both ways (2 * kNearSlots u16)
-  }
+  volatile uint32_t* head = sm.u.m.head[warp];          // low half: the most recent position, high half: the one before; [512 ..]: per-lane dummy slots, always empty
+  for (int i = lane; i < kNearSlots; i += 32) head[i] = 0xFFFFFFFFu;
   __syncwarp();
   const unsigned lt_mask = (1u << lane) - 1u;
   const uint32_t dummy = (1u << kNearBits) + (uint32_t)lane;
@@ -462,16 +483,16 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
     const uint32_t fc = valid ? far_next : kNoFar;
     farp += 32;
     far_next = __ldcg(farp);                          // the next window's, one iteration ahead
-    const uint32_t h = valid ? dfl::hash_near(ld32u(ds + p), kNearBits) : dummy;
+    const uint32_t w4 = ld32u(ds + p);                // (the block is padded: reading past its end is harmless)
+    const uint32_t h = valid ? dfl::hash_near(w4, kNearBits) : dummy;
     const unsigned m = __match_any_sync(kFull, h);    // dummies are unique per lane
     const unsigned lower = m & lt_mask;
-    const uint32_t t0 = head0[h], t1 = head1[h];
+    const uint32_t t01 = head[h], t0 = t01 & 0xFFFFu, t1 = t01 >> 16;
     const int k1 = 31 - __clz((int)lower);            // nearest lower lane with this hash (-1: none)
     const unsigned lower2 = lower & ~(lower ? 1u << k1 : 0u);
     __syncwarp();
     if (valid && (m >> lane) == 1u) {                 // the window's highest position for this hash: the bucket after the window
-      head0[h] = (uint16_t)p;
-      head1[h] = (uint16_t)(lower ? (uint32_t)(base + k1) : t0);
+      head[h] = (uint32_t)p | ((lower ? (uint32_t)(base + k1) : t0) << 16);
     }
     __syncwarp();
     const uint32_t cand1 = lower ? (uint32_t)(base + k1) : t0;
@@ -523,7 +544,7 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
     const unsigned starts = __ballot_sync(kFull, start);
     {   // token + symbol counts, without a literal / match branch (the loads are harmless for the other kind)
       const bool is_match = adv > 1;
-      const uint32_t byte = lds_u8(ds + p);
+      const uint32_t byte = w4 & 0xFFu;
       const uint32_t d1 = is_match ? (uint32_t)dist - 1u : 0u;
       const uint32_t len_f = sm.u.m.len_sym_lut[is_match ? adv - 3 : 0];                  // symbol << 26 | length - 3
       const uint32_t dist_f = sm.u.m.dist_sym_lut[d1 < 256u ? d1 : 256u + (d1 >> 7)];     // symbol << 23
