@@ -477,6 +477,7 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
   // without four bytes are never used: `valid` below; the scratch has a window of slack past the block)
   const uint16_t* farp = far + s0 + lane;
   uint32_t far_next = __ldcg(farp);
+#pragma unroll 2
   for (int base = s0; base < s1; base += 32) {
     const int p = base + lane;
     const bool valid = p + 4 <= n;
