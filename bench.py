@@ -264,7 +264,7 @@ def main():
     ratio_corpus = foreign = None
     if not args.no_extras and rank == 0:
         ratio_corpus = run_ratio_corpus(dev, capi, torch, seg)
-        foreign = run_foreign(dev, torch, data, seg)
+        foreign = run_foreign(dev, torch, data, seg, mib=args.mib)   # the whole workload: fewer streams than lanes of the kernel grid would understate it
 
     # ---------------- BASELINE config 4: 8 GiB per GPU, generated on the device ----------------
     config4 = None
