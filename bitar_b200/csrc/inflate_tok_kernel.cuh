@@ -491,8 +491,16 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
           if (!__any_sync(kFull, status != fl::kStatusOk)) {   // (also orders the lanes' map stores before the loads below)
             const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);
             R.begin(out);
-            for (uint32_t s = 0; s < ns; ++s)
+            for (uint32_t s = 0; s < ns; ++s) {
+              // the next sub-range's map may have left L2 since its lane wrote it (4 736 warps x ~85 KB are in flight):
+              // ask for it now (a 128-byte line per lane covers the tokens, two more the start bits)
+              if (GROUP == 32 && s + 1u < ns) {
+                const uint8_t* nx = slots + (size_t)(s + 1u) * tk::kSlotBytes;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 128u * (uint32_t)lane));
+                if (lane < 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + tk::kSlotBits + 128u * (uint32_t)lane));
+              }
               R.resolve_sub(slots + (size_t)s * tk::kSlotBytes, mis + s * dfl::kSub, min(dfl::kSub, blen - s * dfl::kSub));
+            }
             R.finish(mis + blen);
           }
           __syncwarp(kFull);   // the ring's space goes back to phase A
