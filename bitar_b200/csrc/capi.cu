@@ -28,6 +28,7 @@
 #include "deflate_kernel.cuh"
 #include "inflate_kernel.cuh"
 #include "inflate_tok_kernel.cuh"
+#include "inflate_spec_kernel.cuh"
 
 namespace {
 
@@ -77,7 +78,8 @@ struct QueuePair {
   size_t tasks_cap = 0;
   uint8_t* d_units = nullptr;           //   token units between the two phases: `subs` slots per resident group of lanes
   size_t units_cap = 0;
-  uint32_t* d_generic = nullptr;        // ops left to the whole-stream kernel
+  uint32_t* d_generic = nullptr;        // ops without an index: the speculative kernel's list
+  uint32_t* d_declined = nullptr;       // what that kernel leaves to the whole-stream kernel
   uint32_t* d_indexed = nullptr;        // ops on the two-phase path
   size_t generic_cap = 0;
   // inflate with host (pinned / registered) buffers: stage through device memory
@@ -668,6 +670,16 @@ int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, b
   return BITAR_OK;
 }
 
+bool spec_enabled() {   // BITAR_SPEC=0: streams without an index go straight to the whole-stream kernel (A/B runs)
+  static const int on = getenv("BITAR_SPEC") ? atoi(getenv("BITAR_SPEC")) : 1;
+  return on != 0;
+}
+std::atomic<int> g_spec_target{0};
+uint32_t spec_target() {   // output bytes per speculative range (sp::range_bits)
+  static const int env = getenv("BITAR_SPEC_TARGET") ? atoi(getenv("BITAR_SPEC_TARGET")) : 768;
+  const int o = g_spec_target.load(), t = o > 0 ? o : env;
+  return (uint32_t)(t < 64 ? 64 : t > 1536 ? 1536 : t);
+}
 int inflate_variant() {
   int v = g_inflate_variant.load();
   if (v < 0) {
@@ -858,6 +870,7 @@ int bitar_dev_close(bitar_dev* dev) {
     if (q->d_tasks) cudaFree(q->d_tasks);
     if (q->d_units) cudaFree(q->d_units);
     if (q->d_generic) cudaFree(q->d_generic);
+    if (q->d_declined) cudaFree(q->d_declined);
     if (q->d_indexed) cudaFree(q->d_indexed);
     if (q->h_orig) cudaFreeHost(q->h_orig);
     if (q->d_orig) cudaFree(q->d_orig);
@@ -989,6 +1002,7 @@ inline uint32_t op_blocks(const bitar_chunk& c) {   // 64 KiB blocks an op's out
 }  // namespace
 
 using TokWide = bitar::xk::TokConfig<9, 864, 7, 256, 16, 32, 2>;    // a warp per 64 KiB block
+using SpecWide = bitar::sk::SpecConfig<9, 864, 7, 256, 16, 2>;       // a warp per stream without an index: speculative lane-parallel decode
 using TokSmall = bitar::xk::TokConfig<9, 864, 7, 256, 2, 8, 7>;     // four blocks of at most 8 sub-ranges per warp; small CTAs: shared memory (3.9 KB per block) decides how many warps an SM holds (14)
 
 int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, bitar_result* results) {
@@ -996,7 +1010,7 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
   const int ck = dev ? dev->cfg.checksum_type : 0, id = dev ? dev->id : 0, sms = dev ? dev->sm_count : 0;
   size_t total_blocks = 0;
   uint32_t subs = 32;          // unit slots per task: 32 sub-ranges of a 64 KiB block, fewer when every segment is small
-  bool small_mode = false;
+  bool small_mode = false, spec_mode = false;
   return qp_submit(
       dev, qp, ops, n, results,
       [&](QueuePair* q, uint32_t n_all) -> cudaError_t {
@@ -1012,11 +1026,25 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
         small_mode = max_cap <= kSmallSubs * bitar::dfl::kSub;
         if (small_mode) subs = max_cap ? (max_cap + bitar::dfl::kSub - 1u) >> bitar::dfl::kSubLog2 : 1u;
         // (staged calls run up to kStageLanes batches side by side: one scratch each)
-        const size_t one = small_mode ? TokSmall::scratch_bytes(id, sms, subs) : TokWide::scratch_bytes(id, sms, subs);
+        size_t one = small_mode ? TokSmall::scratch_bytes(id, sms, subs) : TokWide::scratch_bytes(id, sms, subs);
         if (one == 0) return cudaErrorLaunchOutOfResources;
+        // streams without an index are decoded speculatively (inflate_spec_kernel.cuh) in the same scratch, after the
+        // indexed ones; only calls that can hold such a stream pay for its size (a stream of < 64 bytes never is one)
+        spec_mode = variant != 6 && spec_enabled();
+        if (spec_mode) {
+          bool any = false;
+          for (uint32_t i = 0; i < n_all && !any; ++i) any = q->h_ops[i].src_len >= 64u;
+          spec_mode = any;
+        }
+        if (spec_mode) {
+          const size_t sp_one = (SpecWide::scratch_bytes(id, sms) + 15u) / 16u * 16u;
+          if (sp_one == 0) return cudaErrorLaunchOutOfResources;
+          one = sp_one > one ? sp_one : one;
+        }
         cudaError_t e = grow(&q->d_tasks, &q->tasks_cap, total_blocks);
         if (e == cudaSuccess) e = grow(&q->d_units, &q->units_cap, one * (q->nb > 1 ? kStageLanes : 1u));
-        size_t cap2 = q->generic_cap;
+        size_t cap2 = q->generic_cap, cap3 = q->generic_cap;
+        if (e == cudaSuccess) e = grow(&q->d_declined, &cap3, (size_t)n_all);
         if (e == cudaSuccess) e = grow(&q->d_generic, &q->generic_cap, (size_t)n_all);
         if (e == cudaSuccess) e = grow(&q->d_indexed, &cap2, (size_t)n_all);
         return e;
@@ -1056,6 +1084,14 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
           e = cudaGetLastError();
           if (e != cudaSuccess) return e;
           g_launches.fetch_add(1);
+        }
+        if (spec_mode) {
+          // what the speculative kernel declines (stored blocks, damaged streams, ...) is left to the whole-stream kernel
+          uint32_t* const declined = q->d_declined + first;
+          e = SpecWide::launch(d_ops, d_res, generic, pc, declined, units, ck, spec_target(), n, id, sms, st);
+          if (e != cudaSuccess) return e;
+          g_launches.fetch_add(1);
+          return InflateConfig<32, 10, 8, 1024, 4>::launch(d_ops, n, d_res, &pc->generic_next, ck, id, sms, st, declined, &pc->n_declined);
         }
         return InflateConfig<32, 10, 8, 1024, 4>::launch(d_ops, n, d_res, &pc->generic_next, ck, id, sms, st, generic, &pc->n_generic);
       },
@@ -1289,6 +1325,17 @@ BITAR_API int bitar_debug_lane(unsigned int* out16) {
 }
 #endif
 
+// not part of the public header: the 8 work counters of the first batch of the queue pair's last inflate call, after it
+// has completed (xk::Counters: [1] ops without an index, [7] of those, declined by the speculative kernel)
+BITAR_API int bitar_debug_inflate_counters(bitar_dev* dev, uint16_t qp, unsigned int* out8) {
+  if (!dev || qp >= dev->qps.size() || !out8) return BITAR_E_INVALID;
+  QueuePair* q = dev->qps[qp];
+  if (cudaSetDevice(dev->id) != cudaSuccess || cudaStreamSynchronize(q->stream) != cudaSuccess) return BITAR_E_IO_ERROR;
+  return cudaMemcpy(out8, q->d_counter, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost) == cudaSuccess ? BITAR_OK : BITAR_E_IO_ERROR;
+}
+
+// not part of the public header: output bytes per range of the speculative inflate kernel (0 = default)
+BITAR_API void bitar_tune_spec_target(int bytes) { g_spec_target.store(bytes); }
 // not part of the public header: selects the inflate kernel instantiation for tuning sweeps
 BITAR_API void bitar_tune_inflate_variant(int v) { g_inflate_variant.store(v); }
 // not part of the public header: least inflated bytes per batch of a staged (host-buffer) inflate call; 0 = default

@@ -43,7 +43,7 @@ struct Task {
 // device-side work counters of one inflate call (zeroed before the plan kernel)
 struct Counters {
   unsigned int n_tasks, n_generic, task_next, generic_next;
-  unsigned int n_indexed, res_next, ck_next, pad;
+  unsigned int n_indexed, spec_next, ck_next, n_declined;   // spec_next / n_declined: inflate_spec_kernel.cuh
 };
 constexpr uint32_t kSmallSubs = 8;
 

@@ -23,6 +23,7 @@ def lib():
         L.host_inflate_chunk.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
         L.host_inflate_fast.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_int]
         L.host_inflate_indexed.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+        L.host_inflate_spec.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         L.model_deflate_chunk.restype = C.c_long
         L.model_deflate_chunk.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.c_int]
         L.model_selfcheck.restype = C.c_int
@@ -114,3 +115,19 @@ def model_deflate(data, huffman=2, block=0):
     if r < 0:
         raise RuntimeError("model deflate overflow")
     return out[:r].copy()
+
+
+def host_inflate_spec(comp, cap, target=768, misalign=0):
+    """Run the speculative lane-parallel decoder of streams without an index (inflate_spec.h), the 32 lanes of a round one
+    after the other.  Returns (bytes, dict(produced, declined, blocks, rounds, ranges, short_rounds, walk_symbols))."""
+    c = np.ascontiguousarray(comp, dtype=np.uint8)
+    cpad = np.concatenate([c, np.zeros(8, np.uint8)])          # (the bit reader reads whole aligned words)
+    buf = np.full(cap + 64, 0xA5, np.uint8)
+    base = buf.ctypes.data
+    off = (-base) % 16 + misalign
+    res = np.zeros(8, np.uint32)
+    lib().host_inflate_spec(cpad.ctypes.data, c.size, base + off, cap, res.ctypes.data, target)
+    out = buf[off:off + int(res[0])].copy()
+    guard_ok = bool((buf[:off] == 0xA5).all() and (buf[off + cap:] == 0xA5).all())
+    return out, {"produced": int(res[0]), "declined": int(res[1]), "blocks": int(res[2]), "rounds": int(res[3]),
+                 "ranges": int(res[4]), "short_rounds": int(res[5]), "walk_symbols": int(res[6]), "guard_ok": guard_ok}

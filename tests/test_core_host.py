@@ -324,3 +324,80 @@ def test_model_ratio_corpus_within_tolerance_of_zlib_level_1(name):
             out, info = M.host_inflate_indexed(z, ch.size)
             assert info["status"] == 0 and info["indexed"] and np.array_equal(out, ch)
     assert model_bytes <= 1.05 * zlib_bytes, (name, model_bytes, zlib_bytes, model_bytes / zlib_bytes)
+
+
+def _zraw(data, level, strategy=zlib.Z_DEFAULT_STRATEGY):
+    co = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+    return np.frombuffer(co.compress(data.tobytes()) + co.flush(), np.uint8).copy()
+
+
+@pytest.mark.parametrize("level,strategy", [(1, zlib.Z_DEFAULT_STRATEGY), (6, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_DEFAULT_STRATEGY),
+                                            (1, zlib.Z_FIXED), (1, zlib.Z_HUFFMAN_ONLY), (1, zlib.Z_RLE), (0, zlib.Z_DEFAULT_STRATEGY)])
+def test_speculative_lanes_decode_streams_without_an_index(level, strategy):
+    """inflate_spec.h (the lane-parallel decoder of zlib-produced streams: 32 ranges per round start at GUESSED bit
+    offsets and join the true symbol chain) on the CPU: whatever it does not decline is bit-exact, for every block type,
+    alignment and size; stored blocks are declined (the whole-stream kernel's business)."""
+    inputs = dict(synth.ratio_corpus(1 << 18))
+    inputs.update({k: v for k, v in synth.edge_cases(SEG).items() if v.size in (SEG, SEG + 1) or k in ("ab", "period258", "period32768")})
+    decoded = 0
+    for name, d in inputs.items():
+        for seg in (4096, SEG, 1 << 18):
+            ch = d[:seg]
+            if ch.size == 0:
+                continue
+            comp = _zraw(ch, level, strategy)
+            for mis, target in ((0, 768), (5, 300), (0, 1536)):
+                out, info = M.host_inflate_spec(comp, ch.size, target, mis)
+                assert info["guard_ok"], (name, seg, info)
+                if level == 0:
+                    assert info["declined"], (name, seg, info)
+                    continue
+                if not info["declined"]:
+                    assert np.array_equal(out, ch), (name, seg, level, strategy, info)
+                    decoded += 1
+    assert level == 0 or decoded > 50
+
+
+def test_speculative_lanes_keep_most_lanes_busy_on_the_benchmark_streams():
+    """zlib level-1 streams of BASELINE config 2's chunks: nothing is declined, a round uses most of its 32 lanes and
+    nearly every lane finds its successor within the recorded steps (the walk is a few symbols long)."""
+    data = synth.lineitem_like(24 * SEG)
+    tot = {"rounds": 0, "ranges": 0, "short_rounds": 0, "walk_symbols": 0, "blocks": 0}
+    for i in range(24):
+        ch = data[i * SEG:(i + 1) * SEG]
+        out, info = M.host_inflate_spec(_zraw(ch, 1), SEG, 768)
+        assert not info["declined"] and np.array_equal(out, ch) and info["guard_ok"]
+        for k in tot:
+            tot[k] += info[k]
+    assert tot["ranges"] >= 20 * tot["rounds"], tot
+    assert tot["walk_symbols"] <= 16 * tot["ranges"], tot
+
+
+def test_speculative_lanes_on_damaged_streams_agree_with_zlib_or_decline():
+    """DEFLATE carries no integrity check: a damaged stream may still be a valid stream.  The speculative decoder may
+    decline anything, but what it does decode must be what zlib decodes from the same bytes -- and it never writes
+    outside the destination."""
+    rng = np.random.default_rng(23)
+    ch = synth.lineitem_like(SEG)
+    good = [_zraw(ch, 1), _zraw(ch, 6), _zraw(synth.text_source(SEG), 1)]
+    kept = 0
+    for trial in range(240):
+        bad = good[trial % 3].copy()
+        if trial % 5 == 0:
+            bad = bad[:int(rng.integers(8, bad.size))]                        # truncated
+        else:
+            for _ in range(int(rng.integers(1, 4))):
+                bad[int(rng.integers(0, bad.size))] ^= 1 << int(rng.integers(0, 8))
+        out, info = M.host_inflate_spec(bad, SEG, 768, trial % 4)
+        assert info["guard_ok"] and info["produced"] <= SEG, (trial, info)
+        if info["declined"]:
+            continue
+        d = zlib.decompressobj(-15)
+        try:
+            ref = d.decompress(bad.tobytes(), SEG + 1)
+        except zlib.error:
+            ref = None
+        assert ref is not None and d.eof and len(ref) <= SEG, (trial, info)
+        assert np.array_equal(out, np.frombuffer(ref, np.uint8)), trial
+        kept += 1
+    assert kept > 0

@@ -1,5 +1,7 @@
-"""Inflate speed on FOREIGN streams (zlib-produced, no parallel-inflate index): the whole-stream kernels.
-usage: python tools/gpu_foreign_inflate.py [MiB] [level] [variants...]   (variant 0 = default dispatch, 5 = whole-stream kernel only)"""
+"""Inflate speed on FOREIGN streams (zlib-produced, no parallel-inflate index).
+usage: python tools/gpu_foreign_inflate.py [MiB] [level] [variants...]
+variant 0 = default dispatch (speculative kernel, whole-stream kernel for what it declines), 6 = whole-stream kernel for
+every stream without an index, 5 = whole-stream kernel only; 0:T = default dispatch with T output bytes per speculative range"""
 import os
 import sys
 import zlib
@@ -16,7 +18,7 @@ from bitar_b200.engine import CompressDevice, Configuration  # noqa: E402
 
 mib = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 level = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-variants = [int(v) for v in sys.argv[3:]] or [0, 5]
+variants = sys.argv[3:] or ["0", "6"]
 seg = 59460
 data = synth.lineitem_like(mib << 20)
 n = (data.size + seg - 1) // seg
@@ -45,8 +47,11 @@ ops["src_len"] = sizes
 ops["dst"] = np.uint64(out.data_ptr()) + np.arange(n, dtype=np.uint64) * np.uint64(seg)
 ops["dst_cap"] = seg
 print(f"zlib level {level}: ratio {data.size / sizes.sum():.3f}, {n} streams")
-for v in variants:
+for vs in variants:
+    v, _, tgt = vs.partition(":")
+    v = int(v)
     capi.lib().bitar_tune_inflate_variant(v)
+    capi.lib().bitar_tune_spec_target(int(tgt or 0))
     out.zero_()
     best = 1e9
     for _ in range(3):
@@ -54,5 +59,7 @@ for v in variants:
         dev.wait(0)
         k, t = dev.last_ms(0)
         best = min(best, k)
-    print(f"variant {v}: {best:.3f} ms {data.size / best / 1e6:.1f} GB/s ok={bool((out[:data.size] == ref).all().item())}", flush=True)
+    cnt = np.zeros(8, np.uint32)
+    capi.lib().bitar_debug_inflate_counters(dev._h, 0, cnt.ctypes.data)
+    print(f"variant {vs}: no index {cnt[1]}, declined {cnt[7]}; {best:.3f} ms {data.size / best / 1e6:.1f} GB/s ok={bool((out[:data.size] == ref).all().item())}", flush=True)
 dev.close()

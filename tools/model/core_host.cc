@@ -10,6 +10,7 @@
 #include "../../bitar_b200/csrc/inflate_core.h"
 #include "../../bitar_b200/csrc/inflate_fast.h"
 #include "../../bitar_b200/csrc/inflate_tok.h"
+#include "../../bitar_b200/csrc/inflate_spec.h"
 #include "deflate_model.h"
 
 #define API extern "C" __attribute__((visibility("default")))
@@ -148,6 +149,86 @@ API int host_inflate_indexed(const uint8_t* in, uint32_t in_len, uint8_t* out, u
   }
   result4[0] = status == kStatusOk ? ix.total_out : 0;
   result4[1] = status;
+  return 0;
+}
+
+// The speculative path of streams WITHOUT an index (inflate_spec.h) on the CPU: block headers by a whole-stream lane,
+// then rounds of 32 sp::SpecLane ranges run one after the other (the kernel runs them as the lanes of a warp), the same
+// round bookkeeping as inflate_spec_kernel.cuh, ranges resolved by sp::resolve_range_serial.
+// result: [0] produced, [1] 0 = decoded / 1 = declined (the whole-stream kernel's business), [2] blocks, [3] rounds,
+//         [4] ranges that contributed, [5] ranges whose walk found no join point or ran out of slot space, [6] walk symbols
+API int host_inflate_spec(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t cap, uint32_t* result8, uint32_t target) {
+  using namespace bitar::fl;
+  using namespace bitar;
+  constexpr int LB = 9, LT = 864, DB = 7, DT = 256;
+  using Gen = FastLane<LB, LT, DB, DT, 256, false>;
+  using Lane = sp::SpecLane<LB, LT, DB, DT>;
+  alignas(16) static thread_local uint8_t smem[LaneLayout<LB, LT, DB, DT, 256>::kStride];
+  alignas(16) static thread_local uint8_t uring[32][tk::kLaneRingBytes];
+  alignas(16) static thread_local uint8_t slots[32][sp::kSlotBytes];
+  static thread_local LaneScratch scratch;
+  static CtaTables cta;
+  for (int i = 0; i < 32; ++i) cta.dinfo[i] = dist_info(i);
+  for (int i = 0; i < 8; ++i) result8[i] = 0;
+  result8[1] = 1;
+  if (in_len < 8 || cap == 0) return 0;
+  uint32_t total = 0, bit = 0;
+  for (;;) {
+    Gen g;
+    g.bind(smem, &cta, &scratch, 0);
+    g.start(in, in_len, out, cap);
+    g.bits_init(bit >> 3);
+    g.drop(bit & 7u);
+    g.header();
+    result8[2]++;
+    if (g.status != kStatusOk || g.state != Gen::kDecode) return 0;   // stored blocks, bad headers: declined
+    const uint32_t last = g.last;
+    uint32_t first = (uint32_t)(8ll * g.start_off + g.consumed_bits());
+    for (;;) {   // rounds
+      const uint32_t B = sp::range_bits(first, in_len, total, cap, target);
+      static thread_local Lane lanes[32];
+      for (int r = 0; r < 32; ++r) {
+        lanes[r].bind(g.lt, g.dt, uring[r], cta.dinfo, &scratch);
+        const uint64_t start = (uint64_t)first + (uint64_t)r * B;
+        if (start < 8ull * in_len) lanes[r].start_spec(in, in_len, (uint32_t)start, (uint32_t)start + B, slots[r]);
+        else lanes[r].idle();
+      }
+      result8[3]++;
+      for (int r = 0; r < 32; ++r)
+        for (uint32_t i = 0; i < sp::kRec; ++i) lanes[r].step(false);
+      for (int r = 0; r < 32; ++r) lanes[r].set_next(slots[(r + 1) & 31], r < 31 ? lanes[r + 1].nrec : 0u);
+      for (int r = 0; r < 32; ++r) {
+        uint64_t steps = 0;
+        while (lanes[r].state != Lane::kDone && ++steps < (1ull << 24)) {
+          if (lanes[r].state == Lane::kWalk) result8[6]++;
+          lanes[r].step(true);
+        }
+        if (lanes[r].state != Lane::kDone) return 0;
+      }
+      int m = 0;
+      while (m < 31 && lanes[m].end_kind == sp::kEndSync) ++m;
+      if (lanes[m].end_kind == sp::kEndSync) return 0;   // (lane 31 has no successor: it stops)
+      uint32_t j = 0;
+      for (int r = 0; r <= m; ++r) {
+        const sp::RangeOut ro = sp::range_out(lanes[r], j);
+        if ((uint64_t)total + ro.len > cap) return 0;
+        if (!sp::resolve_range_serial(slots[r], out, total, ro.len, ro.tskip, ro.bskip)) return 0;
+        total += ro.len;
+        j = lanes[r].sync_j;
+        result8[4]++;
+      }
+      if (lanes[m].end_kind == sp::kEndStop && m < 31) result8[5]++;
+      if (lanes[m].end_kind == sp::kEndBad) return 0;
+      if (lanes[m].end_bit > 8u * in_len) return 0;     // the chain ran past the input
+      if (lanes[m].end_kind == sp::kEndStop && m == 0 && lanes[0].end_bit == first) return 0;   // no progress
+      first = lanes[m].end_bit;
+      if (lanes[m].end_kind == sp::kEndEob) break;
+    }
+    bit = first;
+    if (last) break;
+  }
+  result8[0] = total;
+  result8[1] = 0;
   return 0;
 }
 
