@@ -59,6 +59,7 @@ struct ConnectionsDefault {
   ConnectionsDefault() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
 } g_connections_default;
 
+constexpr uint32_t kCountersPerBatch = 16;             // device work counters of one batch (xk::Counters)
 constexpr uint32_t kMaxStageBatches = 8;               // measured: ~8 batches of >= 16 MiB per call, whatever its size
 constexpr uint32_t kStageLanes = 3;                     // + the queue pair's own stream: 8 queue pairs fit 32 hardware queues
 constexpr size_t kStageBatchBytes = (size_t)16 << 20;   // least inflated bytes per batch of a staged call
@@ -622,9 +623,9 @@ int qp_submit(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, b
       g_launches.fetch_add(1);
     }
     if (e == cudaSuccess && !lanes && b == 0) e = cudaEventRecord(q->ev_k0, st);
-    unsigned int* counters = q->d_counter + 8 * b;
+    unsigned int* counters = q->d_counter + kCountersPerBatch * b;
     if (e == cudaSuccess) {
-      zero_counters_kernel<<<1, 8, 0, st>>>(counters);
+      zero_counters_kernel<<<1, kCountersPerBatch, 0, st>>>(counters);
       e = cudaGetLastError();
     }
     // the contiguous copy-back below takes whole segments whatever their ops produced: a failed or short op must not hand
@@ -676,7 +677,7 @@ bool spec_enabled() {   // BITAR_SPEC=0: streams without an index go straight to
 }
 std::atomic<int> g_spec_target{0};
 uint32_t spec_target() {   // output bytes per speculative range (sp::range_bits)
-  static const int env = getenv("BITAR_SPEC_TARGET") ? atoi(getenv("BITAR_SPEC_TARGET")) : 768;
+  static const int env = getenv("BITAR_SPEC_TARGET") ? atoi(getenv("BITAR_SPEC_TARGET")) : 1024;
   const int o = g_spec_target.load(), t = o > 0 ? o : env;
   return (uint32_t)(t < 64 ? 64 : t > 1536 ? 1536 : t);
 }
@@ -838,7 +839,7 @@ int bitar_dev_open(int device_id, uint16_t n_qps, const bitar_cfg* cfg_in, bitar
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&q->ev_k0);
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&q->ev_k1);
     if (e2 == cudaSuccess) e2 = cudaEventCreate(&q->ev_stop);
-    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&q->d_counter, 8 * kMaxStageBatches * sizeof(unsigned int));
+    if (e2 == cudaSuccess) e2 = cudaMalloc((void**)&q->d_counter, kCountersPerBatch * kMaxStageBatches * sizeof(unsigned int));
     if (e2 != cudaSuccess) {
       bitar_dev_close(dev);
       return fail(BITAR_E_INVALID, "Failed to setup queue pair %u for device %d: %s", (unsigned)i, device_id, cudaGetErrorString(e2));
@@ -1002,7 +1003,10 @@ inline uint32_t op_blocks(const bitar_chunk& c) {   // 64 KiB blocks an op's out
 }  // namespace
 
 using TokWide = bitar::xk::TokConfig<9, 864, 7, 256, 16, 32, 2>;    // a warp per 64 KiB block
-using SpecWide = bitar::sk::SpecConfig<9, 864, 7, 256, 16, 2>;       // a warp per stream without an index: speculative lane-parallel decode
+using SpecWide = bitar::sk::SpecConfig<9, 864, 7, 256, 14, 2, 2048, 1024>;   // a warp per stream without an index: speculative lane-parallel decode (14 warps, 72 registers, 2 KiB rings)
+using SpecB = bitar::sk::SpecConfig<9, 864, 7, 256, 14, 2, 2048, 1024, 1>;   // (A/B, test variants 7, 8, 9: no seek / ranges of the target size / both)
+using SpecC = bitar::sk::SpecConfig<9, 864, 7, 256, 14, 2, 2048, 1024, 2>;
+using SpecD = bitar::sk::SpecConfig<9, 864, 7, 256, 14, 2, 2048, 1024, 3>;
 using TokSmall = bitar::xk::TokConfig<9, 864, 7, 256, 2, 8, 7>;     // four blocks of at most 8 sub-ranges per warp; small CTAs: shared memory (3.9 KB per block) decides how many warps an SM holds (14)
 
 int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, bitar_result* results) {
@@ -1037,7 +1041,8 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
           spec_mode = any;
         }
         if (spec_mode) {
-          const size_t sp_one = (SpecWide::scratch_bytes(id, sms) + 15u) / 16u * 16u;
+          const size_t sp_raw = SpecWide::scratch_bytes(id, sms);   // (the A/B variants have the same shape)
+          const size_t sp_one = (sp_raw + 15u) / 16u * 16u;
           if (sp_one == 0) return cudaErrorLaunchOutOfResources;
           one = sp_one > one ? sp_one : one;
         }
@@ -1088,7 +1093,10 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
         if (spec_mode) {
           // what the speculative kernel declines (stored blocks, damaged streams, ...) is left to the whole-stream kernel
           uint32_t* const declined = q->d_declined + first;
-          e = SpecWide::launch(d_ops, d_res, generic, pc, declined, units, ck, spec_target(), n, id, sms, st);
+          if (variant == 7) e = SpecB::launch(d_ops, d_res, generic, pc, declined, units, ck, spec_target(), n, id, sms, st);
+          else if (variant == 8) e = SpecC::launch(d_ops, d_res, generic, pc, declined, units, ck, spec_target(), n, id, sms, st);
+          else if (variant == 9) e = SpecD::launch(d_ops, d_res, generic, pc, declined, units, ck, spec_target(), n, id, sms, st);
+          else e = SpecWide::launch(d_ops, d_res, generic, pc, declined, units, ck, spec_target(), n, id, sms, st);
           if (e != cudaSuccess) return e;
           g_launches.fetch_add(1);
           return InflateConfig<32, 10, 8, 1024, 4>::launch(d_ops, n, d_res, &pc->generic_next, ck, id, sms, st, declined, &pc->n_declined);

@@ -46,20 +46,23 @@ static_assert(kSlotBytes % 16u == 0, "slots are vector aligned");
 constexpr uint32_t kOutStop = 2048u - 262u;                     // no fast step starts at or past this many output bytes (a step adds <= 4 + 258)
 constexpr uint32_t kOutStopWalk = 2048u - 258u;                 // no symbol of the walk either (adds <= 258): a lane never passes 2048
 constexpr uint32_t kTokStop = 2048u - 5u;
-enum : uint32_t { kEndNone = 0, kEndSync = 1, kEndStop = 2, kEndEob = 3, kEndBad = 4 };
+constexpr uint32_t kMinRangeBits = 1024u;                       // a range shorter than the record window (kRec steps) joins badly
+constexpr uint32_t kSeek = 48u;                                 // symbols a lane decodes past its successor's last record, looking for the end of the block
+enum : uint32_t { kEndNone = 0, kEndSync = 1, kEndStop = 2, kEndEob = 3, kEndBad = 4, kEndFull = 5 };   // Stop: no join point in the successor's records; Full: the slot has no room for another step
 
-// bits per range for a block whose first symbol sits at bit `first`: aim at `target` output bytes per lane, judged by the
-// stream's overall ratio (what is left of the output capacity over what is left of the input), never more than a 32nd
-// of the rest (all lanes busy in one round)
-BITAR_HD uint32_t range_bits(uint32_t first, uint32_t in_len, uint32_t produced, uint32_t cap, uint32_t target) {
+// Bits per range for a round that starts at bit `first`: aim at `target` output bytes per lane, judged by the stream's
+// overall ratio (what is left of the output capacity over what is left of the input), then cut what is left of the input
+// into a whole number of rounds of 32 equal ranges, so that the last round of a block is as full as the first.
+BITAR_HD uint32_t range_bits(uint32_t first, uint32_t in_len, uint32_t produced, uint32_t cap, uint32_t target, bool even_rounds = true) {
   const uint32_t in_bits = 8u * in_len, rem_bits = in_bits > first ? in_bits - first : 0u;
   const uint32_t rem_out = cap > produced ? cap - produced : 1u;
   uint64_t b = (uint64_t)target * rem_bits / rem_out;
-  const uint32_t all = rem_bits / 32u + 1u;
-  if (b > all) b = all;
-  if (b < 256u) b = 256u;
+  if (b < kMinRangeBits) b = kMinRangeBits;
   if (b > 16384u) b = 16384u;
-  return (uint32_t)b;
+  if (!even_rounds) return (uint32_t)b;
+  const uint32_t rounds = (uint32_t)((rem_bits + 32u * b - 1u) / (32u * b));
+  const uint32_t even = rem_bits / (32u * (rounds ? rounds : 1u)) + 1u;
+  return even < kMinRangeBits ? kMinRangeBits : even;   // (a short rest keeps fewer lanes busy rather than all of them on crumbs)
 }
 
 template <int LBITS, int LT, int DBITS, int DT>
@@ -82,7 +85,7 @@ struct SpecLane : tk::TokLane<LBITS, LT, DBITS, DT> {
   uint32_t nrec;                 // step starts recorded
   uint32_t end_kind, end_bit, end_opos, end_tpos, sync_j;
   const uint32_t* nx_rec;        // the next lane's records
-  uint32_t nx_n, nx_j, nx_pos;
+  uint32_t nx_n, nx_j, nx_pos, seek;
 
   BITAR_HD uint32_t pos() const { return 8u * start_off + 32u * (wpos - 1u) - skip - cnt; }
   BITAR_HD uint32_t* rec() const { return reinterpret_cast<uint32_t*>(slot + kSlotRec); }
@@ -96,7 +99,7 @@ struct SpecLane : tk::TokLane<LBITS, LT, DBITS, DT> {
     end_kind = kEndNone;
     end_bit = end_opos = end_tpos = sync_j = 0;
     nx_rec = nullptr;
-    nx_n = nx_j = nx_pos = 0;
+    nx_n = nx_j = nx_pos = seek = 0;
   }
   BITAR_HD void idle() {
     state = kDone;
@@ -105,11 +108,14 @@ struct SpecLane : tk::TokLane<LBITS, LT, DBITS, DT> {
     end_bit = end_opos = end_tpos = sync_j = 0;
   }
   // after every lane has run its first kRec steps: the successor's records
-  BITAR_HD void set_next(const uint8_t* next_slot, uint32_t n) {
+  // (may_seek: past the successor's last record the lane goes on for up to kSeek symbols -- a successor that ran into
+  // the end of the block a few symbols after its start has left few records, and the end is near for this lane too)
+  BITAR_HD void set_next(const uint8_t* next_slot, uint32_t n, bool may_seek) {
     nx_rec = reinterpret_cast<const uint32_t*>(next_slot + kSlotRec);
     nx_n = n;
     nx_j = 0;
     nx_pos = n ? ld_rec(0) : 0u;
+    seek = may_seek ? kSeek : 0u;
   }
   BITAR_HD uint32_t ld_rec(uint32_t j) const {
 #if defined(__CUDA_ARCH__)
@@ -156,12 +162,14 @@ struct SpecLane : tk::TokLane<LBITS, LT, DBITS, DT> {
       ++nx_j;
       if (nx_j < nx_n) nx_pos = ld_rec(nx_j);
     }
-    if (nx_j >= nx_n) return end(kEndStop, p);                  // past everything the successor recorded (or no successor)
-    if (nx_pos == p) {
+    if (nx_j >= nx_n) {                                         // past everything the successor recorded (or no successor)
+      if (seek == 0) return end(kEndStop, p);
+      --seek;
+    } else if (nx_pos == p) {
       sync_j = nx_j;
       return end(kEndSync, p);
     }
-    if (opos >= kOutStopWalk || tpos >= 2048u) return end(kEndStop, p);
+    if (opos >= kOutStopWalk || tpos >= 2048u) return end(kEndFull, p);
     Base::refill();
     const uint32_t e = Base::ll_lookup();
     if ((e & 0xF0u) == 0) {
@@ -184,7 +192,7 @@ struct SpecLane : tk::TokLane<LBITS, LT, DBITS, DT> {
       if (p >= goal) {
         state = kWalk;
       } else if (opos >= kOutStop || tpos >= kTokStop) {
-        return end(kEndStop, p);
+        return end(kEndFull, p);
       } else {
         if (nrec < kRec) {
           uint32_t* r = rec();

@@ -85,8 +85,16 @@ struct SpecResolve : xk::ResolveBytes<32, RING, FLUSH> {
     Base::masks(1, s2, lit2);
     uint32_t x2 = (uint32_t)__ldcg(toks + (tbase + (uint32_t)__popc(s2 & le) - 1u));
     uint32_t pv = v0 + lane_u;
+    // A distance that reaches below the output (possible in its first 32 KiB only) is looked for where a FAR source is
+    // fetched, and for NEAR sources (the ring: reading it is harmless) while the range lies within the ring's reach of
+    // the start.  Predicated, no branches: `bad` only ever collects.
+    const bool early = v0 - lo_v < (uint32_t)RING;
     uint32_t fb1 = 0;
-    if (!((lit1 >> lane_u) & 1u) && x1 + 1u > kNear && x1 + 1u <= pv - lo_v) fb1 = (uint32_t)__ldcg(vbase + (pv - (x1 + 1u)));
+    {
+      const bool farp = !((lit1 >> lane_u) & 1u) && x1 + 1u > kNear, inb = x1 + 1u <= pv - lo_v;
+      if (farp && inb) fb1 = (uint32_t)__ldcg(vbase + (pv - (x1 + 1u)));
+      bad |= (uint32_t)(farp && !inb);
+    }
 #pragma unroll 2
     for (uint32_t k = 0; k < nsteps; ++k) {
       const uint32_t lit = lit1, x = x1, fb = fb1;
@@ -96,12 +104,16 @@ struct SpecResolve : xk::ResolveBytes<32, RING, FLUSH> {
       Base::masks(k + 2u, s2, lit2);
       x2 = (uint32_t)__ldcg(toks + (tbase + (uint32_t)__popc(s2 & le) - 1u));
       fb1 = 0;
-      if (!((lit1 >> lane_u) & 1u) && x1 + 1u > kNear && x1 + 1u <= pv + G - lo_v) fb1 = (uint32_t)__ldcg(vbase + (pv + G - (x1 + 1u)));
+      {
+        const bool farp = !((lit1 >> lane_u) & 1u) && x1 + 1u > kNear, inb = x1 + 1u <= pv + G - lo_v;
+        if (farp && inb) fb1 = (uint32_t)__ldcg(vbase + (pv + G - (x1 + 1u)));
+        bad |= (uint32_t)(farp && !inb);
+      }
       uint32_t b = x;
       if (lit != kAll) {                            // the step holds match bytes
         const uint32_t dist = x + 1u;
         const bool mb = !((lit >> lane_u) & 1u);
-        if (mb && dist > pv - lo_v && pv < v0 + len) bad = 1u;   // a source before the output (lanes past the end look like literals)
+        bad |= (uint32_t)(early && mb && dist > pv - lo_v);
         const bool inside = mb && dist <= lane_u;   // the source is a byte of this very step
         const bool far = mb && dist > kNear;
         if (mb && !inside && !far) b = xk::r_ld8(ring_s + ((pv - dist) & RM));
@@ -122,12 +134,12 @@ struct SpecResolve : xk::ResolveBytes<32, RING, FLUSH> {
   }
 };
 
-template <int LBITS, int LT, int DBITS, int DT, int WARPS, int MIN_CTAS>
+template <int LBITS, int LT, int DBITS, int DT, int WARPS, int MIN_CTAS, int RING, int FLUSH, int MODE>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
     inflate_spec_kernel(const bitar_chunk* __restrict__ ops, bitar_result* __restrict__ results, const uint32_t* __restrict__ list,
                         xk::Counters* __restrict__ pc, uint32_t* __restrict__ declined, uint8_t* scratch, int checksum_type, uint32_t target) {
   using Lane = sp::SpecLane<LBITS, LT, DBITS, DT>;
-  constexpr int kRing = 1024, kFlush = 512;
+  constexpr int kRing = RING, kFlush = FLUSH;
   using WS = SpecSmem<LT, DT, kRing>;
   using Res = SpecResolve<kRing, kFlush>;
   static_assert(sizeof(WS) % 16 == 0, "warp areas stay vector aligned");
@@ -158,9 +170,11 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
     uint32_t t = 0;
     if (lane == 0) t = atomicAdd(&pc->spec_next, 1u);
     t = __shfl_sync(kFull, t, 0);
-    if (t >= n_list) break;
-    const uint32_t idx = list[t];
+    if (t >= 2u * n_list) break;
+    const bool second = t >= n_list;                // longest first: two passes over the list (xk::first_pass_op)
+    const uint32_t idx = list[second ? t - n_list : t];
     const bitar_chunk op = ops[idx];
+    if (xk::first_pass_op(op.src_len, n_list, pc->sum_generic) == second) continue;
     const uint8_t* src = static_cast<const uint8_t*>(op.src);
     uint8_t* dst = static_cast<uint8_t*>(op.dst);
     const uint32_t src_len = op.src_len, cap = op.dst_cap;
@@ -170,7 +184,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
     R.begin(dst);
     R.lo_v = mis;
     R.bad = 0u;
-    uint32_t total = 0, bit = 0, last = 0;
+    uint32_t total = 0, bit = 0, last = 0, tgt = target;
     while (ok && !last) {
       // ---- block header: every lane reads the same bits ----
       L.in = src;
@@ -246,7 +260,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
       }
       // ---- rounds of 32 ranges ----
       for (;;) {
-        const uint32_t B = sp::range_bits(first, src_len, total, cap, target);
+        const uint32_t B = sp::range_bits(first, src_len, total, cap, tgt, !(MODE & 2));
         const unsigned long long start = (unsigned long long)first + (unsigned long long)lane * B;
         if (start < 8ull * src_len) L.start_spec(src, src_len, (uint32_t)start, (uint32_t)start + B, my_slot);
         else L.idle();
@@ -255,7 +269,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
         __syncwarp(kFull);                           // the records are complete (and visible) before anybody walks
         uint32_t n_next = __shfl_down_sync(kFull, L.nrec, 1);
         if (lane == 31) n_next = 0;
-        L.set_next(slots + (size_t)((lane + 1) & 31) * sp::kSlotBytes, n_next);
+        L.set_next(slots + (size_t)((lane + 1) & 31) * sp::kSlotBytes, n_next, lane < 31 && !(MODE & 1));
         while (L.state != Lane::kDone) L.step(true);
         __syncwarp(kFull);                           // the maps are complete before phase B reads them
         const unsigned synced = __ballot_sync(kFull, L.end_kind == sp::kEndSync);   // (lane 31 never is: it has no successor)
@@ -272,11 +286,11 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
         }
         const uint32_t round_total = __shfl_sync(kFull, incl, m);
         const uint32_t ek = __shfl_sync(kFull, L.end_kind, m), eb = __shfl_sync(kFull, L.end_bit, m);
-        if ((unsigned long long)total + round_total > cap || ek == sp::kEndBad || eb > 8u * src_len ||
-            (ek == sp::kEndStop && eb == first)) {
+        if ((unsigned long long)total + round_total > cap || ek == sp::kEndBad || eb > 8u * src_len || (ek != sp::kEndEob && eb == first)) {
           ok = false;
           break;
         }
+        if (ek == sp::kEndFull && tgt > 128u) tgt >>= 1;   // ranges too long for their slots: shorter ones from here on
         for (int r = 0; r <= m; ++r) {
           const uint32_t len_r = __shfl_sync(kFull, ro.len, r), off_r = __shfl_sync(kFull, incl - ro.len, r);
           const uint32_t ts = __shfl_sync(kFull, ro.tskip, r), bs = __shfl_sync(kFull, ro.bskip, r);
@@ -312,15 +326,15 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
   }
 }
 
-template <int LBITS, int LT, int DBITS, int DT, int WARPS, int MIN_CTAS>
+template <int LBITS, int LT, int DBITS, int DT, int WARPS, int MIN_CTAS, int RING, int FLUSH, int MODE = 0>
 struct SpecConfig {
   static constexpr int kThreads = WARPS * 32;
-  static constexpr size_t kSmem = (size_t)WARPS * sizeof(SpecSmem<LT, DT, 1024>) + 32 * sizeof(uint32_t) + sizeof(ik::CksSmem);
+  static constexpr size_t kSmem = (size_t)WARPS * sizeof(SpecSmem<LT, DT, RING>) + 32 * sizeof(uint32_t) + sizeof(ik::CksSmem);
   static int ctas_per_sm(int device) {
     static int per_device[64] = {0};
     int& c = per_device[device & 63];
     if (c == 0) {
-      auto kern = inflate_spec_kernel<LBITS, LT, DBITS, DT, WARPS, MIN_CTAS>;
+      auto kern = inflate_spec_kernel<LBITS, LT, DBITS, DT, WARPS, MIN_CTAS, RING, FLUSH, MODE>;
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem) != cudaSuccess) return 0;
       cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, kern, kThreads, kSmem) != cudaSuccess) return 0;
@@ -341,7 +355,7 @@ struct SpecConfig {
     const uint32_t want = (n_max + WARPS - 1) / WARPS;
     if (want < grid) grid = want;
     if (grid == 0) return cudaSuccess;
-    inflate_spec_kernel<LBITS, LT, DBITS, DT, WARPS, MIN_CTAS><<<grid, kThreads, kSmem, stream>>>(ops, res, list, pc, declined, scratch,
+    inflate_spec_kernel<LBITS, LT, DBITS, DT, WARPS, MIN_CTAS, RING, FLUSH, MODE><<<grid, kThreads, kSmem, stream>>>(ops, res, list, pc, declined, scratch,
                                                                                                   checksum_type, target);
     return cudaGetLastError();
   }

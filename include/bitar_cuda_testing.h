@@ -12,7 +12,7 @@ extern "C" {
  * 5 = everything through the whole-stream kernel (tests/test_gpu_inflate.py),
  * 6 = no speculative kernel: chunks without an index go straight to the whole-stream kernel */
 void bitar_tune_inflate_variant(int v);
-/* output bytes each lane of the speculative inflate kernel aims at per round (64 .. 1536; 0 = default, 768) */
+/* output bytes each lane of the speculative inflate kernel aims at per round (64 .. 1536; 0 = default, 1024) */
 void bitar_tune_spec_target(int bytes);
 /* least inflated bytes per batch of a staged (host-buffer) inflate call; 0 = default (tests force many small batches) */
 void bitar_tune_stage_batch(unsigned long long bytes);

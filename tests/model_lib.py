@@ -125,9 +125,10 @@ def host_inflate_spec(comp, cap, target=768, misalign=0):
     buf = np.full(cap + 64, 0xA5, np.uint8)
     base = buf.ctypes.data
     off = (-base) % 16 + misalign
-    res = np.zeros(8, np.uint32)
+    res = np.zeros(12, np.uint32)
     lib().host_inflate_spec(cpad.ctypes.data, c.size, base + off, cap, res.ctypes.data, target)
     out = buf[off:off + int(res[0])].copy()
     guard_ok = bool((buf[:off] == 0xA5).all() and (buf[off + cap:] == 0xA5).all())
     return out, {"produced": int(res[0]), "declined": int(res[1]), "blocks": int(res[2]), "rounds": int(res[3]),
-                 "ranges": int(res[4]), "short_rounds": int(res[5]), "walk_symbols": int(res[6]), "guard_ok": guard_ok}
+                 "ranges": int(res[4]), "short_rounds": int(res[5]), "walk_symbols": int(res[6]), "full_rounds": int(res[7]),
+                 "warp_steps": int(res[8]), "lane_steps": int(res[9]), "guard_ok": guard_ok}

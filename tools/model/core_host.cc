@@ -5,6 +5,8 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "../../bitar_b200/csrc/inflate_core.h"
@@ -156,8 +158,11 @@ API int host_inflate_indexed(const uint8_t* in, uint32_t in_len, uint8_t* out, u
 // then rounds of 32 sp::SpecLane ranges run one after the other (the kernel runs them as the lanes of a warp), the same
 // round bookkeeping as inflate_spec_kernel.cuh, ranges resolved by sp::resolve_range_serial.
 // result: [0] produced, [1] 0 = decoded / 1 = declined (the whole-stream kernel's business), [2] blocks, [3] rounds,
-//         [4] ranges that contributed, [5] ranges whose walk found no join point or ran out of slot space, [6] walk symbols
-API int host_inflate_spec(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t cap, uint32_t* result8, uint32_t target) {
+//         [4] ranges that contributed, [5] rounds cut short by a lane without a join point, [6] walk symbols,
+//         [7] rounds cut short by a full slot, [8] sum over the rounds of the longest lane's steps (the warp's time),
+//         [9] steps of the lanes that contributed
+API int host_inflate_spec(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t cap, uint32_t* result12, uint32_t target) {
+  uint32_t* result8 = result12;
   using namespace bitar::fl;
   using namespace bitar;
   constexpr int LB = 9, LT = 864, DB = 7, DT = 256;
@@ -169,10 +174,10 @@ API int host_inflate_spec(const uint8_t* in, uint32_t in_len, uint8_t* out, uint
   static thread_local LaneScratch scratch;
   static CtaTables cta;
   for (int i = 0; i < 32; ++i) cta.dinfo[i] = dist_info(i);
-  for (int i = 0; i < 8; ++i) result8[i] = 0;
+  for (int i = 0; i < 12; ++i) result8[i] = 0;
   result8[1] = 1;
   if (in_len < 8 || cap == 0) return 0;
-  uint32_t total = 0, bit = 0;
+  uint32_t total = 0, bit = 0, tgt = target;
   for (;;) {
     Gen g;
     g.bind(smem, &cta, &scratch, 0);
@@ -185,7 +190,7 @@ API int host_inflate_spec(const uint8_t* in, uint32_t in_len, uint8_t* out, uint
     const uint32_t last = g.last;
     uint32_t first = (uint32_t)(8ll * g.start_off + g.consumed_bits());
     for (;;) {   // rounds
-      const uint32_t B = sp::range_bits(first, in_len, total, cap, target);
+      const uint32_t B = sp::range_bits(first, in_len, total, cap, tgt);
       static thread_local Lane lanes[32];
       for (int r = 0; r < 32; ++r) {
         lanes[r].bind(g.lt, g.dt, uring[r], cta.dinfo, &scratch);
@@ -196,7 +201,9 @@ API int host_inflate_spec(const uint8_t* in, uint32_t in_len, uint8_t* out, uint
       result8[3]++;
       for (int r = 0; r < 32; ++r)
         for (uint32_t i = 0; i < sp::kRec; ++i) lanes[r].step(false);
-      for (int r = 0; r < 32; ++r) lanes[r].set_next(slots[(r + 1) & 31], r < 31 ? lanes[r + 1].nrec : 0u);
+      for (int r = 0; r < 32; ++r) lanes[r].set_next(slots[(r + 1) & 31], r < 31 ? lanes[r + 1].nrec : 0u, r < 31);
+      uint64_t longest = 0;
+      uint32_t lane_steps[32];
       for (int r = 0; r < 32; ++r) {
         uint64_t steps = 0;
         while (lanes[r].state != Lane::kDone && ++steps < (1ull << 24)) {
@@ -204,7 +211,10 @@ API int host_inflate_spec(const uint8_t* in, uint32_t in_len, uint8_t* out, uint
           lanes[r].step(true);
         }
         if (lanes[r].state != Lane::kDone) return 0;
+        longest = steps > longest ? steps : longest;
+        lane_steps[r] = (uint32_t)steps + sp::kRec;
       }
+      result8[8] += (uint32_t)longest + sp::kRec;
       int m = 0;
       while (m < 31 && lanes[m].end_kind == sp::kEndSync) ++m;
       if (lanes[m].end_kind == sp::kEndSync) return 0;   // (lane 31 has no successor: it stops)
@@ -216,11 +226,19 @@ API int host_inflate_spec(const uint8_t* in, uint32_t in_len, uint8_t* out, uint
         total += ro.len;
         j = lanes[r].sync_j;
         result8[4]++;
+        result8[9] += lane_steps[r];
       }
-      if (lanes[m].end_kind == sp::kEndStop && m < 31) result8[5]++;
-      if (lanes[m].end_kind == sp::kEndBad) return 0;
+      const uint32_t ek = lanes[m].end_kind;
+      if (ek == sp::kEndStop && m < 31) result8[5]++;
+      if (getenv("SPEC_DEBUG") && ek == sp::kEndStop && m < 31)
+        fprintf(stderr, "short: m %d B %u first %u in_bits %u | lane m: end_bit %u (start %u) | next: nrec %u end_kind %u end_bit %u start %u last_rec %u\n", m, B, first, 8u * in_len,
+                lanes[m].end_bit, first + m * B, lanes[m + 1].nrec, lanes[m + 1].end_kind, lanes[m + 1].end_bit, first + (m + 1) * B,
+                lanes[m + 1].nrec ? reinterpret_cast<uint32_t*>(slots[m + 1] + sp::kSlotRec)[2 * (lanes[m + 1].nrec - 1)] : 0u);
+      if (ek == sp::kEndFull) result8[7]++;
+      if (ek == sp::kEndBad) return 0;
       if (lanes[m].end_bit > 8u * in_len) return 0;     // the chain ran past the input
-      if (lanes[m].end_kind == sp::kEndStop && m == 0 && lanes[0].end_bit == first) return 0;   // no progress
+      if (ek != sp::kEndEob && lanes[0].end_bit == first) return 0;   // no progress
+      if (ek == sp::kEndFull && tgt > 128u) tgt >>= 1;   // ranges too long for their slots: shorter ones from here on
       first = lanes[m].end_bit;
       if (lanes[m].end_kind == sp::kEndEob) break;
     }
