@@ -1004,9 +1004,6 @@ inline uint32_t op_blocks(const bitar_chunk& c) {   // 64 KiB blocks an op's out
 
 using TokWide = bitar::xk::TokConfig<9, 864, 7, 256, 16, 32, 2>;    // a warp per 64 KiB block
 using SpecWide = bitar::sk::SpecConfig<9, 864, 7, 256, 14, 2, 2048, 1024>;   // a warp per stream without an index: speculative lane-parallel decode (14 warps, 72 registers, 2 KiB rings)
-using SpecB = bitar::sk::SpecConfig<9, 864, 7, 256, 14, 2, 2048, 1024, 1>;   // (A/B, test variants 7, 8, 9: no seek / ranges of the target size / both)
-using SpecC = bitar::sk::SpecConfig<9, 864, 7, 256, 14, 2, 2048, 1024, 2>;
-using SpecD = bitar::sk::SpecConfig<9, 864, 7, 256, 14, 2, 2048, 1024, 3>;
 using TokSmall = bitar::xk::TokConfig<9, 864, 7, 256, 2, 8, 7>;     // four blocks of at most 8 sub-ranges per warp; small CTAs: shared memory (3.9 KB per block) decides how many warps an SM holds (14)
 
 int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32_t n, bitar_result* results) {
@@ -1041,7 +1038,7 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
           spec_mode = any;
         }
         if (spec_mode) {
-          const size_t sp_raw = SpecWide::scratch_bytes(id, sms);   // (the A/B variants have the same shape)
+          const size_t sp_raw = SpecWide::scratch_bytes(id, sms);
           const size_t sp_one = (sp_raw + 15u) / 16u * 16u;
           if (sp_one == 0) return cudaErrorLaunchOutOfResources;
           one = sp_one > one ? sp_one : one;
@@ -1093,10 +1090,7 @@ int bitar_qp_inflate(bitar_dev* dev, uint16_t qp, const bitar_chunk* ops, uint32
         if (spec_mode) {
           // what the speculative kernel declines (stored blocks, damaged streams, ...) is left to the whole-stream kernel
           uint32_t* const declined = q->d_declined + first;
-          if (variant == 7) e = SpecB::launch(d_ops, d_res, generic, pc, declined, units, ck, spec_target(), n, id, sms, st);
-          else if (variant == 8) e = SpecC::launch(d_ops, d_res, generic, pc, declined, units, ck, spec_target(), n, id, sms, st);
-          else if (variant == 9) e = SpecD::launch(d_ops, d_res, generic, pc, declined, units, ck, spec_target(), n, id, sms, st);
-          else e = SpecWide::launch(d_ops, d_res, generic, pc, declined, units, ck, spec_target(), n, id, sms, st);
+          e = SpecWide::launch(d_ops, d_res, generic, pc, declined, units, ck, spec_target(), n, id, sms, st);
           if (e != cudaSuccess) return e;
           g_launches.fetch_add(1);
           return InflateConfig<32, 10, 8, 1024, 4>::launch(d_ops, n, d_res, &pc->generic_next, ck, id, sms, st, declined, &pc->n_declined);

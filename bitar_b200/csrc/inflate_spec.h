@@ -53,13 +53,12 @@ enum : uint32_t { kEndNone = 0, kEndSync = 1, kEndStop = 2, kEndEob = 3, kEndBad
 // Bits per range for a round that starts at bit `first`: aim at `target` output bytes per lane, judged by the stream's
 // overall ratio (what is left of the output capacity over what is left of the input), then cut what is left of the input
 // into a whole number of rounds of 32 equal ranges, so that the last round of a block is as full as the first.
-BITAR_HD uint32_t range_bits(uint32_t first, uint32_t in_len, uint32_t produced, uint32_t cap, uint32_t target, bool even_rounds = true) {
+BITAR_HD uint32_t range_bits(uint32_t first, uint32_t in_len, uint32_t produced, uint32_t cap, uint32_t target) {
   const uint32_t in_bits = 8u * in_len, rem_bits = in_bits > first ? in_bits - first : 0u;
   const uint32_t rem_out = cap > produced ? cap - produced : 1u;
   uint64_t b = (uint64_t)target * rem_bits / rem_out;
   if (b < kMinRangeBits) b = kMinRangeBits;
   if (b > 16384u) b = 16384u;
-  if (!even_rounds) return (uint32_t)b;
   const uint32_t rounds = (uint32_t)((rem_bits + 32u * b - 1u) / (32u * b));
   const uint32_t even = rem_bits / (32u * (rounds ? rounds : 1u)) + 1u;
   return even < kMinRangeBits ? kMinRangeBits : even;   // (a short rest keeps fewer lanes busy rather than all of them on crumbs)

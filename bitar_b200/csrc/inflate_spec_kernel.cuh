@@ -134,7 +134,7 @@ struct SpecResolve : xk::ResolveBytes<32, RING, FLUSH> {
   }
 };
 
-template <int LBITS, int LT, int DBITS, int DT, int WARPS, int MIN_CTAS, int RING, int FLUSH, int MODE>
+template <int LBITS, int LT, int DBITS, int DT, int WARPS, int MIN_CTAS, int RING, int FLUSH>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
     inflate_spec_kernel(const bitar_chunk* __restrict__ ops, bitar_result* __restrict__ results, const uint32_t* __restrict__ list,
                         xk::Counters* __restrict__ pc, uint32_t* __restrict__ declined, uint8_t* scratch, int checksum_type, uint32_t target) {
@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
       }
       // ---- rounds of 32 ranges ----
       for (;;) {
-        const uint32_t B = sp::range_bits(first, src_len, total, cap, tgt, !(MODE & 2));
+        const uint32_t B = sp::range_bits(first, src_len, total, cap, tgt);
         const unsigned long long start = (unsigned long long)first + (unsigned long long)lane * B;
         if (start < 8ull * src_len) L.start_spec(src, src_len, (uint32_t)start, (uint32_t)start + B, my_slot);
         else L.idle();
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
         __syncwarp(kFull);                           // the records are complete (and visible) before anybody walks
         uint32_t n_next = __shfl_down_sync(kFull, L.nrec, 1);
         if (lane == 31) n_next = 0;
-        L.set_next(slots + (size_t)((lane + 1) & 31) * sp::kSlotBytes, n_next, lane < 31 && !(MODE & 1));
+        L.set_next(slots + (size_t)((lane + 1) & 31) * sp::kSlotBytes, n_next, lane < 31);
         while (L.state != Lane::kDone) L.step(true);
         __syncwarp(kFull);                           // the maps are complete before phase B reads them
         const unsigned synced = __ballot_sync(kFull, L.end_kind == sp::kEndSync);   // (lane 31 never is: it has no successor)
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
   }
 }
 
-template <int LBITS, int LT, int DBITS, int DT, int WARPS, int MIN_CTAS, int RING, int FLUSH, int MODE = 0>
+template <int LBITS, int LT, int DBITS, int DT, int WARPS, int MIN_CTAS, int RING, int FLUSH>
 struct SpecConfig {
   static constexpr int kThreads = WARPS * 32;
   static constexpr size_t kSmem = (size_t)WARPS * sizeof(SpecSmem<LT, DT, RING>) + 32 * sizeof(uint32_t) + sizeof(ik::CksSmem);
@@ -334,7 +334,7 @@ struct SpecConfig {
     static int per_device[64] = {0};
     int& c = per_device[device & 63];
     if (c == 0) {
-      auto kern = inflate_spec_kernel<LBITS, LT, DBITS, DT, WARPS, MIN_CTAS, RING, FLUSH, MODE>;
+      auto kern = inflate_spec_kernel<LBITS, LT, DBITS, DT, WARPS, MIN_CTAS, RING, FLUSH>;
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem) != cudaSuccess) return 0;
       cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, kern, kThreads, kSmem) != cudaSuccess) return 0;
@@ -355,7 +355,7 @@ struct SpecConfig {
     const uint32_t want = (n_max + WARPS - 1) / WARPS;
     if (want < grid) grid = want;
     if (grid == 0) return cudaSuccess;
-    inflate_spec_kernel<LBITS, LT, DBITS, DT, WARPS, MIN_CTAS, RING, FLUSH, MODE><<<grid, kThreads, kSmem, stream>>>(ops, res, list, pc, declined, scratch,
+    inflate_spec_kernel<LBITS, LT, DBITS, DT, WARPS, MIN_CTAS, RING, FLUSH><<<grid, kThreads, kSmem, stream>>>(ops, res, list, pc, declined, scratch,
                                                                                                   checksum_type, target);
     return cudaGetLastError();
   }

@@ -5,8 +5,6 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
-#include <cstdio>
-#include <cstdlib>
 #include <vector>
 
 #include "../../bitar_b200/csrc/inflate_core.h"
@@ -230,10 +228,6 @@ API int host_inflate_spec(const uint8_t* in, uint32_t in_len, uint8_t* out, uint
       }
       const uint32_t ek = lanes[m].end_kind;
       if (ek == sp::kEndStop && m < 31) result8[5]++;
-      if (getenv("SPEC_DEBUG") && ek == sp::kEndStop && m < 31)
-        fprintf(stderr, "short: m %d B %u first %u in_bits %u | lane m: end_bit %u (start %u) | next: nrec %u end_kind %u end_bit %u start %u last_rec %u\n", m, B, first, 8u * in_len,
-                lanes[m].end_bit, first + m * B, lanes[m + 1].nrec, lanes[m + 1].end_kind, lanes[m + 1].end_bit, first + (m + 1) * B,
-                lanes[m + 1].nrec ? reinterpret_cast<uint32_t*>(slots[m + 1] + sp::kSlotRec)[2 * (lanes[m + 1].nrec - 1)] : 0u);
       if (ek == sp::kEndFull) result8[7]++;
       if (ek == sp::kEndBad) return 0;
       if (lanes[m].end_bit > 8u * in_len) return 0;     // the chain ran past the input
