@@ -367,7 +367,11 @@ def run_foreign(dev, torch, data, seg, mib=256):
         dev.wait(0)
         best = min(best, dev.last_ms(0)[1])
     ok = int(r["produced"].sum()) == sample.size and bool(torch.equal(out[:sample.size], torch.from_numpy(sample).cuda()))
+    peak, _ = peaks()
+    algo = (sample.size + float(produced.sum())) / (best * 1e-3) / 1e9       # read the stream once, write the output once
     return {"inflate_foreign_gbps": sample.size / (best * 1e-3) / 1e9, "inflate_foreign_ok": ok,
+            "inflate_foreign_roofline": {"kernel": "inflate_spec_kernel", "bound": "hbm", "achieved": algo, "peak": peak, "unit": "GB/s",
+                                         "frac": algo / peak, "zlib_level1_ratio": sample.size / float(produced.sum())},
             "inflate_foreign_sample": f"{sample.size >> 20} MiB of the workload compressed by zlib level 1 (no index): speculative lane-parallel kernel (inflate_spec_kernel.cuh)"}
 
 

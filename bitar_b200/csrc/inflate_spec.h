@@ -124,12 +124,14 @@ struct SpecLane : tk::TokLane<LBITS, LT, DBITS, DT> {
 #endif
   }
 
+  // (the staged tokens and the open word of start bits are stored by the NEXT step -- one copy of that code instead of one
+  // per way a lane can end)
   BITAR_HD void end(uint32_t kind, uint32_t p) {
     end_kind = kind;
     end_bit = p;
     end_opos = opos;
     end_tpos = tpos;
-    Base::finish();              // the staged tokens and the open word of start bits; state = kDone
+    state = Base::kFinish;
   }
 
   // the match whose length code is e (looked up, not yet dropped); distances are checked by phase B
@@ -186,6 +188,7 @@ struct SpecLane : tk::TokLane<LBITS, LT, DBITS, DT> {
   // range is already complete waits.
   BITAR_HD void step(bool walk) {
     if (state == kDone) return;
+    if (state == Base::kFinish) return Base::finish();            // state = kDone
     if (state == kFast) {
       const uint32_t p = pos();
       if (p >= goal) {

@@ -134,6 +134,101 @@ struct SpecResolve : xk::ResolveBytes<32, RING, FLUSH> {
   }
 };
 
+// What the header of a Huffman-coded block yields.  ok = 0: a stored block, a bad header, bad code lengths -- the stream is
+// the whole-stream kernel's.
+struct BlockHead {
+  uint32_t ok, last, first;   // first: bit position of the block's first symbol
+};
+
+// Block header at bit `bit` and the block's two decode tables, by the whole warp: every lane reads the same bits, the
+// tables are built cooperatively (xk::warp_build_table).  Out of line, as is the checksum below: this kernel's warps are
+// spread over very different code (header, lane decode, walk, resolve), and what does not sit in the instruction cache
+// stalls every one of them -- the first version, everything inlined, lost more issue slots to instruction fetch than to
+// any data dependency (ncu: 3.8 warps per issue waiting on "no instruction").
+template <int LBITS, int LT, int DBITS, int DT, class WS>
+__device__ __noinline__ BlockHead block_head(const uint8_t* src, uint32_t src_len, uint32_t bit, WS* wsp, int lane) {
+  constexpr unsigned kFull = 0xFFFFFFFFu;
+  WS& ws = *wsp;
+  tk::TokLane<LBITS, LT, DBITS, DT> L;
+  L.in = src;
+  L.in_len = src_len;
+  L.bits_init(bit >> 3);
+  L.drop(bit & 7u);
+  L.refill();
+  BlockHead h{0u, 0u, 0u};
+  h.last = L.take(1);
+  const uint32_t type = L.take(2);
+  if (type == 0u || type == 3u) return h;          // stored blocks (and bad headers) are the whole-stream kernel's
+  uint32_t status = fl::kStatusOk;
+  int nlen, ndist;
+  if (type == 1u) {
+    for (int i = lane; i < 288; i += 32) ws.sc.lens[i] = (uint8_t)dfl::fixed_ll_len(i);
+    ws.sc.lens[288 + lane] = 5;
+    nlen = 288;
+    ndist = 32;
+    __syncwarp(kFull);
+  } else {
+    nlen = (int)L.take(5) + 257;
+    ndist = (int)L.take(5) + 1;
+    const int ncode = (int)L.take(4) + 4;
+    if (nlen > 286 || ndist > 30) status = fl::kStatusDataError;
+    if (lane < 19) ws.sc.lens[lane] = 0;
+    __syncwarp(kFull);
+    for (int i = 0; i < ncode; ++i) {
+      L.refill();
+      const uint32_t v = L.take(3);
+      if (lane == 0) ws.sc.lens[dfl::cl_order(i)] = (uint8_t)v;
+    }
+    __syncwarp(kFull);
+    if (status == fl::kStatusOk)
+      status = xk::warp_build_table<32>(ws.sc.lens, 19, fl::kCodeLen, ws.dt, 7, 128, ws.sc.d_count, ws.sc.d_first, ws.sc.d_offs,
+                                        ws.sc.d_sorted, ws.cnt, ws.at, lane, kFull);
+    if (status == fl::kStatusOk) {
+      int i2 = 0, prev = 0;
+      const int tot = nlen + ndist;
+      while (i2 < tot) {
+        L.refill();
+        const uint32_t e = ws.dt[L.lo & 127u];
+        if ((e & 15u) == 0) { status = fl::kStatusDataError; break; }
+        L.drop(e & 15u);
+        const int sym = (int)(e >> 4);
+        int rep, val;
+        if (sym < 16) { rep = 1; val = sym; prev = sym; }
+        else if (sym == 16) {
+          if (i2 == 0) { status = fl::kStatusDataError; break; }
+          rep = 3 + (int)L.take(2); val = prev;
+        } else if (sym == 17) { rep = 3 + (int)L.take(3); val = 0; prev = 0; }
+        else { rep = 11 + (int)L.take(7); val = 0; prev = 0; }
+        if (i2 + rep > tot) { status = fl::kStatusDataError; break; }
+        for (int k = lane; k < rep; k += 32) ws.sc.lens[i2 + k] = (uint8_t)val;
+        i2 += rep;
+      }
+      __syncwarp(kFull);
+      if (status == fl::kStatusOk && (L.overrun() || ws.sc.lens[256] == 0)) status = fl::kStatusDataError;
+    }
+  }
+  h.first = (uint32_t)(8ll * (long long)L.start_off + L.consumed_bits());
+  __syncwarp(kFull);
+  // the two tables of the block, one after the other through the same code (kind 1 = distances first: its lengths lie behind
+  // the literal/length ones, and the code-length table it replaces is done with)
+#pragma unroll 1
+  for (int k = 0; k < 2 && status == fl::kStatusOk; ++k) {
+    const bool d = k == 0;
+    status = xk::warp_build_table<32>(d ? ws.sc.lens + nlen : ws.sc.lens, d ? ndist : nlen, d ? fl::kDist : fl::kLitLen, d ? ws.dt : ws.lt,
+                                      d ? DBITS : LBITS, d ? DT : LT, d ? ws.sc.d_count : ws.sc.ll_count, d ? ws.sc.d_first : ws.sc.ll_first,
+                                      d ? ws.sc.d_offs : ws.sc.ll_offs, d ? ws.sc.d_sorted : ws.sc.ll_sorted, ws.cnt, ws.at, lane, kFull);
+  }
+  h.ok = status == fl::kStatusOk ? 1u : 0u;
+  return h;
+}
+
+__device__ __noinline__ uint64_t stream_checksum(const uint8_t* dst, uint32_t n, int type, const ik::CksSmem* ck, int lane) {
+  inf::Group<32> g;
+  g.lane = lane;
+  g.mask = 0xFFFFFFFFu;
+  return ik::group_checksum<32>(dst, n, type, ck, g);
+}
+
 template <int LBITS, int LT, int DBITS, int DT, int WARPS, int MIN_CTAS, int RING, int FLUSH>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
     inflate_spec_kernel(const bitar_chunk* __restrict__ ops, bitar_result* __restrict__ results, const uint32_t* __restrict__ list,
@@ -186,91 +281,33 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
     R.bad = 0u;
     uint32_t total = 0, bit = 0, last = 0, tgt = target;
     while (ok && !last) {
-      // ---- block header: every lane reads the same bits ----
-      L.in = src;
-      L.in_len = src_len;
-      L.bits_init(bit >> 3);
-      L.drop(bit & 7u);
-      L.refill();
-      last = L.take(1);
-      const uint32_t type = L.take(2);
-      if (type == 0u || type == 3u) {               // stored blocks (and bad headers) are the whole-stream kernel's
+      // ---- block header and tables ----
+      const BlockHead bh = block_head<LBITS, LT, DBITS, DT, WS>(src, src_len, bit, &ws, lane);
+      if (!bh.ok) {
         ok = false;
         break;
       }
-      uint32_t status = fl::kStatusOk;
-      int nlen, ndist;
-      if (type == 1u) {
-        for (int i = lane; i < 288; i += 32) ws.sc.lens[i] = (uint8_t)dfl::fixed_ll_len(i);
-        if (lane < 32) ws.sc.lens[288 + lane] = 5;
-        nlen = 288;
-        ndist = 32;
-        __syncwarp(kFull);
-      } else {
-        nlen = (int)L.take(5) + 257;
-        ndist = (int)L.take(5) + 1;
-        const int ncode = (int)L.take(4) + 4;
-        if (nlen > 286 || ndist > 30) status = fl::kStatusDataError;
-        if (lane < 19) ws.sc.lens[lane] = 0;
-        __syncwarp(kFull);
-        for (int i = 0; i < ncode; ++i) {
-          L.refill();
-          const uint32_t v = L.take(3);
-          if (lane == 0) ws.sc.lens[dfl::cl_order(i)] = (uint8_t)v;
-        }
-        __syncwarp(kFull);
-        if (status == fl::kStatusOk)
-          status = xk::warp_build_table<32>(ws.sc.lens, 19, fl::kCodeLen, ws.dt, 7, 128, ws.sc.d_count, ws.sc.d_first, ws.sc.d_offs,
-                                            ws.sc.d_sorted, ws.cnt, ws.at, lane, kFull);
-        if (status == fl::kStatusOk) {
-          int i2 = 0, prev = 0;
-          const int tot = nlen + ndist;
-          while (i2 < tot) {
-            L.refill();
-            const uint32_t e = ws.dt[L.lo & 127u];
-            if ((e & 15u) == 0) { status = fl::kStatusDataError; break; }
-            L.drop(e & 15u);
-            const int sym = (int)(e >> 4);
-            int rep, val;
-            if (sym < 16) { rep = 1; val = sym; prev = sym; }
-            else if (sym == 16) {
-              if (i2 == 0) { status = fl::kStatusDataError; break; }
-              rep = 3 + (int)L.take(2); val = prev;
-            } else if (sym == 17) { rep = 3 + (int)L.take(3); val = 0; prev = 0; }
-            else { rep = 11 + (int)L.take(7); val = 0; prev = 0; }
-            if (i2 + rep > tot) { status = fl::kStatusDataError; break; }
-            for (int k = lane; k < rep; k += 32) ws.sc.lens[i2 + k] = (uint8_t)val;
-            i2 += rep;
-          }
-          __syncwarp(kFull);
-          if (status == fl::kStatusOk && (L.overrun() || ws.sc.lens[256] == 0)) status = fl::kStatusDataError;
-        }
-      }
-      uint32_t first = L.pos();
-      __syncwarp(kFull);
-      if (status == fl::kStatusOk)
-        status = xk::warp_build_table<32>(ws.sc.lens + nlen, ndist, fl::kDist, ws.dt, DBITS, DT, ws.sc.d_count, ws.sc.d_first,
-                                          ws.sc.d_offs, ws.sc.d_sorted, ws.cnt, ws.at, lane, kFull);
-      if (status == fl::kStatusOk)
-        status = xk::warp_build_table<32>(ws.sc.lens, nlen, fl::kLitLen, ws.lt, LBITS, LT, ws.sc.ll_count, ws.sc.ll_first,
-                                          ws.sc.ll_offs, ws.sc.ll_sorted, ws.cnt, ws.at, lane, kFull);
-      if (status != fl::kStatusOk) {
-        ok = false;
-        break;
-      }
+      last = bh.last;
+      uint32_t first = bh.first;
       // ---- rounds of 32 ranges ----
       for (;;) {
         const uint32_t B = sp::range_bits(first, src_len, total, cap, tgt);
         const unsigned long long start = (unsigned long long)first + (unsigned long long)lane * B;
         if (start < 8ull * src_len) L.start_spec(src, src_len, (uint32_t)start, (uint32_t)start + B, my_slot);
         else L.idle();
+        // One loop, one copy of the step: iterations 0 .. kRec - 1 are the lock-step ones during which the lanes record
+        // (nobody walks yet); every lane passes iteration kRec, where the records are complete and the successors' are
+        // handed out; from there on a lane leaves when it is done.
 #pragma unroll 1
-        for (uint32_t i = 0; i < sp::kRec; ++i) L.step(false);
-        __syncwarp(kFull);                           // the records are complete (and visible) before anybody walks
-        uint32_t n_next = __shfl_down_sync(kFull, L.nrec, 1);
-        if (lane == 31) n_next = 0;
-        L.set_next(slots + (size_t)((lane + 1) & 31) * sp::kSlotBytes, n_next, lane < 31);
-        while (L.state != Lane::kDone) L.step(true);
+        for (uint32_t i = 0; i <= sp::kRec || L.state != Lane::kDone; ++i) {
+          if (i == sp::kRec) {
+            __syncwarp(kFull);                       // the records are complete (and visible) before anybody walks
+            uint32_t n_next = __shfl_down_sync(kFull, L.nrec, 1);
+            if (lane == 31) n_next = 0;
+            L.set_next(slots + (size_t)((lane + 1) & 31) * sp::kSlotBytes, n_next, lane < 31);
+          }
+          L.step(i >= sp::kRec);
+        }
         __syncwarp(kFull);                           // the maps are complete before phase B reads them
         const unsigned synced = __ballot_sync(kFull, L.end_kind == sp::kEndSync);   // (lane 31 never is: it has no successor)
         const int m = __ffs((int)~synced) - 1;       // lanes 0 .. m are good
@@ -306,12 +343,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
     if (__any_sync(kFull, R.bad != 0u)) ok = false;
     if (ok) {
       uint64_t sum = 0;
-      if (checksum_type != BITAR_CHECKSUM_NONE) {
-        inf::Group<32> g;
-        g.lane = lane;
-        g.mask = kFull;
-        sum = ik::group_checksum<32>(dst, total, checksum_type, ck, g);
-      }
+      if (checksum_type != BITAR_CHECKSUM_NONE) sum = stream_checksum(dst, total, checksum_type, ck, lane);
       if (lane == 0) {
         bitar_result out;
         out.produced = total;

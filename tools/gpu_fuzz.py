@@ -1,9 +1,13 @@
 """Extended randomized parity run on a GPU box (not part of the test suite: minutes, many seeds).
 Every GPU stream must equal the sequential model (tools/model) byte for byte, and inflate on the GPU to the input;
-chunk sizes cover both deflate instances (<= 16 KiB: 4-warp instance) and multi-block streams.
+chunk sizes cover both deflate instances (<= 16 KiB: 4-warp instance) and multi-block streams.  The same chunks compressed
+by zlib (a level and strategy per chunk: no index) must inflate on the GPU to the input too, with zlib's checksums, through
+the speculative kernel and whatever it declines.
 usage: python tools/gpu_fuzz.py [seeds] [first_seed]"""
 import os
 import sys
+
+import zlib
 
 import numpy as np
 
@@ -38,6 +42,21 @@ for seed in range(first, first + seeds):
                 if not np.array_equal(o, c) or int(r["checksum"]) != int(r0["checksum"]):
                     bad += 1
                     print(f"ROUNDTRIP seed {seed} {name} chunk {i} size {c.size}", flush=True)
+            # zlib-produced streams of the same chunks
+            zs = []
+            for i, c in enumerate(chunks):
+                lvl, strat = [(1, 0), (6, 0), (9, 0), (1, zlib.Z_HUFFMAN_ONLY), (1, zlib.Z_RLE), (1, zlib.Z_FIXED), (0, 0), (1, 0)][(i + seed) % 8]
+                co = zlib.compressobj(lvl, zlib.DEFLATED, -15, 8, strat)
+                zs.append(np.frombuffer(co.compress(c.tobytes()) + co.flush(), np.uint8).copy())
+            outs, zres, err = G.gpu_inflate_chunks(dev, zs, [c.size for c in chunks], src_shift=(seed + 1) % 4, dst_shift=(seed * 3) % 16)
+            assert err is None, err
+            cnt = np.zeros(8, np.uint32)
+            capi.lib().bitar_debug_inflate_counters(dev._h, 0, cnt.ctypes.data)
+            for i, (c, o, r, r0) in enumerate(zip(chunks, outs, zres, res)):
+                if not np.array_equal(o, c) or int(r["checksum"]) != int(r0["checksum"]):
+                    bad += 1
+                    print(f"FOREIGN seed {seed} {name} chunk {i} size {c.size}", flush=True)
+            print(f"  seed {seed} {name}: {cnt[1]} zlib streams, {cnt[7]} declined by the speculative kernel", flush=True)
         finally:
             dev.close()
     print(f"seed {seed} done, mismatches so far {bad}", flush=True)
