@@ -157,84 +157,57 @@ struct SpecLane : tk::TokLane<LBITS, LT, DBITS, DT> {
     end(kEndBad, pos());
   }
 
-  BITAR_HD void walk_step() {
-    const uint32_t p = pos();
-    while (nx_j < nx_n && nx_pos < p) {
-      ++nx_j;
-      if (nx_j < nx_n) nx_pos = ld_rec(nx_j);
-    }
-    if (nx_j >= nx_n) {                                         // past everything the successor recorded (or no successor)
-      if (seek == 0) return end(kEndStop, p);
-      --seek;
-    } else if (nx_pos == p) {
-      sync_j = nx_j;
-      return end(kEndSync, p);
-    }
-    if (opos >= kOutStopWalk || tpos >= 2048u) return end(kEndFull, p);
-    Base::refill();
-    const uint32_t e = Base::ll_lookup();
-    if ((e & 0xF0u) == 0) {
-      Base::drop(e & 15u);
-      Base::literal(e >> 8);
-    } else if ((e & 0x80u) && (e & 0x70u) < 0x60u) {
-      spec_match(e);
-    } else {
-      special(e);
-    }
-    Base::flush();
-  }
-
-  // One step.  `walk` false: the first kRec steps of a round, during which nobody reads the records yet -- a lane whose
-  // range is already complete waits.
+  // One step: up to four literals, then at most one match (a lane inside its range); one symbol (a lane that walks).
+  // `walk` false: the first kRec steps of a round, during which nobody reads the records yet -- a lane whose range is
+  // already complete waits.  One symbol loop serves both modes: the code of a step is what every warp of the kernel
+  // keeps fetching, and it should be small.
   BITAR_HD void step(bool walk) {
     if (state == kDone) return;
     if (state == Base::kFinish) return Base::finish();            // state = kDone
+    const uint32_t p = pos();
+    uint32_t nsym = 4u;
     if (state == kFast) {
-      const uint32_t p = pos();
       if (p >= goal) {
         state = kWalk;
       } else if (opos >= kOutStop || tpos >= kTokStop) {
         return end(kEndFull, p);
-      } else {
-        if (nrec < kRec) {
-          uint32_t* r = rec();
-          r[2u * nrec] = p;
-          r[2u * nrec + 1u] = opos | (tpos << 16);
-          ++nrec;
-        }
-        Base::refill();                             // cnt >= 32
-        uint32_t e = Base::ll_lookup();
-        if ((e & 0xF0u) == 0) {
-          Base::drop(e & 15u);                      // cnt >= 17
-          Base::literal(e >> 8);
-          e = Base::ll_lookup();
-          if ((e & 0xF0u) == 0) {
-            Base::drop(e & 15u);                    // cnt >= 2
-            Base::literal(e >> 8);
-            Base::refill();                         // cnt >= 32
-            e = Base::ll_lookup();
-            if ((e & 0xF0u) == 0) {
-              Base::drop(e & 15u);                  // cnt >= 17
-              Base::literal(e >> 8);
-              e = Base::ll_lookup();
-              if ((e & 0xF0u) == 0) {
-                Base::drop(e & 15u);                // cnt >= 2
-                Base::literal(e >> 8);
-                e = fl::kNoEntry;
-              }
-            }
-          }
-        }
-        if ((e & 0x80u) && (e & 0x70u) < 0x60u) {
-          spec_match(e);
-        } else if (e != fl::kNoEntry) {
-          special(e);
-        }
-        Base::flush();
-        return;
+      } else if (nrec < kRec) {
+        uint32_t* r = rec();
+        r[2u * nrec] = p;
+        r[2u * nrec + 1u] = opos | (tpos << 16);
+        ++nrec;
       }
     }
-    if (walk) walk_step();
+    if (state == kWalk) {
+      if (!walk) return;
+      while (nx_j < nx_n && nx_pos < p) {
+        ++nx_j;
+        if (nx_j < nx_n) nx_pos = ld_rec(nx_j);
+      }
+      if (nx_j >= nx_n) {                                         // past everything the successor recorded (or no successor)
+        if (seek == 0) return end(kEndStop, p);
+        --seek;
+      } else if (nx_pos == p) {
+        sync_j = nx_j;
+        return end(kEndSync, p);
+      }
+      if (opos >= kOutStopWalk || tpos >= 2048u) return end(kEndFull, p);
+      nsym = 1u;
+    }
+    for (;;) {
+      Base::refill();
+      const uint32_t e = Base::ll_lookup();
+      if ((e & 0xF0u) == 0) {
+        Base::drop(e & 15u);
+        Base::literal(e >> 8);
+        if (--nsym == 0) break;
+        continue;
+      }
+      if ((e & 0x80u) && (e & 0x70u) < 0x60u) spec_match(e);
+      else special(e);
+      break;
+    }
+    Base::flush();
   }
 };
 
