@@ -401,3 +401,82 @@ def test_speculative_lanes_on_damaged_streams_agree_with_zlib_or_decline():
         assert np.array_equal(out, np.frombuffer(ref, np.uint8)), trial
         kept += 1
     assert kept > 0
+
+
+def _fixed_stream(tokens):
+    """A raw DEFLATE stream of one fixed-Huffman block from ('L', byte) / ('M', length, distance) tokens (RFC 1951 3.2.6)."""
+    lb = [3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258]
+    le = [0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0]
+    db = [1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577]
+    de = [0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13]
+    bits = []
+
+    def put(v, n):                      # LSB first (header fields, extra bits)
+        bits.extend((v >> i) & 1 for i in range(n))
+
+    def code(v, n):                     # Huffman codes go MSB first
+        bits.extend((v >> (n - 1 - i)) & 1 for i in range(n))
+
+    def litlen(sym):
+        if sym < 144: code(0x30 + sym, 8)
+        elif sym < 256: code(0x190 + sym - 144, 9)
+        elif sym < 280: code(sym - 256, 7)
+        else: code(0xC0 + sym - 280, 8)
+
+    put(1, 1)
+    put(1, 2)
+    for t in tokens:
+        if t[0] == "L":
+            litlen(t[1])
+        else:
+            _, ln, dist = t
+            s = max(i for i in range(29) if lb[i] <= ln and (i != 28 or ln == 258))
+            if ln == 258:
+                s = 28
+            litlen(257 + s)
+            put(ln - lb[s], le[s])
+            d = max(i for i in range(30) if db[i] <= dist)
+            code(d, 5)
+            put(dist - db[d], de[d])
+    litlen(256)
+    bits.extend([0] * (-len(bits) % 8))
+    return np.packbits(np.array(bits, np.uint8), bitorder="little")
+
+
+def test_speculative_lanes_decline_a_match_that_reaches_below_the_output():
+    """A lane of the speculative decoder does not know where its range lies in the output, so it cannot check a distance
+    against it; phase B does (per byte in the kernel, sp::resolve_range_serial here).  A stream whose ONLY fault is one
+    match that reaches below the start of the output -- in the first range or in a later, speculatively decoded one --
+    must be declined; the same stream without it decodes."""
+    rng = np.random.default_rng(41)
+    for where in (0, 3000, 9000, 20000):
+        tokens, out = [], bytearray()
+        bad_at = None
+        while len(out) < 40000:
+            if bad_at is None and len(out) >= where:
+                bad_at = len(tokens)
+            if len(out) > 300 and rng.random() < 0.35:
+                ln, dist = int(rng.integers(3, 40)), int(rng.integers(1, min(len(out), 32768) + 1))
+                tokens.append(("M", ln, dist))
+                for _ in range(ln):
+                    out.append(out[-dist])
+            else:
+                b = int(rng.integers(0, 256))
+                tokens.append(("L", b))
+                out.append(b)
+        good = _fixed_stream(tokens)
+        ref = np.frombuffer(bytes(out), np.uint8)
+        assert zlib.decompress(good.tobytes(), -15) == bytes(out)
+        got, info = M.host_inflate_spec(good, ref.size, 768)
+        assert not info["declined"] and np.array_equal(got, ref)
+        # the faulty twin: a match at output position `pos` whose distance is pos + 1 .. (one byte too far, or more)
+        pos = sum(1 if t[0] == "L" else t[1] for t in tokens[:bad_at])
+        for extra in (1, 700):
+            if pos + extra > 32768:
+                continue
+            faulty = tokens[:bad_at] + [("M", 5, pos + extra)] + tokens[bad_at:]
+            bad = _fixed_stream(faulty)
+            with pytest.raises(zlib.error):
+                zlib.decompress(bad.tobytes(), -15)
+            got, info = M.host_inflate_spec(bad, ref.size + 5, 768)
+            assert info["declined"] and info["guard_ok"], (where, extra, info)

@@ -99,6 +99,30 @@ def test_damaged_streams_same_verdict_as_the_whole_stream_kernel(cuda_device):
                 s[int(rng.integers(0, s.size))] ^= 1 << int(rng.integers(0, 8))
         bad.append(s)
     caps = [SEG if t % 7 else SEG // 2 for t in range(len(bad))]
+    # streams whose only fault is ONE match that reaches below the start of the output, in the first range or in a later,
+    # speculatively decoded one (a lane cannot check a distance against an output position it does not know: phase B does)
+    from test_core_host import _fixed_stream
+    n_crafted = 0
+    for where in (0, 3000, 9000, 20000):
+        tokens, out = [], bytearray()
+        bad_at = None
+        while len(out) < 40000:
+            if bad_at is None and len(out) >= where:
+                bad_at = len(tokens)
+            if len(out) > 300 and rng.random() < 0.35:
+                ln, dist = int(rng.integers(3, 40)), int(rng.integers(1, min(len(out), 32768) + 1))
+                tokens.append(("M", ln, dist))
+                for _ in range(ln):
+                    out.append(out[-dist])
+            else:
+                b = int(rng.integers(0, 256))
+                tokens.append(("L", b))
+                out.append(b)
+        pos = sum(1 if t[0] == "L" else t[1] for t in tokens[:bad_at])
+        for extra in (1, 700):
+            bad.append(_fixed_stream(tokens[:bad_at] + [("M", 5, pos + extra)] + tokens[bad_at:]))
+            caps.append(SEG)
+            n_crafted += 1
     dev = G.open_device(SEG)
     try:
         runs = []
@@ -107,6 +131,7 @@ def test_damaged_streams_same_verdict_as_the_whole_stream_kernel(cuda_device):
             outs, res, err = G.gpu_inflate_chunks(dev, bad, caps)      # asserts the guard bytes
             runs.append((outs, res["status"].copy(), res["produced"].copy()))
         assert np.array_equal(runs[0][1], runs[1][1])
+        assert (runs[0][1][-n_crafted:] == capi.OP_DATA_ERROR).all()
         ok = runs[0][1] == 0
         assert np.array_equal(runs[0][2][ok], runs[1][2][ok])
         for i in np.nonzero(ok)[0]:
