@@ -116,8 +116,9 @@ def lib():
     L.bitar_last_error.restype = C.c_char_p
     L.bitar_version.restype = C.c_char_p
     L.bitar_tune_inflate_variant.argtypes = [i32]
-    L.bitar_tune_spec_target.argtypes = [i32]
-    L.bitar_debug_inflate_counters.argtypes = [vp, u16, vp]
+    if hasattr(L, "bitar_tune_spec_target"):   # (test hooks; absent from older builds loaded through BITAR_CUDA_LIB for A/B runs)
+        L.bitar_tune_spec_target.argtypes = [i32]
+        L.bitar_debug_inflate_counters.argtypes = [vp, u16, vp]
     _lib = L
     return L
 

@@ -44,15 +44,18 @@ struct Task {
 struct Counters {
   unsigned int n_tasks, n_generic, task_next, generic_next;
   unsigned int n_indexed, spec_next, ck_next, n_declined;   // spec_next / n_declined: inflate_spec_kernel.cuh
-  unsigned long long sum_indexed, sum_generic;              // compressed bytes of the indexed ops / of the others
-  unsigned int pad[4];
+  unsigned long long sum_generic;                           // compressed bytes of the ops without an index
+  unsigned int pad[6];
 };
 static_assert(sizeof(Counters) == 16 * sizeof(unsigned int), "capi.cu: kCountersPerBatch");
 
-// Longest first.  Work is handed out by a counter, in list order; a buffer of columns puts its costliest chunks (the least
-// compressible column) wherever that column lies -- at the end in the benchmark's buffer, where they leave the last wave
-// of warps half empty.  The lists are therefore walked twice: the first pass takes the ops whose compressed size is at
-// least the mean of their list (cost follows the token count, i.e. the compressed size), the second pass the rest.
+// Longest first (the speculative kernel's list).  Work is handed out by a counter, in list order; a buffer of columns puts
+// its costliest chunks (the least compressible column) wherever that column lies -- at the end in the benchmark's buffer,
+// where they leave the last wave of warps half empty.  That list is therefore walked twice: the first pass takes the ops
+// whose compressed size is at least the mean of the list (cost follows the token count, i.e. the compressed size), the
+// second pass the rest.  (Not for the tasks of indexed chunks: measured, no gain at a warp per block -- and at four blocks
+// per warp a group that skips a task falls out of step with the other three groups of its warp, which then execute one
+// after the other: 4 KiB segments 44 -> 28 GB/s.)
 __device__ __forceinline__ bool first_pass_op(uint32_t src_len, uint32_t n, unsigned long long sum) {
   return (unsigned long long)src_len * n >= sum;
 }
@@ -80,7 +83,6 @@ __global__ void __launch_bounds__(128)
     results[i] = r;
     const uint32_t nb = dfl::idx_blocks(ix.total_out);
     indexed[atomicAdd(&pc->n_indexed, 1u)] = i;
-    atomicAdd(&pc->sum_indexed, (unsigned long long)op.src_len);
     const uint32_t base = atomicAdd(&pc->n_tasks, nb);
     for (uint32_t b = 0; b < nb; ++b) tasks[base + b] = Task{i, b};
     return;
@@ -382,11 +384,9 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS)
     uint32_t t = 0;
     if (lane == 0) t = atomicAdd(&pc->task_next, 1u);
     t = __shfl_sync(kFull, t, gbase);
-    if (t >= 2u * n_tasks) break;
-    const bool second = t >= n_tasks;               // longest first: two passes over the list (first_pass_op)
-    const Task tk_ = tasks[second ? t - n_tasks : t];
+    if (t >= n_tasks) break;
+    const Task tk_ = tasks[t];
     const bitar_chunk op = ops[tk_.op];
-    if (first_pass_op(op.src_len, pc->n_indexed, pc->sum_indexed) == second) continue;   // (read per task: no registers held for it)
     const uint8_t* src = static_cast<const uint8_t*>(op.src);
     fl::IndexInfo ix;
     fl::parse_index(src, op.src_len, &ix);   // validated by the plan kernel

@@ -44,7 +44,7 @@ def main():
             traffic[key] = dram / nbytes
     with open(os.path.join(ROOT, 'profiles', f'{tag}_ncu_summary.txt'), 'w') as f:
         f.write('\n'.join(lines) + '\n')
-    if len(traffic) == 2:
+    if len(traffic) == 2 and 'seg59460' in tag:   # bench.py's roofline.traffic is quoted on the benchmark's segment size
         traffic['source'] = (f'profiles/{tag}_ncu_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of '
                              f'tools/gpu_roundtrip_once.py over {int(nbytes)} bytes, per uncompressed byte')
         with open(os.path.join(ROOT, 'profiles', 'r02_dram_traffic.json'), 'w') as f:
