@@ -497,6 +497,7 @@ def run_e2e(args, L, capi, C, torch, dist, world, local_rank, data, seg, n, U):
         phase_ms[1] = (time.perf_counter() - t_a) * 1e3 - phase_ms[0]
         return comp, total
 
+    host_share = [0.0, 0.0]                                                 # the driving thread: seconds asleep (nothing to do) / seconds in the loop
     K = 4                                                                   # sub-parts per queue pair (2: 42 ms, 4: 39 ms, 8: 44 ms per GiB)
 
     def step_pipelined():
@@ -518,6 +519,8 @@ def run_e2e(args, L, capi, C, torch, dist, world, local_rank, data, seg, n, U):
         for q in range(0, len(parts), 2):
             start_compress(q)
         done = 0
+        t_busy0 = time.perf_counter()
+        idle_s = 0.0
         while done < len(parts):
             progressed = False
             for q in range(len(parts)):
@@ -543,7 +546,11 @@ def run_e2e(args, L, capi, C, torch, dist, world, local_rank, data, seg, n, U):
                             done += 1
                     progressed = True
             if not progressed:
+                t_i = time.perf_counter()
                 time.sleep(0.00005)
+                idle_s += time.perf_counter() - t_i
+        host_share[0] += idle_s
+        host_share[1] += time.perf_counter() - t_busy0
         return comp, total
 
     e2e_steps = max(args.steps, 12)           # the mean over at least 12 steps: a step is ~40 ms of host-driven scheduling, and one hiccup of the box (a 70 ms step among six was seen) should not decide the number
@@ -572,6 +579,7 @@ def run_e2e(args, L, capi, C, torch, dist, world, local_rank, data, seg, n, U):
         return float(dt.cpu()[0]), step_ms, comp
 
     dt_sep, ms_sep, cbytes = timed(step_separated)
+    host_share[0] = host_share[1] = 0.0
     sep_phases = {"compress_ms": round(phase_ms[0], 3), "decompress_ms": round(phase_ms[1], 3)}
     dt, step_ms, cbytes = timed(step_pipelined)
     # PCIe roofline of this leg, measured in the same run: plain pinned <-> device copies of U bytes, one direction at
@@ -612,6 +620,7 @@ def run_e2e(args, L, capi, C, torch, dist, world, local_rank, data, seg, n, U):
     return {"value": world * U / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(U + cbytes),
             "d2h_bytes_per_step": int(cbytes + U), "ms_per_step": dt * 1e3, "median_ms_per_step": float(np.median(step_ms)), "steps": e2e_steps, "step_ms": step_ms, "queue_pairs": len(parts),
             "schedule": f"pipelined: per queue pair Compress -> Decompress of {K} sub-parts back to back, odd queue pairs half a phase behind",
+            "host_thread_idle_frac": round(host_share[0] / host_share[1], 3) if host_share[1] else None,
             "phase_separated": {"value": world * U / dt_sep / 1e9, "ms_per_step": dt_sep * 1e3, "step_ms": ms_sep, "last_step": sep_phases}, "pcie": pcie,
             "path": "pinned host in/out through the C-ABI: compress reads and writes host memory in place (zero-copy over "
                     "PCIe), decompress is staged through device memory by the library in batches on three extra streams per queue pair (strided copy-engine gather -- rows go at the pitch of the batch's widest stream, so somewhat more than C bytes cross PCIe --, inflate, copy-engine copy-back); Take / op lists / Recycle inside the timed step"}
