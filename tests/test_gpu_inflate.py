@@ -170,7 +170,7 @@ def test_host_resident_buffers_are_staged(cuda_device):
             assert np.array_equal(back[dst_off:dst_off + data.size], data)
             assert (back[dst_off + data.size:] == 0xA5).all(), "inflate wrote past the produced bytes"
             C.memset(h_out.value, 0xA5, n * SEG + 64)
-        # zlib-produced streams in pinned memory take the whole-stream kernel through the same staging
+        # zlib-produced streams in pinned memory (no index: the speculative kernel) go through the same staging
         zs, zp = O.compress_buffer(data, SEG)
         h_z = C.c_void_p()
         capi.check(L.bitar_mem_alloc(capi.MEM_PINNED, 0, zs.size, 64, C.byref(h_z)))
@@ -194,7 +194,7 @@ def test_staged_calls_in_batches_on_lane_streams(cuda_device, ck):
     """A staged inflate call large enough for several batches runs them on the queue pair's lane streams, each batch
     with its own slice of the task / counter / checksum buffers.  Forced here on a small buffer (1 MiB per batch):
     contiguous destination (copy-engine copy-back), scattered destination (scatter kernel), foreign streams mixed in
-    (whole-stream kernel), checksums, two queue pairs at once."""
+    (no index: the speculative kernel, the whole-stream kernel for what it declines), checksums, two queue pairs at once."""
     import ctypes as C
     L = capi.lib()
     L.bitar_tune_stage_batch.argtypes = [C.c_ulonglong]
