@@ -88,6 +88,7 @@ constexpr uint32_t kTokEob = 0x101u;             //                       end of
 //   bits 0..7 length - 3, 8..22 distance - 1, 23..27 distance symbol
 // (the encode phase looks the length code up by length - 3 in a per-block table, the distance code by symbol)
 constexpr uint32_t kNoCand = 0xFFFFu;
+constexpr int kWinUnroll = 1;                    // windows per trip of the match loop (1 / 2 / 3 / 4 in one gpurun call: 56.6 / 56.1 / 56.4 / 56.6 GB/s)
 
 struct PlanPar {                      // scratch of the parallel half of the plan
   uint32_t ll_bl[16], d_bl[16];      // leaves per code length
@@ -477,7 +478,7 @@ __device__ __forceinline__ void match_subrange(Smem& sm, uint32_t ds, int n, int
   // without four bytes are never used: `valid` below; the scratch has a window of slack past the block)
   const uint16_t* farp = far + s0 + lane;
   uint32_t far_next = __ldcg(farp);
-#pragma unroll 2
+#pragma unroll kWinUnroll
   for (int base = s0; base < s1; base += 32) {
     const int p = base + lane;
     const bool valid = p + 4 <= n;
