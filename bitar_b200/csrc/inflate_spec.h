@@ -194,14 +194,20 @@ struct SpecLane : tk::TokLane<LBITS, LT, DBITS, DT> {
       if (opos >= kOutStopWalk || tpos >= 2048u) return end(kEndFull, p);
       nsym = 1u;
     }
-    for (;;) {
-      Base::refill();
-      const uint32_t e = Base::ll_lookup();
+    for (;;) {                                                    // two symbols per refill (a code is at most 15 bits)
+      Base::refill();                                             // cnt >= 32
+      uint32_t e = Base::ll_lookup();
       if ((e & 0xF0u) == 0) {
-        Base::drop(e & 15u);
+        Base::drop(e & 15u);                                      // cnt >= 17
         Base::literal(e >> 8);
         if (--nsym == 0) break;
-        continue;
+        e = Base::ll_lookup();
+        if ((e & 0xF0u) == 0) {
+          Base::drop(e & 15u);                                    // cnt >= 2
+          Base::literal(e >> 8);
+          if (--nsym == 0) break;
+          continue;
+        }
       }
       if ((e & 0x80u) && (e & 0x70u) < 0x60u) spec_match(e);
       else special(e);
