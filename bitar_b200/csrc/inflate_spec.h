@@ -194,7 +194,9 @@ struct SpecLane : tk::TokLane<LBITS, LT, DBITS, DT> {
       if (opos >= kOutStopWalk || tpos >= 2048u) return end(kEndFull, p);
       nsym = 1u;
     }
-    for (;;) {                                                    // two symbols per refill (a code is at most 15 bits)
+    // (four symbols per trip, two per refill -- a code is at most 15 bits; with nsym = 4 the trip is the whole step, with
+    // nsym = 1 it ends after the first symbol: one copy of the code for both modes, no loop overhead in the common one)
+    for (;;) {
       Base::refill();                                             // cnt >= 32
       uint32_t e = Base::ll_lookup();
       if ((e & 0xF0u) == 0) {
@@ -206,7 +208,20 @@ struct SpecLane : tk::TokLane<LBITS, LT, DBITS, DT> {
           Base::drop(e & 15u);                                    // cnt >= 2
           Base::literal(e >> 8);
           if (--nsym == 0) break;
-          continue;
+          Base::refill();                                         // cnt >= 32
+          e = Base::ll_lookup();
+          if ((e & 0xF0u) == 0) {
+            Base::drop(e & 15u);                                  // cnt >= 17
+            Base::literal(e >> 8);
+            if (--nsym == 0) break;
+            e = Base::ll_lookup();
+            if ((e & 0xF0u) == 0) {
+              Base::drop(e & 15u);                                // cnt >= 2
+              Base::literal(e >> 8);
+              if (--nsym == 0) break;
+              continue;
+            }
+          }
         }
       }
       if ((e & 0x80u) && (e & 0x70u) < 0x60u) spec_match(e);
