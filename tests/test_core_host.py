@@ -480,3 +480,26 @@ def test_speculative_lanes_decline_a_match_that_reaches_below_the_output():
                 zlib.decompress(bad.tobytes(), -15)
             got, info = M.host_inflate_spec(bad, ref.size + 5, 768)
             assert info["declined"] and info["guard_ok"], (where, extra, info)
+
+
+def test_speculative_lanes_on_random_structured_inputs():
+    """Randomly structured buffers (runs, periods, small alphabets, far copies) of random sizes, compressed by zlib at a
+    level and strategy per case: the speculative decoder either declines or returns the input, whatever range size it
+    aims at and however the buffers are aligned."""
+    rng = np.random.default_rng(77)
+    decoded = 0
+    for case in range(40):
+        n = int(rng.integers(200, 200000))
+        ch = _structured(rng, n)
+        lvl, strat = [(1, 0), (6, 0), (9, 0), (1, zlib.Z_HUFFMAN_ONLY), (1, zlib.Z_RLE), (1, zlib.Z_FIXED)][case % 6]
+        comp = _zraw(ch, lvl, strat)
+        target = int(rng.integers(64, 1537))
+        out, info = M.host_inflate_spec(comp, n, target, case % 7)
+        assert info["guard_ok"], (case, info)
+        if not info["declined"]:
+            assert np.array_equal(out, ch), (case, n, lvl, strat, target, info)
+            decoded += 1
+        # a destination one byte short is never written past: declined, or produced <= capacity
+        out, info = M.host_inflate_spec(comp, n - 1, target, case % 5)
+        assert info["guard_ok"] and info["declined"], (case, info)
+    assert decoded >= 20
